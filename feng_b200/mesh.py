@@ -1,0 +1,156 @@
+"""Synthetic refined meshes generated in code and a Gmsh 4.1 ASCII writer.
+
+T2D(N): unit square, N x N cells, each split along the same diagonal into two CCW triangles.
+T3D(N): unit cube, N^3 cells, each split into 6 Kuhn tetrahedra.
+
+The writer exists so that the unmodified reference reader (src/feMeshRead.cpp:645-, contract summarised in
+SURVEY.md section 7-1) ingests the IDENTICAL mesh: the vertex order of the file is the host vertex index
+(src/feMeshRead.cpp:942-958), element order inside the single (dim, entity) block is the local element index,
+and boundary facets are oriented like the adjacent cell's facet (src/feMeshRead.cpp:1836-1898).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# local facets of a cell, in the reference's order:
+#   triangle edges (0,1),(1,2),(2,0)                                  src/feMeshRead.cpp:1412-1431
+#   tetrahedron faces {0,2,1},{0,1,3},{0,3,2},{3,1,2}                 src/feTetrahedron.h:30
+TRI_EDGES = np.array([[0, 1], [1, 2], [2, 0]], np.int32)
+TET_FACES = np.array([[0, 2, 1], [0, 1, 3], [0, 3, 2], [3, 1, 2]], np.int32)
+#   tetrahedron edges {0,2},{2,1},{1,0},{1,3},{3,0},{3,2}             src/feTetrahedron.h:31
+TET_EDGES = np.array([[0, 2], [2, 1], [1, 0], [1, 3], [3, 0], [3, 2]], np.int32)
+
+
+@dataclass
+class Mesh:
+    dim: int
+    xyz: np.ndarray                 # (nV, 3) float64
+    cells: np.ndarray               # (nE, dim+1) int32   physical "Domaine"
+    bfacets: np.ndarray             # (nB, dim) int32     physical "Bord", oriented like the adjacent cell
+    point_pressure: int | None = 0  # vertex carrying the 0-D physical "PointPression"
+    names: dict = field(default_factory=lambda: {"domain": "Domaine", "boundary": "Bord",
+                                                 "point": "PointPression"})
+
+    @property
+    def n_vertices(self):
+        return self.xyz.shape[0]
+
+    @property
+    def n_cells(self):
+        return self.cells.shape[0]
+
+
+def boundary_facets(cells: np.ndarray) -> np.ndarray:
+    """Facets that belong to exactly one cell, with the node order of that cell's local facet, listed in
+    (cell, local facet) order."""
+    nv = cells.shape[1]
+    loc = TRI_EDGES if nv == 3 else TET_FACES
+    fac = cells[:, loc]                                  # (nE, nf, dim)
+    flat = fac.reshape(-1, loc.shape[1])
+    key = np.sort(flat, axis=1)
+    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    return np.ascontiguousarray(flat[cnt[inv.reshape(-1)] == 1]).astype(np.int32)
+
+
+def square_mesh(n: int, lx: float = 1.0, ly: float = 1.0, x0: float = 0.0, y0: float = 0.0) -> Mesh:
+    """T2D(n): 2 n^2 triangles, (n+1)^2 vertices numbered row-major (x fastest)."""
+    i, j = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="xy")
+    xyz = np.zeros(((n + 1) ** 2, 3))
+    xyz[:, 0] = x0 + lx * i.reshape(-1) / n
+    xyz[:, 1] = y0 + ly * j.reshape(-1) / n
+    ci, cj = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
+    v00 = (cj * (n + 1) + ci).reshape(-1)
+    v10, v01, v11 = v00 + 1, v00 + (n + 1), v00 + (n + 2)
+    cells = np.empty((2 * n * n, 3), np.int32)
+    cells[0::2] = np.stack([v00, v10, v11], 1)
+    cells[1::2] = np.stack([v00, v11, v01], 1)
+    return Mesh(2, xyz, cells, boundary_facets(cells), 0)
+
+
+# Kuhn split of the unit cube: one tetrahedron per permutation of the axes, all sharing the main diagonal.
+_KUHN = [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)]
+
+
+def cube_mesh(n: int) -> Mesh:
+    """T3D(n): 6 n^3 positively oriented tetrahedra, (n+1)^3 vertices (x fastest, then y, then z)."""
+    g = np.arange(n + 1)
+    k, j, i = np.meshgrid(g, g, g, indexing="ij")
+    xyz = np.stack([i.reshape(-1), j.reshape(-1), k.reshape(-1)], 1) / float(n)
+    c = np.arange(n)
+    ck, cj, ci = np.meshgrid(c, c, c, indexing="ij")
+    base = np.stack([ci.reshape(-1), cj.reshape(-1), ck.reshape(-1)], 1)          # (nc, 3)
+    stride = np.array([1, n + 1, (n + 1) ** 2])
+    cells = np.empty((base.shape[0], 6, 4), np.int64)
+    for t, perm in enumerate(_KUHN):
+        p = base.copy()
+        cells[:, t, 0] = p @ stride
+        for s, ax in enumerate(perm):
+            p = p.copy()
+            p[:, ax] += 1
+            cells[:, t, s + 1] = p @ stride
+    cells = cells.reshape(-1, 4)
+    # make every tetrahedron positively oriented (det > 0) by swapping the last two vertices when needed
+    a = xyz[cells[:, 1]] - xyz[cells[:, 0]]
+    b = xyz[cells[:, 2]] - xyz[cells[:, 0]]
+    d = xyz[cells[:, 3]] - xyz[cells[:, 0]]
+    det = np.einsum("ij,ij->i", np.cross(a, b), d)
+    neg = det < 0
+    cells[neg, 2], cells[neg, 3] = cells[neg, 3].copy(), cells[neg, 2].copy()
+    cells = cells.astype(np.int32)
+    return Mesh(3, np.ascontiguousarray(xyz), cells, boundary_facets(cells), 0)
+
+
+def write_msh(mesh: Mesh, path: str) -> None:
+    """Gmsh 4.1 ASCII with physical groups Domaine / Bord / PointPression, one geometric entity each."""
+    dim, nV, nE, nB = mesh.dim, mesh.n_vertices, mesh.n_cells, mesh.bfacets.shape[0]
+    has_pt = mesh.point_pressure is not None
+    nm = mesh.names
+    lo, hi = mesh.xyz.min(0), mesh.xyz.max(0)
+    box = " ".join(repr(float(v)) for v in (*lo, *hi))
+    out = ["$MeshFormat", "4.1 0 8", "$EndMeshFormat", "$PhysicalNames", str(2 + int(has_pt))]
+    if has_pt:
+        out.append(f'0 1 "{nm["point"]}"')
+    out.append(f'{dim - 1} 2 "{nm["boundary"]}"')
+    out.append(f'{dim} 3 "{nm["domain"]}"')
+    out.append("$EndPhysicalNames")
+    out.append("$Entities")
+    n_pts = 1 if has_pt else 0
+    if dim == 2:
+        out.append(f"{n_pts} 1 1 0")
+    else:
+        out.append(f"{n_pts} 0 1 1")
+    if has_pt:
+        p = [float(v) for v in mesh.xyz[mesh.point_pressure]]
+        out.append(f"1 {p[0]!r} {p[1]!r} {p[2]!r} 1 1 ")
+    out.append(f"1 {box} 1 2 0 ")          # boundary entity (curve in 2D, surface in 3D)
+    out.append(f"1 {box} 1 3 1 1 ")        # domain entity, bounded by the boundary entity
+    out.append("$EndEntities")
+    out.append("$Nodes")
+    out.append(f"1 {nV} 1 {nV}")
+    out.append(f"{dim} 1 0 {nV}")
+    out.extend(str(t) for t in range(1, nV + 1))
+    out.extend(f"{x!r} {y!r} {z!r}" for x, y, z in mesh.xyz.tolist())
+    out.append("$EndNodes")
+    out.append("$Elements")
+    n_blocks = 2 + int(has_pt)
+    n_tot = nE + nB + int(has_pt)
+    out.append(f"{n_blocks} {n_tot} 1 {n_tot}")
+    tag = 1
+    if has_pt:
+        out.append("0 1 15 1")
+        out.append(f"{tag} {mesh.point_pressure + 1}")
+        tag += 1
+    btype, ctype = (1, 2) if dim == 2 else (2, 4)
+    out.append(f"{dim - 1} 1 {btype} {nB}")
+    for row in (mesh.bfacets + 1).tolist():
+        out.append(f"{tag} " + " ".join(map(str, row)))
+        tag += 1
+    out.append(f"{dim} 1 {ctype} {nE}")
+    for row in (mesh.cells + 1).tolist():
+        out.append(f"{tag} " + " ".join(map(str, row)))
+        tag += 1
+    out.append("$EndElements")
+    with open(path, "w") as f:
+        f.write("\n".join(out) + "\n")
