@@ -1,0 +1,262 @@
+"""ctypes binding of the C ABI (include/feng_b200.h) -- the same symbols the C++ adapter links against.
+
+There is no fallback: if the CUDA library is missing this module raises at import of `lib()`, and every compute
+entry point fails with B200_ERR_CUDA when no device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libfeng_b200.so")
+
+# every symbol include/feng_b200.h declares (tests/test_capi_symbols.py checks the list against the header)
+SYMBOLS = [
+    "b200_last_error", "b200_kernel_launches", "b200_reset_kernel_launches", "b200_create", "b200_destroy",
+    "b200_set_mesh", "b200_set_quadrature", "b200_add_space", "b200_add_form", "b200_set_pattern",
+    "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode",
+    "b200_set_constraints", "b200_set_blocks", "b200_finalize", "b200_system_size", "b200_set_solution",
+    "b200_set_to_zero", "b200_assemble", "b200_rhs_max_norm", "b200_du_max_norm", "b200_constrain",
+    "b200_apply_periodicity", "b200_solve", "b200_correct_solution", "b200_get_rhs", "b200_axpy_rhs",
+    "b200_get_matrix_values", "b200_get_du", "b200_get_solution", "b200_spmv", "b200_last_assemble_ms",
+    "b200_last_solve_ms", "b200_time_spmv", "b200_sync",
+]
+
+SCATTER_ATOMIC, SCATTER_COLORED = 0, 1
+PC_NONE, PC_JACOBI, PC_BLOCK_JACOBI, PC_ILU0 = 0, 1, 2, 3
+
+
+class SolverOptions(C.Structure):
+    _fields_ = [("rel_tol", C.c_double), ("abs_tol", C.c_double), ("div_tol", C.c_double), ("max_iter", C.c_int),
+                ("restart", C.c_int), ("pc", C.c_int)]
+
+
+class SolveInfo(C.Structure):
+    _fields_ = [("norm_dx", C.c_double), ("norm_rhs", C.c_double), ("norm_axb", C.c_double),
+                ("iterations", C.c_int), ("converged", C.c_int), ("rel_residual", C.c_double)]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(the engine is CUDA-only; there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.b200_last_error.restype = C.c_char_p
+        L.b200_kernel_launches.restype = C.c_int64
+        L.b200_system_size.restype = C.c_int64
+        L.b200_system_size.argtypes = [C.c_void_p]
+        L.b200_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.b200_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _ptr(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def _d(a):
+    return _ptr(a, C.c_double)
+
+
+def _i32(a):
+    return _ptr(a, C.c_int32)
+
+
+def _i64(a):
+    return _ptr(a, C.c_int64)
+
+
+def check(rc, what=""):
+    if rc < 0:
+        raise B200Error(f"{what}: rc={rc}: {lib().b200_last_error().decode()}")
+    return rc
+
+
+class System:
+    """Thin object wrapper over b200_system*; one method per C entry point."""
+
+    def __init__(self, device: int = 0):
+        self.L = lib()
+        h = C.c_void_p()
+        check(self.L.b200_create(C.byref(h), device), "b200_create")
+        self.h = h
+        self.n_inc = self.n_dof = self.nnz = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- set-up -------------------------------------------------------------------------------------
+    def set_mesh(self, dim, xyz, cells):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        cells = np.ascontiguousarray(cells, np.int32)
+        check(self.L.b200_set_mesh(self.h, dim, C.c_int64(xyz.shape[0]), _d(xyz), C.c_int64(cells.shape[0]),
+                                   cells.shape[1], _i32(cells)), "b200_set_mesh")
+
+    def set_quadrature(self, w):
+        w = np.ascontiguousarray(w, np.float64)
+        check(self.L.b200_set_quadrature(self.h, w.shape[0], _d(w)), "b200_set_quadrature")
+
+    def add_space(self, n_scalar, ncomp, adr, L, dL):
+        adr = np.ascontiguousarray(adr, np.int32)
+        L = np.ascontiguousarray(L, np.float64)
+        dL = np.ascontiguousarray(dL, np.float64)
+        return check(self.L.b200_add_space(self.h, n_scalar, ncomp, _i32(adr), _d(L), _d(dL)), "b200_add_space")
+
+    def add_form(self, kind, su, sp=-1, coeff=1.0, param=1.0, source=None):
+        src = None if source is None else np.ascontiguousarray(source, np.float64)
+        return check(self.L.b200_add_form(self.h, kind, su, sp, C.c_double(coeff), C.c_double(param), _d(src)),
+                     "b200_add_form")
+
+    def set_pattern(self, n_inc, n_dof, ia, ja):
+        ia = np.ascontiguousarray(ia, np.int64)
+        ja = np.ascontiguousarray(ja, np.int32)
+        check(self.L.b200_set_pattern(self.h, C.c_int64(n_inc), C.c_int64(n_dof), _i64(ia), _i32(ja)),
+              "b200_set_pattern")
+        self.n_inc, self.n_dof, self.nnz = int(n_inc), int(n_dof), int(ia[-1])
+
+    def get_pattern(self):
+        ia = np.zeros(self.n_inc + 1, np.int64)
+        ja = np.zeros(self.nnz, np.int32)
+        check(self.L.b200_get_pattern(self.h, _i64(ia), _i32(ja)), "b200_get_pattern")
+        return ia, ja
+
+    def set_colors(self, n_colors, colors):
+        colors = np.ascontiguousarray(colors, np.int32)
+        check(self.L.b200_set_colors(self.h, n_colors, _i32(colors)), "b200_set_colors")
+
+    def set_scatter_mode(self, mode):
+        check(self.L.b200_set_scatter_mode(self.h, mode), "b200_set_scatter_mode")
+
+    def set_constraints(self, rows, master=None, slave=None):
+        rows = np.ascontiguousarray(rows, np.int64)
+        m = None if master is None else np.ascontiguousarray(master, np.int64)
+        s = None if slave is None else np.ascontiguousarray(slave, np.int64)
+        check(self.L.b200_set_constraints(self.h, C.c_int64(rows.shape[0]), _i64(rows),
+                                          C.c_int64(0 if m is None else m.shape[0]), _i64(m), _i64(s)),
+              "b200_set_constraints")
+
+    def set_blocks(self, block_ptr, block_rows):
+        bp = np.ascontiguousarray(block_ptr, np.int64)
+        br = np.ascontiguousarray(block_rows, np.int64)
+        check(self.L.b200_set_blocks(self.h, C.c_int64(bp.shape[0] - 1), _i64(bp), _i64(br)), "b200_set_blocks")
+
+    def finalize(self):
+        check(self.L.b200_finalize(self.h), "b200_finalize")
+
+    # ---- feLinearSystem virtuals ----------------------------------------------------------------------
+    def set_solution(self, sol, sol_dot=None, c0=0.0, t=0.0):
+        sol = np.ascontiguousarray(sol, np.float64)
+        sd = None if sol_dot is None else np.ascontiguousarray(sol_dot, np.float64)
+        check(self.L.b200_set_solution(self.h, _d(sol), _d(sd), C.c_double(c0), C.c_double(t)), "b200_set_solution")
+
+    def set_to_zero(self, what=3):
+        check(self.L.b200_set_to_zero(self.h, what), "b200_set_to_zero")
+
+    def assemble(self, what=3, only_transient=False):
+        check(self.L.b200_assemble(self.h, what, int(only_transient)), "b200_assemble")
+
+    def rhs_max_norm(self):
+        v = C.c_double()
+        check(self.L.b200_rhs_max_norm(self.h, C.byref(v)), "b200_rhs_max_norm")
+        return v.value
+
+    def du_max_norm(self):
+        v = C.c_double()
+        check(self.L.b200_du_max_norm(self.h, C.byref(v)), "b200_du_max_norm")
+        return v.value
+
+    def constrain(self):
+        check(self.L.b200_constrain(self.h), "b200_constrain")
+
+    def apply_periodicity(self):
+        check(self.L.b200_apply_periodicity(self.h), "b200_apply_periodicity")
+
+    def solve(self, rel_tol=1e-8, abs_tol=1e-14, div_tol=1e6, max_iter=10000, restart=30, pc=PC_JACOBI,
+              raise_on_fail=True):
+        opt = SolverOptions(rel_tol, abs_tol, div_tol, max_iter, restart, pc)
+        info = SolveInfo()
+        rc = self.L.b200_solve(self.h, C.byref(opt), C.byref(info))
+        if raise_on_fail:
+            check(rc, "b200_solve")
+        return info
+
+    def correct_solution(self, sol_host=None, correct_dot=False):
+        check(self.L.b200_correct_solution(self.h, _d(sol_host), int(correct_dot)), "b200_correct_solution")
+
+    def get_rhs(self):
+        out = np.zeros(self.n_inc)
+        check(self.L.b200_get_rhs(self.h, _d(out)), "b200_get_rhs")
+        return out
+
+    def axpy_rhs(self, coeff, d):
+        d = np.ascontiguousarray(d, np.float64)
+        check(self.L.b200_axpy_rhs(self.h, C.c_double(coeff), _d(d)), "b200_axpy_rhs")
+
+    def get_matrix_values(self):
+        out = np.zeros(self.nnz)
+        check(self.L.b200_get_matrix_values(self.h, _d(out)), "b200_get_matrix_values")
+        return out
+
+    def get_du(self):
+        out = np.zeros(self.n_inc)
+        check(self.L.b200_get_du(self.h, _d(out)), "b200_get_du")
+        return out
+
+    def get_solution(self):
+        out = np.zeros(self.n_dof)
+        check(self.L.b200_get_solution(self.h, _d(out)), "b200_get_solution")
+        return out
+
+    def spmv(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.zeros(self.n_inc)
+        check(self.L.b200_spmv(self.h, _d(x), _d(y)), "b200_spmv")
+        return y
+
+    # ---- measurement ----------------------------------------------------------------------------------
+    def last_assemble_ms(self):
+        v = C.c_float()
+        check(self.L.b200_last_assemble_ms(self.h, C.byref(v)), "b200_last_assemble_ms")
+        return v.value
+
+    def last_solve_ms(self):
+        v = C.c_float()
+        check(self.L.b200_last_solve_ms(self.h, C.byref(v)), "b200_last_solve_ms")
+        return v.value
+
+    def time_spmv(self, reps=20):
+        v = C.c_float()
+        check(self.L.b200_time_spmv(self.h, reps, C.byref(v)), "b200_time_spmv")
+        return v.value
+
+    def sync(self):
+        check(self.L.b200_sync(self.h), "b200_sync")
+
+
+def kernel_launches() -> int:
+    return int(lib().b200_kernel_launches())
+
+
+def reset_kernel_launches():
+    lib().b200_reset_kernel_launches()

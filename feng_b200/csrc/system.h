@@ -1,0 +1,129 @@
+// Internal state of one b200_system (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/feng_b200.h"
+
+namespace b200 {
+
+void set_error(const std::string &msg);
+void count_launch(int n = 1);
+
+#define B200_CUDA(call)                                                                                       \
+  do {                                                                                                        \
+    cudaError_t _e = (call);                                                                                  \
+    if(_e != cudaSuccess) {                                                                                   \
+      b200::set_error(std::string(#call) + ": " + cudaGetErrorString(_e));                                    \
+      return B200_ERR_CUDA;                                                                                   \
+    }                                                                                                         \
+  } while(0)
+
+struct Space {
+  int                 nS = 0, nc = 1; // scalar functions, components
+  int32_t            *d_adr = nullptr; // [nElm][nS*nc]
+  std::vector<double> L, dL;           // host copies of the reference tables
+};
+
+struct Form {
+  int     kind = 0, su = 0, sp = -1;
+  double  coeff = 1., param = 1.;
+  double *d_source = nullptr; // [nElm][nq][ncomp]
+};
+
+// Coefficients of the fused Taylor-Hood kernel: sums over the registered forms, see assemble.cu
+struct THCoeffs {
+  double c_conv = 0.;  // VECTOR_CONVECTIVE_ACCELERATION coeff
+  double c_sig = 0.;   // DIV_NEWTONIAN_STRESS coeff
+  double sig_mu = 0.;  // DIV_NEWTONIAN_STRESS coeff * viscosity
+  double c_div = 0.;   // MIXED_DIVERGENCE coeff
+  double diff_k = 0.;  // VECTOR_DIFFUSION coeff * diffusivity
+  double c_gradp = 0.; // MIXED_GRADIENT coeff
+  double c_mass = 0.;  // TRANSIENT_VECTOR_MASS coeff
+  double c_src = 0.;   // 1 if a VECTOR_SOURCE form is present
+};
+
+struct ScalarCoeffs {
+  double k = 0.;      // DIFFUSION diffusivity (its coefficient callback)
+  double c_mass = 0.; // TRANSIENT_MASS coeff
+  double c_src = 0.;
+};
+
+enum PlanKind { PLAN_NONE = 0, PLAN_SCALAR = 1, PLAN_TAYLOR_HOOD = 2 };
+
+struct System {
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+  float        last_assemble_ms = 0.f, last_solve_ms = 0.f;
+
+  // mesh
+  int      dim = 0, nv = 0;
+  int64_t  nVert = 0, nElm = 0;
+  double  *d_xyz = nullptr;  // [nVert][dim]
+  int32_t *d_conn = nullptr; // [nElm][nv]
+  int      nq = 0;
+  std::vector<double> w;
+
+  std::vector<Space> spaces;
+  std::vector<Form>  forms;
+
+  // linear system
+  int64_t  nInc = 0, nDOF = 0, nnz = 0;
+  int64_t *d_ia = nullptr;
+  int32_t *d_ja = nullptr;
+  double  *d_val = nullptr, *d_rhs = nullptr, *d_du = nullptr, *d_sol = nullptr, *d_soldot = nullptr;
+  double   c0 = 0., t = 0.;
+  bool     have_soldot = false;
+
+  // fused plan
+  PlanKind     plan = PLAN_NONE;
+  int          su = -1, sp = -1;       // primary / pressure space ids
+  int          M = 0;                  // local rows = local cols of the fused element system
+  THCoeffs     th, th_transient;       // all forms / transient-matrix forms only
+  ScalarCoeffs sc, sc_transient;
+  double      *d_source = nullptr;     // source table of the (single) source form
+  int32_t     *d_slot = nullptr;       // [nElm][M][M] CSR slot or -1
+  double      *d_tab = nullptr;        // packed basis tables + weights for the kernels
+  int          tab_len = 0;
+  bool         has_matrix_block[2][2] = {{false, false}, {false, false}}; // [U|P][U|P]
+
+  // scatter
+  int                  scatter_mode = B200_SCATTER_ATOMIC;
+  int                  n_colors = 0;
+  int32_t             *d_color_elems = nullptr; // elements sorted by colour
+  std::vector<int64_t> color_ptr;               // [n_colors+1]
+
+  // constraints
+  int64_t  n_crow = 0, n_per = 0;
+  int64_t *d_crows = nullptr;
+  char    *d_cflag = nullptr; // [nInc]
+  int64_t *d_master = nullptr, *d_slave = nullptr;
+
+  // block Jacobi
+  int64_t  n_blocks = 0;
+  std::vector<int64_t> block_ptr, block_rows;
+
+  // Krylov workspace (allocated lazily, krylov.cu)
+  void *krylov = nullptr;
+
+  // scratch for reductions
+  double *d_scratch = nullptr;
+  double *h_scratch = nullptr; // pinned
+};
+
+// assemble.cu
+int build_plan(System *S);
+int launch_assemble(System *S, int what, int only_transient);
+// krylov.cu
+int  spmv(System *S, const double *d_x, double *d_y);
+int  gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info);
+void krylov_free(System *S);
+int  max_abs(System *S, const double *d_x, int64_t n, double *out);
+
+} // namespace b200
+
+struct b200_system : public b200::System {};

@@ -1,0 +1,181 @@
+/*
+ * feng_b200 -- B200-native (sm_100a, FP64) finite-element assembly + Newton linear solve engine.
+ *
+ * C ABI of the drop-in boundary.  The reference (arthurbawin/feNG) talks to its linear-system backends only
+ * through the 22 pure virtuals of class feLinearSystem (src/feLinearSystem.h:43-169); the adapter
+ * adapter/feLinearSystemB200.h implements those virtuals on top of the entry points below, next to
+ * feLinearSystemPETSc (src/feLinearSystem.h:174) and feLinearSystemMklPardiso (src/feLinearSystem.h:276).
+ * Each entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative code on failure; b200_last_error() gives the message
+ *     (maps onto feStatus / feErrorMsg, src/feMessage.h:44-97).  There is NO CPU fallback: without a CUDA
+ *     device every compute entry point fails with B200_ERR_CUDA.
+ *   - all pointers are caller-owned HOST memory unless the name ends in _device; set-up tables are copied once.
+ *   - indices: DOF numbers int32 (the reference's feInt tables are narrowed by the adapter), CSR row pointers
+ *     int64, CSR columns int32.
+ *   - sign convention of the reference: Be = -(weak residual), Ae = +d(weak residual)/du, the Newton system is
+ *     A du = rhs (src/feLinearSystem.h:128-129).
+ *   - calls on one system are not thread-safe (the reference drives a backend from one thread,
+ *     src/feNonLinearSolver.cpp:77-123).
+ */
+#ifndef FENG_B200_H
+#define FENG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_system b200_system;
+
+enum {
+  B200_OK          = 0,
+  B200_ERR_ARG     = -1, /* bad argument / call order */
+  B200_ERR_CUDA    = -2, /* CUDA runtime failure or no device */
+  B200_ERR_UNSUPP  = -3, /* weak form or space not supported by the fused kernels */
+  B200_ERR_SOLVER  = -4  /* Krylov solver diverged or broke down */
+};
+
+/* Weak-form kinds: numerically identical to the reference's elementSystemType (src/feSysElm.h:13-77), so the
+ * adapter passes feBilinearForm::getID() (src/feBilinearForm.h:165) through unchanged. */
+enum {
+  B200_FORM_SOURCE                         = 0,  /* feSysElm_Source,                       src/feSysElm.cpp:16-27        */
+  B200_FORM_VECTOR_SOURCE                  = 2,  /* feSysElm_VectorSource<dim>,            src/feVectorSysElm.cpp:112-128 */
+  B200_FORM_TRANSIENT_MASS                 = 13, /* feSysElm_TransientMass,                src/feSysElm.cpp:426-460      */
+  B200_FORM_TRANSIENT_VECTOR_MASS          = 15, /* feSysElm_TransientVectorMass<dim>,     src/feVectorSysElm.cpp:390-425 */
+  B200_FORM_DIFFUSION                      = 16, /* feSysElm_Diffusion<dim>,               src/feSysElm.cpp:530-583      */
+  B200_FORM_VECTOR_DIFFUSION               = 18, /* feSysElm_VectorDiffusion<dim>,         src/feVectorSysElm.cpp:449-503 */
+  B200_FORM_VECTOR_CONVECTIVE_ACCELERATION = 22, /* feSysElm_VectorConvectiveAcceleration, src/feVectorSysElm.cpp:1171-1242 */
+  B200_FORM_DIV_NEWTONIAN_STRESS           = 25, /* feSysElm_DivergenceNewtonianStress,    src/feVectorSysElm.cpp:1454-1532 */
+  B200_FORM_MIXED_GRADIENT                 = 26, /* feSysElm_MixedGradient<dim>,           src/feVectorSysElm.cpp:528-578 */
+  B200_FORM_MIXED_DIVERGENCE               = 31  /* feSysElm_MixedDivergence<dim>,         src/feVectorSysElm.cpp:685-749 */
+};
+
+/* Scatter strategies for the race-free add into the CSR matrix (north-star subsystem 3). */
+enum {
+  B200_SCATTER_ATOMIC  = 0, /* one launch, red.global.add.f64 into precomputed CSR slots               */
+  B200_SCATTER_COLORED = 1  /* one launch per element colour, plain read-modify-write; needs b200_set_colors
+                               (feCncGeo::colorElements, src/feCncGeo.cpp:752-794)                        */
+};
+
+/* Preconditioners of the restarted GMRES (north-star subsystem 4). */
+enum {
+  B200_PC_NONE         = 0,
+  B200_PC_JACOBI       = 1, /* point Jacobi; zero diagonals (pressure rows of Taylor-Hood) are replaced by 1 */
+  B200_PC_BLOCK_JACOBI = 2, /* dense LU of the diagonal blocks given by b200_set_blocks                      */
+  B200_PC_ILU0         = 3  /* ILU(0) on the CSR pattern (PETSc's sequential default, src/feLinearSystem.h:198) */
+};
+
+typedef struct {
+  double rel_tol;   /* feLinearSystem::_rel_tol,  src/feLinearSystem.h:66 (default 1e-8)  */
+  double abs_tol;   /* feLinearSystem::_abs_tol,  src/feLinearSystem.h:67 (default 1e-14) */
+  double div_tol;   /* feLinearSystem::_div_tol,  src/feLinearSystem.h:68 (default 1e6)   */
+  int    max_iter;  /* feLinearSystem::_max_iter, src/feLinearSystem.h:69 (default 1e4)   */
+  int    restart;   /* GMRES restart length m (PETSc default 30)                           */
+  int    pc;        /* B200_PC_*                                                           */
+} b200_solver_options;
+
+typedef struct {
+  double norm_dx;        /* max-norm of du            (solve(): normDx)        */
+  double norm_rhs;       /* max-norm of the rhs       (solve(): normResidual)  */
+  double norm_axb;       /* max-norm of A du - rhs    (solve(): normAxb)       */
+  int    iterations;     /* Krylov iterations         (solve(): nIter)         */
+  int    converged;      /* 1 if the tolerance was met */
+  double rel_residual;   /* final preconditioned residual 2-norm / initial     */
+} b200_solve_info;
+
+const char *b200_last_error(void);
+/* Number of CUDA kernels this library has launched since load / since the last reset (bench.py: gpu_launches). */
+int64_t b200_kernel_launches(void);
+void    b200_reset_kernel_launches(void);
+
+/* ---- life cycle: feLinearSystem ctor/dtor (src/feLinearSystem.h:81-83, src/feLinearSystemMklPardiso.cpp:174-, :1224-1257) */
+int  b200_create(b200_system **out, int device);
+void b200_destroy(b200_system *s);
+
+/* ---- set-up tables, copied once (what feBilinearForm::initialize gathers per element on the host,
+ *      src/feBilinearForm.cpp:284-367) ---- */
+/* vertices and connectivity of the interior ("Domaine") connectivity: feMesh::getVertices (src/feMesh.h:130),
+ * feCncGeo::getVerticesConnectivity (src/feCncGeo.h:178).  Straight simplices only (nv = dim+1): the Jacobians
+ * feCncGeo::_J (src/feCncGeo.cpp:278-418) and the ElementTransformation (src/feCncGeo.cpp:651-692) are
+ * recomputed on the device from the vertices. */
+int b200_set_mesh(b200_system *s, int dim, int64_t n_vertices, const double *xyz /* [n_vertices][3] */,
+                  int64_t n_elements, int n_vertices_per_element, const int32_t *connectivity);
+/* quadrature weights, feSpace::getQuadratureWeights (src/feSpace.h:447) */
+int b200_set_quadrature(b200_system *s, int n_quad, const double *weights);
+/* one interpolation space: element->DOF table from feSpace::initializeAddressingVector (src/feSpace.h:454) and the
+ * SCALAR reference basis at the quadrature nodes, L[k][i], dL[k][i][dim] (feSpace::_L,_dLdr,_dLds,_dLdt,
+ * src/feSpace.h:140-147, layout src/feSpace.h:381-384).  For a vector space (n_components = dim) pass the scalar
+ * tables of its Lagrange basis: function a*dim+c is phi_a e_c (src/feSpace_2D.cpp:41-55).  Returns the space id. */
+int b200_add_space(b200_system *s, int n_scalar_functions, int n_components, const int32_t *adr,
+                   const double *L, const double *dL);
+/* one weak form (createBilinearForm, src/feBilinearForm.h:23): kind = B200_FORM_*, spaces by id (space_p = -1 if
+ * the form has no second field), coeff / param = the constant values of the form's coefficient callbacks
+ * (feFunction, src/feFunction.h:78-118), source = host tabulation of the source callback at every (element,
+ * quadrature node[, component]) or NULL. */
+int b200_add_form(b200_system *s, int kind, int space_u, int space_p, double coeff, double param,
+                  const double *source);
+/* sparsity pattern of feEZCompressedRowStorage (src/feCompressedRowStorage.cpp:15-133), ia[n_inc+1], ja[nnz] */
+int b200_set_pattern(b200_system *s, int64_t n_inc, int64_t n_dof, const int64_t *ia, const int32_t *ja);
+/* same pattern built on the device from the spaces and forms registered so far; b200_get_pattern to read it back */
+int b200_build_pattern(b200_system *s, int64_t n_inc, int64_t n_dof);
+int b200_get_pattern_size(b200_system *s, int64_t *n_inc, int64_t *nnz);
+int b200_get_pattern(b200_system *s, int64_t *ia, int32_t *ja);
+/* element colours, feCncGeo::getColorElm (src/feCncGeo.h:236); only needed for B200_SCATTER_COLORED */
+int b200_set_colors(b200_system *s, int n_colors, const int32_t *element_color);
+int b200_set_scatter_mode(b200_system *s, int mode);
+/* rows of essential vector components (src/feLinearSystemMklPardiso.cpp:998-1041) and periodic (master, slave)
+ * pairs (feMetaNumber::PeriodicDOF, src/feNumber.h:234) */
+int b200_set_constraints(b200_system *s, int64_t n_rows, const int64_t *rows, int64_t n_periodic,
+                         const int64_t *master, const int64_t *slave);
+/* diagonal blocks for B200_PC_BLOCK_JACOBI: block_ptr[n_blocks+1] into block_rows[] */
+int b200_set_blocks(b200_system *s, int64_t n_blocks, const int64_t *block_ptr, const int64_t *block_rows);
+/* compile the fused assembly plan (coefficients, CSR slot map); must follow the set-up calls above */
+int b200_finalize(b200_system *s);
+
+/* ---- the 22 virtuals of feLinearSystem ---- */
+/* getSystemSize (src/feLinearSystem.h:87) */
+int64_t b200_system_size(const b200_system *s);
+/* state upload: what feBilinearForm::initialize reads from feSolution (sol, solDot, c0, tn),
+ * src/feBilinearForm.cpp:291-349; n_dof doubles each, sol_dot may be NULL */
+int b200_set_solution(b200_system *s, const double *sol, const double *sol_dot, double c0, double t);
+/* setToZero / setMatrixToZero / setResidualToZero (src/feLinearSystem.h:110-112): what = 1 rhs, 2 matrix, 3 both */
+int b200_set_to_zero(b200_system *s, int what);
+/* assemble / assembleMatrices / assembleResiduals (src/feLinearSystem.h:115-120): what = 1 residual, 2 matrix,
+ * 3 both in ONE fused pass; only_transient as assembleOnlyTransientMatrices */
+int b200_assemble(b200_system *s, int what, int only_transient);
+/* getRHSMaxNorm / getResidualMaxNorm (src/feLinearSystem.h:106-107) */
+int b200_rhs_max_norm(b200_system *s, double *norm);
+int b200_du_max_norm(b200_system *s, double *norm);
+/* constrainEssentialComponents + applyPeriodicity (src/feLinearSystem.h:122-124) */
+int b200_constrain(b200_system *s);
+int b200_apply_periodicity(b200_system *s);
+/* solve (src/feLinearSystem.h:137-138): restarted GMRES on the device */
+int b200_solve(b200_system *s, const b200_solver_options *opt, b200_solve_info *info);
+/* correctSolution (src/feLinearSystem.h:141-142): sol[i] += du[i] (i < nInc) on the device copy, and into the
+ * host vector if sol_host != NULL (n_dof doubles, the caller's feSolution::getSolution()) */
+int b200_correct_solution(b200_system *s, double *sol_host, int correct_dot);
+/* assignResidualToDCResidual / applyCorrectionToResidual (src/feLinearSystem.h:147-153) */
+int b200_get_rhs(b200_system *s, double *rhs);
+int b200_axpy_rhs(b200_system *s, double coeff, const double *d);
+/* viewMatrix / writeMatrix / writeRHS / writeResidual back-ends (src/feLinearSystem.h:156-168): raw downloads */
+int b200_get_matrix_values(b200_system *s, double *values);
+int b200_get_du(b200_system *s, double *du);
+int b200_get_solution(b200_system *s, double *sol);
+/* y = A x with the assembled matrix (parity checks of the SpMV kernel); n_inc doubles each */
+int b200_spmv(b200_system *s, const double *x, double *y);
+
+/* ---- measurement helpers (bench.py); device time in milliseconds of the last call, from CUDA events recorded on
+ *      the system's own stream ---- */
+int b200_last_assemble_ms(const b200_system *s, float *ms);
+int b200_last_solve_ms(const b200_system *s, float *ms);
+/* time `reps` back-to-back SpMVs (y = A x, device resident) -> average ms per SpMV */
+int b200_time_spmv(b200_system *s, int reps, float *ms_per_spmv);
+int b200_sync(b200_system *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FENG_B200_H */

@@ -1,0 +1,186 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Tolerance: 1e-12 relative (north_star), measured per entry against the largest entry of its matrix row / of the
+rhs (the reference sums form by form, the fused kernel and the atomics reorder the sums).
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_close_rows, assert_close_vec, to_oracle_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda_assemble(pb, sol, sol_dot=None, c0=0.0, what=3, colors=None, mode=0, only_transient=False):
+    from feng_b200.linear_system import LinearSystemB200
+    ls = LinearSystemB200(pb, colors=colors)
+    ls.sys.set_scatter_mode(mode)
+    ls.sys.set_solution(sol, sol_dot, c0, 0.0)
+    ls.sys.set_to_zero(3)
+    ls.sys.assemble(what, only_transient)
+    return ls, ls.sys.get_matrix_values(), ls.sys.get_rhs()
+
+
+@pytest.mark.parametrize("kind", ["ns_div", "ns_lap", "stokes_div", "stokes_lap"])
+@pytest.mark.parametrize("mu,rho", [(1.0, 1.0), (0.025, 1.3)])
+def test_taylor_hood_2d_vs_oracle(kind, mu, rho):
+    from feng_b200 import mesh as M, problems as PB
+    from oracle import fe_oracle as O
+    m = M.square_mesh(12)
+    pb = PB.taylor_hood(m, kind, 8, 0, mu, rho)
+    sol = PB.perturb_unknowns(pb)
+    ov, orr = O.assemble(to_oracle_problem(pb), pb.ia, pb.ja, sol)
+    _, v, r = _cuda_assemble(pb, sol)
+    assert_close_rows(v, ov, pb.ia, 1e-12, "matrix")
+    assert_close_vec(r, orr, 1e-12, "rhs")
+
+
+def test_taylor_hood_2d_transient_and_split_passes():
+    from feng_b200 import mesh as M, problems as PB
+    from oracle import fe_oracle as O
+    m = M.square_mesh(9)
+    pb = PB.taylor_hood(m, "ns_div", 8, 0, 0.1, 1.3, transient=True, p_essential=True)
+    sol = PB.perturb_unknowns(pb)
+    sd = np.random.default_rng(3).standard_normal(pb.n_dof)
+    ov, orr = O.assemble(to_oracle_problem(pb), pb.ia, pb.ja, sol, sd, 3.5)
+    ls, v, r = _cuda_assemble(pb, sol, sd, 3.5)
+    assert_close_rows(v, ov, pb.ia, 1e-12, "matrix")
+    assert_close_vec(r, orr, 1e-12, "rhs")
+    # matrix-only and residual-only passes give the same numbers as the fused pass
+    ls.sys.set_to_zero(3)
+    ls.sys.assemble(2, False)
+    ls.sys.assemble(1, False)
+    assert_close_rows(ls.sys.get_matrix_values(), ov, pb.ia, 1e-12, "matrix (split)")
+    assert_close_vec(ls.sys.get_rhs(), orr, 1e-12, "rhs (split)")
+    # transient-only matrix = mass form alone (assembleOnlyTransientMatrices)
+    pbm = PB.taylor_hood(m, "ns_div", 8, 0, 0.1, 1.3, transient=True, p_essential=True)
+    opb = to_oracle_problem(pbm)
+    opb.forms = [f for f in opb.forms if f.kind == O.TRANSIENT_VECTOR_MASS]
+    mv, _ = O.assemble(opb, pb.ia, pb.ja, sol, sd, 3.5, residual=False)
+    ls.sys.set_to_zero(3)
+    ls.sys.assemble(2, True)
+    got = ls.sys.get_matrix_values()
+    assert np.abs(got - mv).max() <= 1e-12 * np.abs(mv).max()
+
+
+@pytest.mark.parametrize("dim,n,deg,order", [(2, 10, 12, 2), (2, 10, 4, 1), (3, 4, 4, 2), (3, 4, 6, 2), (3, 4, 2, 1)])
+def test_scalar_diffusion_vs_oracle(dim, n, deg, order):
+    from feng_b200 import mesh as M, problems as PB
+    from oracle import fe_oracle as O
+    m = M.square_mesh(n) if dim == 2 else M.cube_mesh(n)
+    pb = PB.scalar_diffusion(m, order, deg, 0, 0.7, transient=True, rho=1.3)
+    sol = PB.perturb_unknowns(pb)
+    sd = np.random.default_rng(5).standard_normal(pb.n_dof)
+    ov, orr = O.assemble(to_oracle_problem(pb), pb.ia, pb.ja, sol, sd, 2.5)
+    _, v, r = _cuda_assemble(pb, sol, sd, 2.5)
+    assert_close_rows(v, ov, pb.ia, 1e-12, "matrix")
+    assert_close_vec(r, orr, 1e-12, "rhs")
+
+
+@pytest.mark.parametrize("kind", ["ns_div", "ns_lap"])
+def test_taylor_hood_3d_vs_oracle(kind):
+    """P2/P1 tetrahedra: no reference implementation exists (src/feVectorSysElm.cpp:1246,1536 instantiate <2> only);
+    the checker is the dim-generic restatement, itself pinned in 2-D against the compiled reference."""
+    from feng_b200 import mesh as M, problems as PB
+    from oracle import fe_oracle as O
+    m = M.cube_mesh(3)
+    pb = PB.taylor_hood(m, kind, 6, 3, 0.05, 1.1)
+    sol = PB.perturb_unknowns(pb)
+    ov, orr = O.assemble(to_oracle_problem(pb), pb.ia, pb.ja, sol)
+    _, v, r = _cuda_assemble(pb, sol)
+    assert_close_rows(v, ov, pb.ia, 1e-12, "matrix")
+    assert_close_vec(r, orr, 1e-12, "rhs")
+
+
+def _greedy_colors(cells, n_vertices):
+    """Host colouring with the rule of feCncGeo::colorElements(1) (src/feCncGeo.cpp:752-794): sweep the uncoloured
+    elements in order and take those whose vertices were not touched earlier in the sweep."""
+    nE = cells.shape[0]
+    color = -np.ones(nE, np.int32)
+    c = 0
+    while (color < 0).any():
+        touched = np.zeros(n_vertices, bool)
+        for e in np.nonzero(color < 0)[0]:
+            if not touched[cells[e]].any():
+                color[e] = c
+                touched[cells[e]] = True
+        c += 1
+    return color
+
+
+def test_colored_scatter_matches_atomic():
+    from feng_b200 import mesh as M, problems as PB
+    from oracle import fe_oracle as O
+    m = M.square_mesh(10)
+    pb = PB.taylor_hood(m, "ns_div", 8, 0, 0.05, 1.0)
+    sol = PB.perturb_unknowns(pb)
+    ov, orr = O.assemble(to_oracle_problem(pb), pb.ia, pb.ja, sol)
+    colors = _greedy_colors(m.cells, m.n_vertices)
+    _, v, r = _cuda_assemble(pb, sol, colors=colors, mode=1)
+    assert_close_rows(v, ov, pb.ia, 1e-12, "matrix (coloured)")
+    assert_close_vec(r, orr, 1e-12, "rhs (coloured)")
+
+
+def test_spmv_and_constraints_and_gmres():
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from feng_b200 import capi, mesh as M, problems as PB
+    from feng_b200.linear_system import LinearSystemB200
+    m = M.square_mesh(8)
+    pb = PB.taylor_hood(m, "ns_div", 8, 0, 1.0, 1.0, p_essential=True)
+    sol = PB.perturb_unknowns(pb, 1e-3)
+    rows = np.unique(pb.adrU[:3].reshape(-1))
+    rows = rows[rows < pb.n_inc][:7]
+    ls = LinearSystemB200(pb, constraint_rows=rows)
+    ls.sys.set_solution(sol)
+    ls.sys.set_to_zero(3)
+    ls.sys.assemble(3)
+    v0, r0 = ls.sys.get_matrix_values(), ls.sys.get_rhs()
+    ls.sys.constrain()
+    v, r = ls.sys.get_matrix_values(), ls.sys.get_rhs()
+    # constraint semantics of src/feLinearSystemMklPardiso.cpp:1092-1114
+    A0 = sp.csr_matrix((v0, pb.ja, pb.ia), shape=(pb.n_inc, pb.n_inc)).tolil()
+    for i in rows:
+        A0[:, i] = 0.0
+        A0[i, :] = 0.0
+        A0[i, i] = 1.0
+    ref = sp.csr_matrix((np.zeros_like(v0), pb.ja, pb.ia), shape=(pb.n_inc, pb.n_inc))
+    A0 = A0.tocsr()
+    A = sp.csr_matrix((v, pb.ja, pb.ia), shape=(pb.n_inc, pb.n_inc))
+    assert abs(A - A0).max() == 0.0
+    rr = r0.copy()
+    rr[rows] = 0.0
+    assert np.array_equal(r, rr)
+    # SpMV, bit-for-bit up to summation order
+    x = np.random.default_rng(0).standard_normal(pb.n_inc)
+    y = ls.sys.spmv(x)
+    assert np.abs(y - A @ x).max() <= 1e-13 * np.abs(A @ x).max()
+    # GMRES + Jacobi reaches the direct solution within the solver tolerance
+    du_ref = spla.spsolve(A.tocsc(), r)
+    info = ls.sys.solve(rel_tol=1e-10, max_iter=20000, restart=60, pc=capi.PC_JACOBI)
+    assert info.converged == 1
+    du = ls.sys.get_du()
+    assert np.abs(du - du_ref).max() <= 1e-6 * np.abs(du_ref).max()
+    assert abs(info.norm_dx - np.abs(du).max()) <= 1e-15 + 1e-12 * np.abs(du).max()
+    assert abs(info.norm_rhs - np.abs(r).max()) == 0.0
+
+
+def test_newton_poisson_and_ns_mms_synthetic():
+    """End-to-end Newton solves through the feLinearSystem mirror; errors against the analytic fields."""
+    from feng_b200 import mesh as M, problems as PB
+    from feng_b200.linear_system import LinearSystemB200, NLSolverOptions, solve_newton_raphson
+    m = M.square_mesh(8)
+    pb = PB.taylor_hood(m, "ns_div", 8, 0, 1.0, 1.0, p_essential=True)
+    ls = LinearSystemB200(pb)
+    ls.setRelativeTol(1e-12)
+    ls.restart = 100
+    sol = pb.sol.copy()
+    sol[:pb.n_inc] = 0.0
+    status, hist = solve_newton_raphson(ls, sol, NLSolverOptions(1e-10, 1e-10, 1e4, 10, 4, 1e-1))
+    assert status == 0, hist
+    # the reference's Newton loop stops on the residual it assembles at the top of the NEXT iteration
+    ls.setToZero()
+    ls.assembleResiduals(sol)
+    assert ls.getRHSMaxNorm() < 1e-9
+    # nodal error against the manufactured solution is at discretisation level
+    assert np.abs(sol - pb.sol).max() < 5e-3
