@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: P2/P1 Navier-Stokes Jacobian + residual assembly (Melem/s) and Newton-step pieces.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload t2d|t3d] [--n SIZE]
+
+A "step" is one pass of the hot path over the whole mesh: setToZero + fused Jacobian+residual assembly of every
+element (what solveNewtonRaphson does each iteration, src/feNonLinearSolver.cpp:77-91).  `value` = elements
+assembled per second with every input resident in HBM; `e2e` = the same through the C ABI with HOST buffers (the
+solution vector is copied host->device inside the timed region, the rhs max-norm is read back).  One process per GPU;
+for N > 1 every rank owns a strip of a [0,1] x [0,N] mesh (weak scaling, owner-computes with one ghost layer of
+elements, no data-path collective in assembly).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ns_p2p1_jacobian_residual_assembly"
+UNIT = "Melem/s"
+MU, RHO = 1.0 / 40.0, 1.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms",
+                                          "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_problem(workload, n, rank, world):
+    from feng_b200 import mesh as M, problems as PB
+    if workload == "t2d":
+        # strip r of the [0,1] x [0,world] domain: n x n owned cells plus one ghost row of cells towards each
+        # neighbour (owner-computes)
+        gb, gt = (1 if rank > 0 else 0), (1 if rank < world - 1 else 0)
+        ny = n + gb + gt
+        m = M.rect_mesh(n, ny, 1.0, ny / n, 0.0, rank - gb / n, cut_bottom=rank > 0, cut_top=rank < world - 1)
+        if rank == 0:
+            m.point_pressure = 0
+        pb = PB.taylor_hood(m, "ns_div", 8, 1, MU, RHO, build_pattern=False, with_source=False)
+        owned = 2 * n * n
+        name = f"T2D({n}) P2/P1 Navier-Stokes (convU+divU+divSigma), Kovasznay Re=40 + noise, quad deg 8 (16 pts)"
+    else:
+        m = M.cube_mesh(n)
+        pb = PB.taylor_hood(m, "ns_div", 6, 3, MU, RHO, build_pattern=False, with_source=False)
+        owned = m.n_cells
+        name = f"T3D({n}) P2/P1 Navier-Stokes tetrahedra, quad deg 6 (24 pts)"
+    sol = PB.perturb_unknowns(pb)
+    return pb, sol, owned, name
+
+
+def algorithmic_bytes_per_element(pb, nnz):
+    """index gather + vertex coordinates + local solution + one write of every CSR value and
+    of every rhs entry (no source table, no transient term in this workload)."""
+    n_loc = pb.adrU.shape[1] + pb.adrP.shape[1]
+    nE = pb.mesh.n_cells
+    return 4 * n_loc + 8 * pb.dim * (pb.dim + 1) + 8 * n_loc + 8 * nnz / nE + 8 * pb.n_inc / nE
+
+
+def cpu_reference_baseline(n_cpu, reps, threads=None):
+    """The reference's own CPU assembly (oracle/_ref = unmodified feNG compiled here) on a bounded sample."""
+    from feng_b200 import mesh as M, problems as PB
+    from oracle import ref
+    if not ref.available():
+        return None
+    import tempfile
+    m = M.square_mesh(n_cpu)
+    path = os.path.join(tempfile.gettempdir(), f"bench_t2d_{n_cpu}_{os.getpid()}.msh")
+    M.write_msh(m, path)
+    if threads:
+        ref.set_threads(threads)
+    P = ref.RefProblem(path, "ns_div", 2, 8, field=1, mu=MU, rho=RHO, p_essential=False)
+    os.remove(path)
+    pb = PB.taylor_hood(m, "ns_div", 8, 1, MU, RHO, build_pattern=False, with_source=True)
+    P.set_solution(PB.perturb_unknowns(pb))
+    P.assemble()                                     # warm-up
+    times = []
+    for _ in range(reps):
+        _, _, sec = P.assemble()
+        times.append(float(sec[0] + sec[1]))
+    nE = m.n_cells
+    P.close()
+    return {"times": times, "n_elm": nE, "cores": ref.max_threads(),
+            "sample": f"T2D({n_cpu}) = {nE} triangles, same forms + the reference's zero vector-source form, "
+                      f"Jacobian+residual, {reps} passes"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    base = cpu_reference_baseline(args.cpu_n, max(args.steps, 1) + args.warmup)
+    if base is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfeng_ref.so not built"}))
+        return
+    t = base["times"][args.warmup:]
+    per = sum(t) / len(t)
+    val = base["n_elm"] / per / 1e6
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(t), "warmup": args.warmup,
+            "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": base["sample"], "timing": "reference's own colour loop over computeMatrix/"
+                       "computeResidual + restated Pardiso-style scatter, OpenMP, host steady_clock"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": base["cores"], "kind": "reference",
+                             "sample": base["sample"]},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="t2d", choices=["t2d", "t3d"])
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--cpu-n", type=int, default=256)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--solve", action="store_true", help="also time one Newton step (assembly + GMRES)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+    n = args.n or (1024 if args.workload == "t2d" else 48)
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from feng_b200 import capi
+    from feng_b200.linear_system import LinearSystemB200
+
+    pb, sol, owned, wl_name = build_problem(args.workload, n, rank, world)
+    ls = LinearSystemB200(pb, device=local_rank, device_pattern=True)
+    S = ls.sys
+    nE = pb.mesh.n_cells
+    host_sol = torch.from_numpy(sol).pin_memory().numpy()        # pinned host buffer of the caller
+    S.set_solution(host_sol)
+
+    def barrier():
+        S.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        S.set_to_zero(3)
+        S.assemble(3)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    capi.reset_kernel_launches()
+    kern_ms = []
+    barrier()
+    S.time_begin()
+    for _ in range(args.steps):
+        S.set_to_zero(3)
+        S.assemble(3)
+    total_ms = S.time_end()
+    launches = capi.kernel_launches()
+    barrier()
+    # per-launch duration of the dominant kernel (events recorded around the assembly launch on its own stream)
+    for _ in range(args.steps):
+        S.set_to_zero(3)
+        S.assemble(3)
+        kern_ms.append(S.last_assemble_ms())
+    clocks = sampler.stop()
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------------
+    for _ in range(2):
+        S.set_solution(host_sol)
+        S.set_to_zero(3)
+        S.assemble(3)
+        S.rhs_max_norm()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        S.set_solution(host_sol)
+        S.set_to_zero(3)
+        S.assemble(3)
+        rn = S.rhs_max_norm()
+    S.sync()
+    e2e_s = time.perf_counter() - t0
+    spmv_ms = S.time_spmv(20)
+
+    t_all = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    owned_all = torch.tensor([float(owned)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        dist.all_reduce(owned_all, op=dist.ReduceOp.SUM)
+    total_ms, e2e_ms = float(t_all[0]), float(t_all[1])
+    tot_owned = float(owned_all[0])
+
+    extra = {}
+    if args.solve and world == 1:
+        extra["newton_step"] = newton_step(ls, sol, pb)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        ms_step = total_ms / args.steps
+        value = tot_owned / (ms_step * 1e-3) / 1e6
+        bpe = algorithmic_bytes_per_element(pb, S.nnz)
+        k_ms = statistics.mean(kern_ms)
+        achieved = bpe * nE / (k_ms * 1e-3) / 1e9
+        spmv_bytes = S.nnz * 12 + (S.n_inc + 1) * 8 + 2 * 8 * S.n_inc
+        fp64 = capi.measure_fp64_peak(local_rank)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(args.workload)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_name, "elements_per_gpu": int(owned), "ghost_elements_per_gpu": int(nE - owned),
+                       "n_dof_per_gpu": int(pb.n_dof), "n_unknowns_per_gpu": int(pb.n_inc), "nnz_per_gpu": int(S.nnz),
+                       "scatter": "atomic (red.global.add.f64) into precomputed CSR slots",
+                       "cache": "inputs larger than L2 (CSR values + slot map = %.1f GB per pass)" %
+                                ((S.nnz * 8 + nE * ls.sys_M() ** 2 * 4) / 1e9),
+                       "partition": "strips, owner-computes with one ghost layer" if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "th_kernel<2,6,3> fused Jacobian+residual+scatter",
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_element": bpe, "peak_source": peak_src,
+                         "kernel_share_of_step": k_ms / ms_step,
+                         "fp64": {"measured_dfma_peak_tflops": fp64}},
+            "spmv": {"ms": spmv_ms, "achieved_gbs": spmv_bytes / (spmv_ms * 1e-3) / 1e9,
+                     "frac": spmv_bytes / (spmv_ms * 1e-3) / 1e9 / peak, "bytes": spmv_bytes},
+            "e2e": {"value": tot_owned / (e2e_ms / args.steps * 1e-3) / 1e6, "unit": UNIT,
+                    "h2d_bytes_per_step": int(pb.n_dof * 8), "d2h_bytes_per_step": 8,
+                    "ms_per_step": e2e_ms / args.steps, "rhs_max_norm": rn},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        line.update(extra)
+        if world == 1 and not args.no_cpu:
+            base = cpu_reference_baseline(args.cpu_n, 3)
+            if base is not None:
+                per = sum(base["times"]) / len(base["times"])
+                line["cpu_baseline"] = {"value": base["n_elm"] / per / 1e6, "unit": UNIT, "cores": base["cores"],
+                                        "kind": "reference", "sample": base["sample"]}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                        "sample": "oracle/_ref missing"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def newton_step(ls, sol, pb):
+    """One loop body of solveNewtonRaphson (src/feNonLinearSolver.cpp:77-123) timed on the host with syncs."""
+    from feng_b200 import capi
+    S = ls.sys
+    s = sol.copy()
+    S.sync()
+    t0 = time.perf_counter()
+    S.set_solution(s)
+    S.set_to_zero(3)
+    S.assemble(1)
+    S.rhs_max_norm()
+    S.assemble(2)
+    S.constrain()
+    info = S.solve(1e-8, 1e-14, 1e6, 2000, 30, ls.pc, raise_on_fail=False)
+    S.correct_solution(s)
+    S.sync()
+    dt = time.perf_counter() - t0
+    return {"ms": dt * 1e3, "gmres_iterations": info.iterations, "converged": bool(info.converged),
+            "solve_ms": S.last_solve_ms(), "rel_residual": info.rel_residual, "pc": ls.pc}
+
+
+if __name__ == "__main__":
+    main()

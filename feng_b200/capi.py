@@ -22,7 +22,8 @@ SYMBOLS = [
     "b200_set_to_zero", "b200_assemble", "b200_rhs_max_norm", "b200_du_max_norm", "b200_constrain",
     "b200_apply_periodicity", "b200_solve", "b200_correct_solution", "b200_get_rhs", "b200_axpy_rhs",
     "b200_get_matrix_values", "b200_get_du", "b200_get_solution", "b200_spmv", "b200_last_assemble_ms",
-    "b200_last_solve_ms", "b200_time_spmv", "b200_sync",
+    "b200_last_solve_ms", "b200_time_spmv", "b200_sync", "b200_time_begin", "b200_time_end",
+    "b200_measure_fp64_peak",
 ]
 
 SCATTER_ATOMIC, SCATTER_COLORED = 0, 1
@@ -134,6 +135,13 @@ class System:
         check(self.L.b200_set_pattern(self.h, C.c_int64(n_inc), C.c_int64(n_dof), _i64(ia), _i32(ja)),
               "b200_set_pattern")
         self.n_inc, self.n_dof, self.nnz = int(n_inc), int(n_dof), int(ia[-1])
+
+    def build_pattern(self, n_inc, n_dof):
+        """device-side EZCRS pattern from the spaces and forms registered so far"""
+        check(self.L.b200_build_pattern(self.h, C.c_int64(n_inc), C.c_int64(n_dof)), "b200_build_pattern")
+        ni, nz = C.c_int64(), C.c_int64()
+        check(self.L.b200_get_pattern_size(self.h, C.byref(ni), C.byref(nz)), "b200_get_pattern_size")
+        self.n_inc, self.n_dof, self.nnz = int(ni.value), int(n_dof), int(nz.value)
 
     def get_pattern(self):
         ia = np.zeros(self.n_inc + 1, np.int64)
@@ -252,6 +260,20 @@ class System:
 
     def sync(self):
         check(self.L.b200_sync(self.h), "b200_sync")
+
+    def time_begin(self):
+        check(self.L.b200_time_begin(self.h), "b200_time_begin")
+
+    def time_end(self):
+        v = C.c_float()
+        check(self.L.b200_time_end(self.h, C.byref(v)), "b200_time_end")
+        return v.value
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    v = C.c_double()
+    check(lib().b200_measure_fp64_peak(device, C.byref(v)), "b200_measure_fp64_peak")
+    return v.value
 
 
 def kernel_launches() -> int:

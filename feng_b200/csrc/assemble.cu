@@ -528,18 +528,16 @@ __global__ void slot_map_kernel(int64_t nElm, int M, int NU, const int32_t *adrU
 // ----------------------------------------------------------------------------------------------------------
 static bool is_scalar_kind(int k) { return k == B200_FORM_SOURCE || k == B200_FORM_TRANSIENT_MASS || k == B200_FORM_DIFFUSION; }
 
-int build_plan(System *S)
+// Classifies the registered forms (scalar / Taylor-Hood), sums their constant coefficients into the fused-kernel
+// coefficient structs and records which blocks of the fused local matrix exist.
+int analyze_forms(System *S)
 {
-  if(S->forms.empty() || S->nElm == 0 || S->nq == 0 || S->d_ia == nullptr) {
-    set_error("b200_finalize: mesh, quadrature, spaces, forms and pattern must be set first");
+  if(S->forms.empty() || S->nElm == 0 || S->nq == 0) {
+    set_error("b200_finalize: mesh, quadrature, spaces and forms must be set first");
     return B200_ERR_ARG;
   }
   if(S->nv != S->dim + 1 || (S->dim != 2 && S->dim != 3)) {
     set_error("b200_finalize: only straight triangles / tetrahedra are supported");
-    return B200_ERR_UNSUPP;
-  }
-  if(S->nnz >= (int64_t)2147483647) {
-    set_error("b200_finalize: nnz >= 2^31 needs the 64-bit slot map (not built)");
     return B200_ERR_UNSUPP;
   }
   bool all_scalar = true, any_scalar = false;
@@ -665,6 +663,21 @@ int build_plan(System *S)
     }
     S->M = U.nS * U.nc + P.nS;
   }
+  return B200_OK;
+}
+
+int build_plan(System *S)
+{
+  if(S->d_ia == nullptr) {
+    set_error("b200_finalize: set or build the CSR pattern first");
+    return B200_ERR_ARG;
+  }
+  if(S->nnz >= (int64_t)2147483647) {
+    set_error("b200_finalize: nnz >= 2^31 needs the 64-bit slot map (not built)");
+    return B200_ERR_UNSUPP;
+  }
+  const int arc = analyze_forms(S);
+  if(arc != B200_OK) return arc;
 
   // packed tables: w | LU | dLU | LP
   {

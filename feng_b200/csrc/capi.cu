@@ -31,6 +31,22 @@ __global__ void axpy_kernel(int64_t n, double a, const double *__restrict__ x, d
   for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += a * x[i];
 }
 
+// 16 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a)
+{
+  double x[16];
+#pragma unroll
+  for(int i = 0; i < 16; ++i) x[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  for(int it = 0; it < iters; ++it) {
+#pragma unroll
+    for(int i = 0; i < 16; ++i) x[i] = fma(x[i], a, 1e-12);
+  }
+  double s = 0.;
+#pragma unroll
+  for(int i = 0; i < 16; ++i) s += x[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // constrainEssentialComponents (src/feLinearSystemMklPardiso.cpp:1092-1114): zero the column, zero the row, unit
 // diagonal, zero rhs.  One warp per matrix row.
 __global__ void constrain_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja, double *__restrict__ val,
@@ -95,6 +111,8 @@ static void free_system(System *S)
   if(S->h_scratch) cudaFreeHost(S->h_scratch);
   if(S->ev0) cudaEventDestroy(S->ev0);
   if(S->ev1) cudaEventDestroy(S->ev1);
+  if(S->ev2) cudaEventDestroy(S->ev2);
+  if(S->ev3) cudaEventDestroy(S->ev3);
   if(S->stream) cudaStreamDestroy(S->stream);
 }
 
@@ -118,6 +136,9 @@ static int alloc_linear_system(System *S)
   B200_CUDA(cudaMemsetAsync(S->d_soldot, 0, (size_t)S->nDOF * sizeof(double), S->stream));
   return B200_OK;
 }
+
+int alloc_linear_system_public(System *S) { return alloc_linear_system(S); }
+int build_pattern_device(System *S, int64_t n_inc, int64_t n_dof, const std::vector<int64_t> &per_master, const std::vector<int64_t> &per_slave);
 
 } // namespace b200
 
@@ -287,11 +308,14 @@ int b200_set_pattern(b200_system *s, int64_t n_inc, int64_t n_dof, const int64_t
   return alloc_linear_system(s);
 }
 
-int b200_build_pattern(b200_system *s, int64_t, int64_t)
+int b200_build_pattern(b200_system *s, int64_t n_inc, int64_t n_dof)
 {
   CHECK_S(s);
-  set_error("b200_build_pattern: device-side pattern construction is not built yet (SURVEY.md section 8f, row N1)");
-  return B200_ERR_UNSUPP;
+  if(n_inc <= 0 || n_dof < n_inc) {
+    set_error("b200_build_pattern: bad sizes");
+    return B200_ERR_ARG;
+  }
+  return build_pattern_device(s, n_inc, n_dof, s->per_master_host, s->per_slave_host);
 }
 
 int b200_get_pattern_size(b200_system *s, int64_t *n_inc, int64_t *nnz)
@@ -373,6 +397,8 @@ int b200_set_constraints(b200_system *s, int64_t n_rows, const int64_t *rows, in
   B200_CUDA(cudaMalloc(&s->d_cflag, (size_t)s->nInc));
   B200_CUDA(cudaMemcpy(s->d_cflag, flag.data(), (size_t)s->nInc, cudaMemcpyHostToDevice));
   s->n_per = n_periodic;
+  s->per_master_host.assign(master, master + (master ? n_periodic : 0));
+  s->per_slave_host.assign(slave, slave + (slave ? n_periodic : 0));
   cudaFree(s->d_master);
   cudaFree(s->d_slave);
   s->d_master = s->d_slave = nullptr;
@@ -610,6 +636,63 @@ int b200_time_spmv(b200_system *s, int reps, float *ms_per_spmv)
   cudaFree(dx);
   cudaFree(dy);
   return rc;
+}
+
+int b200_time_begin(b200_system *s)
+{
+  CHECK_S(s);
+  if(!s->ev2) {
+    B200_CUDA(cudaEventCreate(&s->ev2));
+    B200_CUDA(cudaEventCreate(&s->ev3));
+  }
+  B200_CUDA(cudaEventRecord(s->ev2, s->stream));
+  return B200_OK;
+}
+
+int b200_time_end(b200_system *s, float *ms)
+{
+  CHECK_S(s);
+  if(!s->ev2 || !ms) {
+    set_error("b200_time_end: call b200_time_begin first");
+    return B200_ERR_ARG;
+  }
+  B200_CUDA(cudaEventRecord(s->ev3, s->stream));
+  B200_CUDA(cudaEventSynchronize(s->ev3));
+  B200_CUDA(cudaEventElapsedTime(ms, s->ev2, s->ev3));
+  return B200_OK;
+}
+
+int b200_measure_fp64_peak(int device, double *tflops)
+{
+  if(!tflops || cudaSetDevice(device) != cudaSuccess) {
+    set_error("b200_measure_fp64_peak: bad device");
+    return B200_ERR_CUDA;
+  }
+  double *d = nullptr;
+  B200_CUDA(cudaMalloc(&d, 148 * 8 * 256 * sizeof(double)));
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0));
+  B200_CUDA(cudaEventCreate(&e1));
+  const int iters = 4096;
+  dfma_peak_kernel<<<148 * 8, 256>>>(d, iters, 1.000001);
+  float best = 1e30f;
+  for(int r = 0; r < 5; ++r) {
+    cudaEventRecord(e0);
+    dfma_peak_kernel<<<148 * 8, 256>>>(d, iters, 1.000001);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = ms < best ? ms : best;
+  }
+  count_launch(6);
+  const double flops = 2.0 * 16.0 * iters * 148.0 * 8.0 * 256.0;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
 }
 
 int b200_sync(b200_system *s)

@@ -57,7 +57,7 @@ enum PlanKind { PLAN_NONE = 0, PLAN_SCALAR = 1, PLAN_TAYLOR_HOOD = 2 };
 struct System {
   int          device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t  ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   float        last_assemble_ms = 0.f, last_solve_ms = 0.f;
 
   // mesh
@@ -102,6 +102,7 @@ struct System {
   int64_t *d_crows = nullptr;
   char    *d_cflag = nullptr; // [nInc]
   int64_t *d_master = nullptr, *d_slave = nullptr;
+  std::vector<int64_t> per_master_host, per_slave_host;
 
   // block Jacobi
   int64_t  n_blocks = 0;

@@ -28,7 +28,7 @@ class NLSolverOptions:
 
 class LinearSystemB200:
     def __init__(self, pb: HostProblem, device: int = 0, colors: np.ndarray | None = None,
-                 constraint_rows: np.ndarray | None = None):
+                 constraint_rows: np.ndarray | None = None, device_pattern: bool = False):
         self.pb = pb
         self.sys = capi.System(device)
         s = self.sys
@@ -38,9 +38,10 @@ class LinearSystemB200:
         self.sp = -1
         if pb.adrP is not None:
             self.sp = s.add_space(pb.LP.shape[1], 1, pb.adrP, pb.LP, pb.dLP)
-        if pb.ia is None:
-            pb.build_pattern()
-        s.set_pattern(pb.n_inc, pb.n_dof, pb.ia, pb.ja)
+        if not device_pattern:
+            if pb.ia is None:
+                pb.build_pattern()
+            s.set_pattern(pb.n_inc, pb.n_dof, pb.ia, pb.ja)
         for f in pb.forms:
             rows, cols = form_layout(f.kind)
             if rows == ("P",):                       # MIXED_DIVERGENCE is declared on {p, u}
@@ -48,6 +49,8 @@ class LinearSystemB200:
             else:
                 su, sp = self.su, (self.sp if "P" in cols else -1)
             s.add_form(f.kind, su, sp, f.coeff, f.param, f.source)
+        if device_pattern:
+            s.build_pattern(pb.n_inc, pb.n_dof)      # feEZCompressedRowStorage rules on the device
         if colors is not None:
             s.set_colors(int(colors.max()) + 1, colors)
         if constraint_rows is not None and len(constraint_rows):
@@ -59,6 +62,10 @@ class LinearSystemB200:
         self.restart = 30
         self.pc = capi.PC_JACOBI
         self.last_info = None
+
+    def sys_M(self) -> int:
+        """rows of the fused element system (15 for 2-D P2/P1, 34 for 3-D)"""
+        return self.pb.adrU.shape[1] + (0 if self.pb.adrP is None else self.pb.adrP.shape[1])
 
     # ---- setters of the base class -----------------------------------------------------------------
     def setAbsoluteTol(self, v): self._abs_tol = v

@@ -49,24 +49,45 @@ def boundary_facets(cells: np.ndarray) -> np.ndarray:
     loc = TRI_EDGES if nv == 3 else TET_FACES
     fac = cells[:, loc]                                  # (nE, nf, dim)
     flat = fac.reshape(-1, loc.shape[1])
-    key = np.sort(flat, axis=1)
-    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    srt = np.sort(flat.astype(np.int64), axis=1)
+    nV = np.int64(cells.max()) + 1
+    key = srt[:, 0]
+    for c in range(1, srt.shape[1]):
+        key = key * nV + srt[:, c]
+    _, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
     return np.ascontiguousarray(flat[cnt[inv.reshape(-1)] == 1]).astype(np.int32)
+
+
+def rect_mesh(nx: int, ny: int, lx: float = 1.0, ly: float = 1.0, x0: float = 0.0, y0: float = 0.0,
+              cut_bottom: bool = False, cut_top: bool = False) -> Mesh:
+    """nx x ny cells on [x0, x0+lx] x [y0, y0+ly], each split along the same diagonal into two CCW triangles;
+    vertices numbered row-major (x fastest).  cut_bottom / cut_top mark the lower / upper side as an artificial
+    partition cut (multi-GPU strips): its facets are left out of the physical boundary "Bord"."""
+    i, j = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="xy")
+    xyz = np.zeros(((nx + 1) * (ny + 1), 3))
+    xyz[:, 0] = x0 + lx * i.reshape(-1) / nx
+    xyz[:, 1] = y0 + ly * j.reshape(-1) / ny
+    ci, cj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    v00 = (cj * (nx + 1) + ci).reshape(-1)
+    v10, v01, v11 = v00 + 1, v00 + (nx + 1), v00 + (nx + 2)
+    cells = np.empty((2 * nx * ny, 3), np.int32)
+    cells[0::2] = np.stack([v00, v10, v11], 1)
+    cells[1::2] = np.stack([v00, v11, v01], 1)
+    bf = boundary_facets(cells)
+    if cut_bottom or cut_top:
+        row = bf // (nx + 1)
+        keep = np.ones(bf.shape[0], bool)
+        if cut_bottom:
+            keep &= ~np.all(row == 0, axis=1)
+        if cut_top:
+            keep &= ~np.all(row == ny, axis=1)
+        bf = np.ascontiguousarray(bf[keep])
+    return Mesh(2, xyz, cells, bf, 0 if not cut_bottom else None)
 
 
 def square_mesh(n: int, lx: float = 1.0, ly: float = 1.0, x0: float = 0.0, y0: float = 0.0) -> Mesh:
     """T2D(n): 2 n^2 triangles, (n+1)^2 vertices numbered row-major (x fastest)."""
-    i, j = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="xy")
-    xyz = np.zeros(((n + 1) ** 2, 3))
-    xyz[:, 0] = x0 + lx * i.reshape(-1) / n
-    xyz[:, 1] = y0 + ly * j.reshape(-1) / n
-    ci, cj = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
-    v00 = (cj * (n + 1) + ci).reshape(-1)
-    v10, v01, v11 = v00 + 1, v00 + (n + 1), v00 + (n + 2)
-    cells = np.empty((2 * n * n, 3), np.int32)
-    cells[0::2] = np.stack([v00, v10, v11], 1)
-    cells[1::2] = np.stack([v00, v11, v01], 1)
-    return Mesh(2, xyz, cells, boundary_facets(cells), 0)
+    return rect_mesh(n, n, lx, ly, x0, y0)
 
 
 # Kuhn split of the unit cube: one tetrahedron per permutation of the axes, all sharing the main diagonal.

@@ -180,7 +180,7 @@ def dof_components(num: NB.Numbering, fld: str, n_dof: int) -> np.ndarray:
 
 def taylor_hood(mesh: Mesh, kind: str = "ns_div", quad_degree: int = 8, field_id: int = 0, mu: float = 1.0,
                 rho: float = 1.0, transient: bool = False, p_essential: bool = False,
-                build_pattern: bool = True) -> HostProblem:
+                build_pattern: bool = True, with_source: bool = True) -> HostProblem:
     """P2/P1 (Navier-)Stokes with the form list and sign conventions of the reference's drivers
     (tests/withLinearSolver/navier_stokes.cpp:82-99): convU(-rho), divU(+1), source, then either
     divSigma(+1, mu) or diffU(-1, mu) + gradP(-1); optional transient mass(-rho)."""
@@ -193,15 +193,16 @@ def taylor_hood(mesh: Mesh, kind: str = "ns_div", quad_degree: int = 8, field_id
     LP, dLP = T.basis(dim, 1, q)
     pb = HostProblem(mesh, dim, dim, 2, num, num.adr(mesh, "U", 2), num.adr(mesh, "P", 1), num.n_inc, num.n_dof,
                      w, q, LU, dLU, LP, dLP)
-    xq = quad_points_physical(mesh, q)
-    src = u_source(field_id, xq[..., :dim] if dim == 2 else xq, mu, rho, with_conv)
-    if src.shape[-1] != dim:
-        src = np.zeros(xq.shape[:2] + (dim,))
     forms = []
     if with_conv:
         forms.append(FormSpec(VECTOR_CONVECTIVE_ACCELERATION, -rho))
     forms.append(FormSpec(MIXED_DIVERGENCE, 1.0))
-    forms.append(FormSpec(VECTOR_SOURCE, 1.0, 0.0, np.ascontiguousarray(src)))
+    if with_source:
+        xq = quad_points_physical(mesh, q)
+        src = u_source(field_id, xq[..., :dim] if dim == 2 else xq, mu, rho, with_conv)
+        if src.shape[-1] != dim:
+            src = np.zeros(xq.shape[:2] + (dim,))
+        forms.append(FormSpec(VECTOR_SOURCE, 1.0, 0.0, np.ascontiguousarray(src)))
     if div_form:
         forms.append(FormSpec(DIV_NEWTONIAN_STRESS, 1.0, mu))
     else:

@@ -174,6 +174,12 @@ int b200_last_solve_ms(const b200_system *s, float *ms);
 /* time `reps` back-to-back SpMVs (y = A x, device resident) -> average ms per SpMV */
 int b200_time_spmv(b200_system *s, int reps, float *ms_per_spmv);
 int b200_sync(b200_system *s);
+/* bracket an arbitrary sequence of calls with CUDA events on the system's stream */
+int b200_time_begin(b200_system *s);
+int b200_time_end(b200_system *s, float *ms);
+/* DFMA micro-benchmark on `device`: measured FP64 FMA throughput in TFLOP/s (the assembly kernels' second roofline;
+ * MEASURED_PEAKS.json only holds HBM and bf16 figures) */
+int b200_measure_fp64_peak(int device, double *tflops);
 
 #ifdef __cplusplus
 }
