@@ -215,3 +215,18 @@ def assemble(pb: Problem, ia, ja, sol, soldot=None, c0=0.0, matrix=True, residua
             pos = np.searchsorted(key, (I * n + J)[ok])
             np.add.at(vals, pos, Ae[ok])
     return vals, rhs
+
+
+def constrain(ia, ja, vals, rhs, rows):
+    """constrainEssentialComponents (src/feLinearSystemMklPardiso.cpp:1092-1114): for every constrained row r the
+    column r is zeroed in all rows, the row is zeroed, the diagonal set to 1 and the rhs entry to 0."""
+    vals, rhs = vals.copy(), rhs.copy()
+    n = ia.shape[0] - 1
+    flag = np.zeros(n, bool)
+    flag[np.asarray(rows, np.int64)] = True
+    row_of = np.repeat(np.arange(n), np.diff(ia))
+    vals[flag[ja]] = 0.0
+    vals[flag[row_of]] = 0.0
+    vals[flag[row_of] & (ja == row_of)] = 1.0
+    rhs[flag] = 0.0
+    return vals, rhs

@@ -1,5 +1,14 @@
+# One GPU round: parity tests, bench lines, ncu launch list and one full capture of the assembly kernel.
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python bench.py --n 256 --steps 5 --no-cpu 2>&1 | tail -3
-python bench.py --steps 10 2>&1 | tail -3
-python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -2
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.log
+python bench.py --steps 10 --warmup 3 --solve 2>gpurun_out/bench.err | tee gpurun_out/bench_t2d.json
+python bench.py --workload t3d --steps 5 --warmup 3 --no-cpu 2>>gpurun_out/bench.err | tee gpurun_out/bench_t3d.json
+python bench.py --impl reference --steps 3 --warmup 1 2>>gpurun_out/bench.err | tee gpurun_out/bench_ref.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:th_kernel -s 3 -c 1 -o gpurun_out/prof_th2d \
+    python bench.py --n 512 --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:spmv_kernel -s 3 -c 1 -o gpurun_out/prof_spmv \
+    python bench.py --n 512 --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_spmv.log 2>&1
+ls -la gpurun_out
