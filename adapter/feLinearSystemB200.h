@@ -1,0 +1,543 @@
+// feLinearSystemB200 -- a new feLinearSystem backend for arthurbawin/feNG, next to feLinearSystemPETSc
+// (src/feLinearSystem.h:174) and feLinearSystemMklPardiso (src/feLinearSystem.h:276).
+//
+// Header-only.  Compile against the UNMODIFIED reference headers (-I<feNG>/src) and link libfeng_b200.so
+// (include/feng_b200.h).  A driver changes one line: where it called
+//     createLinearSystem(system, MKLPARDISO, forms, &numbering)      (e.g. tests/withLinearSolver/navier_stokes.cpp:101-108)
+// it calls
+//     createLinearSystemB200(system, forms, &numbering)
+// and the rest -- createTimeIntegrator, solveNewtonRaphson (src/feNonLinearSolver.cpp:38-182), norms -- is untouched.
+//
+// What the constructor extracts ONCE from the host objects (all through public API, except the two documented peeks):
+//   vertices, connectivity           feMesh::getVertices, feCncGeo::getVertexConnectivity   (src/feMesh.h:130, src/feCncGeo.h:191)
+//   element -> DOF tables            feSpace::initializeAddressingVector                      (src/feSpace.h:454)
+//   scalar basis tables, weights     feSpace::getFunctionAtQuadNode / getd...AtQuadNode / L() (src/feSpace.h:381-408, :446-450)
+//   nInc, nDOF, periodic pairs       feMetaNumber                                             (src/feNumber.h:202-203, :234)
+//   sparsity pattern                 feEZCompressedRowStorage through a one-line derived struct exposing the protected
+//                                    ia_Pardiso/ja_Pardiso (src/feCompressedRowStorage.h:33-37)
+//   weak-form kind                   feBilinearForm::getID                                    (src/feBilinearForm.h:165)
+//   weak-form coefficients           protected members of the feSysElm_* classes (src/feSysElm.h:268,311,584,650,689,
+//                                    751-752,887,976-977,1025,1144), read through pointer-to-member of a derived struct;
+//                                    callbacks are sampled and must be constant in space (else FE_STATUS_ERROR), source
+//                                    callbacks are tabulated at every (element, quadrature node) and re-tabulated when the
+//                                    time changes.
+// Per Newton iteration only the state vectors cross the boundary (feSolution::getSolution / getSolutionDot, c0, tn).
+#ifndef _FELINEARSYSTEMB200_
+#define _FELINEARSYSTEMB200_
+
+#include "feLinearSystem.h"
+#include "feSysElm.h"
+#include "feSpace.h"
+#include "feCncGeo.h"
+#include "feMesh.h"
+
+#include "feng_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <map>
+
+struct feB200Options {
+  int device       = 0;
+  int preconditioner = B200_PC_JACOBI; // B200_PC_*
+  int restart      = 30;               // GMRES restart length (PETSc default)
+  int scatter      = B200_SCATTER_ATOMIC;
+  bool devicePattern = false;          // build the EZCRS pattern on the device instead of taking the host one
+  bool alwaysUpload  = false;          // re-upload the state in assembleMatrices even right after assembleResiduals
+};
+
+namespace feB200detail
+{
+  struct FormPeek : public feBilinearForm {
+    static feSysElm *sysElm(feBilinearForm *f) { return f->*(&FormPeek::_sysElm); }
+  };
+  struct PatternPeek : public feEZCompressedRowStorage {
+    using feEZCompressedRowStorage::feEZCompressedRowStorage;
+    const std::vector<feInt> &ia() const { return ia_Pardiso; }
+    const std::vector<feInt> &ja() const { return ja_Pardiso; }
+  };
+  template <class T> struct SysPeek : public T {
+    static const feFunction *coeff(const T *s) { return s->*(&SysPeek::_coeff); }
+  };
+  template <class T> struct SourcePeek : public T {
+    static auto source(const T *s) -> decltype(s->*(&SourcePeek::_source)) { return s->*(&SourcePeek::_source); }
+  };
+  template <class T> struct ViscPeek : public T {
+    static const feFunction *visc(const T *s) { return s->*(&ViscPeek::_viscosity); }
+  };
+  template <class T> struct DiffPeek : public T {
+    static const feFunction *diff(const T *s) { return s->*(&DiffPeek::_diffusivity); }
+  };
+} // namespace feB200detail
+
+class feLinearSystemB200 : public feLinearSystem
+{
+protected:
+  b200_system  *_sys = nullptr;
+  feB200Options _opt;
+  feInt         _nInc = 0, _nDOF = 0;
+  feStatus      _status = FE_STATUS_OK;
+  feMesh       *_mesh = nullptr;
+  const feCncGeo *_cnc = nullptr;
+  int           _dim = 0, _nElm = 0, _nQuad = 0;
+  std::vector<feSpace *> _spaceList; // engine space id -> host space
+  bool          _stateFresh = false;
+  bool          _constraintInit = false;
+  b200_solve_info _lastInfo{};
+  int           _numSolves = 0;
+  long          _totalKrylovIterations = 0;
+
+  struct SourceForm {
+    int                     formId;
+    const feFunction       *scalar;
+    const feVectorFunction *vector;
+    feSpace                *geoSpace;
+    int                     cncGeoTag;
+    double                  time;
+  };
+  std::vector<SourceForm> _sources;
+
+  bool fail(const std::string &what)
+  {
+    feErrorMsg(FE_STATUS_ERROR, "feLinearSystemB200: %s: %s", what.c_str(), b200_last_error());
+    _status = FE_STATUS_ERROR;
+    return false;
+  }
+  bool ok(int rc, const char *what) { return rc >= 0 ? true : fail(what); }
+
+  int spaceId(feSpace *s)
+  {
+    for(size_t i = 0; i < _spaceList.size(); ++i)
+      if(_spaceList[i] == s) return (int)i;
+    // scalar Lagrange tables of the space: for a vector space function a*nc+c is phi_a e_c (src/feSpace_2D.cpp:41-55),
+    // so the scalar basis is component c=0 of functions 0, nc, 2nc, ...
+    const int nF = s->getNumFunctions(), nC = s->getNumComponents(), nS = nF / nC;
+    std::vector<int32_t> adr((size_t)_nElm * nF);
+    std::vector<feInt>   a(nF);
+    for(int e = 0; e < _nElm; ++e) {
+      s->initializeAddressingVector(e, a);
+      for(int j = 0; j < nF; ++j) adr[(size_t)nF * e + j] = (int32_t)a[j];
+    }
+    std::vector<double> L((size_t)_nQuad * nS), dL((size_t)_nQuad * nS * _dim);
+    const std::vector<double> &r = s->getRQuadraturePoints(), &ss = s->getSQuadraturePoints(), &t = s->getTQuadraturePoints();
+    for(int k = 0; k < _nQuad; ++k) {
+      if(nC == 1) {
+        for(int i = 0; i < nS; ++i) {
+          L[(size_t)k * nS + i]                = s->getFunctionAtQuadNode(i, k);
+          dL[((size_t)k * nS + i) * _dim + 0] = s->getdFunctiondrAtQuadNode(i, k);
+          if(_dim >= 2) dL[((size_t)k * nS + i) * _dim + 1] = s->getdFunctiondsAtQuadNode(i, k);
+          if(_dim >= 3) dL[((size_t)k * nS + i) * _dim + 2] = s->getdFunctiondtAtQuadNode(i, k);
+        }
+      } else {
+        double              rr[3] = {r[k], ss[k], t[k]};
+        std::vector<double> l = s->L(rr), da = s->dLdr(rr), db = s->dLds(rr);
+        // vector tables are [i][c]; take component 0 of functions i = a*nC
+        for(int i = 0; i < nS; ++i) {
+          L[(size_t)k * nS + i]                = l[(size_t)(i * nC) * nC + 0];
+          dL[((size_t)k * nS + i) * _dim + 0] = da[(size_t)(i * nC) * nC + 0];
+          dL[((size_t)k * nS + i) * _dim + 1] = db[(size_t)(i * nC) * nC + 0];
+        }
+      }
+    }
+    const int id = b200_add_space(_sys, nS, nC, adr.data(), L.data(), dL.data());
+    if(id < 0) {
+      fail("b200_add_space");
+      return -1;
+    }
+    _spaceList.push_back(s);
+    return id;
+  }
+
+  // value of a coefficient callback, which must not depend on position (sampled on a few elements) -- the engine's
+  // fused kernels take constants (include/feng_b200.h, b200_add_form)
+  bool constantValue(const feFunction *f, feSpace *geoSpace, int cncGeoTag, double t, double &value)
+  {
+    feFunctionArguments args(t);
+    std::vector<double> coord(3 * _cnc->getNumVerticesPerElem(), 0.); // feMesh::getCoord does not resize (src/feMesh.cpp:119-134)
+    bool   first = true;
+    const int step = std::max(1, _nElm / 7);
+    for(int e = 0; e < _nElm; e += step) {
+      _mesh->getCoord(cncGeoTag, e, coord);
+      for(int k = 0; k < _nQuad; k += std::max(1, _nQuad / 3)) {
+        geoSpace->interpolateVectorFieldAtQuadNode(coord, k, args.pos);
+        const double v = f->eval(args);
+        if(first) {
+          value = v;
+          first = false;
+        } else if(std::fabs(v - value) > 1e-14 * std::max(1., std::fabs(value)))
+          return false;
+      }
+    }
+    return true;
+  }
+
+  void tabulateSource(const SourceForm &sf, double t, std::vector<double> &tab)
+  {
+    const int nc = sf.vector ? _dim : 1;
+    tab.resize((size_t)_nElm * _nQuad * nc);
+    feFunctionArguments args(t);
+    std::vector<double> coord(3 * _cnc->getNumVerticesPerElem(), 0.), S(3, 0.);
+    for(int e = 0; e < _nElm; ++e) {
+      _mesh->getCoord(sf.cncGeoTag, e, coord);
+      for(int k = 0; k < _nQuad; ++k) {
+        sf.geoSpace->interpolateVectorFieldAtQuadNode(coord, k, args.pos); // as src/feVectorSysElm.cpp:118, src/feSysElm.cpp:20
+        if(sf.vector) {
+          (*sf.vector)(args, S);
+          for(int c = 0; c < nc; ++c) tab[((size_t)e * _nQuad + k) * nc + c] = S[c];
+        } else
+          tab[(size_t)e * _nQuad + k] = sf.scalar->eval(args);
+      }
+    }
+  }
+
+  template <class T> bool addCoeffForm(feBilinearForm *f, feSysElm *se, int kind, int su, int sp, const feFunction *param)
+  {
+    const T *s = dynamic_cast<const T *>(se);
+    if(!s) return fail("weak form class does not match its elementSystemType");
+    double c = 1., p = 1.;
+    if(!constantValue(feB200detail::SysPeek<T>::coeff(s), f->_geoSpace, f->getCncGeoTag(), 0., c))
+      return fail("non-constant coefficient callbacks are not supported by the fused kernels");
+    if(param && !constantValue(param, f->_geoSpace, f->getCncGeoTag(), 0., p))
+      return fail("non-constant viscosity/diffusivity callbacks are not supported by the fused kernels");
+    return ok(b200_add_form(_sys, kind, su, sp, c, p, nullptr), "b200_add_form");
+  }
+
+  template <int dim> bool addFormDim(feBilinearForm *f, feSysElm *se)
+  {
+    const int id = (int)f->getID();
+    const int s0 = spaceId(f->_intSpaces[0]);
+    const int s1 = f->_intSpaces.size() > 1 ? spaceId(f->_intSpaces[1]) : -1;
+    if(s0 < 0) return false;
+    switch(id) {
+      case VECTOR_CONVECTIVE_ACCELERATION:
+        return addCoeffForm<feSysElm_VectorConvectiveAcceleration<dim>>(f, se, id, s0, -1, nullptr);
+      case DIV_NEWTONIAN_STRESS: {
+        auto *s = dynamic_cast<const feSysElm_DivergenceNewtonianStress<dim> *>(se);
+        if(!s) return fail("DivergenceNewtonianStress cast");
+        return addCoeffForm<feSysElm_DivergenceNewtonianStress<dim>>(
+          f, se, id, s0, s1, feB200detail::ViscPeek<feSysElm_DivergenceNewtonianStress<dim>>::visc(s));
+      }
+      case MIXED_DIVERGENCE: // declared on {p, u}: _intSpaces[0] = P (tests/withLinearSolver/navier_stokes.cpp:85)
+        return addCoeffForm<feSysElm_MixedDivergence<dim>>(f, se, id, s0, s1, nullptr);
+      case MIXED_GRADIENT: return addCoeffForm<feSysElm_MixedGradient<dim>>(f, se, id, s0, s1, nullptr);
+      case VECTOR_DIFFUSION: {
+        auto *s = dynamic_cast<const feSysElm_VectorDiffusion<dim> *>(se);
+        if(!s) return fail("VectorDiffusion cast");
+        return addCoeffForm<feSysElm_VectorDiffusion<dim>>(f, se, id, s0, -1,
+                                                           feB200detail::DiffPeek<feSysElm_VectorDiffusion<dim>>::diff(s));
+      }
+      case TRANSIENT_VECTOR_MASS: return addCoeffForm<feSysElm_TransientVectorMass<dim>>(f, se, id, s0, -1, nullptr);
+      case VECTOR_SOURCE: {
+        auto *s = dynamic_cast<const feSysElm_VectorSource<dim> *>(se);
+        if(!s) return fail("VectorSource cast");
+        SourceForm sf{-1, nullptr, feB200detail::SourcePeek<feSysElm_VectorSource<dim>>::source(s), f->_geoSpace, f->getCncGeoTag(), 0.};
+        std::vector<double> tab;
+        tabulateSource(sf, 0., tab);
+        sf.formId = b200_add_form(_sys, id, s0, -1, 1., 0., tab.data());
+        if(sf.formId < 0) return fail("b200_add_form(source)");
+        _sources.push_back(sf);
+        return true;
+      }
+      default: break;
+    }
+    return fail("weak form " + f->getWeakFormName() + " is not supported by the B200 backend");
+  }
+
+  bool addForm(feBilinearForm *f)
+  {
+    feSysElm *se = feB200detail::FormPeek::sysElm(f);
+    const int id = (int)f->getID();
+    const int s0 = spaceId(f->_intSpaces[0]);
+    if(s0 < 0) return false;
+    switch(id) {
+      case SOURCE: {
+        auto *s = dynamic_cast<const feSysElm_Source *>(se);
+        if(!s) return fail("Source cast");
+        SourceForm sf{-1, feB200detail::SourcePeek<feSysElm_Source>::source(s), nullptr, f->_geoSpace, f->getCncGeoTag(), 0.};
+        std::vector<double> tab;
+        tabulateSource(sf, 0., tab);
+        sf.formId = b200_add_form(_sys, id, s0, -1, 1., 0., tab.data());
+        if(sf.formId < 0) return fail("b200_add_form(source)");
+        _sources.push_back(sf);
+        return true;
+      }
+      case TRANSIENT_MASS: return addCoeffForm<feSysElm_TransientMass>(f, se, id, s0, -1, nullptr);
+      case DIFFUSION:
+        // diffusivity is the form's only callback: kind DIFFUSION uses coeff x param with param = 1
+        if(_dim == 2) return addCoeffForm<feSysElm_Diffusion<2>>(f, se, id, s0, -1, nullptr);
+        return addCoeffForm<feSysElm_Diffusion<3>>(f, se, id, s0, -1, nullptr);
+      default: break;
+    }
+    if(_dim == 2) return addFormDim<2>(f, se);
+    return fail("vector-valued weak forms exist only for dim = 2 in the reference (src/feVectorSysElm.cpp:1246,1536)");
+  }
+
+  void refreshSources(const feSolution *sol)
+  {
+    const double t = sol->getCurrentTime();
+    std::vector<double> tab;
+    for(auto &sf : _sources) {
+      if(sf.time == t) continue;
+      tabulateSource(sf, t, tab);
+      ok(b200_set_source(_sys, sf.formId, tab.data()), "b200_set_source");
+      sf.time = t;
+    }
+  }
+
+  void upload(const feSolution *sol)
+  {
+    refreshSources(sol);
+    ok(b200_set_solution(_sys, sol->getSolution().data(), sol->getSolutionDot().data(), sol->getC0(), sol->getCurrentTime()),
+       "b200_set_solution");
+  }
+
+  // rows of essential vector components, as src/feLinearSystemMklPardiso.cpp:998-1041
+  void initConstraints(const feSolution *sol)
+  {
+    _constraintInit = true;
+    std::vector<int64_t> rows;
+    std::vector<feInt>   adr;
+    for(const auto &space : sol->_spaces) {
+      const int nComponents = space->getNumComponents();
+      if(nComponents <= 1) continue;
+      const int nFunctions = space->getNumFunctions(), nElm = space->getNumElements();
+      adr.resize(nFunctions);
+      for(int c = 0; c < nComponents; ++c) {
+        if(!space->isEssentialComponent(c)) continue;
+        for(int e = 0; e < nElm; ++e) {
+          space->initializeAddressingVector(e, adr);
+          for(int j = 0; j < nFunctions; ++j)
+            if(j % nComponents == c && adr[j] < _nInc) rows.push_back(adr[j]);
+        }
+      }
+    }
+    std::sort(rows.begin(), rows.end());
+    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    std::vector<int64_t> master, slave;
+    for(const auto &pr : _numbering->PeriodicDOF()) {
+      master.push_back(pr.first);
+      slave.push_back(pr.second);
+    }
+    if(!rows.empty() || !master.empty())
+      ok(b200_set_constraints(_sys, (int64_t)rows.size(), rows.data(), (int64_t)master.size(), master.data(), slave.data()),
+         "b200_set_constraints");
+  }
+
+public:
+  feLinearSystemB200(const std::vector<feBilinearForm *> forms, const feMetaNumber *numbering, const feB200Options &opt = feB200Options())
+    : feLinearSystem(forms, numbering), _opt(opt)
+  {
+    _recomputeMatrix = true;
+    _nInc            = numbering->getNbUnknowns();
+    _nDOF            = numbering->getNbDOFs();
+    if(forms.empty()) {
+      fail("no weak form");
+      return;
+    }
+    if(!ok(b200_create(&_sys, opt.device), "b200_create")) return;
+    // one interior connectivity for all forms
+    _cnc = forms[0]->getCncGeo();
+    for(auto *f : forms)
+      if(f->getCncGeo() != _cnc) {
+        fail("all weak forms must live on the same geometric connectivity");
+        return;
+      }
+    feSpace *s0 = forms[0]->_intSpaces[0];
+    _mesh       = s0->getMeshPtr();
+    _dim        = _cnc->getDim();
+    _nElm       = _cnc->getNumElements();
+    _nQuad      = s0->getNumQuadPoints();
+    const int nv = _cnc->getNumVerticesPerElem();
+    {
+      auto               &V = _mesh->getVertices();
+      std::vector<double> xyz(3 * V.size());
+      for(size_t i = 0; i < V.size(); ++i) {
+        xyz[3 * i + 0] = V[i].x();
+        xyz[3 * i + 1] = V[i].y();
+        xyz[3 * i + 2] = V[i].z();
+      }
+      std::vector<int32_t> conn((size_t)_nElm * nv);
+      for(int e = 0; e < _nElm; ++e)
+        for(int j = 0; j < nv; ++j) conn[(size_t)nv * e + j] = _cnc->getVertexConnectivity(e, j);
+      if(!ok(b200_set_mesh(_sys, _dim, (int64_t)V.size(), xyz.data(), _nElm, nv, conn.data()), "b200_set_mesh")) return;
+    }
+    if(!ok(b200_set_quadrature(_sys, _nQuad, s0->getQuadratureWeights().data()), "b200_set_quadrature")) return;
+    // register spaces in the order the forms use them, then the pattern, then the forms
+    for(auto *f : forms)
+      for(auto *s : f->_intSpaces)
+        if(spaceId(s) < 0) return;
+    if(!opt.devicePattern) {
+      feB200detail::PatternPeek crs((int)_nInc, _formMatrices, _numMatrixForms, numbering);
+      std::vector<int64_t> ia(crs.ia().begin(), crs.ia().end());
+      std::vector<int32_t> ja(crs.ja().begin(), crs.ja().end());
+      if(!ok(b200_set_pattern(_sys, _nInc, _nDOF, ia.data(), ja.data()), "b200_set_pattern")) return;
+    }
+    for(auto *f : forms)
+      if(!addForm(f)) return;
+    if(opt.devicePattern && !ok(b200_build_pattern(_sys, _nInc, _nDOF), "b200_build_pattern")) return;
+    if(opt.scatter == B200_SCATTER_COLORED) {
+      const std::vector<int> &c = _cnc->getColorElm();
+      std::vector<int32_t>    col(c.begin(), c.end());
+      if(!ok(b200_set_colors(_sys, _cnc->getNbColor(), col.data()), "b200_set_colors")) return;
+      if(!ok(b200_set_scatter_mode(_sys, B200_SCATTER_COLORED), "b200_set_scatter_mode")) return;
+    }
+    ok(b200_finalize(_sys), "b200_finalize");
+  }
+
+  ~feLinearSystemB200() { b200_destroy(_sys); }
+
+  feStatus getStatus() const { return _status; }
+  const b200_solve_info &getLastSolveInfo() const { return _lastInfo; }
+  int  getNumSolves() const { return _numSolves; }
+  long getTotalKrylovIterations() const { return _totalKrylovIterations; }
+  b200_system *getHandle() { return _sys; }
+
+  feInt getSystemSize() const { return _nInc; }
+  void  getRHSMaxNorm(double *norm) const { b200_rhs_max_norm(_sys, norm); }
+  void  getResidualMaxNorm(double *norm) const { b200_du_max_norm(_sys, norm); }
+
+  void setToZero()
+  {
+    ok(b200_set_to_zero(_sys, _recomputeMatrix ? 3 : 1), "b200_set_to_zero"); // src/feLinearSystemMklPardiso.cpp:967-971
+    _stateFresh = false;
+  }
+  void setMatrixToZero() { ok(b200_set_to_zero(_sys, 2), "b200_set_to_zero"); }
+  void setResidualToZero() { ok(b200_set_to_zero(_sys, 1), "b200_set_to_zero"); }
+
+  void assemble(const feSolution *sol, const bool assembleOnlyTransientMatrices = false)
+  {
+    upload(sol);
+    ok(b200_assemble(_sys, _recomputeMatrix ? 3 : 1, assembleOnlyTransientMatrices), "b200_assemble");
+  }
+  void assembleMatrices(const feSolution *sol, const bool assembleOnlyTransientMatrices = false)
+  {
+    if(!_stateFresh || _opt.alwaysUpload) upload(sol);
+    ok(b200_assemble(_sys, 2, assembleOnlyTransientMatrices), "b200_assemble");
+  }
+  void assembleResiduals(const feSolution *sol)
+  {
+    upload(sol);
+    _stateFresh = true; // solveNewtonRaphson assembles the matrix from the same state (src/feNonLinearSolver.cpp:80-91)
+    ok(b200_assemble(_sys, 1, 0), "b200_assemble");
+  }
+
+  void constrainEssentialComponents(const feSolution *sol)
+  {
+    if(!_constraintInit) initConstraints(sol);
+    ok(b200_constrain(_sys), "b200_constrain");
+  }
+  void applyPeriodicity()
+  {
+    ok(b200_apply_periodicity(_sys), "b200_apply_periodicity");
+  }
+  void permute() {}
+
+  bool solve(double *normDx, double *normResidual, double *normAxb, int *nIter)
+  {
+    b200_solver_options o{_rel_tol, _abs_tol, _div_tol, _max_iter, _opt.restart, _opt.preconditioner};
+    const int           rc = b200_solve(_sys, &o, &_lastInfo);
+    *normDx       = _lastInfo.norm_dx;
+    *normResidual = _lastInfo.norm_rhs;
+    *normAxb      = _lastInfo.norm_axb;
+    *nIter        = _lastInfo.iterations;
+    _numSolves++;
+    _totalKrylovIterations += _lastInfo.iterations;
+    if(rc < 0) return fail("b200_solve");
+    if(!_lastInfo.converged) {
+      feWarning("feLinearSystemB200: GMRES did not reach the tolerance in %d iterations (relative residual %.3e)",
+                _lastInfo.iterations, _lastInfo.rel_residual);
+      return false;
+    }
+    return true;
+  }
+
+  void correctSolution(feSolution *sol, const bool correctSolutionDot = false)
+  {
+    std::vector<double> &v = correctSolutionDot ? sol->getSolutionDot() : sol->getSolution();
+    ok(b200_correct_solution(_sys, v.data(), correctSolutionDot ? 1 : 0), "b200_correct_solution");
+    _stateFresh = false;
+  }
+
+  void assignResidualToDCResidual(feSolutionContainer *solContainer)
+  {
+    std::vector<double> rhs(_nInc);
+    if(ok(b200_get_rhs(_sys, rhs.data()), "b200_get_rhs"))
+      for(feInt i = 0; i < _nInc; ++i) solContainer->_fResidual[0][i] = rhs[i];
+  }
+  void applyCorrectionToResidual(double coeff, std::vector<double> &d) { ok(b200_axpy_rhs(_sys, coeff, d.data()), "b200_axpy_rhs"); }
+
+  void viewMatrix() const
+  {
+    int64_t n, nnz;
+    b200_get_pattern_size(_sys, &n, &nnz);
+    std::vector<int64_t> ia(n + 1);
+    std::vector<int32_t> ja(nnz);
+    std::vector<double>  v(nnz);
+    b200_get_pattern(_sys, ia.data(), ja.data());
+    b200_get_matrix_values(_sys, v.data());
+    for(int64_t i = 0; i < n; ++i)
+      for(int64_t k = ia[i]; k < ia[i + 1]; ++k) printf("A(%ld, %d) = %+-10.10e\n", (long)i, ja[k], v[k]);
+  }
+  void viewRHS() const
+  {
+    std::vector<double> r(_nInc);
+    b200_get_rhs(_sys, r.data());
+    for(feInt i = 0; i < _nInc; ++i) printf("b(%ld) = %+-10.10e\n", (long)i, r[i]);
+  }
+  void viewResidual() const
+  {
+    std::vector<double> r(_nInc);
+    b200_get_du(_sys, r.data());
+    for(feInt i = 0; i < _nInc; ++i) printf("du(%ld) = %+-10.10e\n", (long)i, r[i]);
+  }
+  // one value per line in CSR order, "%+-10.20e" as src/feLinearSystemMklPardiso.cpp:455-485
+  void writeMatrix(const std::string fileName, const double = 0.)
+  {
+    int64_t n, nnz;
+    b200_get_pattern_size(_sys, &n, &nnz);
+    std::vector<double> v(nnz);
+    b200_get_matrix_values(_sys, v.data());
+    FILE *f = fopen(fileName.c_str(), "w");
+    if(!f) return;
+    for(double x : v) fprintf(f, "%+-10.20e\n", x);
+    fclose(f);
+  }
+  void writeRHS(const std::string fileName, const double = 0.)
+  {
+    std::vector<double> r(_nInc);
+    b200_get_rhs(_sys, r.data());
+    FILE *f = fopen(fileName.c_str(), "w");
+    if(!f) return;
+    for(double x : r) fprintf(f, "%+-10.20e\n", x);
+    fclose(f);
+  }
+  void writeResidual(const std::string fileName, const double = 0.)
+  {
+    std::vector<double> r(_nInc);
+    b200_get_du(_sys, r.data());
+    FILE *f = fopen(fileName.c_str(), "w");
+    if(!f) return;
+    for(double x : r) fprintf(f, "%+-10.20e\n", x);
+    fclose(f);
+  }
+};
+
+// Factory in the style of createLinearSystem (src/feLinearSystem.cpp:36-64); the reference's own factory enum lives in
+// the read-only tree, so the B200 backend ships its own entry point.
+inline feStatus createLinearSystemB200(feLinearSystem *&system, const std::vector<feBilinearForm *> bilinearForms,
+                                       const feMetaNumber *numbering, const feB200Options &opt = feB200Options())
+{
+  if(bilinearForms.empty()) return feErrorMsg(FE_STATUS_ERROR, "Cannot create a linear system without weak forms.");
+  feLinearSystemB200 *s = new feLinearSystemB200(bilinearForms, numbering, opt);
+  if(s->getStatus() != FE_STATUS_OK) {
+    delete s;
+    system = nullptr;
+    return FE_STATUS_ERROR;
+  }
+  system = s;
+  return FE_STATUS_OK;
+}
+
+#endif

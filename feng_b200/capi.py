@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libfeng_b200.so")
 # every symbol include/feng_b200.h declares (tests/test_capi_symbols.py checks the list against the header)
 SYMBOLS = [
     "b200_last_error", "b200_kernel_launches", "b200_reset_kernel_launches", "b200_create", "b200_destroy",
-    "b200_set_mesh", "b200_set_quadrature", "b200_add_space", "b200_add_form", "b200_set_pattern",
+    "b200_set_mesh", "b200_set_quadrature", "b200_add_space", "b200_add_form", "b200_set_source", "b200_set_pattern",
     "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode",
     "b200_set_constraints", "b200_set_blocks", "b200_finalize", "b200_system_size", "b200_set_solution",
     "b200_set_to_zero", "b200_assemble", "b200_rhs_max_norm", "b200_du_max_norm", "b200_constrain",
@@ -128,6 +128,10 @@ class System:
         src = None if source is None else np.ascontiguousarray(source, np.float64)
         return check(self.L.b200_add_form(self.h, kind, su, sp, C.c_double(coeff), C.c_double(param), _d(src)),
                      "b200_add_form")
+
+    def set_source(self, form_id, source):
+        src = np.ascontiguousarray(source, np.float64)
+        check(self.L.b200_set_source(self.h, form_id, _d(src)), "b200_set_source")
 
     def set_pattern(self, n_inc, n_dof, ia, ja):
         ia = np.ascontiguousarray(ia, np.int64)

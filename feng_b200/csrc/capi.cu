@@ -287,6 +287,23 @@ int b200_add_form(b200_system *s, int kind, int space_u, int space_p, double coe
   return (int)s->forms.size() - 1;
 }
 
+int b200_set_source(b200_system *s, int form_id, const double *source)
+{
+  CHECK_S(s);
+  if(form_id < 0 || form_id >= (int)s->forms.size() || !source || !s->forms[form_id].d_source) {
+    set_error("b200_set_source: not a source form");
+    return B200_ERR_ARG;
+  }
+  Form        &f     = s->forms[form_id];
+  const int    nc    = f.kind == B200_FORM_VECTOR_SOURCE ? s->dim : 1;
+  const size_t count = (size_t)s->nElm * s->nq * nc;
+  std::vector<double> scaled(source, source + count);
+  if(f.coeff != 1.)
+    for(auto &v : scaled) v *= f.coeff;
+  B200_CUDA(cudaMemcpy(f.d_source, scaled.data(), count * sizeof(double), cudaMemcpyHostToDevice));
+  return B200_OK;
+}
+
 int b200_set_pattern(b200_system *s, int64_t n_inc, int64_t n_dof, const int64_t *ia, const int32_t *ja)
 {
   CHECK_S(s);

@@ -117,6 +117,10 @@ int b200_add_space(b200_system *s, int n_scalar_functions, int n_components, con
  * quadrature node[, component]) or NULL. */
 int b200_add_form(b200_system *s, int kind, int space_u, int space_p, double coeff, double param,
                   const double *source);
+/* replace the tabulated source of form `form_id` (returned by b200_add_form): time-dependent source callbacks are
+ * re-tabulated by the adapter when feSolution::getCurrentTime() changes (the reference evaluates the callback with
+ * args.t = tn on every element visit, src/feBilinearForm.cpp:291-295) */
+int b200_set_source(b200_system *s, int form_id, const double *source);
 /* sparsity pattern of feEZCompressedRowStorage (src/feCompressedRowStorage.cpp:15-133), ia[n_inc+1], ja[nnz] */
 int b200_set_pattern(b200_system *s, int64_t n_inc, int64_t n_dof, const int64_t *ia, const int32_t *ja);
 /* same pattern built on the device from the spaces and forms registered so far; b200_get_pattern to read it back */

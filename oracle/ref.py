@@ -14,6 +14,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libfeng_ref.so")
+# the same harness linked with the product's C++ adapter (adapter/feLinearSystemB200.h) + libfeng_b200.so
+LIB_B200_PATH = os.path.join(_HERE, "_ref", "libfeng_ref_b200.so")
+DATA_DIR = os.path.join(_HERE, "_ref", "data")     # copies of the reference's regression meshes (oracle/Makefile: data)
 
 KIND = {"diffusion": 0, "stokes_div": 1, "ns_div": 2, "ns_lap": 3, "stokes_lap": 4}
 
@@ -27,18 +30,22 @@ def available() -> bool:
     return os.path.exists(LIB_PATH)
 
 
-_lib = None
+def available_b200() -> bool:
+    return os.path.exists(LIB_B200_PATH)
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(LIB_PATH)
-        _lib.ref_create.restype = C.c_void_p
-        _lib.ref_create.argtypes = [C.c_char_p, C.POINTER(Recipe)]
-        _lib.ref_destroy.argtypes = [C.c_void_p]
-        _lib.ref_max_threads.restype = C.c_int
-    return _lib
+_libs = {}
+
+
+def lib(b200: bool = False):
+    if b200 not in _libs:
+        L = C.CDLL(LIB_B200_PATH if b200 else LIB_PATH)
+        L.ref_create.restype = C.c_void_p
+        L.ref_create.argtypes = [C.c_char_p, C.POINTER(Recipe)]
+        L.ref_destroy.argtypes = [C.c_void_p]
+        L.ref_max_threads.restype = C.c_int
+        _libs[b200] = L
+    return _libs[b200]
 
 
 def _p(a, t=C.c_double):
@@ -58,8 +65,9 @@ class RefProblem:
     """One (mesh, recipe) instance of the reference CPU path."""
 
     def __init__(self, mesh_file: str, kind: str, order: int = 2, quad_degree: int = 8, field: int = 0,
-                 mu: float = 1.0, rho: float = 1.0, transient: bool = False, p_essential: bool = True):
-        self.L = lib()
+                 mu: float = 1.0, rho: float = 1.0, transient: bool = False, p_essential: bool = True,
+                 b200: bool = False):
+        self.L = lib(b200)
         rc = Recipe(KIND[kind], order, quad_degree, field, mu, rho, int(transient), int(p_essential))
         self.h = self.L.ref_create(mesh_file.encode(), C.byref(rc))
         if not self.h:
@@ -193,6 +201,20 @@ class RefProblem:
         if rc != 0:
             raise RuntimeError(f"reference Newton failed rc={rc}")
         return sol, out
+
+    def newton_b200(self, tol_res=1e-10, tol_cor=1e-10, max_iter=10, rel_tol=1e-8, pc=1, restart=30,
+                    lin_max_iter=10000, scatter=0, device_pattern=False):
+        """The unmodified reference Newton loop driving the CUDA backend through adapter/feLinearSystemB200.h.
+        -> (solution, dict(errU, errP, n_solves, krylov_iterations, norm_axb, converged))"""
+        sol = np.zeros(self.n_dof)
+        out = np.zeros(8)
+        opts = np.array([pc, restart, lin_max_iter, scatter, int(device_pattern)], np.int32)
+        rc = self.L.ref_newton_b200(self.h, C.c_double(tol_res), C.c_double(tol_cor), max_iter, C.c_double(rel_tol),
+                                    _p(opts, C.c_int32), _p(sol), _p(out))
+        if rc != 0:
+            raise RuntimeError(f"Newton with the B200 backend failed rc={rc}")
+        return sol, dict(errU=out[0], errP=out[1], n_solves=int(out[2]), krylov_iterations=int(out[3]),
+                         norm_axb=out[4], converged=bool(out[5]))
 
     def error_norms(self, sol):
         sol = np.ascontiguousarray(sol, np.float64)

@@ -15,6 +15,9 @@
 // Nothing in feng_b200/ (the product) links or loads this file.
 // =============================================================================
 #include "feAPI.h"
+#ifdef WITH_B200_ADAPTER
+#include "../adapter/feLinearSystemB200.h" // the product's C++ drop-in backend, driven by the unmodified Newton loop
+#endif
 
 #include <Eigen/Sparse>
 #include <Eigen/SparseLU>
@@ -437,6 +440,7 @@ bool hasEntity(feMesh *mesh, const std::string &name)
 } // namespace
 
 extern "C" {
+int ref_error_norms(void *h, const double *sol, double *out);
 
 int ref_max_threads()
 {
@@ -842,6 +846,48 @@ int ref_newton(void *h, double tolRes, double tolCor, int maxIter, double *sol_o
   out[7] = P->sys->_nSolve;
   return 0;
 }
+
+#ifdef WITH_B200_ADAPTER
+// The same stationary solve as ref_newton, but the UNMODIFIED createTimeIntegrator -> solveNewtonRaphson drives the
+// product's feLinearSystemB200 backend (adapter/feLinearSystemB200.h -> libfeng_b200.so) instead of the CPU stub:
+// the one-line change of tests/withLinearSolver/navier_stokes.cpp:101-108.
+// opts: pc, restart, linear max_iter, scatter mode, device pattern (0/1).  out: errU, errP, nSolves, total Krylov
+// iterations, last |Ax-b|, converged flag of the last solve.
+int ref_newton_b200(void *h, double tolRes, double tolCor, int maxIter, double relTol, const int *opts, double *sol_out,
+                    double *out)
+{
+  RefProblem *P = (RefProblem *)h;
+  P->sol->initialize(P->mesh);
+  feB200Options o;
+  o.preconditioner = opts[0];
+  o.restart        = opts[1];
+  o.scatter        = opts[3];
+  o.devicePattern  = opts[4] != 0;
+  feLinearSystem *sys = nullptr;
+  if(createLinearSystemB200(sys, P->forms, P->numbering, o) != FE_STATUS_OK) return -1;
+  sys->setRelativeTol(relTol);
+  sys->setMaxIter(opts[2]);
+  feNLSolverOptions     NL{tolRes, tolCor, 1e4, (double)maxIter, 4, 1e-1};
+  std::vector<feNorm *> norms = {};
+  TimeIntegrator       *solver;
+  if(createTimeIntegrator(solver, timeIntegratorScheme::STATIONARY, NL, sys, P->sol, P->mesh, norms, {nullptr, 1, ""}) !=
+     FE_STATUS_OK) {
+    delete sys;
+    return -2;
+  }
+  const feStatus st = solver->makeSteps(1);
+  delete solver;
+  feLinearSystemB200 *b = static_cast<feLinearSystemB200 *>(sys);
+  out[2] = b->getNumSolves();
+  out[3] = (double)b->getTotalKrylovIterations();
+  out[4] = b->getLastSolveInfo().norm_axb;
+  out[5] = b->getLastSolveInfo().converged;
+  delete sys;
+  if(st != FE_STATUS_OK) return -3;
+  std::memcpy(sol_out, P->sol->getSolution().data(), P->sol->getNumDOFs() * sizeof(double));
+  return ref_error_norms(h, sol_out, out);
+}
+#endif
 
 // L2 error norms of an arbitrary nDOF solution vector against the recipe's analytic fields (feNorm).
 int ref_error_norms(void *h, const double *sol, double *out)
