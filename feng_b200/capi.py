@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libfeng_b200.so")
 SYMBOLS = [
     "b200_last_error", "b200_kernel_launches", "b200_reset_kernel_launches", "b200_create", "b200_destroy",
     "b200_set_mesh", "b200_set_quadrature", "b200_add_space", "b200_add_form", "b200_set_source", "b200_set_pattern",
-    "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode",
+    "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode", "b200_set_assembly_mode", "b200_has_gather_plan",
     "b200_set_constraints", "b200_set_blocks", "b200_finalize", "b200_system_size", "b200_set_solution",
     "b200_set_to_zero", "b200_assemble", "b200_rhs_max_norm", "b200_du_max_norm", "b200_constrain",
     "b200_apply_periodicity", "b200_solve", "b200_correct_solution", "b200_get_rhs", "b200_axpy_rhs",
@@ -27,6 +27,7 @@ SYMBOLS = [
 ]
 
 SCATTER_ATOMIC, SCATTER_COLORED = 0, 1
+ASSEMBLY_AUTO, ASSEMBLY_SCATTER, ASSEMBLY_GATHER = 0, 1, 2
 PC_NONE, PC_JACOBI, PC_BLOCK_JACOBI, PC_ILU0 = 0, 1, 2, 3
 
 
@@ -159,6 +160,12 @@ class System:
 
     def set_scatter_mode(self, mode):
         check(self.L.b200_set_scatter_mode(self.h, mode), "b200_set_scatter_mode")
+
+    def set_assembly_mode(self, mode):
+        check(self.L.b200_set_assembly_mode(self.h, mode), "b200_set_assembly_mode")
+
+    def has_gather_plan(self) -> bool:
+        return bool(self.L.b200_has_gather_plan(self.h))
 
     def set_constraints(self, rows, master=None, slave=None):
         rows = np.ascontiguousarray(rows, np.int64)

@@ -18,6 +18,7 @@
 #include <cstdio>
 
 #include "system.h"
+#include "device_common.cuh"
 
 namespace b200 {
 
@@ -30,48 +31,6 @@ template <bool ATOMIC> __device__ __forceinline__ void add_to(double *p, double 
     atomicAdd(p, v); // result unused -> RED.E.ADD.F64
   else
     *p += v;
-}
-
-// Inverse affine map of a straight simplex; conventions of feCncGeo::computeElementTransformation
-// (src/feCncGeo.cpp:651-692): G[alpha*DIM+m] = d(xi_alpha)/d(x_m); detJ as src/feCncGeo.cpp:332,340,385.
-template <int DIM> __device__ __forceinline__ void element_geometry(const double *__restrict__ xyz, const int32_t *vtx, double *G, double *detJ)
-{
-  if(DIM == 2) {
-    const double x0 = xyz[2 * vtx[0]], y0 = xyz[2 * vtx[0] + 1];
-    const double dxdr = xyz[2 * vtx[1]] - x0, dydr = xyz[2 * vtx[1] + 1] - y0;
-    const double dxds = xyz[2 * vtx[2]] - x0, dyds = xyz[2 * vtx[2] + 1] - y0;
-    const double J = dxdr * dyds - dydr * dxds;
-    G[0] = dyds / J;  // dr/dx
-    G[1] = -dxds / J; // dr/dy
-    G[2] = -dydr / J; // ds/dx
-    G[3] = dxdr / J;  // ds/dy
-    *detJ = J;
-  } else {
-    double F[3][3]; // F[m][alpha] = dx_m / dxi_alpha
-    const double *p0 = xyz + 3 * vtx[0];
-#pragma unroll
-    for(int al = 0; al < 3; ++al) {
-      const double *p = xyz + 3 * vtx[al + 1];
-#pragma unroll
-      for(int m = 0; m < 3; ++m) F[m][al] = p[m] - p0[m];
-    }
-    const double c00 = F[1][1] * F[2][2] - F[1][2] * F[2][1];
-    const double c01 = F[1][2] * F[2][0] - F[1][0] * F[2][2];
-    const double c02 = F[1][0] * F[2][1] - F[1][1] * F[2][0];
-    const double J = F[0][0] * c00 + F[0][1] * c01 + F[0][2] * c02;
-    const double iJ = 1. / J;
-    // inverse of F: G[alpha][m]
-    G[0] = c00 * iJ;
-    G[1] = (F[0][2] * F[2][1] - F[0][1] * F[2][2]) * iJ;
-    G[2] = (F[0][1] * F[1][2] - F[0][2] * F[1][1]) * iJ;
-    G[3] = c01 * iJ;
-    G[4] = (F[0][0] * F[2][2] - F[0][2] * F[2][0]) * iJ;
-    G[5] = (F[0][2] * F[1][0] - F[0][0] * F[1][2]) * iJ;
-    G[6] = c02 * iJ;
-    G[7] = (F[0][1] * F[2][0] - F[0][0] * F[2][1]) * iJ;
-    G[8] = (F[0][0] * F[1][1] - F[0][1] * F[1][0]) * iJ;
-    *detJ = J;
-  }
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -719,6 +678,15 @@ int build_plan(System *S)
       return B200_ERR_ARG;
     }
   }
+  // row-owner gather plan where the problem qualifies
+  gather_free(S);
+  if(S->plan == PLAN_TAYLOR_HOOD && S->assembly_mode != B200_ASSEMBLY_SCATTER) {
+    const int grc = build_gather_plan(S);
+    if(grc != B200_OK && (grc != B200_ERR_UNSUPP || S->assembly_mode == B200_ASSEMBLY_GATHER)) return grc;
+  } else if(S->assembly_mode == B200_ASSEMBLY_GATHER) {
+    set_error("b200_finalize: the gather assembly needs the fused Taylor-Hood system");
+    return B200_ERR_UNSUPP;
+  }
   return B200_OK;
 }
 
@@ -819,6 +787,25 @@ int launch_assemble(System *S, int what, int only_transient)
   if(what < 1 || what > 3) {
     set_error("b200_assemble: what must be 1, 2 or 3");
     return B200_ERR_ARG;
+  }
+  if(S->gather != nullptr && S->assembly_mode != B200_ASSEMBLY_SCATTER) {
+    // every row is overwritten: a pending setToZero of the parts written here is dropped, the rest materialised
+    if(only_transient && (what & 2)) {
+      int rc = B200_OK;
+      if(what & 1) {
+        S->pending_zero &= ~1;
+        rc = launch_gather(S, 1, S->th);
+      }
+      if(rc != B200_OK) return rc;
+      S->pending_zero &= ~2;
+      return launch_gather(S, 2, S->th_transient);
+    }
+    S->pending_zero &= ~what;
+    return launch_gather(S, what, S->th);
+  }
+  {
+    const int zrc = flush_zero(S, 3);
+    if(zrc != B200_OK) return zrc;
   }
   if(only_transient && (what & 2)) {
     // transient-only matrix and full residual cannot share coefficients: two passes

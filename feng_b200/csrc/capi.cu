@@ -89,6 +89,7 @@ static void free_system(System *S)
 {
   cudaSetDevice(S->device);
   krylov_free(S);
+  gather_free(S);
   for(auto &sp : S->spaces) cudaFree(sp.d_adr);
   for(auto &f : S->forms) cudaFree(f.d_source);
   cudaFree(S->d_xyz);
@@ -138,6 +139,16 @@ static int alloc_linear_system(System *S)
 }
 
 int alloc_linear_system_public(System *S) { return alloc_linear_system(S); }
+
+// materialise a lazy setToZero (see System::pending_zero)
+int flush_zero(System *S, int what)
+{
+  const int todo = S->pending_zero & what;
+  if(todo & 2) B200_CUDA(cudaMemsetAsync(S->d_val, 0, (size_t)S->nnz * sizeof(double), S->stream));
+  if(todo & 1) B200_CUDA(cudaMemsetAsync(S->d_rhs, 0, (size_t)S->nInc * sizeof(double), S->stream));
+  S->pending_zero &= ~todo;
+  return B200_OK;
+}
 int build_pattern_device(System *S, int64_t n_inc, int64_t n_dof, const std::vector<int64_t> &per_master, const std::vector<int64_t> &per_slave);
 
 } // namespace b200
@@ -448,6 +459,25 @@ int b200_finalize(b200_system *s)
   return build_plan(s);
 }
 
+int b200_set_assembly_mode(b200_system *s, int mode)
+{
+  CHECK_S(s);
+  if(mode < B200_ASSEMBLY_AUTO || mode > B200_ASSEMBLY_GATHER) {
+    set_error("b200_set_assembly_mode: unknown mode");
+    return B200_ERR_ARG;
+  }
+  if(mode == B200_ASSEMBLY_GATHER && s->plan != PLAN_NONE && s->gather == nullptr) {
+    set_error("b200_set_assembly_mode: no gather plan for this problem");
+    return B200_ERR_UNSUPP;
+  }
+  const int rc = flush_zero(s, 3);
+  if(rc != B200_OK) return rc;
+  s->assembly_mode = mode;
+  return B200_OK;
+}
+
+int b200_has_gather_plan(const b200_system *s) { return s && s->gather != nullptr ? 1 : 0; }
+
 int64_t b200_system_size(const b200_system *s) { return s ? s->nInc : 0; }
 
 int b200_set_solution(b200_system *s, const double *sol, const double *sol_dot, double c0, double t)
@@ -473,8 +503,13 @@ int b200_set_to_zero(b200_system *s, int what)
     set_error("b200_set_to_zero: set the pattern first");
     return B200_ERR_ARG;
   }
+  if(s->gather != nullptr && s->assembly_mode != B200_ASSEMBLY_SCATTER) {
+    s->pending_zero |= (what & 3); // the gather kernels overwrite: memset only if something else touches the arrays
+    return B200_OK;
+  }
   if(what & 2) B200_CUDA(cudaMemsetAsync(s->d_val, 0, (size_t)s->nnz * sizeof(double), s->stream));
   if(what & 1) B200_CUDA(cudaMemsetAsync(s->d_rhs, 0, (size_t)s->nInc * sizeof(double), s->stream));
+  s->pending_zero &= ~(what & 3);
   return B200_OK;
 }
 
@@ -491,6 +526,7 @@ int b200_assemble(b200_system *s, int what, int only_transient)
 int b200_rhs_max_norm(b200_system *s, double *norm)
 {
   CHECK_S(s);
+  if(flush_zero(s, 1) != B200_OK) return B200_ERR_CUDA;
   return max_abs(s, s->d_rhs, s->nInc, norm);
 }
 
@@ -503,6 +539,7 @@ int b200_du_max_norm(b200_system *s, double *norm)
 int b200_constrain(b200_system *s)
 {
   CHECK_S(s);
+  if(flush_zero(s, 3) != B200_OK) return B200_ERR_CUDA;
   if(s->n_crow == 0) return B200_OK;
   constrain_kernel<<<GRID, 256, 0, s->stream>>>(s->nInc, s->d_ia, s->d_ja, s->d_val, s->d_rhs, s->d_cflag);
   count_launch();
@@ -513,6 +550,7 @@ int b200_constrain(b200_system *s)
 int b200_apply_periodicity(b200_system *s)
 {
   CHECK_S(s);
+  if(flush_zero(s, 3) != B200_OK) return B200_ERR_CUDA;
   if(s->n_per == 0) return B200_OK;
   periodic_kernel<<<(unsigned)std::min<int64_t>((s->n_per + 127) / 128, GRID), 128, 0, s->stream>>>(s->n_per, s->d_master, s->d_slave, s->nInc,
                                                                                                  s->d_ia, s->d_ja, s->d_val, s->d_rhs);
@@ -528,6 +566,7 @@ int b200_solve(b200_system *s, const b200_solver_options *opt, b200_solve_info *
     set_error("b200_solve: bad arguments");
     return B200_ERR_ARG;
   }
+  if(flush_zero(s, 3) != B200_OK) return B200_ERR_CUDA;
   B200_CUDA(cudaEventRecord(s->ev0, s->stream));
   const int rc = gmres_solve(s, opt, info);
   cudaEventRecord(s->ev1, s->stream);
@@ -554,6 +593,7 @@ int b200_correct_solution(b200_system *s, double *sol_host, int correct_dot)
 int b200_get_rhs(b200_system *s, double *rhs)
 {
   CHECK_S(s);
+  if(flush_zero(s, 1) != B200_OK) return B200_ERR_CUDA;
   B200_CUDA(cudaMemcpyAsync(rhs, s->d_rhs, (size_t)s->nInc * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   B200_CUDA(cudaStreamSynchronize(s->stream));
   return B200_OK;
@@ -562,6 +602,7 @@ int b200_get_rhs(b200_system *s, double *rhs)
 int b200_axpy_rhs(b200_system *s, double coeff, const double *d)
 {
   CHECK_S(s);
+  if(flush_zero(s, 1) != B200_OK) return B200_ERR_CUDA;
   double *tmp = s->d_du; // du is rewritten by the next solve
   B200_CUDA(cudaMemcpyAsync(tmp, d, (size_t)s->nInc * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   axpy_kernel<<<GRID, 256, 0, s->stream>>>(s->nInc, coeff, tmp, s->d_rhs);
@@ -573,6 +614,7 @@ int b200_axpy_rhs(b200_system *s, double coeff, const double *d)
 int b200_get_matrix_values(b200_system *s, double *values)
 {
   CHECK_S(s);
+  if(flush_zero(s, 2) != B200_OK) return B200_ERR_CUDA;
   B200_CUDA(cudaMemcpyAsync(values, s->d_val, (size_t)s->nnz * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   B200_CUDA(cudaStreamSynchronize(s->stream));
   return B200_OK;
@@ -597,6 +639,7 @@ int b200_get_solution(b200_system *s, double *sol)
 int b200_spmv(b200_system *s, const double *x, double *y)
 {
   CHECK_S(s);
+  if(flush_zero(s, 2) != B200_OK) return B200_ERR_CUDA;
   double *dx = nullptr, *dy = nullptr;
   B200_CUDA(cudaMalloc(&dx, (size_t)s->nInc * sizeof(double)));
   B200_CUDA(cudaMalloc(&dy, (size_t)s->nInc * sizeof(double)));
@@ -632,6 +675,7 @@ int b200_last_solve_ms(const b200_system *s, float *ms)
 int b200_time_spmv(b200_system *s, int reps, float *ms_per_spmv)
 {
   CHECK_S(s);
+  if(flush_zero(s, 2) != B200_OK) return B200_ERR_CUDA;
   if(reps <= 0 || !s->d_val) {
     set_error("b200_time_spmv: bad arguments");
     return B200_ERR_ARG;

@@ -1,0 +1,856 @@
+// Row-owner ("gather") assembly with pre-contracted reference tensors.
+//
+// Same numbers as the reference's per-form quadrature loops (feSysElm_*::computeAe/computeBe, src/feVectorSysElm.cpp,
+// restated in oracle/fe_oracle.py) and the colour-ordered scatter (src/feLinearSystemMklPardiso.cpp:501-749), but
+// organised for the GPU memory system:
+//
+//  * Straight simplices + constant coefficients: every entry of the fused element system is
+//        sum_k w_k (products of reference-basis tables at node k) x (geometry factors constant on the element)
+//        x (local DOFs for the convective terms).
+//    The k-sums are moved into constant tables built ONCE from the tables the host passes (any quadrature rule):
+//        Kref[a][b][al][be] = sum_k w_k dphi_a/dxi_al dphi_b/dxi_be        (viscous / diffusion blocks)
+//        Mref[a][b]         = sum_k w_k phi_a phi_b                        (transient mass)
+//        Bref[q][a][al]     = sum_k w_k psi_q dphi_a/dxi_al                (pressure gradient / divergence blocks)
+//        T3[a][b][v]        = sum_k w_k phi_a phi_b psi_v                  (convection)
+//        E[c][al][v]        : dphi_c/dxi_al (xi_k) = sum_v psi_v(xi_k) E[c][al][v]  (gradients of P2 functions are
+//                             P1: verified on the host at plan time, otherwise the quadrature kernel is used)
+//    This is an exact re-association of the reference's sums (differences are rounding, ~1e-15 relative).
+//  * Each CSR row is produced by ONE thread from the elements adjacent to its DOF ("row owner"): contributions are
+//    accumulated in a shared-memory copy of the row and written to HBM exactly once with coalesced stores -- no
+//    memset, no atomics, deterministic summation order (ascending element index), 16-bit row-local column offsets
+//    instead of a 32-bit CSR slot per local entry.
+#include <thrust/device_vector.h>
+#include <thrust/execution_policy.h>
+#include <thrust/extrema.h>
+#include <thrust/scan.h>
+#include <thrust/sort.h>
+
+#include <cmath>
+
+#include "device_common.cuh"
+#include "system.h"
+
+namespace b200 {
+
+template <int D, int NS, int NP> struct GT {
+  static constexpr int NU = NS * D, M = NU + NP;
+  static constexpr int O_K = 0;                       // Kref[a][b][al][be]
+  static constexpr int O_T3 = O_K + NS * NS * D * D;  // T3[a][b][v]
+  static constexpr int O_M = O_T3 + NS * NS * NP;     // Mref[a][b]
+  static constexpr int O_E = O_M + NS * NS;           // E[c][al][v]
+  static constexpr int O_B = O_E + NS * D * NP;       // Bref[q][a][al]
+  static constexpr int O_W = O_B + NP * NS * D;       // W[k][a] = w_k phi_a(k)   (source forms only)
+  static constexpr int OFFW_U = (M + 7) / 8 * 8;      // uint16 offsets per (U node, element) pair
+  static constexpr int OFFW_P = (NU + 7) / 8 * 8;     // per (P node, element) pair
+};
+
+struct NodeSet {
+  int32_t   nNodes = 0, nCta = 0;
+  int64_t   nPairs = 0;
+  int32_t  *pair = nullptr;     // [nPairs] e * nLoc + local index, sorted by node then element
+  int2     *range = nullptr;    // [nNodes] (first pair, number of pairs)
+  int32_t  *row = nullptr;      // [nNodes][nRow] global rows (>= nInc: essential, not assembled)
+  uint32_t *smoff = nullptr;    // [nNodes] offset (doubles) of the node's row buffer inside its CTA's shared memory
+  uint32_t *cta_size = nullptr; // [nCta] doubles of row buffer per CTA
+  uint16_t *off = nullptr;      // [nPairs][OFFW] row-local column offsets, 0xFFFF = not assembled
+  uint32_t  max_cta = 0;
+  void release()
+  {
+    cudaFree(pair);
+    cudaFree(range);
+    cudaFree(row);
+    cudaFree(smoff);
+    cudaFree(cta_size);
+    cudaFree(off);
+    *this = NodeSet();
+  }
+};
+
+struct GatherPlan {
+  NodeSet  U, P;
+  double  *d_tab = nullptr;
+  int      tab_len = 0, tab_len_src = 0;
+  int      npbU = 0, npbP = 0;
+};
+
+struct GatherArgs {
+  const double   *xyz;
+  const int32_t  *conn, *adrU, *adrP;
+  const double   *sol, *soldot, *source, *tab;
+  const int64_t  *ia;
+  double         *val, *rhs;
+  const int32_t  *pair;
+  const int2     *range;
+  const int32_t  *row;
+  const uint32_t *smoff, *cta_size;
+  const uint16_t *off;
+  int32_t         nNodes;
+  int64_t         nInc;
+  int             nq, ntab;
+  THCoeffs        c;
+  double          c0;
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// U rows: one thread per velocity node (D rows), loop over the adjacent elements
+// ----------------------------------------------------------------------------------------------------------
+template <int D, int NS, int NP, int NPB, bool MAT, bool RES>
+__global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
+{
+  using T = GT<D, NS, NP>;
+  constexpr int NU = T::NU;
+  extern __shared__ double sm[];
+  double *s_tab = sm;
+  double *s_buf = sm + a.ntab;
+  __shared__ int32_t  s_row[NPB * D];
+  __shared__ uint32_t s_base[NPB];
+  __shared__ int32_t  s_len[NPB];
+
+  const int tid = threadIdx.x;
+  for(int i = tid; i < a.ntab; i += NPB) s_tab[i] = a.tab[i];
+  const int32_t n    = blockIdx.x * NPB + tid;
+  const bool    live = n < a.nNodes;
+  int32_t       row[D];
+  int           len = 0;
+  uint32_t      base = 0;
+  if(live) {
+#pragma unroll
+    for(int c = 0; c < D; ++c) row[c] = a.row[n * D + c];
+#pragma unroll
+    for(int c = D - 1; c >= 0; --c)
+      if(row[c] < a.nInc) len = (int)(a.ia[row[c] + 1] - a.ia[row[c]]);
+    base = a.smoff[n];
+  } else {
+#pragma unroll
+    for(int c = 0; c < D; ++c) row[c] = 0x7fffffff;
+  }
+  if(MAT) {
+#pragma unroll
+    for(int c = 0; c < D; ++c) s_row[tid * D + c] = row[c];
+    s_base[tid] = base;
+    s_len[tid]  = len;
+    const uint32_t tot = a.cta_size[blockIdx.x];
+    for(uint32_t i = tid; i < tot; i += NPB) s_buf[i] = 0.;
+  }
+  __syncthreads();
+
+  if(live) {
+    // row buffer of component c (unknown rows only, packed)
+    double *buf[D];
+    {
+      uint32_t o = base;
+#pragma unroll
+      for(int c = 0; c < D; ++c) {
+        buf[c] = s_buf + o;
+        if(row[c] < a.nInc) o += len;
+      }
+    }
+    double res[D];
+#pragma unroll
+    for(int c = 0; c < D; ++c) res[c] = 0.;
+    const THCoeffs c      = a.c;
+    const double   mass0  = c.c_mass * a.c0;
+    const int2     rg     = a.range[n];
+    const bool     domass = (c.c_mass != 0.) && (a.soldot != nullptr);
+
+    for(int p = rg.x; p < rg.x + rg.y; ++p) {
+      const int     ea = a.pair[p];
+      const int     e = ea / NS, la = ea - e * NS;
+      int32_t       vtx[D + 1];
+#pragma unroll
+      for(int v = 0; v <= D; ++v) vtx[v] = a.conn[(int64_t)e * (D + 1) + v];
+      double G[D * D], J;
+      element_geometry<D>(a.xyz, vtx, G, &J);
+      const int32_t *au = a.adrU + (int64_t)e * NU;
+      double         U[NS][D];
+#pragma unroll
+      for(int b = 0; b < NS; ++b)
+#pragma unroll
+        for(int m = 0; m < D; ++m) U[b][m] = a.sol[au[b * D + m]];
+      // contravariant velocity DOFs Ut[c][al] = sum_m U[c][m] dxi_al/dx_m and Z[al][v] = sum_c Ut[c][al] T3[la][c][v]
+      const double *T3a = s_tab + T::O_T3 + la * NS * NP;
+      double        Z[D][NP];
+#pragma unroll
+      for(int al = 0; al < D; ++al)
+#pragma unroll
+        for(int v = 0; v < NP; ++v) Z[al][v] = 0.;
+#pragma unroll
+      for(int cc = 0; cc < NS; ++cc) {
+        double ut[D];
+#pragma unroll
+        for(int al = 0; al < D; ++al) {
+          double s = 0.;
+#pragma unroll
+          for(int m = 0; m < D; ++m) s += U[cc][m] * G[al * D + m];
+          ut[al] = s;
+        }
+#pragma unroll
+        for(int v = 0; v < NP; ++v) {
+          const double t = T3a[cc * NP + v];
+#pragma unroll
+          for(int al = 0; al < D; ++al) Z[al][v] += ut[al] * t;
+        }
+      }
+      // velocity gradient at the vertices: Dv[v][j][i] = d_j u_i (v) = sum_al dxi_al/dx_j sum_c U[c][i] E[c][al][v]
+      double Dv[NP][D][D];
+#pragma unroll
+      for(int i = 0; i < D; ++i) {
+        double X[D][NP];
+#pragma unroll
+        for(int al = 0; al < D; ++al)
+#pragma unroll
+          for(int v = 0; v < NP; ++v) X[al][v] = 0.;
+#pragma unroll
+        for(int cc = 0; cc < NS; ++cc)
+#pragma unroll
+          for(int al = 0; al < D; ++al)
+#pragma unroll
+            for(int v = 0; v < NP; ++v) X[al][v] += U[cc][i] * s_tab[T::O_E + (cc * D + al) * NP + v];
+#pragma unroll
+        for(int v = 0; v < NP; ++v)
+#pragma unroll
+          for(int j = 0; j < D; ++j) {
+            double s = 0.;
+#pragma unroll
+            for(int al = 0; al < D; ++al) s += G[al * D + j] * X[al][v];
+            Dv[v][j][i] = s;
+          }
+      }
+      // row-local column offsets of this (node, element) pair
+      uint16_t of[T::OFFW_U];
+      if(MAT) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.off + (int64_t)p * T::OFFW_U);
+#pragma unroll
+        for(int w = 0; w < T::OFFW_U / 8; ++w) {
+          const uint4 v = src[w];
+          of[8 * w + 0] = (uint16_t)(v.x & 0xffff);
+          of[8 * w + 1] = (uint16_t)(v.x >> 16);
+          of[8 * w + 2] = (uint16_t)(v.y & 0xffff);
+          of[8 * w + 3] = (uint16_t)(v.y >> 16);
+          of[8 * w + 4] = (uint16_t)(v.z & 0xffff);
+          of[8 * w + 5] = (uint16_t)(v.z >> 16);
+          of[8 * w + 6] = (uint16_t)(v.w & 0xffff);
+          of[8 * w + 7] = (uint16_t)(v.w >> 16);
+        }
+      }
+      const int32_t *ap = a.adrP + (int64_t)e * NP;
+
+#pragma unroll
+      for(int b = 0; b < NS; ++b) {
+        const double *Kr = s_tab + T::O_K + (la * NS + b) * D * D;
+        double        K[D][D]; // K[m][n] = int d_m phi_a d_n phi_b
+        {
+          double H[D][D];
+#pragma unroll
+          for(int al = 0; al < D; ++al)
+#pragma unroll
+            for(int nn = 0; nn < D; ++nn) {
+              double s = 0.;
+#pragma unroll
+              for(int be = 0; be < D; ++be) s += Kr[al * D + be] * G[be * D + nn];
+              H[al][nn] = s;
+            }
+#pragma unroll
+          for(int m = 0; m < D; ++m)
+#pragma unroll
+            for(int nn = 0; nn < D; ++nn) {
+              double s = 0.;
+#pragma unroll
+              for(int al = 0; al < D; ++al) s += G[al * D + m] * H[al][nn];
+              K[m][nn] = J * s;
+            }
+        }
+        double trK = 0.;
+#pragma unroll
+        for(int m = 0; m < D; ++m) trK += K[m][m];
+        double        C1 = 0.; // int phi_a (u . grad phi_b)
+        const double *Eb = s_tab + T::O_E + b * D * NP;
+#pragma unroll
+        for(int al = 0; al < D; ++al)
+#pragma unroll
+          for(int v = 0; v < NP; ++v) C1 += Eb[al * NP + v] * Z[al][v];
+        C1 *= J;
+        const double *T3ab = T3a + b * NP;
+        double        t3[NP];
+#pragma unroll
+        for(int v = 0; v < NP; ++v) t3[v] = J * T3ab[v];
+        const double Mab = J * s_tab[T::O_M + la * NS + b];
+        const double s   = c.c_conv * C1 + (c.diff_k - c.sig_mu) * trK + mass0 * Mab;
+        if(MAT) {
+#pragma unroll
+          for(int i = 0; i < D; ++i) {
+            if(row[i] < a.nInc) {
+#pragma unroll
+              for(int j = 0; j < D; ++j) {
+                const uint16_t o = of[b * D + j];
+                if(o != 0xFFFF) {
+                  double C2 = 0.; // int phi_a phi_b d_j u_i
+#pragma unroll
+                  for(int v = 0; v < NP; ++v) C2 += Dv[v][j][i] * t3[v];
+                  buf[i][o] += (i == j ? s : 0.) - c.sig_mu * K[j][i] + c.c_conv * C2;
+                }
+              }
+            }
+          }
+        }
+        if(RES) {
+          const double r1 = (c.sig_mu - c.diff_k) * trK - c.c_conv * C1;
+#pragma unroll
+          for(int i = 0; i < D; ++i) {
+            double r = r1 * U[b][i];
+#pragma unroll
+            for(int m = 0; m < D; ++m) r += c.sig_mu * K[m][i] * U[b][m];
+            if(domass) r -= c.c_mass * Mab * a.soldot[au[b * D + i]];
+            res[i] += r;
+          }
+        }
+      }
+      // pressure columns
+#pragma unroll
+      for(int q = 0; q < NP; ++q) {
+        const double *Br = s_tab + T::O_B + (q * NS + la) * D;
+        const double  pq = RES ? a.sol[ap[q]] : 0.;
+#pragma unroll
+        for(int i = 0; i < D; ++i) {
+          double s = 0.;
+#pragma unroll
+          for(int al = 0; al < D; ++al) s += G[al * D + i] * Br[al];
+          const double Bp = J * s;
+          if(MAT) {
+            const uint16_t o = of[NU + q];
+            if(o != 0xFFFF && row[i] < a.nInc) buf[i][o] += (c.c_sig - c.c_gradp) * Bp;
+          }
+          if(RES) res[i] += (c.c_gradp - c.c_sig) * Bp * pq;
+        }
+      }
+      if(RES && a.source != nullptr) {
+        const double *W   = s_tab + T::O_W;
+        const double *src = a.source + (int64_t)e * a.nq * D;
+        for(int k = 0; k < a.nq; ++k) {
+          const double wj = J * W[k * NS + la];
+#pragma unroll
+          for(int i = 0; i < D; ++i) res[i] -= wj * src[k * D + i];
+        }
+      }
+    }
+    if(RES) {
+#pragma unroll
+      for(int i = 0; i < D; ++i)
+        if(row[i] < a.nInc) a.rhs[row[i]] = res[i];
+    }
+  }
+  if(MAT) {
+    __syncthreads();
+    // coalesced write-out: one warp per row segment
+    const int lane = tid & 31, wid = tid >> 5, nw = NPB / 32;
+    for(int t = wid; t < NPB; t += nw) {
+      const int ln = s_len[t];
+      uint32_t  o  = s_base[t];
+#pragma unroll
+      for(int c = 0; c < D; ++c) {
+        const int32_t r = s_row[t * D + c];
+        if(r < a.nInc) {
+          double *dst = a.val + a.ia[r];
+          for(int k = lane; k < ln; k += 32) dst[k] = s_buf[o + k];
+          o += ln;
+        }
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// P rows: one thread per pressure node (1 row)
+// ----------------------------------------------------------------------------------------------------------
+template <int D, int NS, int NP, int NPB, bool MAT, bool RES>
+__global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
+{
+  using T = GT<D, NS, NP>;
+  constexpr int NU = T::NU;
+  extern __shared__ double sm[];
+  double *s_tab = sm;
+  double *s_buf = sm + a.ntab;
+  __shared__ int32_t  s_row[NPB];
+  __shared__ uint32_t s_base[NPB];
+  __shared__ int32_t  s_len[NPB];
+  const int tid = threadIdx.x;
+  for(int i = tid; i < a.ntab; i += NPB) s_tab[i] = a.tab[i];
+  const int32_t n    = blockIdx.x * NPB + tid;
+  const bool    live = n < a.nNodes;
+  int32_t       row  = 0x7fffffff;
+  int           len  = 0;
+  uint32_t      base = 0;
+  if(live) {
+    row  = a.row[n];
+    len  = row < a.nInc ? (int)(a.ia[row + 1] - a.ia[row]) : 0;
+    base = a.smoff[n];
+  }
+  if(MAT) {
+    s_row[tid]  = row;
+    s_base[tid] = base;
+    s_len[tid]  = len;
+    const uint32_t tot = a.cta_size[blockIdx.x];
+    for(uint32_t i = tid; i < tot; i += NPB) s_buf[i] = 0.;
+  }
+  __syncthreads();
+  if(live && row < a.nInc) {
+    double      *buf = s_buf + base;
+    double       res = 0.;
+    const double cdiv = a.c.c_div;
+    const int2   rg  = a.range[n];
+    for(int p = rg.x; p < rg.x + rg.y; ++p) {
+      const int eq = a.pair[p];
+      const int e = eq / NP, q = eq - e * NP;
+      int32_t   vtx[D + 1];
+#pragma unroll
+      for(int v = 0; v <= D; ++v) vtx[v] = a.conn[(int64_t)e * (D + 1) + v];
+      double G[D * D], J;
+      element_geometry<D>(a.xyz, vtx, G, &J);
+      const int32_t *au = a.adrU + (int64_t)e * NU;
+      uint16_t       of[T::OFFW_P];
+      if(MAT) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.off + (int64_t)p * T::OFFW_P);
+#pragma unroll
+        for(int w = 0; w < T::OFFW_P / 8; ++w) {
+          const uint4 v = src[w];
+          of[8 * w + 0] = (uint16_t)(v.x & 0xffff);
+          of[8 * w + 1] = (uint16_t)(v.x >> 16);
+          of[8 * w + 2] = (uint16_t)(v.y & 0xffff);
+          of[8 * w + 3] = (uint16_t)(v.y >> 16);
+          of[8 * w + 4] = (uint16_t)(v.z & 0xffff);
+          of[8 * w + 5] = (uint16_t)(v.z >> 16);
+          of[8 * w + 6] = (uint16_t)(v.w & 0xffff);
+          of[8 * w + 7] = (uint16_t)(v.w >> 16);
+        }
+      }
+#pragma unroll
+      for(int b = 0; b < NS; ++b) {
+        const double *Br = s_tab + T::O_B + (q * NS + b) * D;
+#pragma unroll
+        for(int j = 0; j < D; ++j) {
+          double s = 0.;
+#pragma unroll
+          for(int al = 0; al < D; ++al) s += G[al * D + j] * Br[al];
+          const double Bp = cdiv * J * s;
+          if(MAT) {
+            const uint16_t o = of[b * D + j];
+            if(o != 0xFFFF) buf[o] += Bp;
+          }
+          if(RES) res -= Bp * a.sol[au[b * D + j]];
+        }
+      }
+    }
+    if(RES) a.rhs[row] = res;
+  }
+  if(MAT) {
+    __syncthreads();
+    const int lane = tid & 31, wid = tid >> 5, nw = NPB / 32;
+    for(int t = wid; t < NPB; t += nw) {
+      const int32_t r = s_row[t];
+      if(r < a.nInc) {
+        double        *dst = a.val + a.ia[r];
+        const uint32_t o   = s_base[t];
+        const int      ln  = s_len[t];
+        for(int k = lane; k < ln; k += 32) dst[k] = s_buf[o + k];
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// plan construction (set-up)
+// ----------------------------------------------------------------------------------------------------------
+__global__ void node_keys_kernel(int64_t nElm, int nLoc, int nF, int stride, const int32_t *adr, int32_t *keys, int32_t *vals)
+{
+  const int64_t tot = nElm * nLoc;
+  for(int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = idx / nLoc;
+    const int     l = (int)(idx - e * nLoc);
+    keys[idx] = adr[e * nF + l * stride]; // DOF of component 0 identifies the node
+    vals[idx] = (int32_t)idx;
+  }
+}
+
+__global__ void node_flag_kernel(int64_t n, const int32_t *keys, int32_t *flag)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// one thread per pair position: node start -> (range, rows)
+__global__ void node_fill_kernel(int64_t n, const int32_t *keys, const int32_t *flag, const int32_t *rank, const int32_t *vals, int nLoc, int nF,
+                                 int nRow, const int32_t *adr, int2 *range, int32_t *row)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if(!flag[i]) continue;
+    const int32_t node = rank[i] - 1;
+    int64_t       j = i + 1;
+    while(j < n && keys[j] == keys[i]) ++j;
+    range[node] = make_int2((int)i, (int)(j - i));
+    const int64_t e = vals[i] / nLoc;
+    const int     l = vals[i] - (int32_t)(e * nLoc);
+    for(int c = 0; c < nRow; ++c) row[(int64_t)node * nRow + c] = adr[e * nF + l * nRow + c];
+  }
+}
+
+// nodes with at least one unknown row are kept (compaction flag)
+__global__ void node_keep_kernel(int32_t nNodes, int nRow, int64_t nInc, const int32_t *row, int32_t *keep)
+{
+  for(int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nNodes; i += gridDim.x * blockDim.x) {
+    int k = 0;
+    for(int c = 0; c < nRow; ++c) k |= row[(int64_t)i * nRow + c] < nInc;
+    keep[i] = k;
+  }
+}
+
+__global__ void node_compact_kernel(int32_t nNodes, int nRow, const int32_t *keep, const int32_t *pos, const int2 *range, const int32_t *row,
+                                    int2 *range2, int32_t *row2)
+{
+  for(int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nNodes; i += gridDim.x * blockDim.x) {
+    if(!keep[i]) continue;
+    const int32_t o = pos[i] - 1;
+    range2[o] = range[i];
+    for(int c = 0; c < nRow; ++c) row2[(int64_t)o * nRow + c] = row[(int64_t)i * nRow + c];
+  }
+}
+
+// shared-memory layout of the row buffers: one thread per CTA
+__global__ void node_smem_kernel(int32_t nNodes, int npb, int nRow, int64_t nInc, const int64_t *ia, const int32_t *row, uint32_t *smoff,
+                                 uint32_t *cta_size, int *err)
+{
+  const int32_t cta = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t n0 = cta * npb;
+  if(n0 >= nNodes) return;
+  uint32_t o = 0;
+  for(int32_t n = n0; n < n0 + npb && n < nNodes; ++n) {
+    smoff[n] = o;
+    int64_t len = -1;
+    int     nun = 0;
+    for(int c = 0; c < nRow; ++c) {
+      const int32_t r = row[(int64_t)n * nRow + c];
+      if(r < nInc) {
+        const int64_t l = ia[r + 1] - ia[r];
+        if(len >= 0 && l != len) atomicExch(err, 2); // rows of one node must share their column structure
+        len = l;
+        ++nun;
+      }
+    }
+    if(len >= 65535) atomicExch(err, 3);
+    o += (uint32_t)(nun * (len > 0 ? len : 0));
+  }
+  cta_size[cta] = o;
+}
+
+// row-local offsets of the columns of every (node, element) pair; one thread per (pair, local column)
+__global__ void node_offsets_kernel(int32_t nNodes, int nRow, int nLoc, int offw, int ncol, int NU, int NP, const int2 *range, const int32_t *row,
+                                    const int32_t *pair, const int32_t *adrU, const int32_t *adrP, const int64_t *ia, const int32_t *ja,
+                                    int64_t nInc, int colmaskU, int colmaskP, uint16_t *off, int *err)
+{
+  // grid-stride over nodes; threads of a block cooperate over (pair, column) of the node
+  for(int32_t n = blockIdx.x; n < nNodes; n += gridDim.x) {
+    const int2 rg = range[n];
+    int32_t    r0 = -1;
+    for(int c = nRow - 1; c >= 0; --c)
+      if(row[(int64_t)n * nRow + c] < nInc) r0 = row[(int64_t)n * nRow + c];
+    const int64_t beg = ia[r0], end = ia[r0 + 1];
+    for(int idx = threadIdx.x; idx < rg.y * offw; idx += blockDim.x) {
+      const int     pp = idx / offw, j = idx - pp * offw;
+      const int64_t p  = rg.x + pp;
+      uint16_t      o  = 0xFFFF;
+      if(j < ncol) {
+        const int64_t e   = pair[p] / nLoc;
+        const bool    isU = j < NU;
+        if(isU ? colmaskU : colmaskP) {
+          const int32_t col = isU ? adrU[e * NU + j] : adrP[e * NP + (j - NU)];
+          if(col < nInc) {
+            int64_t lo = beg, hi = end - 1;
+            while(lo < hi) {
+              const int64_t mid = (lo + hi) >> 1;
+              if(ja[mid] < col)
+                lo = mid + 1;
+              else
+                hi = mid;
+            }
+            if(lo < end && ja[lo] == col) {
+              o = (uint16_t)(lo - beg);
+              // every unknown row of the node must hold this column at the same offset
+              for(int c = 0; c < nRow; ++c) {
+                const int32_t r = row[(int64_t)n * nRow + c];
+                if(r < nInc && r != r0 && ja[ia[r] + (lo - beg)] != col) atomicExch(err, 4);
+              }
+            } else
+              atomicExch(err, 1);
+          }
+        }
+      }
+      off[p * offw + j] = o;
+    }
+  }
+}
+
+static int build_node_set(System *S, NodeSet &N, const int32_t *d_adr, int nLoc, int nF, int nRow, int npb, int offw, int ncol, int NU, int NP,
+                          int colmaskU, int colmaskP)
+{
+  auto          pol = thrust::cuda::par.on(S->stream);
+  const int64_t np  = S->nElm * (int64_t)nLoc;
+  if(np >= (int64_t)2147483647) {
+    set_error("gather plan: more than 2^31 (element, node) pairs");
+    return B200_ERR_UNSUPP;
+  }
+  N.release();
+  N.nPairs = np;
+  thrust::device_vector<int32_t> keys(np), flag(np), rank(np);
+  B200_CUDA(cudaMalloc(&N.pair, np * sizeof(int32_t)));
+  node_keys_kernel<<<148 * 8, 256, 0, S->stream>>>(S->nElm, nLoc, nF, nRow, d_adr, thrust::raw_pointer_cast(keys.data()), N.pair);
+  thrust::stable_sort_by_key(pol, keys.begin(), keys.end(), thrust::device_pointer_cast(N.pair));
+  node_flag_kernel<<<148 * 8, 256, 0, S->stream>>>(np, thrust::raw_pointer_cast(keys.data()), thrust::raw_pointer_cast(flag.data()));
+  thrust::inclusive_scan(pol, flag.begin(), flag.end(), rank.begin());
+  const int32_t nAll = rank[np - 1];
+  thrust::device_vector<int2>    range(nAll);
+  thrust::device_vector<int32_t> row((size_t)nAll * nRow), keep(nAll), pos(nAll);
+  node_fill_kernel<<<148 * 8, 256, 0, S->stream>>>(np, thrust::raw_pointer_cast(keys.data()), thrust::raw_pointer_cast(flag.data()),
+                                                  thrust::raw_pointer_cast(rank.data()), N.pair, nLoc, nF, nRow, d_adr,
+                                                  thrust::raw_pointer_cast(range.data()), thrust::raw_pointer_cast(row.data()));
+  node_keep_kernel<<<148 * 8, 256, 0, S->stream>>>(nAll, nRow, S->nInc, thrust::raw_pointer_cast(row.data()), thrust::raw_pointer_cast(keep.data()));
+  thrust::inclusive_scan(pol, keep.begin(), keep.end(), pos.begin());
+  N.nNodes = pos[nAll - 1];
+  count_launch(4);
+  if(N.nNodes == 0) return B200_OK;
+  B200_CUDA(cudaMalloc(&N.range, (size_t)N.nNodes * sizeof(int2)));
+  B200_CUDA(cudaMalloc(&N.row, (size_t)N.nNodes * nRow * sizeof(int32_t)));
+  node_compact_kernel<<<148 * 8, 256, 0, S->stream>>>(nAll, nRow, thrust::raw_pointer_cast(keep.data()), thrust::raw_pointer_cast(pos.data()),
+                                                     thrust::raw_pointer_cast(range.data()), thrust::raw_pointer_cast(row.data()), N.range, N.row);
+  N.nCta = (N.nNodes + npb - 1) / npb;
+  B200_CUDA(cudaMalloc(&N.smoff, (size_t)N.nNodes * sizeof(uint32_t)));
+  B200_CUDA(cudaMalloc(&N.cta_size, (size_t)N.nCta * sizeof(uint32_t)));
+  B200_CUDA(cudaMalloc(&N.off, (size_t)np * offw * sizeof(uint16_t)));
+  B200_CUDA(cudaMemsetAsync(N.off, 0xFF, (size_t)np * offw * sizeof(uint16_t), S->stream));
+  int *d_err;
+  B200_CUDA(cudaMalloc(&d_err, sizeof(int)));
+  B200_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), S->stream));
+  node_smem_kernel<<<(N.nCta + 127) / 128, 128, 0, S->stream>>>(N.nNodes, npb, nRow, S->nInc, S->d_ia, N.row, N.smoff, N.cta_size, d_err);
+  node_offsets_kernel<<<148 * 16, 64, 0, S->stream>>>(N.nNodes, nRow, nLoc, offw, ncol, NU, NP, N.range, N.row, N.pair, S->spaces[S->su].d_adr,
+                                                     S->sp >= 0 ? S->spaces[S->sp].d_adr : nullptr, S->d_ia, S->d_ja, S->nInc, colmaskU, colmaskP,
+                                                     N.off, d_err);
+  count_launch(3);
+  int h_err = 0;
+  B200_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, S->stream));
+  B200_CUDA(cudaStreamSynchronize(S->stream));
+  cudaFree(d_err);
+  if(h_err) {
+    set_error("gather plan: CSR pattern does not have the regular node-row structure (code " + std::to_string(h_err) + ")");
+    return B200_ERR_UNSUPP;
+  }
+  N.max_cta = *thrust::max_element(pol, thrust::device_pointer_cast(N.cta_size), thrust::device_pointer_cast(N.cta_size) + N.nCta);
+  return B200_OK;
+}
+
+// reference tensors from the host tables
+static bool build_tables(const System *S, int D, int NS, int NP, std::vector<double> &tab, int &len_nosrc)
+{
+  const Space &U = S->spaces[S->su], &P = S->spaces[S->sp];
+  const int    nq = S->nq;
+  const std::vector<double> &w = S->w, &L = U.L, &dL = U.dL, &LP = P.L;
+  std::vector<double> K((size_t)NS * NS * D * D, 0.), T3((size_t)NS * NS * NP, 0.), Mr((size_t)NS * NS, 0.), E((size_t)NS * D * NP, 0.),
+    B((size_t)NP * NS * D, 0.), W((size_t)nq * NS, 0.);
+  for(int k = 0; k < nq; ++k)
+    for(int a = 0; a < NS; ++a) {
+      W[(size_t)k * NS + a] = w[k] * L[(size_t)k * NS + a];
+      for(int b = 0; b < NS; ++b) {
+        Mr[(size_t)a * NS + b] += w[k] * L[(size_t)k * NS + a] * L[(size_t)k * NS + b];
+        for(int v = 0; v < NP; ++v) T3[((size_t)a * NS + b) * NP + v] += w[k] * L[(size_t)k * NS + a] * L[(size_t)k * NS + b] * LP[(size_t)k * NP + v];
+        for(int al = 0; al < D; ++al)
+          for(int be = 0; be < D; ++be)
+            K[(((size_t)a * NS + b) * D + al) * D + be] += w[k] * dL[((size_t)k * NS + a) * D + al] * dL[((size_t)k * NS + b) * D + be];
+      }
+      for(int q = 0; q < NP; ++q)
+        for(int al = 0; al < D; ++al) B[((size_t)q * NS + a) * D + al] += w[k] * LP[(size_t)k * NP + q] * dL[((size_t)k * NS + a) * D + al];
+    }
+  // E: least squares dL[k][c][al] = sum_v LP[k][v] E[c][al][v]  (normal equations, NP x NP, Gauss with pivoting)
+  std::vector<double> N((size_t)NP * NP, 0.);
+  for(int k = 0; k < nq; ++k)
+    for(int v = 0; v < NP; ++v)
+      for(int u = 0; u < NP; ++u) N[(size_t)v * NP + u] += LP[(size_t)k * NP + v] * LP[(size_t)k * NP + u];
+  // invert N
+  std::vector<double> A(N), Inv((size_t)NP * NP, 0.);
+  for(int i = 0; i < NP; ++i) Inv[(size_t)i * NP + i] = 1.;
+  for(int p = 0; p < NP; ++p) {
+    int piv = p;
+    for(int r = p + 1; r < NP; ++r)
+      if(std::fabs(A[(size_t)r * NP + p]) > std::fabs(A[(size_t)piv * NP + p])) piv = r;
+    if(std::fabs(A[(size_t)piv * NP + p]) < 1e-14) return false;
+    for(int j = 0; j < NP; ++j) {
+      std::swap(A[(size_t)p * NP + j], A[(size_t)piv * NP + j]);
+      std::swap(Inv[(size_t)p * NP + j], Inv[(size_t)piv * NP + j]);
+    }
+    const double ip = 1. / A[(size_t)p * NP + p];
+    for(int j = 0; j < NP; ++j) {
+      A[(size_t)p * NP + j] *= ip;
+      Inv[(size_t)p * NP + j] *= ip;
+    }
+    for(int r = 0; r < NP; ++r) {
+      if(r == p) continue;
+      const double f = A[(size_t)r * NP + p];
+      for(int j = 0; j < NP; ++j) {
+        A[(size_t)r * NP + j] -= f * A[(size_t)p * NP + j];
+        Inv[(size_t)r * NP + j] -= f * Inv[(size_t)p * NP + j];
+      }
+    }
+  }
+  double worst = 0.;
+  for(int c = 0; c < NS; ++c)
+    for(int al = 0; al < D; ++al) {
+      double rhs[8] = {0.};
+      for(int k = 0; k < nq; ++k)
+        for(int v = 0; v < NP; ++v) rhs[v] += LP[(size_t)k * NP + v] * dL[((size_t)k * NS + c) * D + al];
+      for(int v = 0; v < NP; ++v) {
+        double s = 0.;
+        for(int u = 0; u < NP; ++u) s += Inv[(size_t)v * NP + u] * rhs[u];
+        // the exact coefficients of P2-gradient-in-P1 are small integers: snap away the least-squares rounding
+        const double r = std::nearbyint(s);
+        E[((size_t)c * D + al) * NP + v] = (std::fabs(s - r) < 1e-10) ? r : s;
+      }
+      for(int k = 0; k < nq; ++k) {
+        double s = 0.;
+        for(int v = 0; v < NP; ++v) s += LP[(size_t)k * NP + v] * E[((size_t)c * D + al) * NP + v];
+        worst = std::fmax(worst, std::fabs(s - dL[((size_t)k * NS + c) * D + al]));
+      }
+    }
+  if(worst > 1e-12) return false; // gradients of the velocity basis are not in the span of the pressure basis
+  tab.clear();
+  tab.insert(tab.end(), K.begin(), K.end());
+  tab.insert(tab.end(), T3.begin(), T3.end());
+  tab.insert(tab.end(), Mr.begin(), Mr.end());
+  tab.insert(tab.end(), E.begin(), E.end());
+  tab.insert(tab.end(), B.begin(), B.end());
+  len_nosrc = (int)tab.size();
+  tab.insert(tab.end(), W.begin(), W.end());
+  return true;
+}
+
+void gather_free(System *S)
+{
+  GatherPlan *G = static_cast<GatherPlan *>(S->gather);
+  if(!G) return;
+  G->U.release();
+  G->P.release();
+  cudaFree(G->d_tab);
+  delete G;
+  S->gather = nullptr;
+}
+
+// Builds the gather plan if the registered problem qualifies (Taylor-Hood P2/P1, no P-P block); B200_ERR_UNSUPP otherwise.
+int build_gather_plan(System *S)
+{
+  gather_free(S);
+  if(S->plan != PLAN_TAYLOR_HOOD || S->has_matrix_block[1][1]) {
+    set_error("gather plan: only the fused Taylor-Hood system is supported");
+    return B200_ERR_UNSUPP;
+  }
+  const int D = S->dim, NS = S->spaces[S->su].nS, NP = S->spaces[S->sp].nS, NU = NS * D, M = NU + NP;
+  std::vector<double> tab;
+  int                 len_nosrc = 0;
+  if(!build_tables(S, D, NS, NP, tab, len_nosrc)) {
+    set_error("gather plan: velocity-basis gradients are not in the span of the pressure basis at the quadrature nodes");
+    return B200_ERR_UNSUPP;
+  }
+  GatherPlan *G = new GatherPlan;
+  S->gather     = G;
+  G->tab_len     = len_nosrc;
+  G->tab_len_src = (int)tab.size();
+  G->npbU        = D == 2 ? 64 : 32;
+  G->npbP        = D == 2 ? 64 : 32;
+  try {
+    B200_CUDA(cudaMalloc(&G->d_tab, tab.size() * sizeof(double)));
+    B200_CUDA(cudaMemcpyAsync(G->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, S->stream));
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    const int offwU = (M + 7) / 8 * 8, offwP = (NU + 7) / 8 * 8;
+    int       rc = build_node_set(S, G->U, S->spaces[S->su].d_adr, NS, NU, D, G->npbU, offwU, M, NU, NP, S->has_matrix_block[0][0] ? 1 : 0,
+                                  S->has_matrix_block[0][1] ? 1 : 0);
+    if(rc == B200_OK)
+      rc = build_node_set(S, G->P, S->spaces[S->sp].d_adr, NP, NP, 1, G->npbP, offwP, NU, NU, NP, S->has_matrix_block[1][0] ? 1 : 0, 0);
+    if(rc != B200_OK) {
+      gather_free(S);
+      return rc;
+    }
+  } catch(const std::exception &ex) {
+    set_error(std::string("gather plan: ") + ex.what());
+    gather_free(S);
+    return B200_ERR_CUDA;
+  }
+  const size_t smem = ((size_t)G->tab_len_src + std::max(G->U.max_cta, G->P.max_cta)) * sizeof(double);
+  if(smem > 220 * 1024) {
+    set_error("gather plan: row buffers exceed shared memory");
+    gather_free(S);
+    return B200_ERR_UNSUPP;
+  }
+  return B200_OK;
+}
+
+template <int D, int NS, int NP, int NPB> static int launch_gather_t(System *S, int what, const THCoeffs &c)
+{
+  GatherPlan *G = static_cast<GatherPlan *>(S->gather);
+  GatherArgs  a;
+  a.xyz    = S->d_xyz;
+  a.conn   = S->d_conn;
+  a.adrU   = S->spaces[S->su].d_adr;
+  a.adrP   = S->spaces[S->sp].d_adr;
+  a.sol    = S->d_sol;
+  a.soldot = S->have_soldot ? S->d_soldot : nullptr;
+  a.source = (c.c_src != 0.) ? S->d_source : nullptr;
+  a.tab    = G->d_tab;
+  a.ia     = S->d_ia;
+  a.val    = S->d_val;
+  a.rhs    = S->d_rhs;
+  a.nInc   = S->nInc;
+  a.nq     = S->nq;
+  a.ntab   = a.source ? G->tab_len_src : G->tab_len;
+  a.c      = c;
+  a.c0     = S->c0;
+  const bool mat = what & 2;
+  for(int pass = 0; pass < 2; ++pass) {
+    const NodeSet &N = pass == 0 ? G->U : G->P;
+    if(N.nNodes == 0) continue;
+    a.pair     = N.pair;
+    a.range    = N.range;
+    a.row      = N.row;
+    a.smoff    = N.smoff;
+    a.cta_size = N.cta_size;
+    a.off      = N.off;
+    a.nNodes   = N.nNodes;
+    const size_t smem = ((size_t)a.ntab + (mat ? N.max_cta : 0)) * sizeof(double);
+#define B200_LAUNCH_G(KERN)                                                                                                              \
+  do {                                                                                                                                   \
+    B200_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                                       \
+    KERN<<<N.nCta, NPB, smem, S->stream>>>(a);                                                                                           \
+  } while(0)
+    if(pass == 0) {
+      if(what == 3)
+        B200_LAUNCH_G((gather_u_kernel<D, NS, NP, NPB, true, true>));
+      else if(what == 2)
+        B200_LAUNCH_G((gather_u_kernel<D, NS, NP, NPB, true, false>));
+      else
+        B200_LAUNCH_G((gather_u_kernel<D, NS, NP, NPB, false, true>));
+    } else {
+      if(what == 3)
+        B200_LAUNCH_G((gather_p_kernel<D, NS, NP, NPB, true, true>));
+      else if(what == 2)
+        B200_LAUNCH_G((gather_p_kernel<D, NS, NP, NPB, true, false>));
+      else
+        B200_LAUNCH_G((gather_p_kernel<D, NS, NP, NPB, false, true>));
+    }
+#undef B200_LAUNCH_G
+    count_launch();
+  }
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+// what: bit 0 residual, bit 1 matrix; OVERWRITES val / rhs (every row is written exactly once)
+int launch_gather(System *S, int what, const THCoeffs &c)
+{
+  if(S->dim == 2) return launch_gather_t<2, 6, 3, 64>(S, what, c);
+  return launch_gather_t<3, 10, 4, 32>(S, what, c);
+}
+
+} // namespace b200

@@ -111,6 +111,13 @@ struct System {
   // Krylov workspace (allocated lazily, krylov.cu)
   void *krylov = nullptr;
 
+  // row-owner gather plan (gather.cu); assembly_mode: B200_ASSEMBLY_*
+  void *gather = nullptr;
+  int   assembly_mode = 0;
+  // setToZero is lazy: the gather kernels overwrite every row, so the memset is only materialised when something
+  // else reads or accumulates into the arrays (bit 0 rhs, bit 1 matrix)
+  int   pending_zero = 0;
+
   // scratch for reductions
   double *d_scratch = nullptr;
   double *h_scratch = nullptr; // pinned
@@ -119,6 +126,12 @@ struct System {
 // assemble.cu
 int build_plan(System *S);
 int launch_assemble(System *S, int what, int only_transient);
+// gather.cu
+int  build_gather_plan(System *S);
+int  launch_gather(System *S, int what, const THCoeffs &c);
+void gather_free(System *S);
+// capi.cu
+int  flush_zero(System *S, int what);
 // krylov.cu
 int  spmv(System *S, const double *d_x, double *d_y);
 int  gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info);

@@ -60,6 +60,15 @@ enum {
                                (feCncGeo::colorElements, src/feCncGeo.cpp:752-794)                        */
 };
 
+/* Assembly strategies.  AUTO picks GATHER whenever the registered problem qualifies (fused Taylor-Hood P2/P1 on straight
+ * simplices), else SCATTER. */
+enum {
+  B200_ASSEMBLY_AUTO    = 0,
+  B200_ASSEMBLY_SCATTER = 1, /* element-major quadrature-loop kernel + B200_SCATTER_* into precomputed CSR slots          */
+  B200_ASSEMBLY_GATHER  = 2  /* row-owner kernel on pre-contracted reference tensors: every CSR row written exactly once,
+                                no memset, no atomics, deterministic                                                    */
+};
+
 /* Preconditioners of the restarted GMRES (north-star subsystem 4). */
 enum {
   B200_PC_NONE         = 0,
@@ -130,6 +139,11 @@ int b200_get_pattern(b200_system *s, int64_t *ia, int32_t *ja);
 /* element colours, feCncGeo::getColorElm (src/feCncGeo.h:236); only needed for B200_SCATTER_COLORED */
 int b200_set_colors(b200_system *s, int n_colors, const int32_t *element_color);
 int b200_set_scatter_mode(b200_system *s, int mode);
+/* B200_ASSEMBLY_*; may be called before or after b200_finalize.  Returns B200_ERR_UNSUPP if GATHER is requested for a
+ * problem that does not qualify. */
+int b200_set_assembly_mode(b200_system *s, int mode);
+/* 1 if the last b200_finalize built a gather plan */
+int b200_has_gather_plan(const b200_system *s);
 /* rows of essential vector components (src/feLinearSystemMklPardiso.cpp:998-1041) and periodic (master, slave)
  * pairs (feMetaNumber::PeriodicDOF, src/feNumber.h:234) */
 int b200_set_constraints(b200_system *s, int64_t n_rows, const int64_t *rows, int64_t n_periodic,

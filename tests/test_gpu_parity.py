@@ -11,31 +11,39 @@ from conftest import assert_close_rows, assert_close_vec, to_oracle_problem
 pytestmark = pytest.mark.gpu
 
 
-def _cuda_assemble(pb, sol, sol_dot=None, c0=0.0, what=3, colors=None, mode=0, only_transient=False):
+ASSEMBLY = {"scatter": 1, "gather": 2}   # B200_ASSEMBLY_SCATTER / B200_ASSEMBLY_GATHER
+
+
+def _cuda_assemble(pb, sol, sol_dot=None, c0=0.0, what=3, colors=None, mode=0, only_transient=False, assembly="auto"):
     from feng_b200.linear_system import LinearSystemB200
     ls = LinearSystemB200(pb, colors=colors)
     ls.sys.set_scatter_mode(mode)
+    if assembly != "auto":
+        ls.sys.set_assembly_mode(ASSEMBLY[assembly])
+        assert ls.sys.has_gather_plan()
     ls.sys.set_solution(sol, sol_dot, c0, 0.0)
     ls.sys.set_to_zero(3)
     ls.sys.assemble(what, only_transient)
     return ls, ls.sys.get_matrix_values(), ls.sys.get_rhs()
 
 
+@pytest.mark.parametrize("assembly", ["scatter", "gather"])
 @pytest.mark.parametrize("kind", ["ns_div", "ns_lap", "stokes_div", "stokes_lap"])
 @pytest.mark.parametrize("mu,rho", [(1.0, 1.0), (0.025, 1.3)])
-def test_taylor_hood_2d_vs_oracle(kind, mu, rho):
+def test_taylor_hood_2d_vs_oracle(kind, mu, rho, assembly):
     from feng_b200 import mesh as M, problems as PB
     from oracle import fe_oracle as O
     m = M.square_mesh(12)
     pb = PB.taylor_hood(m, kind, 8, 0, mu, rho)
     sol = PB.perturb_unknowns(pb)
     ov, orr = O.assemble(to_oracle_problem(pb), pb.ia, pb.ja, sol)
-    _, v, r = _cuda_assemble(pb, sol)
+    _, v, r = _cuda_assemble(pb, sol, assembly=assembly)
     assert_close_rows(v, ov, pb.ia, 1e-12, "matrix")
     assert_close_vec(r, orr, 1e-12, "rhs")
 
 
-def test_taylor_hood_2d_transient_and_split_passes():
+@pytest.mark.parametrize("assembly", ["scatter", "gather"])
+def test_taylor_hood_2d_transient_and_split_passes(assembly):
     from feng_b200 import mesh as M, problems as PB
     from oracle import fe_oracle as O
     m = M.square_mesh(9)
@@ -43,7 +51,7 @@ def test_taylor_hood_2d_transient_and_split_passes():
     sol = PB.perturb_unknowns(pb)
     sd = np.random.default_rng(3).standard_normal(pb.n_dof)
     ov, orr = O.assemble(to_oracle_problem(pb), pb.ia, pb.ja, sol, sd, 3.5)
-    ls, v, r = _cuda_assemble(pb, sol, sd, 3.5)
+    ls, v, r = _cuda_assemble(pb, sol, sd, 3.5, assembly=assembly)
     assert_close_rows(v, ov, pb.ia, 1e-12, "matrix")
     assert_close_vec(r, orr, 1e-12, "rhs")
     # matrix-only and residual-only passes give the same numbers as the fused pass
@@ -77,8 +85,9 @@ def test_scalar_diffusion_vs_oracle(dim, n, deg, order):
     assert_close_vec(r, orr, 1e-12, "rhs")
 
 
+@pytest.mark.parametrize("assembly", ["scatter", "gather"])
 @pytest.mark.parametrize("kind", ["ns_div", "ns_lap"])
-def test_taylor_hood_3d_vs_oracle(kind):
+def test_taylor_hood_3d_vs_oracle(kind, assembly):
     """P2/P1 tetrahedra: no reference implementation exists (src/feVectorSysElm.cpp:1246,1536 instantiate <2> only);
     the checker is the dim-generic restatement, itself pinned in 2-D against the compiled reference."""
     from feng_b200 import mesh as M, problems as PB
@@ -87,9 +96,67 @@ def test_taylor_hood_3d_vs_oracle(kind):
     pb = PB.taylor_hood(m, kind, 6, 3, 0.05, 1.1)
     sol = PB.perturb_unknowns(pb)
     ov, orr = O.assemble(to_oracle_problem(pb), pb.ia, pb.ja, sol)
-    _, v, r = _cuda_assemble(pb, sol)
+    _, v, r = _cuda_assemble(pb, sol, assembly=assembly)
     assert_close_rows(v, ov, pb.ia, 1e-12, "matrix")
     assert_close_vec(r, orr, 1e-12, "rhs")
+
+
+@pytest.mark.parametrize("name", ["ref_square1_ns_div", "ref_square1_ns_lap", "ref_square1_stokes_div",
+                                  "ref_square1_ns_div_transient", "syn_t2d5_ns_div_ppoint"])
+@pytest.mark.parametrize("assembly", ["scatter", "gather"])
+def test_taylor_hood_against_reference_fixtures(name, assembly):
+    """The CUDA path fed with the reference's OWN tables (unstructured data/square1.msh, its element->DOF maps, basis
+    tables, pattern) against the values the unmodified reference assembled (tests/golden/*.npz)."""
+    from conftest import golden_to_oracle_problem, load_golden
+    from feng_b200 import capi
+    g = load_golden(name)
+    opb = golden_to_oracle_problem(g)
+    S = capi.System(0)
+    S.set_mesh(opb.dim, opb.xyz, opb.cells)
+    S.set_quadrature(opb.w)
+    su = S.add_space(opb.LU.shape[1], opb.ncomp, opb.adrU, opb.LU, opb.dLU)
+    sp = S.add_space(opb.LP.shape[1], 1, opb.adrP, opb.LP, np.zeros(opb.LP.shape + (opb.dim,)))
+    S.set_pattern(int(g["n_inc"]), int(g["n_dof"]), g["ia"], g["ja"])
+    from feng_b200.problems import form_layout
+    for f in opb.forms:
+        rows, cols = form_layout(f.kind)
+        if rows == ("P",):
+            S.add_form(f.kind, sp, su, f.coeff, f.param, f.source)
+        else:
+            S.add_form(f.kind, su, sp if "P" in cols else -1, f.coeff, f.param, f.source)
+    S.finalize()
+    S.set_assembly_mode(ASSEMBLY[assembly])
+    sd = g["sol_dot"] if "sol_dot" in g else None
+    S.set_solution(g["sol"], sd, float(g["c0"]), 0.0)
+    S.set_to_zero(3)
+    S.assemble(3)
+    assert_close_rows(S.get_matrix_values(), g["vals"], g["ia"], 1e-12, "matrix vs reference")
+    assert_close_vec(S.get_rhs(), g["rhs"], 1e-12, "rhs vs reference")
+    # constraint on the reference's row list
+    if len(g["constraint_rows"]):
+        S.set_constraints(g["constraint_rows"])
+        S.constrain()
+        assert_close_rows(S.get_matrix_values(), g["vals_constrained"], g["ia"], 1e-12, "constrained matrix")
+        assert_close_vec(S.get_rhs(), g["rhs_constrained"], 1e-12, "constrained rhs")
+
+
+def test_gather_is_deterministic_and_lazy_zero_is_exact():
+    from feng_b200 import mesh as M, problems as PB
+    m = M.square_mesh(16)
+    pb = PB.taylor_hood(m, "ns_div", 8, 0, 0.05, 1.0)
+    sol = PB.perturb_unknowns(pb)
+    ls, v1, r1 = _cuda_assemble(pb, sol, assembly="gather")
+    ls.sys.set_to_zero(3)
+    ls.sys.assemble(3)
+    assert np.array_equal(ls.sys.get_matrix_values(), v1) and np.array_equal(ls.sys.get_rhs(), r1)   # bitwise
+    # setToZero alone must read back as zeros (the memset is lazy, not skipped)
+    ls.sys.set_to_zero(3)
+    assert not ls.sys.get_matrix_values().any() and not ls.sys.get_rhs().any()
+    # residual-only pass after setToZero(rhs) leaves the matrix of the previous pass untouched
+    ls.sys.assemble(3)
+    ls.sys.set_to_zero(1)
+    ls.sys.assemble(1)
+    assert np.array_equal(ls.sys.get_matrix_values(), v1) and np.array_equal(ls.sys.get_rhs(), r1)
 
 
 def _greedy_colors(cells, n_vertices):
