@@ -52,6 +52,9 @@ struct NodeSet {
   int32_t  *row = nullptr;      // [nNodes][nRow] global rows (>= nInc: essential, not assembled)
   uint32_t *smoff = nullptr;    // [nNodes] offset (doubles) of the node's row buffer inside its CTA's shared memory
   uint32_t *cta_size = nullptr; // [nCta] doubles of row buffer per CTA
+  int64_t  *cta_g0 = nullptr;   // [nCta] first CSR slot of the CTA's rows if they are consecutive in memory, else -1
+  std::vector<int32_t>  seg_begin; // launch segments: CTAs with similar row-buffer sizes share one launch
+  std::vector<uint32_t> seg_smem;  // doubles of row buffer for the segment
   uint16_t *off = nullptr;      // [nPairs][OFFW] row-local column offsets, 0xFFFF = not assembled
   uint32_t  max_cta = 0;
   void release()
@@ -61,6 +64,7 @@ struct NodeSet {
     cudaFree(row);
     cudaFree(smoff);
     cudaFree(cta_size);
+    cudaFree(cta_g0);
     cudaFree(off);
     *this = NodeSet();
   }
@@ -69,6 +73,7 @@ struct NodeSet {
 struct GatherPlan {
   NodeSet  U, P;
   double  *d_tab = nullptr;
+  double  *d_geo = nullptr; // [nElm][D*D+1] inverse affine map + detJ of every element (the mesh is static)
   int      tab_len = 0, tab_len_src = 0;
   int      npbU = 0, npbP = 0;
 };
@@ -76,13 +81,15 @@ struct GatherPlan {
 struct GatherArgs {
   const double   *xyz;
   const int32_t  *conn, *adrU, *adrP;
-  const double   *sol, *soldot, *source, *tab;
+  const double   *sol, *soldot, *source, *tab, *geo;
   const int64_t  *ia;
   double         *val, *rhs;
   const int32_t  *pair;
   const int2     *range;
   const int32_t  *row;
   const uint32_t *smoff, *cta_size;
+  const int64_t  *cta_g0;
+  int32_t         cta0; // first CTA of this launch segment
   const uint16_t *off;
   int32_t         nNodes;
   int64_t         nInc;
@@ -108,7 +115,8 @@ __global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
 
   const int tid = threadIdx.x;
   for(int i = tid; i < a.ntab; i += NPB) s_tab[i] = a.tab[i];
-  const int32_t n    = blockIdx.x * NPB + tid;
+  const int32_t cta  = a.cta0 + blockIdx.x;
+  const int32_t n    = cta * NPB + tid;
   const bool    live = n < a.nNodes;
   int32_t       row[D];
   int           len = 0;
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
     for(int c = 0; c < D; ++c) s_row[tid * D + c] = row[c];
     s_base[tid] = base;
     s_len[tid]  = len;
-    const uint32_t tot = a.cta_size[blockIdx.x];
+    const uint32_t tot = a.cta_size[cta];
     for(uint32_t i = tid; i < tot; i += NPB) s_buf[i] = 0.;
   }
   __syncthreads();
@@ -156,11 +164,13 @@ __global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
     for(int p = rg.x; p < rg.x + rg.y; ++p) {
       const int     ea = a.pair[p];
       const int     e = ea / NS, la = ea - e * NS;
-      int32_t       vtx[D + 1];
-#pragma unroll
-      for(int v = 0; v <= D; ++v) vtx[v] = a.conn[(int64_t)e * (D + 1) + v];
       double G[D * D], J;
-      element_geometry<D>(a.xyz, vtx, G, &J);
+      {
+        const double *ge = a.geo + (int64_t)e * (D * D + 1);
+#pragma unroll
+        for(int i = 0; i < D * D; ++i) G[i] = ge[i];
+        J = ge[D * D];
+      }
       const int32_t *au = a.adrU + (int64_t)e * NU;
       double         U[NS][D];
 #pragma unroll
@@ -341,18 +351,26 @@ __global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
   }
   if(MAT) {
     __syncthreads();
-    // coalesced write-out: one warp per row segment
-    const int lane = tid & 31, wid = tid >> 5, nw = NPB / 32;
-    for(int t = wid; t < NPB; t += nw) {
-      const int ln = s_len[t];
-      uint32_t  o  = s_base[t];
+    const int64_t g0 = a.cta_g0[cta];
+    if(g0 >= 0) {
+      // the CTA's rows are consecutive in the CSR arrays: the row buffers are a contiguous image of val[g0 ...]
+      const uint32_t tot = a.cta_size[cta];
+      double        *dst = a.val + g0;
+      for(uint32_t i = tid; i < tot; i += NPB) dst[i] = s_buf[i];
+    } else {
+      // general numbering: one warp per row segment
+      const int lane = tid & 31, wid = tid >> 5, nw = NPB / 32;
+      for(int t = wid; t < NPB; t += nw) {
+        const int ln = s_len[t];
+        uint32_t  o  = s_base[t];
 #pragma unroll
-      for(int c = 0; c < D; ++c) {
-        const int32_t r = s_row[t * D + c];
-        if(r < a.nInc) {
-          double *dst = a.val + a.ia[r];
-          for(int k = lane; k < ln; k += 32) dst[k] = s_buf[o + k];
-          o += ln;
+        for(int c = 0; c < D; ++c) {
+          const int32_t r = s_row[t * D + c];
+          if(r < a.nInc) {
+            double *dst = a.val + a.ia[r];
+            for(int k = lane; k < ln; k += 32) dst[k] = s_buf[o + k];
+            o += ln;
+          }
         }
       }
     }
@@ -375,7 +393,8 @@ __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
   __shared__ int32_t  s_len[NPB];
   const int tid = threadIdx.x;
   for(int i = tid; i < a.ntab; i += NPB) s_tab[i] = a.tab[i];
-  const int32_t n    = blockIdx.x * NPB + tid;
+  const int32_t cta  = a.cta0 + blockIdx.x;
+  const int32_t n    = cta * NPB + tid;
   const bool    live = n < a.nNodes;
   int32_t       row  = 0x7fffffff;
   int           len  = 0;
@@ -389,7 +408,7 @@ __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
     s_row[tid]  = row;
     s_base[tid] = base;
     s_len[tid]  = len;
-    const uint32_t tot = a.cta_size[blockIdx.x];
+    const uint32_t tot = a.cta_size[cta];
     for(uint32_t i = tid; i < tot; i += NPB) s_buf[i] = 0.;
   }
   __syncthreads();
@@ -401,11 +420,13 @@ __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
     for(int p = rg.x; p < rg.x + rg.y; ++p) {
       const int eq = a.pair[p];
       const int e = eq / NP, q = eq - e * NP;
-      int32_t   vtx[D + 1];
-#pragma unroll
-      for(int v = 0; v <= D; ++v) vtx[v] = a.conn[(int64_t)e * (D + 1) + v];
       double G[D * D], J;
-      element_geometry<D>(a.xyz, vtx, G, &J);
+      {
+        const double *ge = a.geo + (int64_t)e * (D * D + 1);
+#pragma unroll
+        for(int i = 0; i < D * D; ++i) G[i] = ge[i];
+        J = ge[D * D];
+      }
       const int32_t *au = a.adrU + (int64_t)e * NU;
       uint16_t       of[T::OFFW_P];
       if(MAT) {
@@ -444,14 +465,21 @@ __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
   }
   if(MAT) {
     __syncthreads();
-    const int lane = tid & 31, wid = tid >> 5, nw = NPB / 32;
-    for(int t = wid; t < NPB; t += nw) {
-      const int32_t r = s_row[t];
-      if(r < a.nInc) {
-        double        *dst = a.val + a.ia[r];
-        const uint32_t o   = s_base[t];
-        const int      ln  = s_len[t];
-        for(int k = lane; k < ln; k += 32) dst[k] = s_buf[o + k];
+    const int64_t g0 = a.cta_g0[cta];
+    if(g0 >= 0) {
+      const uint32_t tot = a.cta_size[cta];
+      double        *dst = a.val + g0;
+      for(uint32_t i = tid; i < tot; i += NPB) dst[i] = s_buf[i];
+    } else {
+      const int lane = tid & 31, wid = tid >> 5, nw = NPB / 32;
+      for(int t = wid; t < NPB; t += nw) {
+        const int32_t r = s_row[t];
+        if(r < a.nInc) {
+          double        *dst = a.val + a.ia[r];
+          const uint32_t o   = s_base[t];
+          const int      ln  = s_len[t];
+          for(int k = lane; k < ln; k += 32) dst[k] = s_buf[o + k];
+        }
       }
     }
   }
@@ -460,6 +488,22 @@ __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
 // ----------------------------------------------------------------------------------------------------------
 // plan construction (set-up)
 // ----------------------------------------------------------------------------------------------------------
+// element geometry table: the reference tabulates the same quantities once per mesh (feCncGeo::_J, src/feCncGeo.cpp:278-418,
+// and the constant ElementTransformation of P1 geometry, :489-509)
+template <int D> __global__ void geometry_kernel(int64_t nElm, const double *xyz, const int32_t *conn, double *geo)
+{
+  for(int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nElm; e += (int64_t)gridDim.x * blockDim.x) {
+    int32_t vtx[D + 1];
+#pragma unroll
+    for(int v = 0; v <= D; ++v) vtx[v] = conn[e * (D + 1) + v];
+    double G[D * D], J;
+    element_geometry<D>(xyz, vtx, G, &J);
+#pragma unroll
+    for(int i = 0; i < D * D; ++i) geo[e * (D * D + 1) + i] = G[i];
+    geo[e * (D * D + 1) + D * D] = J;
+  }
+}
+
 __global__ void node_keys_kernel(int64_t nElm, int nLoc, int nF, int stride, const int32_t *adr, int32_t *keys, int32_t *vals)
 {
   const int64_t tot = nElm * nLoc;
@@ -516,12 +560,14 @@ __global__ void node_compact_kernel(int32_t nNodes, int nRow, const int32_t *kee
 
 // shared-memory layout of the row buffers: one thread per CTA
 __global__ void node_smem_kernel(int32_t nNodes, int npb, int nRow, int64_t nInc, const int64_t *ia, const int32_t *row, uint32_t *smoff,
-                                 uint32_t *cta_size, int *err)
+                                 uint32_t *cta_size, int64_t *cta_g0, int *err)
 {
   const int32_t cta = blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t n0 = cta * npb;
   if(n0 >= nNodes) return;
   uint32_t o = 0;
+  int64_t  prev = -1, g0 = -1;
+  bool     contiguous = true;
   for(int32_t n = n0; n < n0 + npb && n < nNodes; ++n) {
     smoff[n] = o;
     int64_t len = -1;
@@ -533,12 +579,18 @@ __global__ void node_smem_kernel(int32_t nNodes, int npb, int nRow, int64_t nInc
         if(len >= 0 && l != len) atomicExch(err, 2); // rows of one node must share their column structure
         len = l;
         ++nun;
+        if(prev < 0)
+          g0 = ia[r];
+        else if(r != prev + 1)
+          contiguous = false;
+        prev = r;
       }
     }
     if(len >= 65535) atomicExch(err, 3);
     o += (uint32_t)(nun * (len > 0 ? len : 0));
   }
   cta_size[cta] = o;
+  cta_g0[cta]   = contiguous ? g0 : -1;
 }
 
 // row-local offsets of the columns of every (node, element) pair; one thread per (pair, local column)
@@ -623,12 +675,13 @@ static int build_node_set(System *S, NodeSet &N, const int32_t *d_adr, int nLoc,
   N.nCta = (N.nNodes + npb - 1) / npb;
   B200_CUDA(cudaMalloc(&N.smoff, (size_t)N.nNodes * sizeof(uint32_t)));
   B200_CUDA(cudaMalloc(&N.cta_size, (size_t)N.nCta * sizeof(uint32_t)));
+  B200_CUDA(cudaMalloc(&N.cta_g0, (size_t)N.nCta * sizeof(int64_t)));
   B200_CUDA(cudaMalloc(&N.off, (size_t)np * offw * sizeof(uint16_t)));
   B200_CUDA(cudaMemsetAsync(N.off, 0xFF, (size_t)np * offw * sizeof(uint16_t), S->stream));
   int *d_err;
   B200_CUDA(cudaMalloc(&d_err, sizeof(int)));
   B200_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), S->stream));
-  node_smem_kernel<<<(N.nCta + 127) / 128, 128, 0, S->stream>>>(N.nNodes, npb, nRow, S->nInc, S->d_ia, N.row, N.smoff, N.cta_size, d_err);
+  node_smem_kernel<<<(N.nCta + 127) / 128, 128, 0, S->stream>>>(N.nNodes, npb, nRow, S->nInc, S->d_ia, N.row, N.smoff, N.cta_size, N.cta_g0, d_err);
   node_offsets_kernel<<<148 * 16, 64, 0, S->stream>>>(N.nNodes, nRow, nLoc, offw, ncol, NU, NP, N.range, N.row, N.pair, S->spaces[S->su].d_adr,
                                                      S->sp >= 0 ? S->spaces[S->sp].d_adr : nullptr, S->d_ia, S->d_ja, S->nInc, colmaskU, colmaskP,
                                                      N.off, d_err);
@@ -641,7 +694,41 @@ static int build_node_set(System *S, NodeSet &N, const int32_t *d_adr, int nLoc,
     set_error("gather plan: CSR pattern does not have the regular node-row structure (code " + std::to_string(h_err) + ")");
     return B200_ERR_UNSUPP;
   }
-  N.max_cta = *thrust::max_element(pol, thrust::device_pointer_cast(N.cta_size), thrust::device_pointer_cast(N.cta_size) + N.nCta);
+  // launch segments: consecutive CTAs whose row buffers have similar sizes share one launch (and its shared-memory
+  // request), so that CTAs of short rows (edge nodes) are not limited by the occupancy of the longest rows
+  std::vector<uint32_t> h_size(N.nCta);
+  B200_CUDA(cudaMemcpy(h_size.data(), N.cta_size, (size_t)N.nCta * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  N.seg_begin.clear();
+  N.seg_smem.clear();
+  N.max_cta = 0;
+  {
+    int32_t  b = 0;
+    uint32_t mx = 0, mn = 0xffffffffu;
+    for(int32_t i = 0; i <= N.nCta; ++i) {
+      const bool last = i == N.nCta;
+      if(!last) {
+        const uint32_t v = h_size[i];
+        // cut where the size leaves the +-25 % band of the running segment (at most 8 segments, at least 64 CTAs each)
+        const bool cut = i > b + 64 && N.seg_smem.size() < 7 &&
+                         ((double)v > 1.25 * (double)std::max<uint32_t>(mn, 1u) || 1.25 * (double)v < (double)mx);
+        if(!cut) {
+          mx = std::max(mx, v);
+          mn = std::min(mn, v);
+          continue;
+        }
+      }
+      if(i > b) {
+        N.seg_begin.push_back(b);
+        N.seg_smem.push_back(mx);
+        N.max_cta = std::max(N.max_cta, mx);
+      }
+      if(!last) {
+        b  = i;
+        mx = mn = h_size[i];
+      }
+    }
+    N.seg_begin.push_back(N.nCta);
+  }
   return B200_OK;
 }
 
@@ -735,6 +822,7 @@ void gather_free(System *S)
   G->U.release();
   G->P.release();
   cudaFree(G->d_tab);
+  cudaFree(G->d_geo);
   delete G;
   S->gather = nullptr;
 }
@@ -763,6 +851,12 @@ int build_gather_plan(System *S)
   try {
     B200_CUDA(cudaMalloc(&G->d_tab, tab.size() * sizeof(double)));
     B200_CUDA(cudaMemcpyAsync(G->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, S->stream));
+    B200_CUDA(cudaMalloc(&G->d_geo, (size_t)S->nElm * (D * D + 1) * sizeof(double)));
+    if(D == 2)
+      geometry_kernel<2><<<148 * 8, 256, 0, S->stream>>>(S->nElm, S->d_xyz, S->d_conn, G->d_geo);
+    else
+      geometry_kernel<3><<<148 * 8, 256, 0, S->stream>>>(S->nElm, S->d_xyz, S->d_conn, G->d_geo);
+    count_launch();
     B200_CUDA(cudaStreamSynchronize(S->stream));
     const int offwU = (M + 7) / 8 * 8, offwP = (NU + 7) / 8 * 8;
     int       rc = build_node_set(S, G->U, S->spaces[S->su].d_adr, NS, NU, D, G->npbU, offwU, M, NU, NP, S->has_matrix_block[0][0] ? 1 : 0,
@@ -799,6 +893,7 @@ template <int D, int NS, int NP, int NPB> static int launch_gather_t(System *S, 
   a.soldot = S->have_soldot ? S->d_soldot : nullptr;
   a.source = (c.c_src != 0.) ? S->d_source : nullptr;
   a.tab    = G->d_tab;
+  a.geo    = G->d_geo;
   a.ia     = S->d_ia;
   a.val    = S->d_val;
   a.rhs    = S->d_rhs;
@@ -818,11 +913,19 @@ template <int D, int NS, int NP, int NPB> static int launch_gather_t(System *S, 
     a.cta_size = N.cta_size;
     a.off      = N.off;
     a.nNodes   = N.nNodes;
-    const size_t smem = ((size_t)a.ntab + (mat ? N.max_cta : 0)) * sizeof(double);
+    a.cta_g0   = N.cta_g0;
+    const size_t smem_max = ((size_t)a.ntab + (mat ? N.max_cta : 0)) * sizeof(double);
+    const int    nseg     = mat ? (int)N.seg_smem.size() : 1;
 #define B200_LAUNCH_G(KERN)                                                                                                              \
   do {                                                                                                                                   \
-    B200_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                                       \
-    KERN<<<N.nCta, NPB, smem, S->stream>>>(a);                                                                                           \
+    B200_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));                                   \
+    for(int sg = 0; sg < nseg; ++sg) {                                                                                                   \
+      a.cta0            = mat ? N.seg_begin[sg] : 0;                                                                                     \
+      const int    nc   = mat ? N.seg_begin[sg + 1] - N.seg_begin[sg] : N.nCta;                                                          \
+      const size_t smem = ((size_t)a.ntab + (mat ? N.seg_smem[sg] : 0)) * sizeof(double);                                                \
+      KERN<<<nc, NPB, smem, S->stream>>>(a);                                                                                             \
+      count_launch();                                                                                                                    \
+    }                                                                                                                                    \
   } while(0)
     if(pass == 0) {
       if(what == 3)
@@ -840,7 +943,6 @@ template <int D, int NS, int NP, int NPB> static int launch_gather_t(System *S, 
         B200_LAUNCH_G((gather_p_kernel<D, NS, NP, NPB, false, true>));
     }
 #undef B200_LAUNCH_G
-    count_launch();
   }
   B200_CUDA(cudaGetLastError());
   return B200_OK;
