@@ -42,6 +42,7 @@ template <int D, int NS, int NP> struct GT {
   static constexpr int O_W = O_B + NP * NS * D;       // W[k][a] = w_k phi_a(k)   (source forms only)
   static constexpr int OFFW_U = (M + 7) / 8 * 8;      // uint16 offsets per (U node, element) pair
   static constexpr int OFFW_P = (NU + 7) / 8 * 8;     // per (P node, element) pair
+  static constexpr int GW = (D * D + 1 + 1) / 2 * 2;  // doubles per element of the geometry table (16-byte aligned records)
 };
 
 struct NodeSet {
@@ -55,6 +56,7 @@ struct NodeSet {
   int64_t  *cta_g0 = nullptr;   // [nCta] first CSR slot of the CTA's rows if they are consecutive in memory, else -1
   std::vector<int32_t>  seg_begin; // launch segments: CTAs with similar row-buffer sizes share one launch
   std::vector<uint32_t> seg_smem;  // doubles of row buffer for the segment
+  std::vector<double>   seg_pairs; // average number of adjacent elements per node in the segment
   uint16_t *off = nullptr;      // [nPairs][OFFW] row-local column offsets, 0xFFFF = not assembled
   uint32_t  max_cta = 0;
   void release()
@@ -101,8 +103,100 @@ struct GatherArgs {
 // ----------------------------------------------------------------------------------------------------------
 // U rows: one thread per velocity node (D rows), loop over the adjacent elements
 // ----------------------------------------------------------------------------------------------------------
-template <int D, int NS, int NP, int NPB, bool MAT, bool RES>
-__global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
+// per (node, element) pair: indices (stage 1) and values (stage 2) of the software pipeline
+template <int D, int NS, int NP> struct PairIdx {
+  int     e, la;
+  int32_t au[NS * D], ap[NP];
+};
+template <int D, int NS, int NP> struct PairVal {
+  double G[D * D], J, U[NS][D], P[NP];
+  uint4  ow[GT<D, NS, NP>::OFFW_U / 8];
+};
+
+template <int D, int NS, int NP> __device__ __forceinline__ void load_pair_idx(const GatherArgs &a, int ea, PairIdx<D, NS, NP> &I)
+{
+  constexpr int NU = NS * D;
+  I.e  = ea / NS;
+  I.la = ea - I.e * NS;
+  const int32_t *au = a.adrU + (int64_t)I.e * NU;
+  if(NU % 4 == 0) {
+    const int4 *a4 = reinterpret_cast<const int4 *>(au);
+#pragma unroll
+    for(int k = 0; k < NU / 4; ++k) {
+      const int4 v    = a4[k];
+      I.au[4 * k + 0] = v.x;
+      I.au[4 * k + 1] = v.y;
+      I.au[4 * k + 2] = v.z;
+      I.au[4 * k + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for(int k = 0; k < NU; ++k) I.au[k] = au[k];
+  }
+  const int32_t *ap = a.adrP + (int64_t)I.e * NP;
+#pragma unroll
+  for(int q = 0; q < NP; ++q) I.ap[q] = ap[q];
+}
+
+template <int D, int NS, int NP, bool MAT, bool RES>
+__device__ __forceinline__ void load_pair_val(const GatherArgs &a, const PairIdx<D, NS, NP> &I, int p, PairVal<D, NS, NP> &V)
+{
+  {
+    constexpr int GW = GT<D, NS, NP>::GW;
+    const double2 *ge = reinterpret_cast<const double2 *>(a.geo + (int64_t)I.e * GW);
+    double         g[GW];
+#pragma unroll
+    for(int i = 0; i < GW / 2; ++i) {
+      const double2 v = ge[i];
+      g[2 * i]     = v.x;
+      g[2 * i + 1] = v.y;
+    }
+#pragma unroll
+    for(int i = 0; i < D * D; ++i) V.G[i] = g[i];
+    V.J = g[D * D];
+  }
+  if(D == 2) {
+    // the two components of a node are consecutive DOFs in the reference numbering (src/feNumber.cpp:370-483): one
+    // 16-byte load per node when the pair is aligned, two 8-byte loads otherwise
+#pragma unroll
+    for(int b = 0; b < NS; ++b) {
+      const int32_t d0 = I.au[b * D], d1 = I.au[b * D + 1];
+      if(((d0 & 1) == 0) && d1 == d0 + 1) {
+        const double2 v = *reinterpret_cast<const double2 *>(a.sol + d0);
+        V.U[b][0] = v.x;
+        V.U[b][1] = v.y;
+      } else {
+        V.U[b][0] = a.sol[d0];
+        V.U[b][1] = a.sol[d1];
+      }
+    }
+  } else {
+#pragma unroll
+    for(int b = 0; b < NS; ++b)
+#pragma unroll
+      for(int m = 0; m < D; ++m) V.U[b][m] = a.sol[I.au[b * D + m]];
+  }
+  if(RES) {
+#pragma unroll
+    for(int q = 0; q < NP; ++q) V.P[q] = a.sol[I.ap[q]];
+  }
+  if(MAT) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.off + (int64_t)p * GT<D, NS, NP>::OFFW_U);
+#pragma unroll
+    for(int w = 0; w < GT<D, NS, NP>::OFFW_U / 8; ++w) V.ow[w] = src[w];
+  }
+}
+
+__device__ __forceinline__ uint32_t off16(const uint4 *ow, int j)
+{
+  const uint4    v = ow[j >> 3];
+  const int      k = j & 7;
+  const uint32_t w = (k >> 1) == 0 ? v.x : (k >> 1) == 1 ? v.y : (k >> 1) == 2 ? v.z : v.w;
+  return (k & 1) ? (w >> 16) : (w & 0xffffu);
+}
+
+template <int D, int NS, int NP, int NPB, bool MAT, bool RES, bool PIPE>
+__global__ void __launch_bounds__(NPB, (D == 2 && !PIPE) ? 8 : 1) gather_u_kernel(const GatherArgs a)
 {
   using T = GT<D, NS, NP>;
   constexpr int NU = T::NU;
@@ -115,12 +209,13 @@ __global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
 
   const int tid = threadIdx.x;
   for(int i = tid; i < a.ntab; i += NPB) s_tab[i] = a.tab[i];
-  const int32_t cta  = a.cta0 + blockIdx.x;
-  const int32_t n    = cta * NPB + tid;
-  const bool    live = n < a.nNodes;
-  int32_t       row[D];
-  int           len = 0;
-  uint32_t      base = 0;
+  const int32_t  cta  = a.cta0 + blockIdx.x;
+  const int32_t  n    = cta * NPB + tid;
+  const bool     live = n < a.nNodes;
+  const uint32_t tot  = MAT ? a.cta_size[cta] : 0;
+  int32_t        row[D];
+  int            len = 0;
+  uint32_t       base = 0;
   if(live) {
 #pragma unroll
     for(int c = 0; c < D; ++c) row[c] = a.row[n * D + c];
@@ -137,19 +232,21 @@ __global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
     for(int c = 0; c < D; ++c) s_row[tid * D + c] = row[c];
     s_base[tid] = base;
     s_len[tid]  = len;
-    const uint32_t tot = a.cta_size[cta];
     for(uint32_t i = tid; i < tot; i += NPB) s_buf[i] = 0.;
   }
   __syncthreads();
 
   if(live) {
-    // row buffer of component c (unknown rows only, packed)
-    double *buf[D];
+    // shared-memory index of the row buffer of component c (unknown rows only, packed); entries that are not
+    // assembled (essential row or column) are redirected to a per-thread trash slot behind the CTA's buffers, so the
+    // read-modify-write sequences below are branch-free and can be issued as independent batches
+    const int trash = (int)tot + tid;
+    int       bi[D];
     {
       uint32_t o = base;
 #pragma unroll
       for(int c = 0; c < D; ++c) {
-        buf[c] = s_buf + o;
+        bi[c] = row[c] < a.nInc ? (int)o : -1;
         if(row[c] < a.nInc) o += len;
       }
     }
@@ -159,24 +256,42 @@ __global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
     const THCoeffs c      = a.c;
     const double   mass0  = c.c_mass * a.c0;
     const int2     rg     = a.range[n];
+    const int      pend   = rg.x + rg.y;
     const bool     domass = (c.c_mass != 0.) && (a.soldot != nullptr);
 
-    for(int p = rg.x; p < rg.x + rg.y; ++p) {
-      const int     ea = a.pair[p];
-      const int     e = ea / NS, la = ea - e * NS;
-      double G[D * D], J;
-      {
-        const double *ge = a.geo + (int64_t)e * (D * D + 1);
-#pragma unroll
-        for(int i = 0; i < D * D; ++i) G[i] = ge[i];
-        J = ge[D * D];
+    // software pipeline over the adjacent elements: while pair p is computed, the values of pair p+1 and the
+    // indices of pair p+2 are in flight (the chain pair -> element DOF table -> solution entries is three dependent
+    // global loads deep and only ~8 warps per SM are resident)
+    PairIdx<D, NS, NP> I1, I2;
+    PairVal<D, NS, NP> V1;
+    int                ea3 = 0;
+    if(PIPE) {
+      load_pair_idx<D, NS, NP>(a, a.pair[rg.x], I1);
+      load_pair_idx<D, NS, NP>(a, a.pair[min(rg.x + 1, pend - 1)], I2);
+      ea3 = a.pair[min(rg.x + 2, pend - 1)];
+      load_pair_val<D, NS, NP, MAT, RES>(a, I1, rg.x, V1);
+    }
+
+    for(int p = rg.x; p < pend; ++p) {
+      if(!PIPE) { // plain variant: fewer live registers, higher occupancy
+        load_pair_idx<D, NS, NP>(a, a.pair[p], I1);
+        load_pair_val<D, NS, NP, MAT, RES>(a, I1, p, V1);
       }
-      const int32_t *au = a.adrU + (int64_t)e * NU;
-      double         U[NS][D];
+      const PairVal<D, NS, NP> V  = V1;
+      const int                e  = I1.e, la = I1.la;
+      int32_t                  aud[NU];
+      if(domass) {
 #pragma unroll
-      for(int b = 0; b < NS; ++b)
-#pragma unroll
-        for(int m = 0; m < D; ++m) U[b][m] = a.sol[au[b * D + m]];
+        for(int k = 0; k < NU; ++k) aud[k] = I1.au[k];
+      }
+      if(PIPE) {
+        load_pair_val<D, NS, NP, MAT, RES>(a, I2, min(p + 1, pend - 1), V1);
+        I1 = I2;
+        load_pair_idx<D, NS, NP>(a, ea3, I2);
+        ea3 = a.pair[min(p + 3, pend - 1)];
+      }
+      const double *G = V.G;
+      const double  J = V.J;
       // contravariant velocity DOFs Ut[c][al] = sum_m U[c][m] dxi_al/dx_m and Z[al][v] = sum_c Ut[c][al] T3[la][c][v]
       const double *T3a = s_tab + T::O_T3 + la * NS * NP;
       double        Z[D][NP];
@@ -191,7 +306,7 @@ __global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
         for(int al = 0; al < D; ++al) {
           double s = 0.;
 #pragma unroll
-          for(int m = 0; m < D; ++m) s += U[cc][m] * G[al * D + m];
+          for(int m = 0; m < D; ++m) s += V.U[cc][m] * G[al * D + m];
           ut[al] = s;
         }
 #pragma unroll
@@ -215,7 +330,7 @@ __global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
 #pragma unroll
           for(int al = 0; al < D; ++al)
 #pragma unroll
-            for(int v = 0; v < NP; ++v) X[al][v] += U[cc][i] * s_tab[T::O_E + (cc * D + al) * NP + v];
+            for(int v = 0; v < NP; ++v) X[al][v] += V.U[cc][i] * s_tab[T::O_E + (cc * D + al) * NP + v];
 #pragma unroll
         for(int v = 0; v < NP; ++v)
 #pragma unroll
@@ -226,24 +341,6 @@ __global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
             Dv[v][j][i] = s;
           }
       }
-      // row-local column offsets of this (node, element) pair
-      uint16_t of[T::OFFW_U];
-      if(MAT) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.off + (int64_t)p * T::OFFW_U);
-#pragma unroll
-        for(int w = 0; w < T::OFFW_U / 8; ++w) {
-          const uint4 v = src[w];
-          of[8 * w + 0] = (uint16_t)(v.x & 0xffff);
-          of[8 * w + 1] = (uint16_t)(v.x >> 16);
-          of[8 * w + 2] = (uint16_t)(v.y & 0xffff);
-          of[8 * w + 3] = (uint16_t)(v.y >> 16);
-          of[8 * w + 4] = (uint16_t)(v.z & 0xffff);
-          of[8 * w + 5] = (uint16_t)(v.z >> 16);
-          of[8 * w + 6] = (uint16_t)(v.w & 0xffff);
-          of[8 * w + 7] = (uint16_t)(v.w >> 16);
-        }
-      }
-      const int32_t *ap = a.adrP + (int64_t)e * NP;
 
 #pragma unroll
       for(int b = 0; b < NS; ++b) {
@@ -287,50 +384,69 @@ __global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
         const double Mab = J * s_tab[T::O_M + la * NS + b];
         const double s   = c.c_conv * C1 + (c.diff_k - c.sig_mu) * trK + mass0 * Mab;
         if(MAT) {
+          int    idx[D][D];
+          double A[D][D], old[D][D];
 #pragma unroll
-          for(int i = 0; i < D; ++i) {
-            if(row[i] < a.nInc) {
+          for(int j = 0; j < D; ++j) {
+            const uint32_t o = off16(V.ow, b * D + j);
 #pragma unroll
-              for(int j = 0; j < D; ++j) {
-                const uint16_t o = of[b * D + j];
-                if(o != 0xFFFF) {
-                  double C2 = 0.; // int phi_a phi_b d_j u_i
+            for(int i = 0; i < D; ++i) {
+              idx[i][j] = (bi[i] >= 0 && o != 0xFFFFu) ? bi[i] + (int)o : trash;
+              double C2 = 0.; // int phi_a phi_b d_j u_i
 #pragma unroll
-                  for(int v = 0; v < NP; ++v) C2 += Dv[v][j][i] * t3[v];
-                  buf[i][o] += (i == j ? s : 0.) - c.sig_mu * K[j][i] + c.c_conv * C2;
-                }
-              }
+              for(int v = 0; v < NP; ++v) C2 += Dv[v][j][i] * t3[v];
+              A[i][j] = (i == j ? s : 0.) - c.sig_mu * K[j][i] + c.c_conv * C2;
             }
           }
+#pragma unroll
+          for(int i = 0; i < D; ++i)
+#pragma unroll
+            for(int j = 0; j < D; ++j) old[i][j] = s_buf[idx[i][j]];
+#pragma unroll
+          for(int i = 0; i < D; ++i)
+#pragma unroll
+            for(int j = 0; j < D; ++j) s_buf[idx[i][j]] = old[i][j] + A[i][j];
         }
         if(RES) {
           const double r1 = (c.sig_mu - c.diff_k) * trK - c.c_conv * C1;
 #pragma unroll
           for(int i = 0; i < D; ++i) {
-            double r = r1 * U[b][i];
+            double r = r1 * V.U[b][i];
 #pragma unroll
-            for(int m = 0; m < D; ++m) r += c.sig_mu * K[m][i] * U[b][m];
-            if(domass) r -= c.c_mass * Mab * a.soldot[au[b * D + i]];
+            for(int m = 0; m < D; ++m) r += c.sig_mu * K[m][i] * V.U[b][m];
+            if(domass) r -= c.c_mass * Mab * a.soldot[aud[b * D + i]];
             res[i] += r;
           }
         }
       }
       // pressure columns
+      {
+        int    idx[NP][D];
+        double Bp[NP][D];
 #pragma unroll
-      for(int q = 0; q < NP; ++q) {
-        const double *Br = s_tab + T::O_B + (q * NS + la) * D;
-        const double  pq = RES ? a.sol[ap[q]] : 0.;
+        for(int q = 0; q < NP; ++q) {
+          const double  *Br = s_tab + T::O_B + (q * NS + la) * D;
+          const uint32_t o  = MAT ? off16(V.ow, NU + q) : 0xFFFFu;
 #pragma unroll
-        for(int i = 0; i < D; ++i) {
-          double s = 0.;
+          for(int i = 0; i < D; ++i) {
+            double s = 0.;
 #pragma unroll
-          for(int al = 0; al < D; ++al) s += G[al * D + i] * Br[al];
-          const double Bp = J * s;
-          if(MAT) {
-            const uint16_t o = of[NU + q];
-            if(o != 0xFFFF && row[i] < a.nInc) buf[i][o] += (c.c_sig - c.c_gradp) * Bp;
+            for(int al = 0; al < D; ++al) s += G[al * D + i] * Br[al];
+            Bp[q][i]  = J * s;
+            idx[q][i] = (bi[i] >= 0 && o != 0xFFFFu) ? bi[i] + (int)o : trash;
+            if(RES) res[i] += (c.c_gradp - c.c_sig) * Bp[q][i] * V.P[q];
           }
-          if(RES) res[i] += (c.c_gradp - c.c_sig) * Bp * pq;
+        }
+        if(MAT) {
+          double old[NP][D];
+#pragma unroll
+          for(int q = 0; q < NP; ++q)
+#pragma unroll
+            for(int i = 0; i < D; ++i) old[q][i] = s_buf[idx[q][i]];
+#pragma unroll
+          for(int q = 0; q < NP; ++q)
+#pragma unroll
+            for(int i = 0; i < D; ++i) s_buf[idx[q][i]] = old[q][i] + (c.c_sig - c.c_gradp) * Bp[q][i];
         }
       }
       if(RES && a.source != nullptr) {
@@ -354,8 +470,7 @@ __global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
     const int64_t g0 = a.cta_g0[cta];
     if(g0 >= 0) {
       // the CTA's rows are consecutive in the CSR arrays: the row buffers are a contiguous image of val[g0 ...]
-      const uint32_t tot = a.cta_size[cta];
-      double        *dst = a.val + g0;
+      double *dst = a.val + g0;
       for(uint32_t i = tid; i < tot; i += NPB) dst[i] = s_buf[i];
     } else {
       // general numbering: one warp per row segment
@@ -380,11 +495,63 @@ __global__ void __launch_bounds__(NPB) gather_u_kernel(const GatherArgs a)
 // ----------------------------------------------------------------------------------------------------------
 // P rows: one thread per pressure node (1 row)
 // ----------------------------------------------------------------------------------------------------------
+template <int D, int NS, int NP> struct PPairVal {
+  double G[D * D], J, U[NS][D];
+  uint4  ow[GT<D, NS, NP>::OFFW_P / 8];
+};
+
+template <int D, int NS, int NP, bool MAT, bool RES>
+__device__ __forceinline__ void load_ppair(const GatherArgs &a, int eq, int p, int &q, PPairVal<D, NS, NP> &V)
+{
+  constexpr int NU = NS * D, GW = GT<D, NS, NP>::GW;
+  const int     e = eq / NP;
+  q               = eq - e * NP;
+  int32_t        au[NU];
+  const int32_t *pu = a.adrU + (int64_t)e * NU;
+  if(RES) {
+    if(NU % 4 == 0) {
+      const int4 *a4 = reinterpret_cast<const int4 *>(pu);
+#pragma unroll
+      for(int k = 0; k < NU / 4; ++k) {
+        const int4 v  = a4[k];
+        au[4 * k + 0] = v.x;
+        au[4 * k + 1] = v.y;
+        au[4 * k + 2] = v.z;
+        au[4 * k + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for(int k = 0; k < NU; ++k) au[k] = pu[k];
+    }
+  }
+  const double2 *ge = reinterpret_cast<const double2 *>(a.geo + (int64_t)e * GW);
+  double         g[GW];
+#pragma unroll
+  for(int i = 0; i < GW / 2; ++i) {
+    const double2 v = ge[i];
+    g[2 * i]     = v.x;
+    g[2 * i + 1] = v.y;
+  }
+#pragma unroll
+  for(int i = 0; i < D * D; ++i) V.G[i] = g[i];
+  V.J = g[D * D];
+  if(MAT) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.off + (int64_t)p * GT<D, NS, NP>::OFFW_P);
+#pragma unroll
+    for(int w = 0; w < GT<D, NS, NP>::OFFW_P / 8; ++w) V.ow[w] = src[w];
+  }
+  if(RES) {
+#pragma unroll
+    for(int b = 0; b < NS; ++b)
+#pragma unroll
+      for(int m = 0; m < D; ++m) V.U[b][m] = a.sol[au[b * D + m]];
+  }
+}
+
 template <int D, int NS, int NP, int NPB, bool MAT, bool RES>
 __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
 {
   using T = GT<D, NS, NP>;
-  constexpr int NU = T::NU;
   extern __shared__ double sm[];
   double *s_tab = sm;
   double *s_buf = sm + a.ntab;
@@ -393,12 +560,13 @@ __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
   __shared__ int32_t  s_len[NPB];
   const int tid = threadIdx.x;
   for(int i = tid; i < a.ntab; i += NPB) s_tab[i] = a.tab[i];
-  const int32_t cta  = a.cta0 + blockIdx.x;
-  const int32_t n    = cta * NPB + tid;
-  const bool    live = n < a.nNodes;
-  int32_t       row  = 0x7fffffff;
-  int           len  = 0;
-  uint32_t      base = 0;
+  const int32_t  cta  = a.cta0 + blockIdx.x;
+  const int32_t  n    = cta * NPB + tid;
+  const bool     live = n < a.nNodes;
+  const uint32_t tot  = MAT ? a.cta_size[cta] : 0;
+  int32_t        row  = 0x7fffffff;
+  int            len  = 0;
+  uint32_t       base = 0;
   if(live) {
     row  = a.row[n];
     len  = row < a.nInc ? (int)(a.ia[row + 1] - a.ia[row]) : 0;
@@ -408,42 +576,27 @@ __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
     s_row[tid]  = row;
     s_base[tid] = base;
     s_len[tid]  = len;
-    const uint32_t tot = a.cta_size[cta];
     for(uint32_t i = tid; i < tot; i += NPB) s_buf[i] = 0.;
   }
   __syncthreads();
   if(live && row < a.nInc) {
-    double      *buf = s_buf + base;
-    double       res = 0.;
-    const double cdiv = a.c.c_div;
-    const int2   rg  = a.range[n];
-    for(int p = rg.x; p < rg.x + rg.y; ++p) {
-      const int eq = a.pair[p];
-      const int e = eq / NP, q = eq - e * NP;
-      double G[D * D], J;
-      {
-        const double *ge = a.geo + (int64_t)e * (D * D + 1);
-#pragma unroll
-        for(int i = 0; i < D * D; ++i) G[i] = ge[i];
-        J = ge[D * D];
-      }
-      const int32_t *au = a.adrU + (int64_t)e * NU;
-      uint16_t       of[T::OFFW_P];
-      if(MAT) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.off + (int64_t)p * T::OFFW_P);
-#pragma unroll
-        for(int w = 0; w < T::OFFW_P / 8; ++w) {
-          const uint4 v = src[w];
-          of[8 * w + 0] = (uint16_t)(v.x & 0xffff);
-          of[8 * w + 1] = (uint16_t)(v.x >> 16);
-          of[8 * w + 2] = (uint16_t)(v.y & 0xffff);
-          of[8 * w + 3] = (uint16_t)(v.y >> 16);
-          of[8 * w + 4] = (uint16_t)(v.z & 0xffff);
-          of[8 * w + 5] = (uint16_t)(v.z >> 16);
-          of[8 * w + 6] = (uint16_t)(v.w & 0xffff);
-          of[8 * w + 7] = (uint16_t)(v.w >> 16);
-        }
-      }
+    const int    trash = (int)tot + tid;
+    double       res   = 0.;
+    const double cdiv  = a.c.c_div;
+    const int2   rg    = a.range[n];
+    const int    pend  = rg.x + rg.y;
+    PPairVal<D, NS, NP> V1;
+    int                 q1;
+    load_ppair<D, NS, NP, MAT, RES>(a, a.pair[rg.x], rg.x, q1, V1);
+    int eq2 = a.pair[min(rg.x + 1, pend - 1)];
+    for(int p = rg.x; p < pend; ++p) {
+      const PPairVal<D, NS, NP> V = V1;
+      const int                 q = q1;
+      // values of the next pair and the pair index after it are in flight while this one is computed
+      load_ppair<D, NS, NP, MAT, RES>(a, eq2, min(p + 1, pend - 1), q1, V1);
+      eq2 = a.pair[min(p + 2, pend - 1)];
+      double Bp[NS][D];
+      int    idx[NS][D];
 #pragma unroll
       for(int b = 0; b < NS; ++b) {
         const double *Br = s_tab + T::O_B + (q * NS + b) * D;
@@ -451,14 +604,26 @@ __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
         for(int j = 0; j < D; ++j) {
           double s = 0.;
 #pragma unroll
-          for(int al = 0; al < D; ++al) s += G[al * D + j] * Br[al];
-          const double Bp = cdiv * J * s;
+          for(int al = 0; al < D; ++al) s += V.G[al * D + j] * Br[al];
+          Bp[b][j] = cdiv * V.J * s;
+          if(RES) res -= Bp[b][j] * V.U[b][j];
           if(MAT) {
-            const uint16_t o = of[b * D + j];
-            if(o != 0xFFFF) buf[o] += Bp;
+            const uint32_t o = off16(V.ow, b * D + j);
+            idx[b][j] = o != 0xFFFFu ? (int)base + (int)o : trash;
           }
-          if(RES) res -= Bp * a.sol[au[b * D + j]];
         }
+      }
+      if(MAT) {
+        // distinct columns of one row: the read-modify-writes are independent and issued as one batch
+        double old[NS][D];
+#pragma unroll
+        for(int b = 0; b < NS; ++b)
+#pragma unroll
+          for(int j = 0; j < D; ++j) old[b][j] = s_buf[idx[b][j]];
+#pragma unroll
+        for(int b = 0; b < NS; ++b)
+#pragma unroll
+          for(int j = 0; j < D; ++j) s_buf[idx[b][j]] = old[b][j] + Bp[b][j];
       }
     }
     if(RES) a.rhs[row] = res;
@@ -467,8 +632,7 @@ __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
     __syncthreads();
     const int64_t g0 = a.cta_g0[cta];
     if(g0 >= 0) {
-      const uint32_t tot = a.cta_size[cta];
-      double        *dst = a.val + g0;
+      double *dst = a.val + g0;
       for(uint32_t i = tid; i < tot; i += NPB) dst[i] = s_buf[i];
     } else {
       const int lane = tid & 31, wid = tid >> 5, nw = NPB / 32;
@@ -492,6 +656,7 @@ __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
 // and the constant ElementTransformation of P1 geometry, :489-509)
 template <int D> __global__ void geometry_kernel(int64_t nElm, const double *xyz, const int32_t *conn, double *geo)
 {
+  constexpr int GW = (D * D + 1 + 1) / 2 * 2;
   for(int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nElm; e += (int64_t)gridDim.x * blockDim.x) {
     int32_t vtx[D + 1];
 #pragma unroll
@@ -499,8 +664,9 @@ template <int D> __global__ void geometry_kernel(int64_t nElm, const double *xyz
     double G[D * D], J;
     element_geometry<D>(xyz, vtx, G, &J);
 #pragma unroll
-    for(int i = 0; i < D * D; ++i) geo[e * (D * D + 1) + i] = G[i];
-    geo[e * (D * D + 1) + D * D] = J;
+    for(int i = 0; i < D * D; ++i) geo[e * GW + i] = G[i];
+    geo[e * GW + D * D] = J;
+    if(GW > D * D + 1) geo[e * GW + D * D + 1] = 0.;
   }
 }
 
@@ -559,8 +725,8 @@ __global__ void node_compact_kernel(int32_t nNodes, int nRow, const int32_t *kee
 }
 
 // shared-memory layout of the row buffers: one thread per CTA
-__global__ void node_smem_kernel(int32_t nNodes, int npb, int nRow, int64_t nInc, const int64_t *ia, const int32_t *row, uint32_t *smoff,
-                                 uint32_t *cta_size, int64_t *cta_g0, int *err)
+__global__ void node_smem_kernel(int32_t nNodes, int npb, int nRow, int64_t nInc, const int64_t *ia, const int32_t *row, const int2 *range,
+                                 uint32_t *smoff, uint32_t *cta_size, int64_t *cta_g0, int32_t *cta_pairs, int *err)
 {
   const int32_t cta = blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t n0 = cta * npb;
@@ -568,8 +734,10 @@ __global__ void node_smem_kernel(int32_t nNodes, int npb, int nRow, int64_t nInc
   uint32_t o = 0;
   int64_t  prev = -1, g0 = -1;
   bool     contiguous = true;
+  int32_t  npairs = 0;
   for(int32_t n = n0; n < n0 + npb && n < nNodes; ++n) {
     smoff[n] = o;
+    npairs += range[n].y;
     int64_t len = -1;
     int     nun = 0;
     for(int c = 0; c < nRow; ++c) {
@@ -589,8 +757,9 @@ __global__ void node_smem_kernel(int32_t nNodes, int npb, int nRow, int64_t nInc
     if(len >= 65535) atomicExch(err, 3);
     o += (uint32_t)(nun * (len > 0 ? len : 0));
   }
-  cta_size[cta] = o;
-  cta_g0[cta]   = contiguous ? g0 : -1;
+  cta_size[cta]  = o;
+  cta_g0[cta]    = contiguous ? g0 : -1;
+  cta_pairs[cta] = npairs;
 }
 
 // row-local offsets of the columns of every (node, element) pair; one thread per (pair, local column)
@@ -678,10 +847,12 @@ static int build_node_set(System *S, NodeSet &N, const int32_t *d_adr, int nLoc,
   B200_CUDA(cudaMalloc(&N.cta_g0, (size_t)N.nCta * sizeof(int64_t)));
   B200_CUDA(cudaMalloc(&N.off, (size_t)np * offw * sizeof(uint16_t)));
   B200_CUDA(cudaMemsetAsync(N.off, 0xFF, (size_t)np * offw * sizeof(uint16_t), S->stream));
+  thrust::device_vector<int32_t> cta_pairs(N.nCta);
   int *d_err;
   B200_CUDA(cudaMalloc(&d_err, sizeof(int)));
   B200_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), S->stream));
-  node_smem_kernel<<<(N.nCta + 127) / 128, 128, 0, S->stream>>>(N.nNodes, npb, nRow, S->nInc, S->d_ia, N.row, N.smoff, N.cta_size, N.cta_g0, d_err);
+  node_smem_kernel<<<(N.nCta + 127) / 128, 128, 0, S->stream>>>(N.nNodes, npb, nRow, S->nInc, S->d_ia, N.row, N.range, N.smoff, N.cta_size, N.cta_g0,
+                                                            thrust::raw_pointer_cast(cta_pairs.data()), d_err);
   node_offsets_kernel<<<148 * 16, 64, 0, S->stream>>>(N.nNodes, nRow, nLoc, offw, ncol, NU, NP, N.range, N.row, N.pair, S->spaces[S->su].d_adr,
                                                      S->sp >= 0 ? S->spaces[S->sp].d_adr : nullptr, S->d_ia, S->d_ja, S->nInc, colmaskU, colmaskP,
                                                      N.off, d_err);
@@ -698,8 +869,11 @@ static int build_node_set(System *S, NodeSet &N, const int32_t *d_adr, int nLoc,
   // request), so that CTAs of short rows (edge nodes) are not limited by the occupancy of the longest rows
   std::vector<uint32_t> h_size(N.nCta);
   B200_CUDA(cudaMemcpy(h_size.data(), N.cta_size, (size_t)N.nCta * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  std::vector<int32_t> h_pairs(N.nCta);
+  B200_CUDA(cudaMemcpy(h_pairs.data(), thrust::raw_pointer_cast(cta_pairs.data()), (size_t)N.nCta * sizeof(int32_t), cudaMemcpyDeviceToHost));
   N.seg_begin.clear();
   N.seg_smem.clear();
+  N.seg_pairs.clear();
   N.max_cta = 0;
   {
     int32_t  b = 0;
@@ -709,7 +883,7 @@ static int build_node_set(System *S, NodeSet &N, const int32_t *d_adr, int nLoc,
       if(!last) {
         const uint32_t v = h_size[i];
         // cut where the size leaves the +-25 % band of the running segment (at most 8 segments, at least 64 CTAs each)
-        const bool cut = i > b + 64 && N.seg_smem.size() < 7 &&
+        const bool cut = i > b + std::max(64, N.nCta / 50) && N.nCta - i > std::max(64, N.nCta / 50) && N.seg_smem.size() < 7 &&
                          ((double)v > 1.25 * (double)std::max<uint32_t>(mn, 1u) || 1.25 * (double)v < (double)mx);
         if(!cut) {
           mx = std::max(mx, v);
@@ -728,6 +902,12 @@ static int build_node_set(System *S, NodeSet &N, const int32_t *d_adr, int nLoc,
       }
     }
     N.seg_begin.push_back(N.nCta);
+    for(size_t sg = 0; sg + 1 < N.seg_begin.size(); ++sg) {
+      double np = 0.;
+      for(int32_t i = N.seg_begin[sg]; i < N.seg_begin[sg + 1]; ++i) np += h_pairs[i];
+      const double nn = std::min<double>((double)(N.seg_begin[sg + 1] - N.seg_begin[sg]) * npb, (double)N.nNodes);
+      N.seg_pairs.push_back(np / std::max(1., nn));
+    }
   }
   return B200_OK;
 }
@@ -851,7 +1031,7 @@ int build_gather_plan(System *S)
   try {
     B200_CUDA(cudaMalloc(&G->d_tab, tab.size() * sizeof(double)));
     B200_CUDA(cudaMemcpyAsync(G->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, S->stream));
-    B200_CUDA(cudaMalloc(&G->d_geo, (size_t)S->nElm * (D * D + 1) * sizeof(double)));
+    B200_CUDA(cudaMalloc(&G->d_geo, (size_t)S->nElm * ((D * D + 2) / 2 * 2) * sizeof(double)));
     if(D == 2)
       geometry_kernel<2><<<148 * 8, 256, 0, S->stream>>>(S->nElm, S->d_xyz, S->d_conn, G->d_geo);
     else
@@ -914,26 +1094,44 @@ template <int D, int NS, int NP, int NPB> static int launch_gather_t(System *S, 
     a.off      = N.off;
     a.nNodes   = N.nNodes;
     a.cta_g0   = N.cta_g0;
-    const size_t smem_max = ((size_t)a.ntab + (mat ? N.max_cta : 0)) * sizeof(double);
+    const size_t smem_max = ((size_t)a.ntab + (mat ? N.max_cta + NPB : 0)) * sizeof(double);
     const int    nseg     = mat ? (int)N.seg_smem.size() : 1;
 #define B200_LAUNCH_G(KERN)                                                                                                              \
   do {                                                                                                                                   \
     B200_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));                                   \
     for(int sg = 0; sg < nseg; ++sg) {                                                                                                   \
+      if(pass == 0 && ((D == 2) && N.seg_pairs[mat ? sg : 0] >= 3.5) != pipe) continue;                                                  \
       a.cta0            = mat ? N.seg_begin[sg] : 0;                                                                                     \
       const int    nc   = mat ? N.seg_begin[sg + 1] - N.seg_begin[sg] : N.nCta;                                                          \
-      const size_t smem = ((size_t)a.ntab + (mat ? N.seg_smem[sg] : 0)) * sizeof(double);                                                \
+      const size_t smem = ((size_t)a.ntab + (mat ? N.seg_smem[sg] + NPB : 0)) * sizeof(double);                                          \
       KERN<<<nc, NPB, smem, S->stream>>>(a);                                                                                             \
       count_launch();                                                                                                                    \
     }                                                                                                                                    \
   } while(0)
+    bool pipe = false;
     if(pass == 0) {
-      if(what == 3)
-        B200_LAUNCH_G((gather_u_kernel<D, NS, NP, NPB, true, true>));
-      else if(what == 2)
-        B200_LAUNCH_G((gather_u_kernel<D, NS, NP, NPB, true, false>));
-      else
-        B200_LAUNCH_G((gather_u_kernel<D, NS, NP, NPB, false, true>));
+      // software-pipelined variant (more registers) for segments of nodes with many adjacent elements, plain variant
+      // (higher occupancy) for the others; 3-D always plain (register budget)
+      for(int v = 0; v < 2; ++v) {
+        pipe = v == 1;
+        if(pipe && D != 2) continue;
+        if(what == 3) {
+          if(pipe)
+            B200_LAUNCH_G((gather_u_kernel<D, NS, NP, NPB, true, true, (D == 2)>));
+          else
+            B200_LAUNCH_G((gather_u_kernel<D, NS, NP, NPB, true, true, false>));
+        } else if(what == 2) {
+          if(pipe)
+            B200_LAUNCH_G((gather_u_kernel<D, NS, NP, NPB, true, false, (D == 2)>));
+          else
+            B200_LAUNCH_G((gather_u_kernel<D, NS, NP, NPB, true, false, false>));
+        } else {
+          if(pipe)
+            B200_LAUNCH_G((gather_u_kernel<D, NS, NP, NPB, false, true, (D == 2)>));
+          else
+            B200_LAUNCH_G((gather_u_kernel<D, NS, NP, NPB, false, true, false>));
+        }
+      }
     } else {
       if(what == 3)
         B200_LAUNCH_G((gather_p_kernel<D, NS, NP, NPB, true, true>));
