@@ -75,7 +75,8 @@ struct NodeSet {
 struct GatherPlan {
   NodeSet  U, P;
   double  *d_tab = nullptr;
-  double  *d_geo = nullptr; // [nElm][D*D+1] inverse affine map + detJ of every element (the mesh is static)
+  double  *d_geo = nullptr; // [nElm][GW] inverse affine map + detJ of every element (the mesh is static)
+  double   E[120] = {0.};
   int      tab_len = 0, tab_len_src = 0;
   int      npbU = 0, npbP = 0;
 };
@@ -98,6 +99,9 @@ struct GatherArgs {
   int             nq, ntab;
   THCoeffs        c;
   double          c0;
+  // E[c][al][v] lives in the kernel-parameter constant bank: its indices are compile-time constants after unrolling,
+  // so every use is a constant operand of a DFMA instead of a shared-memory load (sized for P2/P1 tetrahedra)
+  double          E[120];
 };
 
 // ----------------------------------------------------------------------------------------------------------
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(NPB, (D == 2 && !PIPE) ? 8 : 1) gather_u_kerne
 #pragma unroll
           for(int al = 0; al < D; ++al)
 #pragma unroll
-            for(int v = 0; v < NP; ++v) X[al][v] += V.U[cc][i] * s_tab[T::O_E + (cc * D + al) * NP + v];
+            for(int v = 0; v < NP; ++v) X[al][v] += V.U[cc][i] * a.E[(cc * D + al) * NP + v];
 #pragma unroll
         for(int v = 0; v < NP; ++v)
 #pragma unroll
@@ -371,11 +375,10 @@ __global__ void __launch_bounds__(NPB, (D == 2 && !PIPE) ? 8 : 1) gather_u_kerne
 #pragma unroll
         for(int m = 0; m < D; ++m) trK += K[m][m];
         double        C1 = 0.; // int phi_a (u . grad phi_b)
-        const double *Eb = s_tab + T::O_E + b * D * NP;
 #pragma unroll
         for(int al = 0; al < D; ++al)
 #pragma unroll
-          for(int v = 0; v < NP; ++v) C1 += Eb[al * NP + v] * Z[al][v];
+          for(int v = 0; v < NP; ++v) C1 += a.E[(b * D + al) * NP + v] * Z[al][v];
         C1 *= J;
         const double *T3ab = T3a + b * NP;
         double        t3[NP];
@@ -541,10 +544,25 @@ __device__ __forceinline__ void load_ppair(const GatherArgs &a, int eq, int p, i
     for(int w = 0; w < GT<D, NS, NP>::OFFW_P / 8; ++w) V.ow[w] = src[w];
   }
   if(RES) {
+    if(D == 2) {
 #pragma unroll
-    for(int b = 0; b < NS; ++b)
+      for(int b = 0; b < NS; ++b) {
+        const int32_t d0 = au[b * D], d1 = au[b * D + 1];
+        if(((d0 & 1) == 0) && d1 == d0 + 1) {
+          const double2 v = *reinterpret_cast<const double2 *>(a.sol + d0);
+          V.U[b][0] = v.x;
+          V.U[b][1] = v.y;
+        } else {
+          V.U[b][0] = a.sol[d0];
+          V.U[b][1] = a.sol[d1];
+        }
+      }
+    } else {
 #pragma unroll
-      for(int m = 0; m < D; ++m) V.U[b][m] = a.sol[au[b * D + m]];
+      for(int b = 0; b < NS; ++b)
+#pragma unroll
+        for(int m = 0; m < D; ++m) V.U[b][m] = a.sol[au[b * D + m]];
+    }
   }
 }
 
@@ -1024,6 +1042,15 @@ int build_gather_plan(System *S)
   }
   GatherPlan *G = new GatherPlan;
   S->gather     = G;
+  {
+    const int oE = NS * NS * D * D + NS * NS * NP + NS * NS; // GT<D,NS,NP>::O_E
+    if(NS * D * NP > 120) {
+      set_error("gather plan: E table too large");
+      gather_free(S);
+      return B200_ERR_UNSUPP;
+    }
+    for(int i = 0; i < NS * D * NP; ++i) G->E[i] = tab[oE + i];
+  }
   G->tab_len     = len_nosrc;
   G->tab_len_src = (int)tab.size();
   G->npbU        = D == 2 ? 64 : 32;
@@ -1082,6 +1109,7 @@ template <int D, int NS, int NP, int NPB> static int launch_gather_t(System *S, 
   a.ntab   = a.source ? G->tab_len_src : G->tab_len;
   a.c      = c;
   a.c0     = S->c0;
+  for(int i = 0; i < 120; ++i) a.E[i] = G->E[i];
   const bool mat = what & 2;
   for(int pass = 0; pass < 2; ++pass) {
     const NodeSet &N = pass == 0 ? G->U : G->P;
