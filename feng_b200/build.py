@@ -10,10 +10,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfeng_b200.so")
-SOURCES = ["capi.cu", "assemble.cu", "krylov.cu", "pattern.cu", "gather.cu"]
+SOURCES = ["capi.cu", "assemble.cu", "krylov.cu", "pattern.cu", "gather.cu", "comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr"]
+         "--expt-relaxed-constexpr", "-I/usr/include"]
 
 
 def _stale(target, deps):
@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for l in logs:
             print(l)
     if jobs or not os.path.exists(LIB):
-        run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"])
+        run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"])
     return LIB
 
 

@@ -23,7 +23,7 @@ SYMBOLS = [
     "b200_apply_periodicity", "b200_solve", "b200_correct_solution", "b200_get_rhs", "b200_axpy_rhs",
     "b200_get_matrix_values", "b200_get_du", "b200_get_solution", "b200_spmv", "b200_last_assemble_ms",
     "b200_last_solve_ms", "b200_time_spmv", "b200_sync", "b200_time_begin", "b200_time_end",
-    "b200_measure_fp64_peak",
+    "b200_measure_fp64_peak", "b200_comm_unique_id", "b200_comm_init", "b200_set_halo", "b200_halo_exchange_host",
 ]
 
 SCATTER_ATOMIC, SCATTER_COLORED = 0, 1
@@ -85,6 +85,12 @@ def check(rc, what=""):
     if rc < 0:
         raise B200Error(f"{what}: rc={rc}: {lib().b200_last_error().decode()}")
     return rc
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(lib().b200_comm_unique_id(buf), "b200_comm_unique_id")
+    return buf.raw
 
 
 class System:
@@ -160,6 +166,22 @@ class System:
 
     def set_scatter_mode(self, mode):
         check(self.L.b200_set_scatter_mode(self.h, mode), "b200_set_scatter_mode")
+
+    def comm_init(self, ident: bytes, rank: int, world: int):
+        check(self.L.b200_comm_init(self.h, C.c_char_p(ident), rank, world), "b200_comm_init")
+
+    def set_halo(self, owned, neighbors, send_ptr, send_idx, recv_ptr, recv_idx):
+        owned = np.ascontiguousarray(owned, np.uint8)
+        nb = np.ascontiguousarray(neighbors, np.int32)
+        sp, si = np.ascontiguousarray(send_ptr, np.int64), np.ascontiguousarray(send_idx, np.int32)
+        rp, ri = np.ascontiguousarray(recv_ptr, np.int64), np.ascontiguousarray(recv_idx, np.int32)
+        check(self.L.b200_set_halo(self.h, owned.ctypes.data_as(C.POINTER(C.c_uint8)), nb.shape[0], _i32(nb), _i64(sp),
+                                   _i32(si), _i64(rp), _i32(ri)), "b200_set_halo")
+
+    def halo_exchange_host(self, x):
+        x = np.ascontiguousarray(x, np.float64).copy()
+        check(self.L.b200_halo_exchange_host(self.h, _d(x)), "b200_halo_exchange_host")
+        return x
 
     def set_assembly_mode(self, mode):
         check(self.L.b200_set_assembly_mode(self.h, mode), "b200_set_assembly_mode")

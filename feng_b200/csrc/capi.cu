@@ -90,6 +90,7 @@ static void free_system(System *S)
   cudaSetDevice(S->device);
   krylov_free(S);
   gather_free(S);
+  comm_free(S);
   for(auto &sp : S->spaces) cudaFree(sp.d_adr);
   for(auto &f : S->forms) cudaFree(f.d_source);
   cudaFree(S->d_xyz);

@@ -39,14 +39,14 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t n, const int64_t *__r
 // out[j] += sum_i V[j*ld + i] * w[i]   for j < nv (grid.y = ceil(nv / JB)); out must be zeroed
 template <int JB>
 __global__ void __launch_bounds__(256) multi_dot_kernel(int64_t n, const double *__restrict__ V, int64_t ld, int nv, const double *__restrict__ w,
-                                                        double *__restrict__ out)
+                                                        double *__restrict__ out, const double *__restrict__ mask)
 {
   const int j0 = blockIdx.y * JB;
   double    s[JB];
 #pragma unroll
   for(int j = 0; j < JB; ++j) s[j] = 0.;
   for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double wi = w[i];
+    const double wi = mask ? w[i] * mask[i] : w[i]; // ghost rows are owned (and counted) by another rank
 #pragma unroll
     for(int j = 0; j < JB; ++j)
       if(j0 + j < nv) s[j] += V[(int64_t)(j0 + j) * ld + i] * wi;
@@ -97,10 +97,11 @@ __global__ void axpby_kernel(int64_t n, double a, const double *__restrict__ x, 
   for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = a * x[i] + b * y[i];
 }
 
-__global__ void max_abs_kernel(int64_t n, const double *__restrict__ x, double *out)
+__global__ void max_abs_kernel(int64_t n, const double *__restrict__ x, double *out, const double *__restrict__ mask)
 {
   double m = 0.;
-  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmax(m, fabs(x[i]));
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmax(m, mask ? fabs(x[i]) * mask[i] : fabs(x[i]));
 #pragma unroll
   for(int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
   __shared__ double red[32];
@@ -296,8 +297,12 @@ int spmv(System *S, const double *d_x, double *d_y)
 int max_abs(System *S, const double *d_x, int64_t n, double *out)
 {
   B200_CUDA(cudaMemsetAsync(S->d_scratch, 0, sizeof(double), S->stream));
-  max_abs_kernel<<<GRID, 256, 0, S->stream>>>(n, d_x, S->d_scratch);
+  max_abs_kernel<<<GRID, 256, 0, S->stream>>>(n, d_x, S->d_scratch, comm_mask(S));
   count_launch();
+  {
+    const int crc = comm_allreduce(S, S->d_scratch, 1, true);
+    if(crc != B200_OK) return crc;
+  }
   B200_CUDA(cudaMemcpyAsync(S->h_scratch, S->d_scratch, sizeof(double), cudaMemcpyDeviceToHost, S->stream));
   B200_CUDA(cudaStreamSynchronize(S->stream));
   *out = S->h_scratch[0];
@@ -404,6 +409,7 @@ int gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info
   }
 
   double *hbuf = K->h, *hacc = K->h + (m + 1), *nrm = K->h + (2 * m + 2);
+  const double *mask = comm_mask(S); // multi-GPU: dot products over owned rows + all-reduce, halo update before every SpMV
   std::vector<double> H((size_t)(m + 1) * m, 0.), cs(m, 0.), sn(m, 0.), g(m + 1, 0.), y(m, 0.);
   std::vector<double> hh(m + 3, 0.);
 
@@ -414,8 +420,12 @@ int gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info
 
   auto norm2_of = [&](const double *v, double *out) -> int {
     B200_CUDA(cudaMemsetAsync(nrm, 0, sizeof(double), S->stream));
-    multi_dot_kernel<1><<<dim3(GRID, 1), 256, 0, S->stream>>>(n, v, n, 1, v, nrm);
+    multi_dot_kernel<1><<<dim3(GRID, 1), 256, 0, S->stream>>>(n, v, n, 1, v, nrm, mask);
     count_launch();
+    {
+      const int crc = comm_allreduce(S, nrm, 1, false);
+      if(crc != B200_OK) return crc;
+    }
     B200_CUDA(cudaMemcpyAsync(S->h_scratch, nrm, sizeof(double), cudaMemcpyDeviceToHost, S->stream));
     B200_CUDA(cudaStreamSynchronize(S->stream));
     *out = sqrt(S->h_scratch[0]);
@@ -441,6 +451,8 @@ int gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info
       ++its;
       double *vk = K->V + (int64_t)k * n, *vk1 = K->V + (int64_t)(k + 1) * n;
       // w = M^-1 A v_k
+      rc = comm_halo_exchange(S, vk);
+      if(rc != B200_OK) return rc;
       rc = spmv(S, vk, K->z);
       if(rc != B200_OK) return rc;
       rc = apply_pc(S, K, pc, K->z, K->w);
@@ -449,12 +461,16 @@ int gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info
       B200_CUDA(cudaMemsetAsync(hbuf, 0, (size_t)(2 * m + 3) * sizeof(double), S->stream));
       for(int pass = 0; pass < 2; ++pass) {
         if(pass == 1) B200_CUDA(cudaMemsetAsync(hbuf, 0, (size_t)(m + 1) * sizeof(double), S->stream));
-        multi_dot_kernel<4><<<dim3(GRID / 4, (k + 1 + 3) / 4), 256, 0, S->stream>>>(n, K->V, n, k + 1, K->w, hbuf);
+        multi_dot_kernel<4><<<dim3(GRID / 4, (k + 1 + 3) / 4), 256, 0, S->stream>>>(n, K->V, n, k + 1, K->w, hbuf, mask);
+        rc = comm_allreduce(S, hbuf, k + 1, false);
+        if(rc != B200_OK) return rc;
         multi_axpy_kernel<<<GRID, 256, (k + 1) * sizeof(double), S->stream>>>(n, K->V, n, k + 1, hbuf, -1., K->w, hacc);
         count_launch(2);
       }
-      multi_dot_kernel<1><<<dim3(GRID, 1), 256, 0, S->stream>>>(n, K->w, n, 1, K->w, nrm);
+      multi_dot_kernel<1><<<dim3(GRID, 1), 256, 0, S->stream>>>(n, K->w, n, 1, K->w, nrm, mask);
       count_launch();
+      rc = comm_allreduce(S, nrm, 1, false);
+      if(rc != B200_OK) return rc;
       B200_CUDA(cudaMemcpyAsync(S->h_scratch, hacc, (size_t)(m + 2) * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
       B200_CUDA(cudaStreamSynchronize(S->stream));
       for(int j = 0; j <= k; ++j) hh[j] = S->h_scratch[j];
@@ -510,6 +526,8 @@ int gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info
     }
     if(converged || diverged) break;
     // true preconditioned residual for the restart: r = M^-1 (b - A x)
+    rc = comm_halo_exchange(S, K->x);
+    if(rc != B200_OK) return rc;
     rc = spmv(S, K->x, K->z);
     if(rc != B200_OK) return rc;
     axpby_kernel<<<GRID, 256, 0, S->stream>>>(n, 1., S->d_rhs, -1., K->z);
@@ -522,6 +540,8 @@ int gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info
   }
 
   // du = x; norms reported to the Newton loop are max-norms (src/feLinearSystemMklPardiso.cpp:960-961)
+  rc = comm_halo_exchange(S, K->x); // ghost entries of du <- owner's values: every rank corrects its whole local state
+  if(rc != B200_OK) return rc;
   B200_CUDA(cudaMemcpyAsync(S->d_du, K->x, n * sizeof(double), cudaMemcpyDeviceToDevice, S->stream));
   rc = spmv(S, K->x, K->z);
   if(rc != B200_OK) return rc;

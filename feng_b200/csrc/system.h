@@ -111,6 +111,9 @@ struct System {
   // Krylov workspace (allocated lazily, krylov.cu)
   void *krylov = nullptr;
 
+  // multi-GPU communicator + halo plan (comm.cu)
+  void *comm = nullptr;
+
   // row-owner gather plan (gather.cu); assembly_mode: B200_ASSEMBLY_*
   void *gather = nullptr;
   int   assembly_mode = 0;
@@ -132,6 +135,12 @@ int  launch_gather(System *S, int what, const THCoeffs &c);
 void gather_free(System *S);
 // capi.cu
 int  flush_zero(System *S, int what);
+// comm.cu
+void          comm_free(System *S);
+bool          comm_active(const System *S);
+const double *comm_mask(const System *S); // 1/0 per row (owned / ghost) or nullptr on a single GPU
+int           comm_halo_exchange(System *S, double *d_x);
+int           comm_allreduce(System *S, double *d_buf, int count, bool max_op);
 // krylov.cu
 int  spmv(System *S, const double *d_x, double *d_y);
 int  gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info);

@@ -28,7 +28,7 @@ class NLSolverOptions:
 
 class LinearSystemB200:
     def __init__(self, pb: HostProblem, device: int = 0, colors: np.ndarray | None = None,
-                 constraint_rows: np.ndarray | None = None, device_pattern: bool = False):
+                 constraint_rows: np.ndarray | None = None, device_pattern: bool = False, partition=None):
         self.pb = pb
         self.sys = capi.System(device)
         s = self.sys
@@ -56,6 +56,20 @@ class LinearSystemB200:
         if constraint_rows is not None and len(constraint_rows):
             s.set_constraints(constraint_rows)
         s.finalize()
+        self.partition = partition
+        if partition is not None and partition.world > 1:
+            # one NCCL communicator per system, its unique id broadcast through torch.distributed
+            import torch
+            import torch.distributed as dist
+            ident = torch.zeros(128, dtype=torch.uint8)
+            if partition.rank == 0:
+                ident = torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8).clone()
+            dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            ident = ident.to(dev)
+            dist.broadcast(ident, 0)
+            s.comm_init(bytes(ident.cpu().numpy().tobytes()), partition.rank, partition.world)
+            s.set_halo(partition.owned, partition.neighbors, partition.send_ptr, partition.send_idx, partition.recv_ptr,
+                       partition.recv_idx)
         # feLinearSystem defaults (src/feLinearSystem.h:60-69)
         self._recomputeMatrix = True
         self._rel_tol, self._abs_tol, self._div_tol, self._max_iter = 1e-8, 1e-14, 1e6, 10000

@@ -1,0 +1,119 @@
+"""Element / row partition for the multi-GPU path: strips of the structured generators.
+
+The reference offers no domain decomposition (every MPI rank holds the whole mesh and keeps its row range,
+src/feLinearSystemPETSc.cpp:626-640); METIS is a CMake option no source file uses.  Here every rank builds ONLY its own
+strip of the mesh plus one ghost layer of elements towards each neighbour:
+
+  * assembly is owner-computes: every row a rank owns sees all of its elements locally, no exchange of matrix entries;
+  * each row (unknown DOF) is owned by exactly one rank; rows on a cut line belong to the lower rank;
+  * ghost rows are incomplete locally and never used: dot products run over owned rows, the SpMV input gets its ghost
+    entries from the owners (halo exchange) before every product.
+
+Rows are matched across ranks through a geometric key (field, component, position on the fine lattice), so the
+halo plan needs one all-gather of the ghost keys at set-up and nothing else.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import mesh as M
+from . import problems as PB
+
+
+@dataclass
+class Partition:
+    rank: int
+    world: int
+    owned: np.ndarray            # (n_inc,) uint8, 1 if this rank owns the row
+    keys: np.ndarray             # (n_inc,) int64 global key of every unknown
+    neighbors: np.ndarray        # (n_nbr,) int32
+    send_ptr: np.ndarray         # (n_nbr + 1,) int64
+    send_idx: np.ndarray         # local rows sent to the neighbours (this rank owns them)
+    recv_ptr: np.ndarray
+    recv_idx: np.ndarray         # local ghost rows received from the neighbours
+    owned_cells: int = 0
+
+    @property
+    def n_owned(self):
+        return int(self.owned.sum())
+
+
+def strip_mesh(n: int, rank: int, world: int) -> tuple[M.Mesh, int]:
+    """Strip `rank` of the [0,1] x [0,world] domain: n x n owned cells plus one ghost row of cells towards each
+    neighbour; the artificial cuts carry no physical boundary."""
+    gb, gt = (1 if rank > 0 else 0), (1 if rank < world - 1 else 0)
+    ny = n + gb + gt
+    m = M.rect_mesh(n, ny, 1.0, ny / n, 0.0, rank - gb / n, cut_bottom=rank > 0, cut_top=rank < world - 1)
+    if rank == 0:
+        m.point_pressure = 0
+    return m, 2 * n * n
+
+
+def dof_keys_and_owner(pb: PB.HostProblem, n: int, world: int):
+    """Global key and owning rank of every unknown of a strip problem (unit cells of size 1/n, strips of height 1)."""
+    num, mesh, n_dof = pb.num, pb.mesh, pb.n_dof
+    keys = np.full(n_dof, -1, np.int64)
+    own = np.zeros(n_dof, np.int64)
+    for f, fld in enumerate(num.fields):
+        xyz = PB.dof_coordinates(mesh, num, fld, n_dof)
+        comp = PB.dof_components(num, fld, n_dof)
+        sel = comp >= 0
+        ix = np.rint(xyz[sel, 0] * 2 * n).astype(np.int64)
+        iy = np.rint(xyz[sel, 1] * 2 * n).astype(np.int64)
+        keys[sel] = ((f * 4 + comp[sel]) << 56) | (iy << 28) | ix
+        # strip r owns y in (r, r + 1]; the bottom line y = 0 belongs to rank 0
+        r = np.ceil(iy / (2.0 * n)).astype(np.int64) - 1
+        own[sel] = np.clip(r, 0, world - 1)
+    return keys[:pb.n_inc], own[:pb.n_inc]
+
+
+def build_halo(keys: np.ndarray, owner: np.ndarray, rank: int, world: int, allgather, owned_cells: int = 0) -> Partition:
+    """allgather(obj) -> list of every rank's obj (torch.distributed.all_gather_object or a test double)."""
+    owned = (owner == rank)
+    ghost = np.nonzero(~owned)[0]
+    need = {}
+    for r in np.unique(owner[ghost]):
+        idx = ghost[owner[ghost] == r]
+        order = np.argsort(keys[idx], kind="stable")
+        need[int(r)] = (keys[idx][order], idx[order])
+    everyone = allgather({r: k for r, (k, _) in need.items()})
+    own_idx = np.nonzero(owned)[0]
+    order = np.argsort(keys[own_idx], kind="stable")
+    own_keys, own_loc = keys[own_idx][order], own_idx[order]
+    nbrs = sorted(set(need) | {r for r, req in enumerate(everyone) if rank in req and r != rank})
+    send_ptr, recv_ptr, send_idx, recv_idx = [0], [0], [], []
+    for r in nbrs:
+        req = everyone[r].get(rank)
+        if req is not None and len(req):
+            pos = np.searchsorted(own_keys, req)
+            if (pos >= own_keys.size).any() or (own_keys[np.minimum(pos, own_keys.size - 1)] != req).any():
+                raise RuntimeError(f"rank {rank}: neighbour {r} asks for rows this rank does not own")
+            send_idx.append(own_loc[pos])
+        send_ptr.append(send_ptr[-1] + (0 if req is None else len(req)))
+        if r in need:
+            recv_idx.append(need[r][1])
+        recv_ptr.append(recv_ptr[-1] + (len(need[r][1]) if r in need else 0))
+    cat = lambda parts: np.concatenate(parts).astype(np.int32) if parts else np.zeros(0, np.int32)
+    return Partition(rank, world, owned.astype(np.uint8), keys, np.array(nbrs, np.int32), np.array(send_ptr, np.int64),
+                     cat(send_idx), np.array(recv_ptr, np.int64), cat(recv_idx), owned_cells)
+
+
+def strip_problem(n: int, rank: int, world: int, kind: str = "ns_div", quad_degree: int = 8, field_id: int = 1,
+                  mu: float = 1.0 / 40.0, rho: float = 1.0, allgather=None, build_pattern: bool = False,
+                  with_source: bool = False):
+    """(HostProblem, Partition) of strip `rank`."""
+    m, owned_cells = strip_mesh(n, rank, world)
+    pb = PB.taylor_hood(m, kind, quad_degree, field_id, mu, rho, build_pattern=build_pattern, with_source=with_source)
+    if world == 1:
+        return pb, None
+    keys, owner = dof_keys_and_owner(pb, n, world)
+    if allgather is None:
+        import torch.distributed as dist
+
+        def allgather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+    return pb, build_halo(keys, owner, rank, world, allgather, owned_cells)

@@ -185,6 +185,21 @@ int b200_get_solution(b200_system *s, double *sol);
 /* y = A x with the assembled matrix (parity checks of the SpMV kernel); n_inc doubles each */
 int b200_spmv(b200_system *s, const double *x, double *y);
 
+/* ---- multi-GPU (one process per GPU).  Elements are partitioned with one ghost layer, so the
+ *      assembly needs no exchange; every row is owned by exactly one rank.  The solve exchanges the ghost entries of
+ *      the SpMV input with the neighbours (ncclSend/ncclRecv) and all-reduces the Krylov dot products; norms returned by
+ *      b200_solve / b200_rhs_max_norm / b200_du_max_norm are global.  Replaces the replicated-mesh MPI scheme of the
+ *      reference (src/feLinearSystemPETSc.cpp:626-640, :1055). ---- */
+/* 128-byte NCCL unique id created on one rank and broadcast by the host (e.g. torch.distributed) */
+int b200_comm_unique_id(char *id128);
+int b200_comm_init(b200_system *s, const char *id128, int rank, int world);
+/* owned[n_inc]: 1 if this rank owns the row.  For neighbour k: this rank sends x[send_idx[send_ptr[k]..send_ptr[k+1])]
+ * and receives into x[recv_idx[recv_ptr[k]..recv_ptr[k+1])] (both sides list the shared rows in the same order). */
+int b200_set_halo(b200_system *s, const uint8_t *owned, int n_neighbors, const int32_t *neighbor_rank, const int64_t *send_ptr,
+                  const int32_t *send_idx, const int64_t *recv_ptr, const int32_t *recv_idx);
+/* ghost entries of a host vector (n_inc doubles) <- owner's values, through the device path (tests) */
+int b200_halo_exchange_host(b200_system *s, double *x);
+
 /* ---- measurement helpers (bench.py); device time in milliseconds of the last call, from CUDA events recorded on
  *      the system's own stream ---- */
 int b200_last_assemble_ms(const b200_system *s, float *ms);

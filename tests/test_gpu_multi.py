@@ -1,0 +1,21 @@
+"""NCCL path of the Newton linear solve on >= 2 GPUs of one node (skipped on a single-GPU box): halo exchange, owned-row
+dot products + all-reduce, distributed GMRES inside the Newton loop; see scripts/multi_gpu_check.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("world", [2])
+def test_distributed_newton_matches_single_gpu(world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "scripts", "multi_gpu_check.py"), "--n", "12"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MULTI_GPU_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
