@@ -87,16 +87,12 @@ class ClockSampler:
 
 
 def build_problem(workload, n, rank, world):
-    from feng_b200 import mesh as M, problems as PB
+    from feng_b200 import mesh as M, partition as PT, problems as PB
+    part = None
     if workload == "t2d":
         # strip r of the [0,1] x [0,world] domain: n x n owned cells plus one ghost row of cells towards each
-        # neighbour (owner-computes)
-        gb, gt = (1 if rank > 0 else 0), (1 if rank < world - 1 else 0)
-        ny = n + gb + gt
-        m = M.rect_mesh(n, ny, 1.0, ny / n, 0.0, rank - gb / n, cut_bottom=rank > 0, cut_top=rank < world - 1)
-        if rank == 0:
-            m.point_pressure = 0
-        pb = PB.taylor_hood(m, "ns_div", 8, 1, MU, RHO, build_pattern=False, with_source=False)
+        # neighbour (owner-computes); rows owned by one rank, halo plan for the SpMV input
+        pb, part = PT.strip_problem(n, rank, world, "ns_div", 8, 1, MU, RHO, build_pattern=False, with_source=False)
         owned = 2 * n * n
         name = f"T2D({n}) P2/P1 Navier-Stokes (convU+divU+divSigma), Kovasznay Re=40 + noise, quad deg 8 (16 pts)"
     else:
@@ -105,7 +101,7 @@ def build_problem(workload, n, rank, world):
         owned = m.n_cells
         name = f"T3D({n}) P2/P1 Navier-Stokes tetrahedra, quad deg 6 (24 pts)"
     sol = PB.perturb_unknowns(pb)
-    return pb, sol, owned, name
+    return pb, sol, owned, name, part
 
 
 def algorithmic_bytes_per_element(pb, nnz):
@@ -173,7 +169,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="t2d", choices=["t2d", "t3d"])
-    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--n", "--size", dest="n", type=int, default=0)
     ap.add_argument("--cpu-n", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--solve", action="store_true", help="also time one Newton step (assembly + GMRES)")
@@ -197,8 +193,8 @@ def main():
     from feng_b200 import capi
     from feng_b200.linear_system import LinearSystemB200
 
-    pb, sol, owned, wl_name = build_problem(args.workload, n, rank, world)
-    ls = LinearSystemB200(pb, device=local_rank, device_pattern=True)
+    pb, sol, owned, wl_name, part = build_problem(args.workload, n, rank, world)
+    ls = LinearSystemB200(pb, device=local_rank, device_pattern=True, partition=part)
     S = ls.sys
     if args.assembly != "auto":
         S.set_assembly_mode({"scatter": capi.ASSEMBLY_SCATTER, "gather": capi.ASSEMBLY_GATHER}[args.assembly])
@@ -289,7 +285,9 @@ def main():
                                     "no memset, no atomics") if gather else
                                    "quadrature-loop kernel + atomic (red.global.add.f64) scatter into precomputed CSR slots",
                        "cache": "inputs larger than L2 (CSR values written per pass = %.1f GB)" % (S.nnz * 8 / 1e9),
-                       "partition": "strips, owner-computes with one ghost layer" if world > 1 else "single GPU"},
+                       "partition": ("strips, owner-computes with one ghost layer of elements (no collective in assembly); "
+                                     "SpMV input halo over NCCL send/recv, Krylov dots all-reduced") if world > 1
+                       else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
                          "kernel": ("gather_u_kernel + gather_p_kernel (one assembly pass = 2 launches, timed together)"
