@@ -10,6 +10,7 @@
 // (k+2) Hessenberg entries; the Givens rotations run on the host.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "system.h"
@@ -33,6 +34,56 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t n, const int64_t *__r
 #pragma unroll
     for(int o = LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LPR);
     if(lane == 0) y[row] = s;
+  }
+}
+
+// Same product with RPG rows per lane group in flight: the value / column streams are read with streaming loads
+// (ld.global.cs, no reuse) and every lane keeps RPG independent load chains (val, ja -> x[ja]) outstanding, which is what
+// the r01a profile asked for (latency-bound at 39 % of DRAM peak with one chain per lane).
+template <int LPR, int RPG, bool CS>
+__global__ void __launch_bounds__(256) spmv_rpg_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
+                                                       const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+  const int     lane = threadIdx.x % LPR;
+  const int64_t g0   = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
+  const int64_t ng   = (gridDim.x * (int64_t)blockDim.x) / LPR;
+  for(int64_t row0 = g0 * RPG; row0 < n; row0 += ng * RPG) {
+    int64_t beg[RPG], end[RPG];
+#pragma unroll
+    for(int r = 0; r < RPG; ++r) {
+      const int64_t row = row0 + r;
+      beg[r] = row < n ? ia[row] : 0;
+      end[r] = row < n ? ia[row + 1] : 0;
+    }
+    double s[RPG];
+#pragma unroll
+    for(int r = 0; r < RPG; ++r) s[r] = 0.;
+    int64_t longest = 0;
+#pragma unroll
+    for(int r = 0; r < RPG; ++r) longest = max(longest, end[r] - beg[r]);
+    for(int64_t off = lane; off < longest; off += LPR) {
+      double  v[RPG];
+      int32_t c[RPG];
+#pragma unroll
+      for(int r = 0; r < RPG; ++r) {
+        const int64_t k  = beg[r] + off;
+        const bool    ok = k < end[r];
+        v[r] = ok ? (CS ? __ldcs(val + k) : val[k]) : 0.;
+        c[r] = ok ? (CS ? __ldcs(ja + k) : ja[k]) : 0;
+      }
+#pragma unroll
+      for(int r = 0; r < RPG; ++r) s[r] += v[r] * x[c[r]];
+    }
+#pragma unroll
+    for(int r = 0; r < RPG; ++r) {
+#pragma unroll
+      for(int o = LPR / 2; o > 0; o >>= 1) s[r] += __shfl_down_sync(0xffffffffu, s[r], o, LPR);
+    }
+    if(lane == 0) {
+#pragma unroll
+      for(int r = 0; r < RPG; ++r)
+        if(row0 + r < n) y[row0 + r] = s[r];
+    }
   }
 }
 
@@ -279,16 +330,22 @@ int spmv(System *S, const double *d_x, double *d_y)
 {
   const int64_t n   = S->nInc;
   const double  avg = n > 0 ? (double)S->nnz / (double)n : 0.;
-  if(avg > 48.) {
-    const int64_t blocks = (n * 32 + 255) / 256;
-    spmv_kernel<32><<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, S->stream>>>(n, S->d_ia, S->d_ja, S->d_val, d_x, d_y);
-  } else if(avg > 20.) {
-    const int64_t blocks = (n * 16 + 255) / 256;
-    spmv_kernel<16><<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, S->stream>>>(n, S->d_ia, S->d_ja, S->d_val, d_x, d_y);
-  } else {
-    const int64_t blocks = (n * 8 + 255) / 256;
-    spmv_kernel<8><<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, S->stream>>>(n, S->d_ia, S->d_ja, S->d_val, d_x, d_y);
+  // lanes per row / rows in flight per lane group picked on the B200 (profiles/README.md, r01c SpMV sweep): few lanes
+  // per row and two rows per group keep the most independent loads outstanding: 71 % (2-D) / 68 % (3-D) of the
+  // measured copy bandwidth against 49 % / 59 % for one 16- / 32-lane group per row
+#define B200_SPMV_V(L, R)                                                                                     \
+  {                                                                                                           \
+    const int64_t blocks = (n * L / R + 255) / 256;                                                           \
+    spmv_rpg_kernel<L, R, false><<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, S->stream>>>(   \
+      n, S->d_ia, S->d_ja, S->d_val, d_x, d_y);                                                               \
   }
+  if(avg > 48.)
+    B200_SPMV_V(8, 2)
+  else if(avg > 12.)
+    B200_SPMV_V(4, 2)
+  else
+    B200_SPMV_V(2, 2)
+#undef B200_SPMV_V
   count_launch();
   B200_CUDA(cudaGetLastError());
   return B200_OK;
