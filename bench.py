@@ -274,7 +274,8 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(args.workload)
+                per_elem = json.load(f).get(args.workload)      # measured DRAM bytes per element (ncu --set full)
+            traffic = per_elem * nE if per_elem else None       # per assembly pass, like `achieved`
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
