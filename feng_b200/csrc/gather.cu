@@ -26,6 +26,8 @@
 #include <thrust/sort.h>
 
 #include <cmath>
+#include <cstdlib>
+#include <string>
 
 #include "device_common.cuh"
 #include "system.h"
@@ -79,6 +81,9 @@ struct GatherPlan {
   double   E[120] = {0.};
   int      tab_len = 0, tab_len_src = 0;
   int      npbU = 0, npbP = 0;
+  int      lanes = 1;       // lanes per node of the lane-group kernels
+  bool     lane = true;     // lane-per-column kernels (gather_lane.cuh) or thread-per-node kernels (B200_GATHER_KERNEL=node)
+  double  *d_es = nullptr;  // [nElm][ES::W] per-element convective state, rewritten by every assembly pass
 };
 
 struct GatherArgs {
@@ -87,6 +92,7 @@ struct GatherArgs {
   const double   *sol, *soldot, *source, *tab, *geo;
   const int64_t  *ia;
   double         *val, *rhs;
+  const double   *es; // per-element state (lane kernels)
   const int32_t  *pair;
   const int2     *range;
   const int32_t  *row;
@@ -667,6 +673,39 @@ __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
   }
 }
 
+} // namespace b200
+#include "gather_lane.cuh"
+namespace b200 {
+
+// lanes per node -> (warps per CTA, register budget); the plan's nodes-per-CTA follows from it
+struct LaneCfg {
+  int L, NW;
+};
+static LaneCfg lane_cfg(int D, int L)
+{
+  if(D == 2) {
+    switch(L) {
+    case 1: return {1, 2};
+    case 2: return {2, 4};
+    case 3: return {3, 4};
+    default: return {6, 8};
+    }
+  }
+  switch(L) {
+  case 1: return {1, 1};
+  case 2: return {2, 2};
+  case 5: return {5, 4};
+  default: return {10, 4};
+  }
+}
+static int lane_default(int D)
+{
+  const char *k = getenv("B200_GATHER_LANES");
+  if(k) return atoi(k);
+  return D == 2 ? 1 : 10;
+}
+
+
 // ----------------------------------------------------------------------------------------------------------
 // plan construction (set-up)
 // ----------------------------------------------------------------------------------------------------------
@@ -828,7 +867,7 @@ __global__ void node_offsets_kernel(int32_t nNodes, int nRow, int nLoc, int offw
 }
 
 static int build_node_set(System *S, NodeSet &N, const int32_t *d_adr, int nLoc, int nF, int nRow, int npb, int offw, int ncol, int NU, int NP,
-                          int colmaskU, int colmaskP)
+                          int colmaskU, int colmaskP, double band = 1.25, int min_div = 50)
 {
   auto          pol = thrust::cuda::par.on(S->stream);
   const int64_t np  = S->nElm * (int64_t)nLoc;
@@ -901,8 +940,8 @@ static int build_node_set(System *S, NodeSet &N, const int32_t *d_adr, int nLoc,
       if(!last) {
         const uint32_t v = h_size[i];
         // cut where the size leaves the +-25 % band of the running segment (at most 8 segments, at least 64 CTAs each)
-        const bool cut = i > b + std::max(64, N.nCta / 50) && N.nCta - i > std::max(64, N.nCta / 50) && N.seg_smem.size() < 7 &&
-                         ((double)v > 1.25 * (double)std::max<uint32_t>(mn, 1u) || 1.25 * (double)v < (double)mx);
+        const bool cut = i > b + std::max(64, N.nCta / min_div) && N.nCta - i > std::max(64, N.nCta / min_div) && N.seg_smem.size() < 7 &&
+                         ((double)v > band * (double)std::max<uint32_t>(mn, 1u) || band * (double)v < (double)mx);
         if(!cut) {
           mx = std::max(mx, v);
           mn = std::min(mn, v);
@@ -1021,6 +1060,7 @@ void gather_free(System *S)
   G->P.release();
   cudaFree(G->d_tab);
   cudaFree(G->d_geo);
+  cudaFree(G->d_es);
   delete G;
   S->gather = nullptr;
 }
@@ -1053,9 +1093,26 @@ int build_gather_plan(System *S)
   }
   G->tab_len     = len_nosrc;
   G->tab_len_src = (int)tab.size();
-  G->npbU        = D == 2 ? 64 : 32;
-  G->npbP        = D == 2 ? 64 : 32;
+  {
+    // measured on the B200 (profiles/README.md, r01d): in 2-D the thread-per-node kernels that re-gather the solution
+    // from the L2-resident state vector win (the per-element state is 512 B/element of extra HBM traffic); in 3-D the
+    // lane-group kernels win 2.3x (the row images of one node are 2-5 KB, one thread per node leaves the SM empty)
+    const char *k = getenv("B200_GATHER_KERNEL");
+    G->lane       = k ? std::string(k) == "lane" : D == 3;
+  }
+  if(G->lane) {
+    const LaneCfg lc = lane_cfg(D, lane_default(D));
+    G->lanes         = lc.L;
+    G->npbU = G->npbP = lc.NW * (32 / lc.L);
+  } else {
+    G->npbU = D == 2 ? 64 : 32;
+    G->npbP = D == 2 ? 64 : 32;
+  }
   try {
+    if(G->lane) {
+      const size_t esw = (size_t)(NP * D * D + NS * NS + NS * D + NP + 1) / 2 * 2; // ES<D,NS,NP>::W
+      B200_CUDA(cudaMalloc(&G->d_es, (size_t)S->nElm * esw * sizeof(double)));
+    }
     B200_CUDA(cudaMalloc(&G->d_tab, tab.size() * sizeof(double)));
     B200_CUDA(cudaMemcpyAsync(G->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, S->stream));
     B200_CUDA(cudaMalloc(&G->d_geo, (size_t)S->nElm * ((D * D + 2) / 2 * 2) * sizeof(double)));
@@ -1066,10 +1123,14 @@ int build_gather_plan(System *S)
     count_launch();
     B200_CUDA(cudaStreamSynchronize(S->stream));
     const int offwU = (M + 7) / 8 * 8, offwP = (NU + 7) / 8 * 8;
+    // lane-group kernels are not limited by the shared memory of the longest rows: few, large launch segments
+    const double band    = (G->lane && G->lanes > 1) ? 1.6 : 1.25;
+    const int    min_div = (G->lane && G->lanes > 1) ? 12 : 50;
     int       rc = build_node_set(S, G->U, S->spaces[S->su].d_adr, NS, NU, D, G->npbU, offwU, M, NU, NP, S->has_matrix_block[0][0] ? 1 : 0,
-                                  S->has_matrix_block[0][1] ? 1 : 0);
+                                  S->has_matrix_block[0][1] ? 1 : 0, band, min_div);
     if(rc == B200_OK)
-      rc = build_node_set(S, G->P, S->spaces[S->sp].d_adr, NP, NP, 1, G->npbP, offwP, NU, NU, NP, S->has_matrix_block[1][0] ? 1 : 0, 0);
+      rc = build_node_set(S, G->P, S->spaces[S->sp].d_adr, NP, NP, 1, G->npbP, offwP, NU, NU, NP, S->has_matrix_block[1][0] ? 1 : 0, 0, band,
+                          min_div);
     if(rc != B200_OK) {
       gather_free(S);
       return rc;
@@ -1174,9 +1235,129 @@ template <int D, int NS, int NP, int NPB> static int launch_gather_t(System *S, 
   return B200_OK;
 }
 
+// lane-group kernels: element-state pre-pass, then one launch per (node set, launch segment)
+template <int D, int NS, int NP, int NW, int L, int REGS> static int launch_gather_lane_t(System *S, int what, const THCoeffs &c)
+{
+  GatherPlan *G = static_cast<GatherPlan *>(S->gather);
+  using X = ES<D, NS, NP>;
+  using T = GT<D, NS, NP>;
+  constexpr int NT = NW * 32, MINB = 65536 / (NT * REGS) > 0 ? 65536 / (NT * REGS) : 1;
+  const double *d_source = (c.c_src != 0.) ? S->d_source : nullptr;
+  const int     ntab     = d_source ? G->tab_len_src : G->tab_len;
+  {
+    ElementStateArgs ea;
+    ea.nElm   = S->nElm;
+    ea.adrU   = S->spaces[S->su].d_adr;
+    ea.adrP   = S->spaces[S->sp].d_adr;
+    ea.sol    = S->d_sol;
+    ea.soldot = S->have_soldot ? S->d_soldot : nullptr;
+    ea.source = d_source;
+    ea.geo    = G->d_geo;
+    ea.tab    = G->d_tab;
+    ea.es     = G->d_es;
+    ea.nq     = S->nq;
+    ea.ntab   = ntab;
+    ea.c      = c;
+    for(int i = 0; i < 120; ++i) ea.E[i] = G->E[i];
+    static_assert(X::W % 2 == 0, "element state records must be 16-byte aligned");
+    const size_t smem = (size_t)(ntab - T::O_T3) * sizeof(double);
+    B200_CUDA(cudaFuncSetAttribute(element_state_kernel<D, NS, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    element_state_kernel<D, NS, NP><<<(unsigned)((S->nElm + 127) / 128), 128, smem, S->stream>>>(ea);
+    count_launch();
+  }
+  GatherArgs a;
+  a.xyz    = S->d_xyz;
+  a.conn   = S->d_conn;
+  a.adrU   = S->spaces[S->su].d_adr;
+  a.adrP   = S->spaces[S->sp].d_adr;
+  a.sol    = S->d_sol;
+  a.soldot = S->have_soldot ? S->d_soldot : nullptr;
+  a.source = d_source;
+  a.tab    = G->d_tab;
+  a.geo    = G->d_geo;
+  a.es     = G->d_es;
+  a.ia     = S->d_ia;
+  a.val    = S->d_val;
+  a.rhs    = S->d_rhs;
+  a.nInc   = S->nInc;
+  a.nq     = S->nq;
+  a.ntab   = G->tab_len; // the W table (sources) is only used by the pre-pass
+  a.c      = c;
+  a.c0     = S->c0;
+  for(int i = 0; i < 120; ++i) a.E[i] = G->E[i];
+  const bool mat = what & 2;
+  for(int pass = 0; pass < 2; ++pass) {
+    const NodeSet &N = pass == 0 ? G->U : G->P;
+    if(N.nNodes == 0) continue;
+    a.pair     = N.pair;
+    a.range    = N.range;
+    a.row      = N.row;
+    a.smoff    = N.smoff;
+    a.cta_size = N.cta_size;
+    a.off      = N.off;
+    a.nNodes   = N.nNodes;
+    a.cta_g0   = N.cta_g0;
+    if(!mat) {
+      // residual only: sum of the per-element contributions, one thread per node
+      a.cta0 = 0;
+      const int nc = (N.nNodes + 255) / 256;
+      if(pass == 0)
+        gather_lane_kernel<D, NS, NP, 8, 1, 1, false, true, false><<<nc, 256, 0, S->stream>>>(a);
+      else
+        gather_lane_kernel<D, NS, NP, 8, 1, 1, false, true, true><<<nc, 256, 0, S->stream>>>(a);
+      count_launch();
+      continue;
+    }
+    const size_t smem_max = ((size_t)a.ntab + N.max_cta + NT) * sizeof(double);
+    const int    nseg     = (int)N.seg_smem.size();
+#define B200_LAUNCH_L(KERN)                                                                                                              \
+  do {                                                                                                                                   \
+    B200_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));                                   \
+    for(int sg = 0; sg < nseg; ++sg) {                                                                                                   \
+      a.cta0            = N.seg_begin[sg];                                                                                               \
+      const int    nc   = N.seg_begin[sg + 1] - N.seg_begin[sg];                                                                         \
+      const size_t smem = ((size_t)a.ntab + N.seg_smem[sg] + NT) * sizeof(double);                                                       \
+      KERN<<<nc, NT, smem, S->stream>>>(a);                                                                                              \
+      count_launch();                                                                                                                    \
+    }                                                                                                                                    \
+  } while(0)
+    if(pass == 0) {
+      if(what == 3)
+        B200_LAUNCH_L((gather_lane_kernel<D, NS, NP, NW, L, MINB, true, true, false>));
+      else
+        B200_LAUNCH_L((gather_lane_kernel<D, NS, NP, NW, L, MINB, true, false, false>));
+    } else {
+      if(what == 3)
+        B200_LAUNCH_L((gather_lane_kernel<D, NS, NP, NW, L, MINB, true, true, true>));
+      else
+        B200_LAUNCH_L((gather_lane_kernel<D, NS, NP, NW, L, MINB, true, false, true>));
+    }
+#undef B200_LAUNCH_L
+  }
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
 // what: bit 0 residual, bit 1 matrix; OVERWRITES val / rhs (every row is written exactly once)
 int launch_gather(System *S, int what, const THCoeffs &c)
 {
+  const GatherPlan *G = static_cast<const GatherPlan *>(S->gather);
+  if(G->lane) {
+    if(S->dim == 2) {
+      switch(G->lanes) {
+      case 1: return launch_gather_lane_t<2, 6, 3, 2, 1, 96>(S, what, c);
+      case 2: return launch_gather_lane_t<2, 6, 3, 4, 2, 96>(S, what, c);
+      case 3: return launch_gather_lane_t<2, 6, 3, 4, 3, 96>(S, what, c);
+      default: return launch_gather_lane_t<2, 6, 3, 8, 6, 80>(S, what, c);
+      }
+    }
+    switch(G->lanes) {
+    case 1: return launch_gather_lane_t<3, 10, 4, 1, 1, 168>(S, what, c);
+    case 2: return launch_gather_lane_t<3, 10, 4, 2, 2, 128>(S, what, c);
+    case 5: return launch_gather_lane_t<3, 10, 4, 4, 5, 128>(S, what, c);
+    default: return launch_gather_lane_t<3, 10, 4, 4, 10, 128>(S, what, c);
+    }
+  }
   if(S->dim == 2) return launch_gather_t<2, 6, 3, 64>(S, what, c);
   return launch_gather_t<3, 10, 4, 32>(S, what, c);
 }
