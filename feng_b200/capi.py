@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libfeng_b200.so")
 SYMBOLS = [
     "b200_last_error", "b200_kernel_launches", "b200_reset_kernel_launches", "b200_create", "b200_destroy",
     "b200_set_mesh", "b200_set_quadrature", "b200_add_space", "b200_add_form", "b200_set_source", "b200_set_pattern",
-    "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode", "b200_set_assembly_mode", "b200_has_gather_plan",
+    "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode", "b200_set_assembly_mode", "b200_has_gather_plan", "b200_add_form_chns",
     "b200_set_constraints", "b200_set_blocks", "b200_finalize", "b200_system_size", "b200_set_solution",
     "b200_set_to_zero", "b200_assemble", "b200_rhs_max_norm", "b200_du_max_norm", "b200_constrain",
     "b200_apply_periodicity", "b200_solve", "b200_correct_solution", "b200_get_rhs", "b200_axpy_rhs",
@@ -34,6 +34,18 @@ PC_NONE, PC_JACOBI, PC_BLOCK_JACOBI, PC_ILU0 = 0, 1, 2, 3
 class SolverOptions(C.Structure):
     _fields_ = [("rel_tol", C.c_double), ("abs_tol", C.c_double), ("div_tol", C.c_double), ("max_iter", C.c_int),
                 ("restart", C.c_int), ("pc", C.c_int)]
+
+
+class ChnsParams(C.Structure):
+    """b200_chns_params (include/feng_b200.h)"""
+    _fields_ = [("rho_a", C.c_double), ("rho_b", C.c_double), ("visc_a", C.c_double), ("visc_b", C.c_double),
+                ("mobility", C.c_double), ("surface_tension", C.c_double), ("epsilon", C.c_double),
+                ("force", C.c_double * 3), ("source_u", C.c_double * 3), ("source_p", C.c_double),
+                ("source_phi", C.c_double), ("source_mu", C.c_double), ("limiter", C.c_int),
+                ("degenerate_mobility", C.c_int)]
+
+
+FORM_CHNS_ABELS = 35
 
 
 class SolveInfo(C.Structure):
@@ -135,6 +147,14 @@ class System:
         src = None if source is None else np.ascontiguousarray(source, np.float64)
         return check(self.L.b200_add_form(self.h, kind, su, sp, C.c_double(coeff), C.c_double(param), _d(src)),
                      "b200_add_form")
+
+    def add_form_chns(self, su, sp, sf, sm, model, kind=FORM_CHNS_ABELS):
+        """model: any object with the attributes of feng_b200.problems.ChnsModel"""
+        prm = ChnsParams(model.rhoA, model.rhoB, model.viscA, model.viscB, model.mobility, model.sigma, model.epsilon,
+                         (C.c_double * 3)(model.force[0], model.force[1], 0.0),
+                         (C.c_double * 3)(model.src_u[0], model.src_u[1], 0.0), model.src_p, model.src_phi,
+                         model.src_mu, int(model.limiter), int(model.degenerate_mobility))
+        return check(self.L.b200_add_form_chns(self.h, kind, su, sp, sf, sm, C.byref(prm)), "b200_add_form_chns")
 
     def set_source(self, form_id, source):
         src = np.ascontiguousarray(source, np.float64)

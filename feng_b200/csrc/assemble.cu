@@ -499,6 +499,11 @@ int analyze_forms(System *S)
     set_error("b200_finalize: only straight triangles / tetrahedra are supported");
     return B200_ERR_UNSUPP;
   }
+  if(S->chns_active) {
+    for(int bi = 0; bi < 2; ++bi)
+      for(int bj = 0; bj < 2; ++bj) S->has_matrix_block[bi][bj] = false;
+    return chns_analyze(S);
+  }
   bool all_scalar = true, any_scalar = false;
   for(auto &f : S->forms) {
     if(is_scalar_kind(f.kind))
@@ -638,6 +643,14 @@ int build_plan(System *S)
   const int arc = analyze_forms(S);
   if(arc != B200_OK) return arc;
 
+  if(S->plan == PLAN_CHNS) {
+    gather_free(S);
+    if(S->assembly_mode == B200_ASSEMBLY_GATHER) {
+      set_error("b200_finalize: the gather assembly needs the fused Taylor-Hood system");
+      return B200_ERR_UNSUPP;
+    }
+    return chns_build_plan(S);
+  }
   // packed tables: w | LU | dLU | LP
   {
     const Space        &U = S->spaces[S->su];
@@ -806,6 +819,11 @@ int launch_assemble(System *S, int what, int only_transient)
   {
     const int zrc = flush_zero(S, 3);
     if(zrc != B200_OK) return zrc;
+  }
+  if(S->plan == PLAN_CHNS) {
+    // the monolithic form is not a "transient matrix" form (feBilinearForm::isTransientMatrix is false for it)
+    if(only_transient) what &= ~2;
+    return what ? chns_launch(S, what) : B200_OK;
   }
   if(only_transient && (what & 2)) {
     // transient-only matrix and full residual cannot share coefficients: two passes

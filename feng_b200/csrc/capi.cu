@@ -90,6 +90,7 @@ static void free_system(System *S)
   cudaSetDevice(S->device);
   krylov_free(S);
   gather_free(S);
+  chns_free(S);
   comm_free(S);
   for(auto &sp : S->spaces) cudaFree(sp.d_adr);
   for(auto &f : S->forms) cudaFree(f.d_source);
@@ -295,6 +296,33 @@ int b200_add_form(b200_system *s, int kind, int space_u, int space_p, double coe
     B200_CUDA(cudaMemcpy(f.d_source, scaled.data(), count * sizeof(double), cudaMemcpyHostToDevice));
   }
   s->forms.push_back(f);
+  s->plan = PLAN_NONE;
+  return (int)s->forms.size() - 1;
+}
+
+int b200_add_form_chns(b200_system *s, int kind, int space_u, int space_p, int space_phi, int space_mu, const b200_chns_params *params)
+{
+  CHECK_S(s);
+  const int ns = (int)s->spaces.size();
+  const int sp[4] = {space_u, space_p, space_phi, space_mu};
+  for(int k = 0; k < 4; ++k)
+    if(sp[k] < 0 || sp[k] >= ns) {
+      set_error("b200_add_form_chns: unknown space id");
+      return B200_ERR_ARG;
+    }
+  if(kind != B200_FORM_CHNS_ABELS || !params) {
+    set_error("b200_add_form_chns: only B200_FORM_CHNS_ABELS is built (the other CHNS formulations are not)");
+    return B200_ERR_UNSUPP;
+  }
+  Form f;
+  f.kind = kind;
+  f.su   = space_u;
+  f.sp   = space_p;
+  s->forms.push_back(f);
+  s->chns_active = true;
+  for(int k = 0; k < 4; ++k) s->chns_space[k] = sp[k];
+  s->chns_prm = *params;
+  chns_free(s);
   s->plan = PLAN_NONE;
   return (int)s->forms.size() - 1;
 }

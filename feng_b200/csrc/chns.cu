@@ -1,0 +1,378 @@
+// Monolithic Cahn-Hilliard Navier-Stokes weak form with finite-difference Jacobian.
+//
+// Reference: CHNS_Abels<2>::computeBe (src/feSysElmCHNS.cpp:66-273) evaluated N+1 times per element by
+// feBilinearForm::computeMatrixFiniteDifference (src/feBilinearForm.cpp:388-428), one weak form on the fields
+// [U (vector P2), P (P1), Phi, Mu (P1 or P2)] (layout src/feSysElmCHNS.cpp:13-14), property laws of CHNS_Solver
+// (src/CHNS_Solver.cpp:124-235) as enums instead of host callbacks.
+//
+// GPU organisation: ONE WARP PER ELEMENT.  Lane j < N carries the residual of the state perturbed in local column j,
+// lane N the unperturbed residual R0, so the N+1 residual evaluations of the reference run side by side and the
+// Jacobian column is -(Rh - R0)/delta after one shuffle broadcast of R0.  The interpolated fields at a quadrature
+// node are linear in the local DOFs: they are computed once per element (lane k <-> node k) and every lane adds
+// delta x (its own basis function) to them.  The quadrature tables live in shared memory.  Local entries are added
+// to the CSR arrays with red.global.add.f64 after a binary search of the column in the row (the reference scans the
+// row, src/feLinearSystemMklPardiso.cpp:648-658).
+#include <cfloat>
+#include <cmath>
+
+#include "device_common.cuh"
+#include "system.h"
+
+namespace b200 {
+
+struct ChnsArgs {
+  int64_t         nElm;
+  const double   *xyz;
+  const int32_t  *conn, *adr; // adr: [nElm][M] local DOFs in field order U | P | Phi | Mu
+  const double   *sol, *soldot, *tab;
+  const int64_t  *ia;
+  const int32_t  *ja;
+  double         *val, *rhs;
+  int64_t         nInc;
+  int             nq, ntab, what;
+  double          c0, h0;
+  b200_chns_params prm;
+};
+
+constexpr int CHNS_NSU = 6, CHNS_NSP = 3, CHNS_WPB = 4, CHNS_NFLD = 16;
+
+template <int NSF> struct ChnsT {
+  static constexpr int NU = CHNS_NSU * 2, M = NU + CHNS_NSP + 2 * NSF;
+  // table layout (doubles): w[nq] | LU[nq][6] | dLU[nq][6][2] | LP[nq][3] | LF[nq][NSF] | dLF[nq][NSF][2]
+  __host__ __device__ static int o_lu(int nq) { return nq; }
+  __host__ __device__ static int o_dlu(int nq) { return nq + nq * CHNS_NSU; }
+  __host__ __device__ static int o_lp(int nq) { return nq + nq * CHNS_NSU * 3; }
+  __host__ __device__ static int o_lf(int nq) { return nq + nq * CHNS_NSU * 3 + nq * CHNS_NSP; }
+  __host__ __device__ static int o_dlf(int nq) { return nq + nq * CHNS_NSU * 3 + nq * CHNS_NSP + nq * NSF; }
+  __host__ __device__ static int len(int nq) { return nq + nq * CHNS_NSU * 3 + nq * CHNS_NSP + nq * NSF * 3; }
+};
+
+template <int NSF> __global__ void __launch_bounds__(CHNS_WPB * 32) chns_kernel(const ChnsArgs a)
+{
+  using T = ChnsT<NSF>;
+  constexpr int M = T::M, NU = T::NU, NSU = CHNS_NSU, NSP = CHNS_NSP;
+  static_assert(M + 1 <= 32, "one lane per local column plus the base lane");
+  extern __shared__ double sm[];
+  double *s_tab = sm;                                    // ntab
+  double *s_loc = s_tab + a.ntab;                        // [WPB][M]
+  double *s_dot = s_loc + CHNS_WPB * M;                  // [WPB][M]
+  double *s_fld = s_dot + CHNS_WPB * M;                  // [WPB][nq][NFLD]
+  int32_t *s_adr = reinterpret_cast<int32_t *>(s_fld + (size_t)CHNS_WPB * a.nq * CHNS_NFLD); // [WPB][M]
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nq = a.nq;
+  for(int i = tid; i < a.ntab; i += CHNS_WPB * 32) s_tab[i] = a.tab[i];
+  __syncthreads();
+  const int64_t e = blockIdx.x * (int64_t)CHNS_WPB + wid;
+  if(e >= a.nElm) return;
+  const double *w = s_tab, *LU = s_tab + T::o_lu(nq), *dLU = s_tab + T::o_dlu(nq), *LP = s_tab + T::o_lp(nq), *LF = s_tab + T::o_lf(nq),
+               *dLF = s_tab + T::o_dlf(nq);
+  double  *loc = s_loc + wid * M, *dot = s_dot + wid * M, *fld = s_fld + (size_t)wid * nq * CHNS_NFLD;
+  int32_t *adr = s_adr + wid * M;
+  for(int i = lane; i < M; i += 32) {
+    const int32_t d = a.adr[e * M + i];
+    adr[i] = d;
+    loc[i] = a.sol[d];
+    dot[i] = a.soldot ? a.soldot[d] : 0.;
+  }
+  double G[4], J;
+  {
+    int32_t vtx[3];
+#pragma unroll
+    for(int v = 0; v < 3; ++v) vtx[v] = a.conn[e * 3 + v];
+    element_geometry<2>(a.xyz, vtx, G, &J);
+  }
+  __syncwarp();
+  const double *Ul = loc, *Pl = loc + NU, *Fl = loc + NU + NSP, *Ml = loc + NU + NSP + NSF;
+  const double *Ud = dot, *Fd = dot + NU + NSP;
+  // ---- unperturbed fields at the quadrature nodes (lane k <-> node k):
+  // fld = {u0,u1,p,phi,mu,dudt0,dudt1,dphidt, gu[m][n] (4, d_m u_n, src/feSpace.cpp:1391-1394), gphi[2], gmu[2]}
+  for(int k = lane; k < nq; k += 32) {
+    double f[CHNS_NFLD];
+#pragma unroll
+    for(int i = 0; i < CHNS_NFLD; ++i) f[i] = 0.;
+    for(int b = 0; b < NSU; ++b) {
+      const double L = LU[k * NSU + b], dr = dLU[(k * NSU + b) * 2], ds = dLU[(k * NSU + b) * 2 + 1];
+      const double gx = dr * G[0] + ds * G[2], gy = dr * G[1] + ds * G[3];
+      f[0] += L * Ul[b * 2];
+      f[1] += L * Ul[b * 2 + 1];
+      f[5] += L * Ud[b * 2];
+      f[6] += L * Ud[b * 2 + 1];
+      f[8] += gx * Ul[b * 2];      // d_x u_0
+      f[9] += gx * Ul[b * 2 + 1];  // d_x u_1
+      f[10] += gy * Ul[b * 2];     // d_y u_0
+      f[11] += gy * Ul[b * 2 + 1]; // d_y u_1
+    }
+    for(int q = 0; q < NSP; ++q) f[2] += LP[k * NSP + q] * Pl[q];
+    for(int i = 0; i < NSF; ++i) {
+      const double L = LF[k * NSF + i], dr = dLF[(k * NSF + i) * 2], ds = dLF[(k * NSF + i) * 2 + 1];
+      const double gx = dr * G[0] + ds * G[2], gy = dr * G[1] + ds * G[3];
+      f[3] += L * Fl[i];
+      f[7] += L * Fd[i];
+      f[12] += gx * Fl[i];
+      f[13] += gy * Fl[i];
+      f[4] += L * Ml[i];
+      f[14] += gx * Ml[i];
+      f[15] += gy * Ml[i];
+    }
+#pragma unroll
+    for(int i = 0; i < CHNS_NFLD; ++i) fld[k * CHNS_NFLD + i] = f[i];
+  }
+  __syncwarp();
+
+  // ---- my perturbation: delta = h0 max(|u_j|, 1), solDot += delta c0 (src/feBilinearForm.cpp:404-410)
+  const int  j      = lane;
+  const bool column = j < M;
+  const bool active = (column && (a.what & 2)) || j == M;
+  double     delta = 0.;
+  if(column) delta = a.h0 * fmax(fabs(loc[j]), 1.);
+  double du0 = 0., du1 = 0., dp = 0., dphi = 0., dmu = 0.;
+  int    aU = 0, qP = 0, iF = 0, iM = 0;
+  if(j < NU) {
+    aU = j >> 1;
+    if(j & 1)
+      du1 = delta;
+    else
+      du0 = delta;
+  } else if(j < NU + NSP) {
+    qP = j - NU;
+    dp = delta;
+  } else if(j < NU + NSP + NSF) {
+    iF   = j - NU - NSP;
+    dphi = delta;
+  } else if(j < M) {
+    iM  = j - NU - NSP - NSF;
+    dmu = delta;
+  }
+  double R[M];
+#pragma unroll
+  for(int i = 0; i < M; ++i) R[i] = 0.;
+  const b200_chns_params pr  = a.prm;
+  const double           lam = 3. / (2. * sqrt(2.)) * pr.surface_tension * pr.epsilon; // src/feSysElm.h:1338
+  const double           dw  = lam / (pr.epsilon * pr.epsilon);
+  const double           drho = (pr.rho_a - pr.rho_b) * 0.5;
+
+  if(active) {
+    for(int k = 0; k < nq; ++k) {
+      const double jw = J * w[k];
+      const double *f = fld + k * CHNS_NFLD;
+      double u0 = f[0], u1 = f[1], p = f[2], phi = f[3], mu = f[4], dt0 = f[5], dt1 = f[6], dphidt = f[7];
+      double gu00 = f[8], gu01 = f[9], gu10 = f[10], gu11 = f[11], gp0 = f[12], gp1 = f[13], gm0 = f[14], gm1 = f[15];
+      // test functions and their physical gradients at this node
+      double lu[NSU], gux[NSU], guy[NSU], lf[NSF], gfx[NSF], gfy[NSF];
+#pragma unroll
+      for(int b = 0; b < NSU; ++b) {
+        const double dr = dLU[(k * NSU + b) * 2], ds = dLU[(k * NSU + b) * 2 + 1];
+        lu[b]  = LU[k * NSU + b];
+        gux[b] = dr * G[0] + ds * G[2];
+        guy[b] = dr * G[1] + ds * G[3];
+      }
+#pragma unroll
+      for(int i = 0; i < NSF; ++i) {
+        const double dr = dLF[(k * NSF + i) * 2], ds = dLF[(k * NSF + i) * 2 + 1];
+        lf[i]  = LF[k * NSF + i];
+        gfx[i] = dr * G[0] + ds * G[2];
+        gfy[i] = dr * G[1] + ds * G[3];
+      }
+      // perturbed fields: linear in the local DOFs
+      {
+        const double L = LU[k * NSU + aU], dr = dLU[(k * NSU + aU) * 2], ds = dLU[(k * NSU + aU) * 2 + 1];
+        const double gx = dr * G[0] + ds * G[2], gy = dr * G[1] + ds * G[3];
+        u0 += du0 * L;
+        u1 += du1 * L;
+        dt0 += du0 * a.c0 * L;
+        dt1 += du1 * a.c0 * L;
+        gu00 += du0 * gx;
+        gu01 += du1 * gx;
+        gu10 += du0 * gy;
+        gu11 += du1 * gy;
+        p += dp * LP[k * NSP + qP];
+        const double Lf = LF[k * NSF + iF], fr = dLF[(k * NSF + iF) * 2], fs = dLF[(k * NSF + iF) * 2 + 1];
+        phi += dphi * Lf;
+        dphidt += dphi * a.c0 * Lf;
+        gp0 += dphi * (fr * G[0] + fs * G[2]);
+        gp1 += dphi * (fr * G[1] + fs * G[3]);
+        const double Lm = LF[k * NSF + iM], mr = dLF[(k * NSF + iM) * 2], ms = dLF[(k * NSF + iM) * 2 + 1];
+        mu += dmu * Lm;
+        gm0 += dmu * (mr * G[0] + ms * G[2]);
+        gm1 += dmu * (mr * G[1] + ms * G[3]);
+      }
+      // property laws (src/CHNS_Solver.cpp:124-235)
+      const double pc  = pr.limiter ? fmax(-1., fmin(1., phi)) : phi;
+      const double rho = drho * pc + (pr.rho_a + pr.rho_b) * 0.5;
+      const double eta = (pr.visc_a - pr.visc_b) * 0.5 * pc + (pr.visc_a + pr.visc_b) * 0.5;
+      const double Mob = pr.degenerate_mobility ? pr.mobility * fabs(1. - phi * phi) : pr.mobility;
+      // src/feSysElmCHNS.cpp:158-171
+      const double ugu0 = u0 * gu00 + u1 * gu10, ugu1 = u0 * gu01 + u1 * gu11;
+      const double gmgu0 = gm0 * gu00 + gm1 * gu10, gmgu1 = gm0 * gu01 + gm1 * gu11;
+      const double S00 = gu00 + gu00, S01 = gu01 + gu10, S11 = gu11 + gu11;
+      const double divu = gu00 + gu11, ugphi = u0 * gp0 + u1 * gp1;
+      // momentum (:192-219): test function i = 2a + c is phi_a e_c
+      const double v0 = rho * (dt0 + ugu0 - pr.force[0]) - drho * Mob * gmgu0 + phi * gm0 + pr.source_u[0];
+      const double v1 = rho * (dt1 + ugu1 - pr.force[1]) - drho * Mob * gmgu1 + phi * gm1 + pr.source_u[1];
+#pragma unroll
+      for(int b = 0; b < NSU; ++b) {
+        R[2 * b] -= jw * (v0 * lu[b] - p * gux[b] + eta * (gux[b] * S00 + guy[b] * S01));
+        R[2 * b + 1] -= jw * (v1 * lu[b] - p * guy[b] + eta * (gux[b] * S01 + guy[b] * S11));
+      }
+      // continuity (:224-227)
+#pragma unroll
+      for(int q = 0; q < NSP; ++q) R[NU + q] -= jw * (divu + pr.source_p) * LP[k * NSP + q];
+      // tracer (:232-250) and potential (:255-271)
+      const double tf = dphidt + ugphi + pr.source_phi;
+      const double tm = mu - dw * phi * (phi * phi - 1.) + pr.source_mu;
+#pragma unroll
+      for(int i = 0; i < NSF; ++i) {
+        R[NU + NSP + i] -= jw * (tf * lf[i] + Mob * (gm0 * gfx[i] + gm1 * gfy[i]));
+        R[NU + NSP + NSF + i] -= jw * (tm * lf[i] - lam * (gp0 * gfx[i] + gp1 * gfy[i]));
+      }
+    }
+  }
+  // ---- Jacobian column: Ae[i][j] = -(Rh[i] - R0[i]) / delta (src/feBilinearForm.cpp:419-422); residual = R0
+  const double inv = column ? 1. / delta : 0.;
+  const int32_t J_ = column ? adr[j] : 0x7fffffff;
+#pragma unroll
+  for(int i = 0; i < M; ++i) {
+    const double  r0 = __shfl_sync(0xffffffffu, R[i], M);
+    const int32_t I  = adr[i];
+    if(I >= a.nInc) continue;
+    if(j == M && (a.what & 1)) atomicAdd(a.rhs + I, r0);
+    if(column && (a.what & 2) && J_ < a.nInc) {
+      const double v  = -(R[i] - r0) * inv;
+      int64_t      lo = a.ia[I], hi = a.ia[I + 1] - 1;
+      while(lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if(a.ja[mid] < J_)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      if(a.ja[lo] == J_) atomicAdd(a.val + lo, v);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------------
+__global__ void chns_concat_adr_kernel(int64_t nElm, int M, int n0, int n1, int n2, int n3, const int32_t *a0, const int32_t *a1, const int32_t *a2,
+                                       const int32_t *a3, int32_t *out)
+{
+  const int64_t tot = nElm * M;
+  for(int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = idx / M;
+    int           i = (int)(idx - e * M);
+    int32_t       v;
+    if(i < n0)
+      v = a0[e * n0 + i];
+    else if((i -= n0) < n1)
+      v = a1[e * n1 + i];
+    else if((i -= n1) < n2)
+      v = a2[e * n2 + i];
+    else
+      v = a3[e * n3 + (i - n2)];
+    out[idx] = v;
+  }
+}
+
+void chns_free(System *S)
+{
+  cudaFree(S->chns_adr);
+  cudaFree(S->chns_tab);
+  S->chns_adr = nullptr;
+  S->chns_tab = nullptr;
+}
+
+// Validates the CHNS registration and builds the concatenated element->DOF table (also used by the pattern builder).
+int chns_analyze(System *S)
+{
+  if(S->dim != 2) {
+    set_error("CHNS weak forms exist for dim = 2 only (src/feSysElmCHNS.cpp:275)");
+    return B200_ERR_UNSUPP;
+  }
+  if(S->forms.size() != 1) {
+    set_error("the CHNS weak form is monolithic: it must be the only form of the system");
+    return B200_ERR_UNSUPP;
+  }
+  const Space &U = S->spaces[S->chns_space[0]], &P = S->spaces[S->chns_space[1]], &F = S->spaces[S->chns_space[2]],
+              &Mu = S->spaces[S->chns_space[3]];
+  if(U.nS != CHNS_NSU || U.nc != 2 || P.nS != CHNS_NSP || P.nc != 1 || F.nc != 1 || Mu.nc != 1 || F.nS != Mu.nS || (F.nS != 3 && F.nS != 6)) {
+    set_error("CHNS kernel: U must be vector P2, P scalar P1, Phi and Mu the same scalar P1 or P2 space");
+    return B200_ERR_UNSUPP;
+  }
+  S->plan = PLAN_CHNS;
+  S->su   = S->chns_space[0];
+  S->sp   = S->chns_space[1];
+  S->M    = U.nS * 2 + P.nS + 2 * F.nS;
+  S->has_matrix_block[0][0] = true;
+  if(S->chns_adr == nullptr) {
+    B200_CUDA(cudaMalloc(&S->chns_adr, (size_t)S->nElm * S->M * sizeof(int32_t)));
+    chns_concat_adr_kernel<<<148 * 8, 256, 0, S->stream>>>(S->nElm, S->M, U.nS * 2, P.nS, F.nS, Mu.nS, U.d_adr, P.d_adr, F.d_adr, Mu.d_adr,
+                                                          S->chns_adr);
+    count_launch();
+    B200_CUDA(cudaGetLastError());
+  }
+  return B200_OK;
+}
+
+int chns_build_plan(System *S)
+{
+  const Space &U = S->spaces[S->chns_space[0]], &P = S->spaces[S->chns_space[1]], &F = S->spaces[S->chns_space[2]];
+  std::vector<double> tab(S->w);
+  tab.insert(tab.end(), U.L.begin(), U.L.end());
+  tab.insert(tab.end(), U.dL.begin(), U.dL.end());
+  tab.insert(tab.end(), P.L.begin(), P.L.end());
+  tab.insert(tab.end(), F.L.begin(), F.L.end());
+  tab.insert(tab.end(), F.dL.begin(), F.dL.end());
+  const int expect = F.nS == 3 ? ChnsT<3>::len(S->nq) : ChnsT<6>::len(S->nq);
+  if((int)tab.size() != expect) {
+    set_error("CHNS kernel: basis tables have unexpected sizes");
+    return B200_ERR_ARG;
+  }
+  cudaFree(S->chns_tab);
+  S->chns_tab     = nullptr;
+  S->chns_tab_len = (int)tab.size();
+  B200_CUDA(cudaMalloc(&S->chns_tab, tab.size() * sizeof(double)));
+  B200_CUDA(cudaMemcpyAsync(S->chns_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, S->stream));
+  B200_CUDA(cudaStreamSynchronize(S->stream));
+  return B200_OK;
+}
+
+// what: bit 0 residual, bit 1 matrix; ADDS into val / rhs (the caller has zeroed them)
+int chns_launch(System *S, int what)
+{
+  ChnsArgs a;
+  a.nElm   = S->nElm;
+  a.xyz    = S->d_xyz;
+  a.conn   = S->d_conn;
+  a.adr    = S->chns_adr;
+  a.sol    = S->d_sol;
+  a.soldot = S->have_soldot ? S->d_soldot : nullptr;
+  a.tab    = S->chns_tab;
+  a.ia     = S->d_ia;
+  a.ja     = S->d_ja;
+  a.val    = S->d_val;
+  a.rhs    = S->d_rhs;
+  a.nInc   = S->nInc;
+  a.nq     = S->nq;
+  a.ntab   = S->chns_tab_len;
+  a.what   = what;
+  a.c0     = S->c0;
+  a.h0     = sqrt(DBL_EPSILON); // src/feBilinearForm.cpp:170
+  a.prm    = S->chns_prm;
+  const int    nsf  = S->spaces[S->chns_space[2]].nS;
+  const int    M    = S->M;
+  const size_t smem = ((size_t)a.ntab + 2 * CHNS_WPB * M + (size_t)CHNS_WPB * a.nq * CHNS_NFLD) * sizeof(double) + (size_t)CHNS_WPB * M * sizeof(int32_t);
+  const unsigned grid = (unsigned)((S->nElm + CHNS_WPB - 1) / CHNS_WPB);
+  if(nsf == 3) {
+    B200_CUDA(cudaFuncSetAttribute(chns_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    chns_kernel<3><<<grid, CHNS_WPB * 32, smem, S->stream>>>(a);
+  } else {
+    B200_CUDA(cudaFuncSetAttribute(chns_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    chns_kernel<6><<<grid, CHNS_WPB * 32, smem, S->stream>>>(a);
+  }
+  count_launch();
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+} // namespace b200

@@ -63,7 +63,10 @@ int build_pattern_device(System *S, int64_t n_inc, int64_t n_dof, const std::vec
   int rc  = analyze_forms(S);
   if(rc != B200_OK) return rc;
   const Space &U  = S->spaces[S->su];
-  const int    NU = U.nS * U.nc, NP = S->sp >= 0 ? S->spaces[S->sp].nS : 0, M = S->M;
+  const bool   chns = S->plan == PLAN_CHNS; // one monolithic M x M block on the concatenated element->DOF table
+  const int    M = S->M, NU = chns ? M : U.nS * U.nc, NP = chns ? 0 : (S->sp >= 0 ? S->spaces[S->sp].nS : 0);
+  const int32_t *d_adr_u = chns ? S->chns_adr : U.d_adr;
+  const int32_t *d_adr_p = (!chns && S->sp >= 0) ? S->spaces[S->sp].d_adr : nullptr;
   int          mask = 0;
   for(int bi = 0; bi < 2; ++bi)
     for(int bj = 0; bj < 2; ++bj)
@@ -89,7 +92,7 @@ int build_pattern_device(System *S, int64_t n_inc, int64_t n_dof, const std::vec
     for(int64_t e0 = 0; e0 < S->nElm; e0 += chunk_elems) {
       const int64_t e1 = std::min(S->nElm, e0 + chunk_elems);
       chunk.resize((e1 - e0) * per_elem);
-      pattern_keys_kernel<<<148 * 16, 256, 0, S->stream>>>(e0, e1, M, NU, U.d_adr, S->sp >= 0 ? S->spaces[S->sp].d_adr : nullptr, NP, n_inc, mask,
+      pattern_keys_kernel<<<148 * 16, 256, 0, S->stream>>>(e0, e1, M, NU, d_adr_u, d_adr_p, NP, n_inc, mask,
                                                           thrust::raw_pointer_cast(chunk.data()));
       count_launch();
       thrust::sort(pol, chunk.begin(), chunk.end());

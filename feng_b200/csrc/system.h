@@ -52,7 +52,7 @@ struct ScalarCoeffs {
   double c_src = 0.;
 };
 
-enum PlanKind { PLAN_NONE = 0, PLAN_SCALAR = 1, PLAN_TAYLOR_HOOD = 2 };
+enum PlanKind { PLAN_NONE = 0, PLAN_SCALAR = 1, PLAN_TAYLOR_HOOD = 2, PLAN_CHNS = 3 };
 
 struct System {
   int          device = 0;
@@ -121,6 +121,14 @@ struct System {
   // else reads or accumulates into the arrays (bit 0 rhs, bit 1 matrix)
   int   pending_zero = 0;
 
+  // monolithic CHNS weak form (chns.cu): spaces U, P, Phi, Mu; concatenated element->DOF table; packed tables
+  bool             chns_active = false;
+  int              chns_space[4] = {-1, -1, -1, -1};
+  b200_chns_params chns_prm = {};
+  int32_t         *chns_adr = nullptr;
+  double          *chns_tab = nullptr;
+  int              chns_tab_len = 0;
+
   // scratch for reductions
   double *d_scratch = nullptr;
   double *h_scratch = nullptr; // pinned
@@ -133,6 +141,11 @@ int launch_assemble(System *S, int what, int only_transient);
 int  build_gather_plan(System *S);
 int  launch_gather(System *S, int what, const THCoeffs &c);
 void gather_free(System *S);
+// chns.cu
+int  chns_analyze(System *S);
+int  chns_build_plan(System *S);
+int  chns_launch(System *S, int what);
+void chns_free(System *S);
 // capi.cu
 int  flush_zero(System *S, int what);
 // comm.cu

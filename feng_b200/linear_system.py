@@ -38,10 +38,16 @@ class LinearSystemB200:
         self.sp = -1
         if pb.adrP is not None:
             self.sp = s.add_space(pb.LP.shape[1], 1, pb.adrP, pb.LP, pb.dLP)
+        if pb.chns is not None:
+            # monolithic CHNS form on {U, P, Phi, Mu} (src/CHNS_Solver.cpp:236-420)
+            self.sf = s.add_space(pb.LF.shape[1], 1, pb.adrF, pb.LF, pb.dLF)
+            self.sm = s.add_space(pb.LF.shape[1], 1, pb.adrM, pb.LF, pb.dLF)
         if not device_pattern:
             if pb.ia is None:
                 pb.build_pattern()
             s.set_pattern(pb.n_inc, pb.n_dof, pb.ia, pb.ja)
+        if pb.chns is not None:
+            s.add_form_chns(self.su, self.sp, self.sf, self.sm, pb.chns)
         for f in pb.forms:
             rows, cols = form_layout(f.kind)
             if rows == ("P",):                       # MIXED_DIVERGENCE is declared on {p, u}

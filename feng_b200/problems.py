@@ -127,8 +127,17 @@ class HostProblem:
     ia: np.ndarray | None = None
     ja: np.ndarray | None = None
     meta: dict = field(default_factory=dict)
+    # Cahn-Hilliard Navier-Stokes (config 5): phase marker / chemical potential spaces and the model parameters
+    adrF: np.ndarray | None = None
+    adrM: np.ndarray | None = None
+    LF: np.ndarray | None = None
+    dLF: np.ndarray | None = None
+    chns: object | None = None
 
     def couplings(self):
+        if self.chns is not None:
+            a = np.concatenate([self.adrU, self.adrP, self.adrF, self.adrM], 1)
+            return [(a, a)]
         adr = {"U": self.adrU, "P": self.adrP}
         out = []
         for f in self.forms:
@@ -249,6 +258,77 @@ def scalar_diffusion(mesh: Mesh, order: int = 2, quad_degree: int = 12, field_id
     sol[ess] = s_exact(field_id, xu[ess][:, :dim])          # interior initialised to zero, boundary to the field
     pb.sol = sol
     pb.meta = dict(kind="diffusion", quad_degree=quad_degree, field=field_id, mu=k, transient=transient)
+    if build_pattern:
+        pb.build_pattern()
+    return pb
+
+
+@dataclass
+class ChnsModel:
+    """Parameters of the CHNS weak form (CHNS_Solver, src/CHNS_Solver.cpp:236-420; feSysElm CHNS_Abels,
+    src/feSysElm.h:1269-1345).  Property laws as device enums: linear mixing in phi with optional clipping
+    (density_f / densityLimiter_f / viscosity_f / viscosityLimiter_f), constant or degenerate mobility
+    (degenerateMobility_f), src/CHNS_Solver.cpp:124-235."""
+    rhoA: float = 1.0
+    rhoB: float = 1.0
+    viscA: float = 1.0
+    viscB: float = 1.0
+    mobility: float = 1.0
+    sigma: float = 1.0
+    epsilon: float = 0.1
+    force: tuple = (0.0, 0.0)
+    src_u: tuple = (0.0, 0.0)
+    src_p: float = 0.0
+    src_phi: float = 0.0
+    src_mu: float = 0.0
+    limiter: bool = False
+    degenerate_mobility: bool = False
+    phi_order: int = 1
+
+
+def phi_init(x):
+    """numpy twin of chnsPhiCb (oracle/ref_harness.cpp)"""
+    return 1.2 * np.cos(np.pi * x[..., 0]) * np.cos(np.pi * x[..., 1])
+
+
+def mu_init(x):
+    """numpy twin of chnsMuCb (oracle/ref_harness.cpp)"""
+    return 0.3 * np.sin(np.pi * x[..., 0]) * np.sin(2. * np.pi * x[..., 1]) + 0.1 * x[..., 0]
+
+
+def chns(mesh: Mesh, model: ChnsModel | None = None, quad_degree: int = 8, field_id: int = 1, mu: float = 1.0,
+         rho: float = 1.0, build_pattern: bool = True) -> HostProblem:
+    """Monolithic CHNS system [U (P2 vector), P (P1), Phi, Mu (P1 or P2)] with the single CHNS_ABELS weak form, as
+    CHNS_Solver sets it up (src/CHNS_Solver.cpp:236-420): velocity essential on the boundary, pressure pinned at
+    `PointPression` when the mesh has one, natural conditions for Phi and Mu."""
+    assert mesh.dim == 2, "the reference instantiates its CHNS forms for dim = 2 only (src/feSysElmCHNS.cpp:275)"
+    model = model or ChnsModel()
+    dim, fo = 2, model.phi_order
+    sp = [NB.SpaceSpec("U", "domain", 2, dim), NB.SpaceSpec("U", "boundary", 2, dim, True),
+          NB.SpaceSpec("P", "domain", 1, 1), NB.SpaceSpec("Phi", "domain", fo, 1), NB.SpaceSpec("Mu", "domain", fo, 1)]
+    if mesh.point_pressure is not None:
+        sp.append(NB.SpaceSpec("P", "point", 0, 1, True))
+    num = NB.build_numbering(mesh, sp)
+    w, q = T.quadrature(dim, quad_degree)
+    LU, dLU = T.basis(dim, 2, q)
+    LP, dLP = T.basis(dim, 1, q)
+    LF, dLF = T.basis(dim, fo, q)
+    pb = HostProblem(mesh, dim, dim, 2, num, num.adr(mesh, "U", 2), num.adr(mesh, "P", 1), num.n_inc, num.n_dof,
+                     w, q, LU, dLU, LP, dLP)
+    pb.adrF, pb.adrM, pb.LF, pb.dLF, pb.chns = num.adr(mesh, "Phi", fo), num.adr(mesh, "Mu", fo), LF, dLF, model
+    pb.forms = []
+    sol = np.zeros(num.n_dof)
+    xu = dof_coordinates(mesh, num, "U", num.n_dof)
+    cu = dof_components(num, "U", num.n_dof)
+    isU = cu >= 0
+    uval = u_exact(field_id, xu[isU], mu, rho)
+    sol[isU] = uval[np.arange(uval.shape[0]), cu[isU]]
+    for fld, fn in (("P", lambda x: p_exact(field_id, x, mu, rho)), ("Phi", phi_init), ("Mu", mu_init)):
+        xf = dof_coordinates(mesh, num, fld, num.n_dof)
+        ok = dof_components(num, fld, num.n_dof) >= 0
+        sol[ok] = fn(xf[ok])
+    pb.sol = sol
+    pb.meta = dict(kind="chns_abels", quad_degree=quad_degree, field=field_id, mu=mu, rho=rho)
     if build_pattern:
         pb.build_pattern()
     return pb

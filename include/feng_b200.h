@@ -50,8 +50,22 @@ enum {
   B200_FORM_VECTOR_CONVECTIVE_ACCELERATION = 22, /* feSysElm_VectorConvectiveAcceleration, src/feVectorSysElm.cpp:1171-1242 */
   B200_FORM_DIV_NEWTONIAN_STRESS           = 25, /* feSysElm_DivergenceNewtonianStress,    src/feVectorSysElm.cpp:1454-1532 */
   B200_FORM_MIXED_GRADIENT                 = 26, /* feSysElm_MixedGradient<dim>,           src/feVectorSysElm.cpp:528-578 */
-  B200_FORM_MIXED_DIVERGENCE               = 31  /* feSysElm_MixedDivergence<dim>,         src/feVectorSysElm.cpp:685-749 */
+  B200_FORM_MIXED_DIVERGENCE               = 31, /* feSysElm_MixedDivergence<dim>,         src/feVectorSysElm.cpp:685-749 */
+  B200_FORM_CHNS_ABELS                     = 35  /* CHNS_Abels<2> (volume-averaged CHNS),  src/feSysElmCHNS.cpp:66-273; Jacobian by
+                                                    finite differences, src/feBilinearForm.cpp:388-428 */
 };
+
+/* Parameters of the monolithic Cahn-Hilliard Navier-Stokes weak form.  The reference passes host callbacks
+ * (feFunction) for density, viscosity and mobility; CHNS_Solver only ever installs the laws below
+ * (src/CHNS_Solver.cpp:124-235), which the device evaluates itself:
+ *   rho(phi) = (rho_a - rho_b)/2 phi + (rho_a + rho_b)/2, eta(phi) likewise; limiter != 0 clips phi to [-1, 1] first;
+ *   mobility M, or M |1 - phi^2| if degenerate_mobility != 0;  lambda = 3/(2 sqrt 2) sigma epsilon (src/feSysElm.h:1338).
+ * Volume force and the four source terms are constants here (the reference's tests use zero sources). */
+typedef struct {
+  double rho_a, rho_b, visc_a, visc_b, mobility, surface_tension, epsilon;
+  double force[3], source_u[3], source_p, source_phi, source_mu;
+  int    limiter, degenerate_mobility;
+} b200_chns_params;
 
 /* Scatter strategies for the race-free add into the CSR matrix (north-star subsystem 3). */
 enum {
@@ -126,6 +140,11 @@ int b200_add_space(b200_system *s, int n_scalar_functions, int n_components, con
  * quadrature node[, component]) or NULL. */
 int b200_add_form(b200_system *s, int kind, int space_u, int space_p, double coeff, double param,
                   const double *source);
+/* the monolithic CHNS weak form on the spaces {U, P, Phi, Mu} (createBilinearForm(..., {u, p, phi, mu}, new CHNS_Abels<2>),
+ * src/CHNS_Solver.cpp:236-420).  It must be the only form of the system; both the residual and the finite-difference
+ * Jacobian (N+1 residual evaluations per element) run on the device. */
+int b200_add_form_chns(b200_system *s, int kind, int space_u, int space_p, int space_phi, int space_mu,
+                       const b200_chns_params *params);
 /* replace the tabulated source of form `form_id` (returned by b200_add_form): time-dependent source callbacks are
  * re-tabulated by the adapter when feSolution::getCurrentTime() changes (the reference evaluates the callback with
  * args.t = tn on every element visit, src/feBilinearForm.cpp:291-295) */

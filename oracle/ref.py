@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libfeng_ref.so")
 LIB_B200_PATH = os.path.join(_HERE, "_ref", "libfeng_ref_b200.so")
 DATA_DIR = os.path.join(_HERE, "_ref", "data")     # copies of the reference's regression meshes (oracle/Makefile: data)
 
-KIND = {"diffusion": 0, "stokes_div": 1, "ns_div": 2, "ns_lap": 3, "stokes_lap": 4}
+KIND = {"diffusion": 0, "stokes_div": 1, "ns_div": 2, "ns_lap": 3, "stokes_lap": 4, "chns": 5}
 
 
 class Recipe(C.Structure):
@@ -66,8 +66,12 @@ class RefProblem:
 
     def __init__(self, mesh_file: str, kind: str, order: int = 2, quad_degree: int = 8, field: int = 0,
                  mu: float = 1.0, rho: float = 1.0, transient: bool = False, p_essential: bool = True,
-                 b200: bool = False):
+                 b200: bool = False, chns=None):
         self.L = lib(b200)
+        if chns is not None:
+            # parameter block of the CHNS recipe (oracle/ref_harness.cpp: g_chns), see oracle/chns_oracle.ChnsParams
+            a = np.ascontiguousarray(chns, np.float64)
+            self.L.ref_set_chns_params(_p(a), int(a.size))
         rc = Recipe(KIND[kind], order, quad_degree, field, mu, rho, int(transient), int(p_essential))
         self.h = self.L.ref_create(mesh_file.encode(), C.byref(rc))
         if not self.h:

@@ -381,6 +381,41 @@ public:
   void writeResidual(const std::string, const double) {}
 };
 
+// ---- CHNS (config 5): parameters and property callbacks ------------------------------------------------
+// g_chns = {rhoA, rhoB, viscA, viscB, mobility, sigma, epsilon, fx, fy, Su0, Su1, Sp, Sphi, Smu, limiter, degenerateMobility,
+//           phiOrder}; set by ref_set_chns_params before ref_create(kind = 5).  The property laws are the ones
+// CHNS_Solver hands to its weak form (src/CHNS_Solver.cpp:124-235): linear mixing in phi, optional clipping of phi to
+// [-1, 1], constant or degenerate mobility M |1 - phi^2|.
+double g_chns[17] = {1., 1., 1., 1., 1., 1., 0.1, 0., 0., 0., 0., 0., 0., 0., 0., 0., 1.};
+
+double chnsLinearCb(const feFunctionArguments &args, const std::vector<double> &par)
+{
+  const double phi = par[2] != 0. ? fmax(-1., fmin(1., args.u)) : args.u;
+  return (par[0] - par[1]) / 2. * phi + (par[0] + par[1]) / 2.;
+}
+double chnsSlopeCb(const feFunctionArguments &, const std::vector<double> &par) { return (par[0] - par[1]) / 2.; }
+double chnsMobilityCb(const feFunctionArguments &args, const std::vector<double> &par)
+{
+  return par[1] != 0. ? par[0] * fabs(1. - args.u * args.u) : par[0];
+}
+void chnsVecConstCb(const feFunctionArguments &, const std::vector<double> &par, std::vector<double> &res)
+{
+  res[0] = par[0];
+  res[1] = par[1];
+}
+// initial phase marker / potential (smooth, |phi| crosses 1 so that the limiter is exercised)
+double chnsPhiCb(const feFunctionArguments &args, const std::vector<double> &)
+{
+  const double x = args.pos[0], y = args.pos[1];
+  return 1.2 * cos(PI * x) * cos(PI * y);
+}
+double chnsMuCb(const feFunctionArguments &args, const std::vector<double> &)
+{
+  const double x = args.pos[0], y = args.pos[1];
+  return 0.3 * sin(PI * x) * sin(2. * PI * y) + 0.1 * x;
+}
+
+
 struct RefProblem {
   ref_recipe_t rc;
   feMesh2DP1  *mesh = nullptr;
@@ -442,6 +477,12 @@ bool hasEntity(feMesh *mesh, const std::string &name)
 extern "C" {
 int ref_error_norms(void *h, const double *sol, double *out);
 
+// CHNS parameter block for the next ref_create(kind = 5); see g_chns
+void ref_set_chns_params(const double *p, int n)
+{
+  for(int i = 0; i < n && i < 17; ++i) g_chns[i] = p[i];
+}
+
 int ref_max_threads()
 {
 #if defined(HAVE_OMP)
@@ -498,6 +539,50 @@ void *ref_create(const char *meshFile, const ref_recipe_t *rc)
       CHK(createBilinearForm(mass, {u}, new feSysElm_TransientMass(r)));
       P->forms.push_back(mass);
     }
+  } else if(rc->kind == 5) {
+    // Cahn-Hilliard Navier-Stokes, Abels et al. (CHNS_Solver, src/CHNS_Solver.cpp:236-420): fields U (P2 vector), P (P1),
+    // Phi, Mu (P1 or P2), ONE monolithic weak form whose Jacobian is computed by finite differences
+    const double     *g    = g_chns;
+    feVectorFunction *uSol = mkV(P, uSolCb, {fld, rc->mu, rc->rho});
+    feFunction       *pSol = mkS(P, pSolCb, {fld, rc->mu, rc->rho});
+    feFunction       *fSol = mkS(P, chnsPhiCb, {});
+    feFunction       *mSol = mkS(P, chnsMuCb, {});
+    P->uExact              = uSol;
+    P->pExact              = pSol;
+    const int fo = (int)g[16];
+    feSpace  *u = nullptr, *uB = nullptr, *p = nullptr, *pB = nullptr, *phi = nullptr, *mu = nullptr;
+    CHK(createFiniteElementSpace(u, P->mesh, elementType::VECTOR_LAGRANGE, 2, "U", "Domaine", rc->quad_degree, uSol));
+    CHK(createFiniteElementSpace(uB, P->mesh, elementType::VECTOR_LAGRANGE, 2, "U", "Bord", rc->quad_degree, uSol));
+    CHK(createFiniteElementSpace(p, P->mesh, elementType::LAGRANGE, 1, "P", "Domaine", rc->quad_degree, pSol));
+    CHK(createFiniteElementSpace(phi, P->mesh, elementType::LAGRANGE, fo, "Phi", "Domaine", rc->quad_degree, fSol));
+    CHK(createFiniteElementSpace(mu, P->mesh, elementType::LAGRANGE, fo, "Mu", "Domaine", rc->quad_degree, mSol));
+    P->spaces          = {u, uB, p, phi, mu};
+    P->essentialSpaces = {uB};
+    if(hasEntity(P->mesh, "PointPression")) {
+      CHK(createFiniteElementSpace(pB, P->mesh, elementType::LAGRANGE, 0, "P", "PointPression", rc->quad_degree, pSol));
+      P->spaces.push_back(pB);
+      P->essentialSpaces.push_back(pB);
+    }
+    P->interior  = {u, p, phi, mu};
+    P->uSpace    = u;
+    P->pSpace    = p;
+    P->numbering = new feMetaNumber(P->mesh, P->spaces, P->essentialSpaces);
+    P->sol       = new feSolution(P->numbering->getNbDOFs(), P->spaces, P->essentialSpaces);
+    feFunction       *rho   = mkS(P, chnsLinearCb, {g[0], g[1], g[14]});
+    feFunction       *drho  = mkS(P, chnsSlopeCb, {g[0], g[1]});
+    feFunction       *visc  = mkS(P, chnsLinearCb, {g[2], g[3], g[14]});
+    feFunction       *dvisc = mkS(P, chnsSlopeCb, {g[2], g[3]});
+    feFunction       *mob   = mkS(P, chnsMobilityCb, {g[4], g[15]});
+    feVectorFunction *force = mkV(P, chnsVecConstCb, {g[7], g[8]});
+    feVectorFunction *srcU  = mkV(P, chnsVecConstCb, {g[9], g[10]});
+    feFunction       *srcP  = mkS(P, constantCallback, {g[11]});
+    feFunction       *srcF  = mkS(P, constantCallback, {g[12]});
+    feFunction       *srcM  = mkS(P, constantCallback, {g[13]});
+    std::vector<double> prm = {g[5], g[6]};
+    feBilinearForm     *chns = nullptr;
+    CHK(createBilinearForm(chns, {u, p, phi, mu},
+                           new CHNS_Abels<2>(rho, drho, visc, dvisc, mob, force, srcP, srcU, srcF, srcM, prm)));
+    P->forms.push_back(chns);
   } else {
     // (Navier-)Stokes Taylor-Hood: tests/withLinearSolver/navier_stokes.cpp:63-99, stokes.cpp
     const bool withConv = (rc->kind == 2 || rc->kind == 3);

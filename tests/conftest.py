@@ -47,7 +47,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_names(prefix=""):
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith(prefix))
+    """fixtures of tests/golden/make_golden.py (the CHNS fixtures of make_golden_chns.py have their own tests, test_chns.py)"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith(prefix) and "chns" not in f)
 
 
 def load_golden(name):
