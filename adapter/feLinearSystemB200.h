@@ -70,6 +70,20 @@ namespace feB200detail
   template <class T> struct DiffPeek : public T {
     static const feFunction *diff(const T *s) { return s->*(&DiffPeek::_diffusivity); }
   };
+  // CHNS_Abels<2> keeps its property callbacks and constants protected (src/feSysElm.h:1272-1284)
+  struct ChnsPeek : public CHNS_Abels<2> {
+    static const feFunction *density(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_density); }
+    static const feFunction *drhodphi(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_drhodphi); }
+    static const feFunction *viscosity(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_viscosity); }
+    static const feFunction *mobility(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_mobility); }
+    static const feVectorFunction *volumeForce(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_volumeForce); }
+    static const feVectorFunction *sourceU(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_sourceU); }
+    static const feFunction *sourceP(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_sourceP); }
+    static const feFunction *sourcePhi(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_sourcePhi); }
+    static const feFunction *sourceMu(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_sourceMu); }
+    static double surfaceTension(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_surfaceTension); }
+    static double epsilon(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_epsilon); }
+  };
 } // namespace feB200detail
 
 class feLinearSystemB200 : public feLinearSystem
@@ -192,6 +206,86 @@ protected:
     }
   }
 
+  // The monolithic CHNS weak form (CHNS_Solver, src/CHNS_Solver.cpp:236-420).  Its property callbacks are functions of
+  // the phase marker (args.u): the engine evaluates the laws CHNS_Solver installs (src/CHNS_Solver.cpp:124-235) itself,
+  // so the callbacks are PROBED here and must reproduce one of those laws: linear mixing in phi (optionally clipped to
+  // [-1, 1]) for density and viscosity, constant or degenerate mobility M |1 - phi^2|, constant force and sources.
+  static double evalAt(const feFunction *f, double phi)
+  {
+    feFunctionArguments args(0.);
+    args.u = phi;
+    return f->eval(args);
+  }
+  bool probeLinearLaw(const feFunction *f, double &a, double &b, bool &limiter)
+  {
+    a = evalAt(f, 1.);
+    b = evalAt(f, -1.);
+    const double mid = evalAt(f, 0.3), out = evalAt(f, 1.7), scale = std::max(1., std::max(std::fabs(a), std::fabs(b)));
+    if(std::fabs(mid - ((a - b) / 2. * 0.3 + (a + b) / 2.)) > 1e-13 * scale) return false;
+    if(std::fabs(out - a) <= 1e-13 * scale)
+      limiter = true;
+    else if(std::fabs(out - ((a - b) / 2. * 1.7 + (a + b) / 2.)) <= 1e-13 * scale)
+      limiter = false;
+    else
+      return false;
+    return true;
+  }
+  bool constantVector(const feVectorFunction *f, double *out)
+  {
+    std::vector<double> r0(3, 0.), r1(3, 0.);
+    feFunctionArguments a0(0.), a1(0.);
+    a0.u = 0.2;
+    a1.u = -0.9;
+    a1.pos[0] = 0.37;
+    a1.pos[1] = -0.61;
+    (*f)(a0, r0);
+    (*f)(a1, r1);
+    for(int c = 0; c < 2; ++c) {
+      if(std::fabs(r0[c] - r1[c]) > 1e-14 * std::max(1., std::fabs(r0[c]))) return false;
+      out[c] = r0[c];
+    }
+    out[2] = 0.;
+    return true;
+  }
+  bool addChnsForm(feBilinearForm *f, feSysElm *se)
+  {
+    auto *s = dynamic_cast<const CHNS_Abels<2> *>(se);
+    if(!s || f->_intSpaces.size() != 4) return fail("CHNS_ABELS form must be a CHNS_Abels<2> on {U, P, Phi, Mu}");
+    using Pk = feB200detail::ChnsPeek;
+    b200_chns_params prm{};
+    bool limRho = false, limVisc = false;
+    if(!probeLinearLaw(Pk::density(s), prm.rho_a, prm.rho_b, limRho) || !probeLinearLaw(Pk::viscosity(s), prm.visc_a, prm.visc_b, limVisc) ||
+       limRho != limVisc)
+      return fail("CHNS density / viscosity callbacks are not the (clipped) linear mixing laws of CHNS_Solver");
+    if(std::fabs(evalAt(Pk::drhodphi(s), 0.3) - (prm.rho_a - prm.rho_b) / 2.) > 1e-13 * std::max(1., std::fabs(prm.rho_a)))
+      return fail("CHNS drhodphi callback does not match the density law");
+    prm.limiter = limRho ? 1 : 0;
+    {
+      const feFunction *m = Pk::mobility(s);
+      const double m0 = evalAt(m, 0.), m1 = evalAt(m, 1.), mh = evalAt(m, 0.5), mo = evalAt(m, 1.5);
+      prm.mobility = m0;
+      if(std::fabs(m1 - m0) <= 1e-14 * std::max(1., m0) && std::fabs(mh - m0) <= 1e-14 * std::max(1., m0))
+        prm.degenerate_mobility = 0;
+      else if(std::fabs(m1) <= 1e-14 * std::max(1., m0) && std::fabs(mh - 0.75 * m0) <= 1e-13 * std::max(1., m0) &&
+              std::fabs(mo - 1.25 * m0) <= 1e-13 * std::max(1., m0))
+        prm.degenerate_mobility = 1;
+      else
+        return fail("CHNS mobility callback is neither constant nor M |1 - phi^2|");
+    }
+    prm.surface_tension = Pk::surfaceTension(s);
+    prm.epsilon         = Pk::epsilon(s);
+    if(!constantVector(Pk::volumeForce(s), prm.force) || !constantVector(Pk::sourceU(s), prm.source_u))
+      return fail("CHNS volume force / momentum source must be constant");
+    if(!constantValue(Pk::sourceP(s), f->_geoSpace, f->getCncGeoTag(), 0., prm.source_p) ||
+       !constantValue(Pk::sourcePhi(s), f->_geoSpace, f->getCncGeoTag(), 0., prm.source_phi) ||
+       !constantValue(Pk::sourceMu(s), f->_geoSpace, f->getCncGeoTag(), 0., prm.source_mu))
+      return fail("CHNS scalar sources must be constant");
+    int sp[4];
+    for(int k = 0; k < 4; ++k)
+      if((sp[k] = spaceId(f->_intSpaces[k])) < 0) return false;
+    return ok(b200_add_form_chns(_sys, B200_FORM_CHNS_ABELS, sp[0], sp[1], sp[2], sp[3], &prm), "b200_add_form_chns");
+  }
+
   template <class T> bool addCoeffForm(feBilinearForm *f, feSysElm *se, int kind, int su, int sp, const feFunction *param)
   {
     const T *s = dynamic_cast<const T *>(se);
@@ -263,6 +357,7 @@ protected:
         _sources.push_back(sf);
         return true;
       }
+      case CHNS_ABELS: return addChnsForm(f, se);
       case TRANSIENT_MASS: return addCoeffForm<feSysElm_TransientMass>(f, se, id, s0, -1, nullptr);
       case DIFFUSION:
         // diffusivity is the form's only callback: kind DIFFUSION uses coeff x param with param = 1

@@ -220,6 +220,17 @@ class RefProblem:
         return sol, dict(errU=out[0], errP=out[1], n_solves=int(out[2]), krylov_iterations=int(out[3]),
                          norm_axb=out[4], converged=bool(out[5]))
 
+    def assemble_b200(self, matrix=True, residual=True, device_pattern=False):
+        """One assembly of the current state by the CUDA backend, driven through adapter/feLinearSystemB200.h from the
+        reference's own host objects (b200=True instances only)."""
+        vals = np.zeros(self.nnz)
+        rhs = np.zeros(self.n_inc)
+        what = (2 if matrix else 0) | (1 if residual else 0)
+        rc = self.L.ref_assemble_b200(self.h, what, int(device_pattern), _p(vals), _p(rhs))
+        if rc != 0:
+            raise RuntimeError(f"assembly through the B200 adapter failed rc={rc}")
+        return vals, rhs
+
     def error_norms(self, sol):
         sol = np.ascontiguousarray(sol, np.float64)
         out = np.zeros(2)

@@ -974,6 +974,30 @@ int ref_newton_b200(void *h, double tolRes, double tolCor, int maxIter, double r
 }
 #endif
 
+#ifdef WITH_B200_ADAPTER
+// One assembly of the CURRENT state through the product's C++ adapter (feLinearSystemB200 built from the unmodified host
+// objects: forms, spaces, numbering) -> CSR values and rhs of the CUDA backend.  what: bit 0 residual, bit 1 matrix.
+int ref_assemble_b200(void *h, int what, int devicePattern, double *values, double *rhs)
+{
+  RefProblem   *P = (RefProblem *)h;
+  feB200Options o;
+  o.devicePattern = devicePattern != 0;
+  feLinearSystem *sys = nullptr;
+  if(createLinearSystemB200(sys, P->forms, P->numbering, o) != FE_STATUS_OK) return -1;
+  solAtTimeN = P->sol->getSolution();
+  sys->setToZero();
+  if(what & 1) sys->assembleResiduals(P->sol);
+  if(what & 2) sys->assembleMatrices(P->sol, false);
+  feLinearSystemB200 *b  = static_cast<feLinearSystemB200 *>(sys);
+  int                 rc = 0;
+  if(values && b200_get_matrix_values(b->getHandle(), values) != B200_OK) rc = -2;
+  if(rhs && b200_get_rhs(b->getHandle(), rhs) != B200_OK) rc = -3;
+  if(b->getStatus() != FE_STATUS_OK) rc = -4;
+  delete sys;
+  return rc;
+}
+#endif
+
 // L2 error norms of an arbitrary nDOF solution vector against the recipe's analytic fields (feNorm).
 int ref_error_norms(void *h, const double *sol, double *out)
 {

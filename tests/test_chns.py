@@ -172,3 +172,29 @@ def test_cuda_chns_vs_golden_fixture():
     S.assemble(3, False)
     assert_close_vec(S.get_rhs(), g["rhs"], 1e-12, "rhs")
     assert_close_rows(S.get_matrix_values(), g["values"], g["ia"], FD_TOL, "FD matrix")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("phi_order,device_pattern", [(1, False), (2, True)])
+def test_chns_through_the_cpp_adapter(phi_order, device_pattern):
+    """The reference's own host objects (mesh reader, feSpace, feMetaNumber, CHNS_Abels<2> with its property CALLBACKS)
+    drive the CUDA backend through adapter/feLinearSystemB200.h: the adapter probes the callbacks, recognises the laws
+    of CHNS_Solver (src/CHNS_Solver.cpp:124-235) and registers the monolithic form; the result must match the
+    reference's own CPU assembly of the same state (both computed here, in the same process)."""
+    from oracle import chns_oracle as CO, ref
+    if not ref.available_b200():
+        pytest.skip("oracle/_ref/libfeng_ref_b200.so not built (make -C oracle)")
+    prm = CO.ChnsParams(phi_order=phi_order, **MODELS["full"])
+    P = ref.RefProblem(os.path.join(ref.DATA_DIR, "square2.msh"), "chns", 2, 8, 1, 0.05, 1.3, b200=True,
+                       chns=prm.as_array())
+    sol, _ = P.solution()
+    rng = np.random.default_rng(3)
+    sol[:P.n_inc] += rng.uniform(-1e-2, 1e-2, P.n_inc)
+    sd = rng.standard_normal(P.n_dof)
+    P.set_solution(sol, sd, 2.5, 0.0)
+    v, r, _ = P.assemble()                        # reference CPU path (colour loop + FD Jacobian + scatter)
+    gv, gr = P.assemble_b200(device_pattern=device_pattern)
+    ia, _ = P.pattern()
+    assert_close_vec(gr, r, 1e-12, "rhs")
+    assert_close_rows(gv, v, ia, FD_TOL, "FD matrix")
+    P.close()
