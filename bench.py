@@ -1,14 +1,15 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: P2/P1 Navier-Stokes Jacobian + residual assembly (Melem/s) and Newton-step pieces.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload t2d|t3d] [--n SIZE]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload t3d|t2d] [--n SIZE]
 
 A "step" is one pass of the hot path over the whole mesh: setToZero + fused Jacobian+residual assembly of every
 element (what solveNewtonRaphson does each iteration, src/feNonLinearSolver.cpp:77-91).  `value` = elements
 assembled per second with every input resident in HBM; `e2e` = the same through the C ABI with HOST buffers (the
 solution vector is copied host->device inside the timed region, the rhs max-norm is read back).  One process per GPU;
-for N > 1 every rank owns a strip of a [0,1] x [0,N] mesh (weak scaling, owner-computes with one ghost layer of
-elements, no data-path collective in assembly).
+for N > 1 every rank owns a slab of a [0,1]^2 x [0,N] box (t3d) or a strip of a [0,1] x [0,N] rectangle (t2d): weak
+scaling, owner-computes with one ghost layer of elements, no data-path collective in assembly.  Default workload: T3D(92)
+per GPU = 4.67 M tetrahedra, 19.8 M DOF, the "~20 M-DOF tetrahedral cube" of BASELINE.json.
 """
 from __future__ import annotations
 
@@ -96,10 +97,11 @@ def build_problem(workload, n, rank, world):
         owned = 2 * n * n
         name = f"T2D({n}) P2/P1 Navier-Stokes (convU+divU+divSigma), Kovasznay Re=40 + noise, quad deg 8 (16 pts)"
     else:
-        m = M.cube_mesh(n)
-        pb = PB.taylor_hood(m, "ns_div", 6, 3, MU, RHO, build_pattern=False, with_source=False)
-        owned = m.n_cells
-        name = f"T3D({n}) P2/P1 Navier-Stokes tetrahedra, quad deg 6 (24 pts)"
+        # slab r of the [0,1]^2 x [0,world] box: n^3 owned cells of 6 Kuhn tetrahedra plus one ghost layer of cells
+        pb, part = PT.slab_problem(n, rank, world, "ns_div", 6, 3, MU, RHO, build_pattern=False, with_source=False)
+        owned = 6 * n * n * n
+        name = (f"T3D({n}) P2/P1 Navier-Stokes tetrahedra (convU+divU+divSigma), trigonometric field + noise, "
+                f"quad deg 6 (24 pts)")
     sol = PB.perturb_unknowns(pb)
     return pb, sol, owned, name, part
 
@@ -140,10 +142,38 @@ def cpu_reference_baseline(n_cpu, reps, threads=None):
                       f"Jacobian+residual, {reps} passes"}
 
 
+def cpu_port_baseline(n_cpu, reps):
+    """3-D workload: the reference has no vector-valued space on tetrahedra (src/feSpace.cpp:762-767 instantiates the 2-D
+    ones only), so its CPU arm is the oracle port (oracle/fe_oracle.py, numpy restatement of the same weak forms and of
+    the sorted scatter, pinned on the compiled reference in 2-D) on a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import to_oracle_problem
+    from feng_b200 import mesh as M, problems as PB
+    from oracle import fe_oracle as O
+    m = M.cube_mesh(n_cpu)
+    pb = PB.taylor_hood(m, "ns_div", 6, 3, MU, RHO, build_pattern=True, with_source=False)
+    sol = PB.perturb_unknowns(pb)
+    op = to_oracle_problem(pb)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.assemble(op, pb.ia, pb.ja, sol)
+        times.append(time.perf_counter() - t0)
+    return {"times": times, "n_elm": m.n_cells, "cores": 1, "kind": "port",
+            "sample": f"T3D({n_cpu}) = {m.n_cells} tetrahedra, same forms, Jacobian+residual + sorted scatter, numpy oracle "
+                      f"port (the reference has no 3-D vector spaces), {reps} passes"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    base = cpu_reference_baseline(args.cpu_n, max(args.steps, 1) + args.warmup)
+    if args.workload == "t3d":
+        base = cpu_port_baseline(args.cpu_n3, max(args.steps, 1) + args.warmup)
+        kind, timing = "port", "oracle/fe_oracle.py element loops (numpy) + sorted scatter, host perf_counter"
+    else:
+        base = cpu_reference_baseline(args.cpu_n, max(args.steps, 1) + args.warmup)
+        kind, timing = "reference", ("reference's own colour loop over computeMatrix/computeResidual + restated "
+                                     "Pardiso-style scatter, OpenMP, host steady_clock")
     if base is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfeng_ref.so not built"}))
         return
@@ -153,9 +183,8 @@ def run_reference(args, rank, world):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(t), "warmup": args.warmup,
             "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": base["sample"], "timing": "reference's own colour loop over computeMatrix/"
-                       "computeResidual + restated Pardiso-style scatter, OpenMP, host steady_clock"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": base["cores"], "kind": "reference",
+            "config": {"workload": base["sample"], "timing": timing},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": base["cores"], "kind": kind,
                              "sample": base["sample"]},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -168,11 +197,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="t2d", choices=["t2d", "t3d"])
+    ap.add_argument("--workload", default="t3d", choices=["t2d", "t3d"],
+                    help="t3d: the ~20 M-DOF tetrahedral cube BASELINE.json quotes the metric on (default); t2d: refined triangles")
     ap.add_argument("--n", "--size", dest="n", type=int, default=0)
-    ap.add_argument("--cpu-n", type=int, default=256)
+    ap.add_argument("--cpu-n", type=int, default=256, help="T2D size of the reference CPU sample")
+    ap.add_argument("--cpu-n3", type=int, default=8, help="T3D size of the oracle-port CPU sample")
+    ap.add_argument("--solve-maxit", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--solve", action="store_true", help="also time one Newton step (assembly + GMRES)")
+    ap.add_argument("--no-solve", action="store_true", help="skip the Newton-step timing (assembly + GMRES)")
     ap.add_argument("--assembly", default="auto", choices=["auto", "scatter", "gather"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -182,7 +214,7 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
-    n = args.n or (1024 if args.workload == "t2d" else 48)
+    n = args.n or (1024 if args.workload == "t2d" else 92)
 
     import torch
     import torch.distributed as dist
@@ -199,6 +231,7 @@ def main():
     if args.assembly != "auto":
         S.set_assembly_mode({"scatter": capi.ASSEMBLY_SCATTER, "gather": capi.ASSEMBLY_GATHER}[args.assembly])
     gather = S.has_gather_plan() and args.assembly != "scatter"
+    patch = gather and S.gather_plan_kind() == 2
     nE = pb.mesh.n_cells
     host_sol = torch.from_numpy(sol).pin_memory().numpy()        # pinned host buffer of the caller
     S.set_solution(host_sol)
@@ -258,8 +291,8 @@ def main():
     tot_owned = float(owned_all[0])
 
     extra = {}
-    if args.solve and world == 1:
-        extra["newton_step"] = newton_step(ls, sol, pb)
+    if not args.no_solve:
+        extra["newton_step"] = newton_step(ls, sol, pb, args.solve_maxit)
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -282,7 +315,10 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_name, "elements_per_gpu": int(owned), "ghost_elements_per_gpu": int(nE - owned),
                        "n_dof_per_gpu": int(pb.n_dof), "n_unknowns_per_gpu": int(pb.n_inc), "nnz_per_gpu": int(S.nnz),
-                       "assembly": ("row-owner gather on pre-contracted reference tensors: every CSR row written once, "
+                       "assembly": ("patch kernel: block-slot owners over Morton patches of elements, element state staged "
+                                    "in shared memory, pre-contracted reference tensors; every CSR value written once, "
+                                    "no memset, no atomics") if patch else
+                                   ("row-owner gather on pre-contracted reference tensors: every CSR row written once, "
                                     "no memset, no atomics") if gather else
                                    "quadrature-loop kernel + atomic (red.global.add.f64) scatter into precomputed CSR slots",
                        "cache": "inputs larger than L2 (CSR values written per pass = %.1f GB)" % (S.nnz * 8 / 1e9),
@@ -291,7 +327,8 @@ def main():
                        else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
-                         "kernel": ("gather_u_kernel + gather_p_kernel (one assembly pass = 2 launches, timed together)"
+                         "kernel": ("patch_kernel (one launch per assembly pass) + patch_zero_kernel" if patch else
+                                    "gather kernels (one assembly pass = several launches, timed together)"
                                     if gather else "th_kernel fused Jacobian+residual+scatter"),
                          "kernel_ms": k_ms, "algorithmic_bytes_per_element": bpe, "peak_source": peak_src,
                          "kernel_share_of_step": k_ms / ms_step,
@@ -305,21 +342,28 @@ def main():
         }
         line.update(extra)
         if world == 1 and not args.no_cpu:
-            base = cpu_reference_baseline(args.cpu_n, 3)
+            ref2d = cpu_reference_baseline(args.cpu_n, 3)
+            base = ref2d if args.workload == "t2d" else cpu_port_baseline(args.cpu_n3, 3)
             if base is not None:
                 per = sum(base["times"]) / len(base["times"])
                 line["cpu_baseline"] = {"value": base["n_elm"] / per / 1e6, "unit": UNIT, "cores": base["cores"],
-                                        "kind": "reference", "sample": base["sample"]}
+                                        "kind": base.get("kind", "reference"), "sample": base["sample"]}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                         "sample": "oracle/_ref missing"}
+            if args.workload == "t3d" and ref2d is not None:
+                # for context: the unmodified reference on its own (2-D) implementation of the same forms
+                per = sum(ref2d["times"]) / len(ref2d["times"])
+                line["cpu_reference_2d"] = {"value": ref2d["n_elm"] / per / 1e6, "unit": UNIT, "cores": ref2d["cores"],
+                                            "kind": "reference", "sample": ref2d["sample"]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def newton_step(ls, sol, pb):
-    """One loop body of solveNewtonRaphson (src/feNonLinearSolver.cpp:77-123) timed on the host with syncs."""
+def newton_step(ls, sol, pb, maxit):
+    """One loop body of solveNewtonRaphson (src/feNonLinearSolver.cpp:77-123) timed on the host with syncs; the Krylov
+    solve is capped at `maxit` iterations (reported with its convergence flag and relative residual)."""
     from feng_b200 import capi
     S = ls.sys
     s = sol.copy()
@@ -331,12 +375,15 @@ def newton_step(ls, sol, pb):
     S.rhs_max_norm()
     S.assemble(2)
     S.constrain()
-    info = S.solve(1e-8, 1e-14, 1e6, 2000, 30, ls.pc, raise_on_fail=False)
+    info = S.solve(1e-8, 1e-14, 1e6, maxit, 30, ls.pc, raise_on_fail=False)
     S.correct_solution(s)
     S.sync()
     dt = time.perf_counter() - t0
-    return {"ms": dt * 1e3, "gmres_iterations": info.iterations, "converged": bool(info.converged),
-            "solve_ms": S.last_solve_ms(), "rel_residual": info.rel_residual, "pc": ls.pc}
+    its = max(int(info.iterations), 1)
+    return {"ms": dt * 1e3, "gmres_iterations": info.iterations, "gmres_max_iterations": maxit,
+            "converged": bool(info.converged), "solve_ms": S.last_solve_ms(), "solve_ms_per_iteration": S.last_solve_ms() / its,
+            "rel_residual": info.rel_residual, "pc": ls.pc,
+            "assembly_and_update_ms": dt * 1e3 - S.last_solve_ms()}
 
 
 if __name__ == "__main__":

@@ -209,6 +209,10 @@ class System:
     def has_gather_plan(self) -> bool:
         return bool(self.L.b200_has_gather_plan(self.h))
 
+    def gather_plan_kind(self) -> int:
+        """0 scatter kernels, 1 row-owner gather plan, 2 patch plan"""
+        return int(self.L.b200_has_gather_plan(self.h))
+
     def set_constraints(self, rows, master=None, slave=None):
         rows = np.ascontiguousarray(rows, np.int64)
         m = None if master is None else np.ascontiguousarray(master, np.int64)

@@ -691,6 +691,7 @@ int build_plan(System *S)
       return B200_ERR_ARG;
     }
   }
+  log_stage("plan: slot map");
   // row-owner gather plan where the problem qualifies
   gather_free(S);
   if(S->plan == PLAN_TAYLOR_HOOD && S->assembly_mode != B200_ASSEMBLY_SCATTER) {

@@ -1,3 +1,5 @@
+#include <cstdio>
+#include <cstdlib>
 // C ABI of the engine (include/feng_b200.h): set-up, state transfer, constraints and the feLinearSystem virtuals.
 #include <algorithm>
 #include <atomic>
@@ -11,8 +13,20 @@ namespace b200 {
 static thread_local std::string g_error;
 static std::atomic<int64_t>     g_launches{0};
 
-void set_error(const std::string &msg) { g_error = msg; }
+void set_error(const std::string &msg)
+{
+  g_error = msg;
+  if(getenv("B200_VERBOSE")) fprintf(stderr, "[feng_b200] %s\n", msg.c_str());
+}
 void count_launch(int n) { g_launches += n; }
+void log_stage(const char *what)
+{
+  if(!getenv("B200_VERBOSE")) return;
+  const cudaError_t e = cudaDeviceSynchronize();
+  size_t fr = 0, tot = 0;
+  cudaMemGetInfo(&fr, &tot);
+  fprintf(stderr, "[feng_b200] stage %-28s %s, %.1f GB in use\n", what, cudaGetErrorString(e), (double)(tot - fr) / 1e9);
+}
 
 static const int GRID = 148 * 8;
 
@@ -505,7 +519,7 @@ int b200_set_assembly_mode(b200_system *s, int mode)
   return B200_OK;
 }
 
-int b200_has_gather_plan(const b200_system *s) { return s && s->gather != nullptr ? 1 : 0; }
+int b200_has_gather_plan(const b200_system *s) { return s && s->gather != nullptr ? (s->patch != nullptr ? 2 : 1) : 0; }
 
 int64_t b200_system_size(const b200_system *s) { return s ? s->nInc : 0; }
 

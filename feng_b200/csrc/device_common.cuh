@@ -47,4 +47,18 @@ template <int DIM> __device__ __forceinline__ void element_geometry(const double
 }
 
 
+// Layout of the pre-contracted reference tensors (built by gather.cu:build_tables from the host tables)
+template <int D, int NS, int NP> struct GT {
+  static constexpr int NU = NS * D, M = NU + NP;
+  static constexpr int O_K = 0;                       // Kref[a][b][al][be]
+  static constexpr int O_T3 = O_K + NS * NS * D * D;  // T3[a][b][v]
+  static constexpr int O_M = O_T3 + NS * NS * NP;     // Mref[a][b]
+  static constexpr int O_E = O_M + NS * NS;           // E[c][al][v]
+  static constexpr int O_B = O_E + NS * D * NP;       // Bref[q][a][al]
+  static constexpr int O_W = O_B + NP * NS * D;       // W[k][a] = w_k phi_a(k)   (source forms only)
+  static constexpr int OFFW_U = (M + 7) / 8 * 8;      // uint16 offsets per (U node, element) pair
+  static constexpr int OFFW_P = (NU + 7) / 8 * 8;     // per (P node, element) pair
+  static constexpr int GW = (D * D + 1 + 1) / 2 * 2;  // doubles per element of the geometry table (16-byte aligned records)
+};
+
 } // namespace b200

@@ -34,18 +34,6 @@
 
 namespace b200 {
 
-template <int D, int NS, int NP> struct GT {
-  static constexpr int NU = NS * D, M = NU + NP;
-  static constexpr int O_K = 0;                       // Kref[a][b][al][be]
-  static constexpr int O_T3 = O_K + NS * NS * D * D;  // T3[a][b][v]
-  static constexpr int O_M = O_T3 + NS * NS * NP;     // Mref[a][b]
-  static constexpr int O_E = O_M + NS * NS;           // E[c][al][v]
-  static constexpr int O_B = O_E + NS * D * NP;       // Bref[q][a][al]
-  static constexpr int O_W = O_B + NP * NS * D;       // W[k][a] = w_k phi_a(k)   (source forms only)
-  static constexpr int OFFW_U = (M + 7) / 8 * 8;      // uint16 offsets per (U node, element) pair
-  static constexpr int OFFW_P = (NU + 7) / 8 * 8;     // per (P node, element) pair
-  static constexpr int GW = (D * D + 1 + 1) / 2 * 2;  // doubles per element of the geometry table (16-byte aligned records)
-};
 
 struct NodeSet {
   int32_t   nNodes = 0, nCta = 0;
@@ -82,6 +70,7 @@ struct GatherPlan {
   int      tab_len = 0, tab_len_src = 0;
   int      npbU = 0, npbP = 0;
   int      lanes = 1;       // lanes per node of the lane-group kernels
+  bool     patch = true;    // patch kernel (patch.cu) instead of the row-owner kernels of this file
   bool     lane = true;     // lane-per-column kernels (gather_lane.cuh) or thread-per-node kernels (B200_GATHER_KERNEL=node)
   double  *d_es = nullptr;  // [nElm][ES::W] per-element convective state, rewritten by every assembly pass
 };
@@ -1052,8 +1041,20 @@ static bool build_tables(const System *S, int D, int NS, int NP, std::vector<dou
   return true;
 }
 
+bool gather_tables(const System *S, GatherTables *out)
+{
+  const GatherPlan *G = static_cast<const GatherPlan *>(S->gather);
+  if(!G || !G->d_tab || !G->d_geo) return false;
+  out->d_tab       = G->d_tab;
+  out->d_geo       = G->d_geo;
+  out->tab_len     = G->tab_len;
+  out->tab_len_src = G->tab_len_src;
+  return true;
+}
+
 void gather_free(System *S)
 {
+  patch_free(S);
   GatherPlan *G = static_cast<GatherPlan *>(S->gather);
   if(!G) return;
   G->U.release();
@@ -1099,6 +1100,9 @@ int build_gather_plan(System *S)
     // lane-group kernels win 2.3x (the row images of one node are 2-5 KB, one thread per node leaves the SM empty)
     const char *k = getenv("B200_GATHER_KERNEL");
     G->lane       = k ? std::string(k) == "lane" : D == 3;
+    // default: the patch kernel (patch.cu, block-slot owners over Morton patches); "node" / "lane" select the row-owner
+    // kernels of this file, which also remain the fallback when the numbering does not have the regular node-block structure
+    G->patch      = k ? std::string(k) == "patch" : false;
   }
   if(G->lane) {
     const LaneCfg lc = lane_cfg(D, lane_default(D));
@@ -1109,10 +1113,6 @@ int build_gather_plan(System *S)
     G->npbP = D == 2 ? 64 : 32;
   }
   try {
-    if(G->lane) {
-      const size_t esw = (size_t)(NP * D * D + NS * NS + NS * D + NP + 1) / 2 * 2; // ES<D,NS,NP>::W
-      B200_CUDA(cudaMalloc(&G->d_es, (size_t)S->nElm * esw * sizeof(double)));
-    }
     B200_CUDA(cudaMalloc(&G->d_tab, tab.size() * sizeof(double)));
     B200_CUDA(cudaMemcpyAsync(G->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, S->stream));
     B200_CUDA(cudaMalloc(&G->d_geo, (size_t)S->nElm * ((D * D + 2) / 2 * 2) * sizeof(double)));
@@ -1122,15 +1122,30 @@ int build_gather_plan(System *S)
       geometry_kernel<3><<<148 * 8, 256, 0, S->stream>>>(S->nElm, S->d_xyz, S->d_conn, G->d_geo);
     count_launch();
     B200_CUDA(cudaStreamSynchronize(S->stream));
+    if(G->patch) {
+      if(build_patch_plan(S) == B200_OK) return B200_OK;
+      if(getenv("B200_GATHER_KERNEL")) { // explicitly requested: report why (b200_last_error)
+        gather_free(S);
+        return B200_ERR_UNSUPP;
+      }
+      G->patch = false;
+    }
+    if(G->lane) {
+      const size_t esw = (size_t)(NP * D * D + NS * NS + NS * D + NP + 1) / 2 * 2; // ES<D,NS,NP>::W
+      B200_CUDA(cudaMalloc(&G->d_es, (size_t)S->nElm * esw * sizeof(double)));
+    }
+    log_stage("gather plan: geometry");
     const int offwU = (M + 7) / 8 * 8, offwP = (NU + 7) / 8 * 8;
     // lane-group kernels are not limited by the shared memory of the longest rows: few, large launch segments
     const double band    = (G->lane && G->lanes > 1) ? 1.6 : 1.25;
     const int    min_div = (G->lane && G->lanes > 1) ? 12 : 50;
     int       rc = build_node_set(S, G->U, S->spaces[S->su].d_adr, NS, NU, D, G->npbU, offwU, M, NU, NP, S->has_matrix_block[0][0] ? 1 : 0,
                                   S->has_matrix_block[0][1] ? 1 : 0, band, min_div);
+    log_stage("gather plan: U node set");
     if(rc == B200_OK)
       rc = build_node_set(S, G->P, S->spaces[S->sp].d_adr, NP, NP, 1, G->npbP, offwP, NU, NU, NP, S->has_matrix_block[1][0] ? 1 : 0, 0, band,
                           min_div);
+    log_stage("gather plan: P node set");
     if(rc != B200_OK) {
       gather_free(S);
       return rc;
@@ -1342,6 +1357,7 @@ template <int D, int NS, int NP, int NW, int L, int REGS> static int launch_gath
 int launch_gather(System *S, int what, const THCoeffs &c)
 {
   const GatherPlan *G = static_cast<const GatherPlan *>(S->gather);
+  if(G->patch && S->patch != nullptr) return launch_patch(S, what, c);
   if(G->lane) {
     if(S->dim == 2) {
       switch(G->lanes) {

@@ -87,6 +87,7 @@ int build_pattern_device(System *S, int64_t n_inc, int64_t n_dof, const std::vec
       merged.resize(end - merged.begin());
       acc.swap(merged);
     }
+    log_stage("pattern: diagonal keys");
     const int64_t per_elem = (int64_t)M * M;
     const int64_t chunk_elems = std::max<int64_t>(1, (int64_t)(1ll << 28) / per_elem); // <= 2 GiB of keys per chunk
     for(int64_t e0 = 0; e0 < S->nElm; e0 += chunk_elems) {
@@ -100,9 +101,30 @@ int build_pattern_device(System *S, int64_t n_inc, int64_t n_dof, const std::vec
       int64_t nu = uend - chunk.begin();
       if(nu > 0 && chunk[nu - 1] == ~0ull) --nu; // drop the sentinel of filtered pairs
       merged.resize(acc.size() + nu);
-      auto end = thrust::set_union(pol, acc.begin(), acc.end(), chunk.begin(), chunk.begin() + nu, merged.begin());
-      merged.resize(end - merged.begin());
+      // thrust's set operations index with 32 bits: merge key range by key range (both inputs are sorted, so the
+      // pieces concatenate), every piece well below 2^31 entries
+      {
+        const int64_t na = (int64_t)acc.size(), piece = (int64_t)1 << 27;
+        const int64_t nseg = std::max<int64_t>(1, (na + nu + piece - 1) / piece);
+        int64_t       a0 = 0, c0 = 0, o = 0;
+        for(int64_t sgm = 1; sgm <= nseg; ++sgm) {
+          int64_t a1 = na, c1 = nu;
+          if(sgm < nseg) {
+            a1 = std::min(na, sgm * (na / nseg + 1));
+            if(a1 < na) {
+              const uint64_t split = acc[a1]; // first key of the next piece
+              c1 = thrust::lower_bound(pol, chunk.begin() + c0, chunk.begin() + nu, split) - chunk.begin();
+            }
+          }
+          auto end = thrust::set_union(pol, acc.begin() + a0, acc.begin() + a1, chunk.begin() + c0, chunk.begin() + c1, merged.begin() + o);
+          o  = end - merged.begin();
+          a0 = a1;
+          c0 = c1;
+        }
+        merged.resize(o);
+      }
       acc.swap(merged);
+      log_stage("pattern: chunk merged");
     }
     chunk.clear();
     chunk.shrink_to_fit();
@@ -119,6 +141,7 @@ int build_pattern_device(System *S, int64_t n_inc, int64_t n_dof, const std::vec
     split_keys_kernel<<<148 * 16, 256, 0, S->stream>>>(S->nnz, n_inc, thrust::raw_pointer_cast(acc.data()), S->d_ja);
     count_launch(2);
     B200_CUDA(cudaStreamSynchronize(S->stream));
+    log_stage("pattern: ia/ja");
   } catch(const std::exception &ex) {
     set_error(std::string("b200_build_pattern: ") + ex.what());
     return B200_ERR_CUDA;

@@ -12,6 +12,8 @@ namespace b200 {
 
 void set_error(const std::string &msg);
 void count_launch(int n = 1);
+// B200_VERBOSE=1: synchronise, report the CUDA error state and the device memory in use after a set-up stage
+void log_stage(const char *what);
 
 #define B200_CUDA(call)                                                                                       \
   do {                                                                                                        \
@@ -117,6 +119,8 @@ struct System {
   // row-owner gather plan (gather.cu); assembly_mode: B200_ASSEMBLY_*
   void *gather = nullptr;
   int   assembly_mode = 0;
+  // patch plan (patch.cu): block-slot owners over spatially compact element patches, built on top of the gather plan
+  void *patch = nullptr;
   // setToZero is lazy: the gather kernels overwrite every row, so the memset is only materialised when something
   // else reads or accumulates into the arrays (bit 0 rhs, bit 1 matrix)
   int   pending_zero = 0;
@@ -141,6 +145,15 @@ int launch_assemble(System *S, int what, int only_transient);
 int  build_gather_plan(System *S);
 int  launch_gather(System *S, int what, const THCoeffs &c);
 void gather_free(System *S);
+struct GatherTables {
+  const double *d_tab = nullptr, *d_geo = nullptr; // pre-contracted reference tensors (GT layout), per-element inverse map + detJ
+  int           tab_len = 0, tab_len_src = 0;
+};
+bool gather_tables(const System *S, GatherTables *out);
+// patch.cu
+int  build_patch_plan(System *S);
+int  launch_patch(System *S, int what, const THCoeffs &c);
+void patch_free(System *S);
 // chns.cu
 int  chns_analyze(System *S);
 int  chns_build_plan(System *S);

@@ -94,15 +94,16 @@ def square_mesh(n: int, lx: float = 1.0, ly: float = 1.0, x0: float = 0.0, y0: f
 _KUHN = [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)]
 
 
-def cube_mesh(n: int) -> Mesh:
-    """T3D(n): 6 n^3 positively oriented tetrahedra, (n+1)^3 vertices (x fastest, then y, then z)."""
-    g = np.arange(n + 1)
-    k, j, i = np.meshgrid(g, g, g, indexing="ij")
-    xyz = np.stack([i.reshape(-1), j.reshape(-1), k.reshape(-1)], 1) / float(n)
-    c = np.arange(n)
-    ck, cj, ci = np.meshgrid(c, c, c, indexing="ij")
+def box_mesh(nx: int, ny: int, nz: int, lz: float = 1.0, z0: float = 0.0, cut_bottom: bool = False,
+             cut_top: bool = False) -> Mesh:
+    """nx x ny x nz cells on [0,1]^2 x [z0, z0+lz], each split into 6 positively oriented Kuhn tetrahedra; vertices
+    numbered x fastest, then y, then z.  cut_bottom / cut_top mark the z = z0 / z = z0+lz side as an artificial
+    partition cut (multi-GPU slabs): its facets are left out of the physical boundary "Bord"."""
+    k, j, i = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+    xyz = np.stack([i.reshape(-1) / float(nx), j.reshape(-1) / float(ny), z0 + lz * k.reshape(-1) / float(nz)], 1)
+    ck, cj, ci = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
     base = np.stack([ci.reshape(-1), cj.reshape(-1), ck.reshape(-1)], 1)          # (nc, 3)
-    stride = np.array([1, n + 1, (n + 1) ** 2])
+    stride = np.array([1, nx + 1, (nx + 1) * (ny + 1)])
     cells = np.empty((base.shape[0], 6, 4), np.int64)
     for t, perm in enumerate(_KUHN):
         p = base.copy()
@@ -120,7 +121,21 @@ def cube_mesh(n: int) -> Mesh:
     neg = det < 0
     cells[neg, 2], cells[neg, 3] = cells[neg, 3].copy(), cells[neg, 2].copy()
     cells = cells.astype(np.int32)
-    return Mesh(3, np.ascontiguousarray(xyz), cells, boundary_facets(cells), 0)
+    bf = boundary_facets(cells)
+    if cut_bottom or cut_top:
+        layer = bf // ((nx + 1) * (ny + 1))
+        keep = np.ones(bf.shape[0], bool)
+        if cut_bottom:
+            keep &= ~np.all(layer == 0, axis=1)
+        if cut_top:
+            keep &= ~np.all(layer == nz, axis=1)
+        bf = np.ascontiguousarray(bf[keep])
+    return Mesh(3, np.ascontiguousarray(xyz), cells, bf, 0 if not cut_bottom else None)
+
+
+def cube_mesh(n: int) -> Mesh:
+    """T3D(n): 6 n^3 positively oriented tetrahedra, (n+1)^3 vertices (x fastest, then y, then z)."""
+    return box_mesh(n, n, n)
 
 
 def write_msh(mesh: Mesh, path: str) -> None:

@@ -1,4 +1,5 @@
-"""Element / row partition for the multi-GPU path: strips of the structured generators.
+"""Element / row partition for the multi-GPU path: strips (2-D) and slabs (3-D) of the structured
+generators.
 
 The reference offers no domain decomposition (every MPI rank holds the whole mesh and keeps its row range,
 src/feLinearSystemPETSc.cpp:626-640); METIS is a CMake option no source file uses.  Here every rank builds ONLY its own
@@ -51,9 +52,22 @@ def strip_mesh(n: int, rank: int, world: int) -> tuple[M.Mesh, int]:
     return m, 2 * n * n
 
 
+def slab_mesh(n: int, rank: int, world: int) -> tuple[M.Mesh, int]:
+    """Slab `rank` of the [0,1]^2 x [0,world] box: n^3 owned cells (6 n^3 tetrahedra) plus one ghost layer of cells towards
+    each neighbour; the artificial cuts carry no physical boundary."""
+    gb, gt = (1 if rank > 0 else 0), (1 if rank < world - 1 else 0)
+    nz = n + gb + gt
+    m = M.box_mesh(n, n, nz, nz / n, rank - gb / n, cut_bottom=rank > 0, cut_top=rank < world - 1)
+    if rank == 0:
+        m.point_pressure = 0
+    return m, 6 * n * n * n
+
+
 def dof_keys_and_owner(pb: PB.HostProblem, n: int, world: int):
-    """Global key and owning rank of every unknown of a strip problem (unit cells of size 1/n, strips of height 1)."""
+    """Global key and owning rank of every unknown of a strip (2-D, cut along y) or slab (3-D, cut along z) problem:
+    unit cells of size 1/n, parts of height 1."""
     num, mesh, n_dof = pb.num, pb.mesh, pb.n_dof
+    axis = pb.dim - 1
     keys = np.full(n_dof, -1, np.int64)
     own = np.zeros(n_dof, np.int64)
     for f, fld in enumerate(num.fields):
@@ -62,9 +76,15 @@ def dof_keys_and_owner(pb: PB.HostProblem, n: int, world: int):
         sel = comp >= 0
         ix = np.rint(xyz[sel, 0] * 2 * n).astype(np.int64)
         iy = np.rint(xyz[sel, 1] * 2 * n).astype(np.int64)
-        keys[sel] = ((f * 4 + comp[sel]) << 56) | (iy << 28) | ix
-        # strip r owns y in (r, r + 1]; the bottom line y = 0 belongs to rank 0
-        r = np.ceil(iy / (2.0 * n)).astype(np.int64) - 1
+        if pb.dim == 2:
+            keys[sel] = ((f * 4 + comp[sel]) << 56) | (iy << 28) | ix
+            ic = iy
+        else:
+            iz = np.rint(xyz[sel, 2] * 2 * n).astype(np.int64)
+            keys[sel] = ((f * 4 + comp[sel]) << 58) | (iz << 38) | (iy << 19) | ix
+            ic = iz
+        # part r owns the coordinate range (r, r + 1] along the cut axis; the bottom side belongs to rank 0
+        r = np.ceil(ic / (2.0 * n)).astype(np.int64) - 1
         own[sel] = np.clip(r, 0, world - 1)
     return keys[:pb.n_inc], own[:pb.n_inc]
 
@@ -105,6 +125,25 @@ def strip_problem(n: int, rank: int, world: int, kind: str = "ns_div", quad_degr
                   with_source: bool = False):
     """(HostProblem, Partition) of strip `rank`."""
     m, owned_cells = strip_mesh(n, rank, world)
+    pb = PB.taylor_hood(m, kind, quad_degree, field_id, mu, rho, build_pattern=build_pattern, with_source=with_source)
+    if world == 1:
+        return pb, None
+    keys, owner = dof_keys_and_owner(pb, n, world)
+    if allgather is None:
+        import torch.distributed as dist
+
+        def allgather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+    return pb, build_halo(keys, owner, rank, world, allgather, owned_cells)
+
+
+def slab_problem(n: int, rank: int, world: int, kind: str = "ns_div", quad_degree: int = 6, field_id: int = 3,
+                 mu: float = 1.0 / 40.0, rho: float = 1.0, allgather=None, build_pattern: bool = False,
+                 with_source: bool = False):
+    """(HostProblem, Partition) of slab `rank` of the tetrahedral box (the 3-D counterpart of strip_problem)."""
+    m, owned_cells = slab_mesh(n, rank, world)
     pb = PB.taylor_hood(m, kind, quad_degree, field_id, mu, rho, build_pattern=build_pattern, with_source=with_source)
     if world == 1:
         return pb, None

@@ -161,7 +161,8 @@ int b200_set_scatter_mode(b200_system *s, int mode);
 /* B200_ASSEMBLY_*; may be called before or after b200_finalize.  Returns B200_ERR_UNSUPP if GATHER is requested for a
  * problem that does not qualify. */
 int b200_set_assembly_mode(b200_system *s, int mode);
-/* 1 if the last b200_finalize built a gather plan */
+/* 0: no write-once plan (scatter kernels); 1: the last b200_finalize built the row-owner gather plan; 2: it built the
+ * patch plan (block-slot owners over Morton patches of elements, the default where the numbering qualifies) */
 int b200_has_gather_plan(const b200_system *s);
 /* rows of essential vector components (src/feLinearSystemMklPardiso.cpp:998-1041) and periodic (master, slave)
  * pairs (feMetaNumber::PeriodicDOF, src/feNumber.h:234) */

@@ -13,7 +13,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, n, out):
+def _worker(rank, world, port, n, out, dim=2):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import scipy.sparse as sp
@@ -25,11 +25,17 @@ def _worker(rank, world, port, n, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        pb, part = PT.strip_problem(n, rank, world, "ns_div", 8, 1, 0.05, 1.0, build_pattern=True, with_source=True)
-        # undecomposed problem, identical on every rank
-        mg = M.rect_mesh(n, n * world, 1.0, float(world))
-        mg.point_pressure = 0
-        pg = PB.taylor_hood(mg, "ns_div", 8, 1, 0.05, 1.0, with_source=True)
+        if dim == 2:
+            pb, part = PT.strip_problem(n, rank, world, "ns_div", 8, 1, 0.05, 1.0, build_pattern=True, with_source=True)
+            # undecomposed problem, identical on every rank
+            mg = M.rect_mesh(n, n * world, 1.0, float(world))
+            mg.point_pressure = 0
+            pg = PB.taylor_hood(mg, "ns_div", 8, 1, 0.05, 1.0, with_source=True)
+        else:
+            pb, part = PT.slab_problem(n, rank, world, "ns_div", 6, 3, 0.05, 1.0, build_pattern=True, with_source=False)
+            mg = M.box_mesh(n, n, n * world, float(world))
+            mg.point_pressure = 0
+            pg = PB.taylor_hood(mg, "ns_div", 6, 3, 0.05, 1.0, with_source=False)
 
         class G:     # global keys of the undecomposed numbering (same key function, one "strip" of height world)
             pass
@@ -94,5 +100,17 @@ def test_strip_partition_over_gloo(world):
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, 4, out), nprocs=world, join=True)
+    for r in range(world):
+        assert out.get(r) == "ok", out.get(r)
+
+
+def test_slab_partition_over_gloo():
+    """3-D counterpart: slabs of the tetrahedral box cut along z (the partition bench.py uses for T3D at N > 1)."""
+    import torch.multiprocessing as mp
+    world = 2
+    port = 31500 + os.getpid() % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, 2, out, 3), nprocs=world, join=True)
     for r in range(world):
         assert out.get(r) == "ok", out.get(r)
