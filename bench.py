@@ -96,6 +96,14 @@ def build_problem(workload, n, rank, world):
         pb, part = PT.strip_problem(n, rank, world, "ns_div", 8, 1, MU, RHO, build_pattern=False, with_source=False)
         owned = 2 * n * n
         name = f"T2D({n}) P2/P1 Navier-Stokes (convU+divU+divSigma), Kovasznay Re=40 + noise, quad deg 8 (16 pts)"
+    elif workload == "chns":
+        # config 5: monolithic CHNS_Abels on [U (P2), P, Phi, Mu (P1)] with finite-difference Jacobian (22 residual
+        # evaluations per element, src/feBilinearForm.cpp:388-428), BDF2-like state (solDot, c0) supplied by the host
+        m, _ = PT.strip_mesh(n, rank, world)
+        pb = PB.chns(m, chns_model(), 8, 1, MU, RHO, build_pattern=False)
+        owned = m.n_cells if world == 1 else 2 * n * n
+        name = (f"T2D({n}) transient CHNS_Abels P2/P1/P1/P1, residual + finite-difference Jacobian (M = 21 columns), "
+                f"quad deg 8 (16 pts)")
     else:
         # slab r of the [0,1]^2 x [0,world] box: n^3 owned cells of 6 Kuhn tetrahedra plus one ghost layer of cells
         pb, part = PT.slab_problem(n, rank, world, "ns_div", 6, 3, MU, RHO, build_pattern=False, with_source=False)
@@ -110,11 +118,28 @@ def algorithmic_bytes_per_element(pb, nnz):
     """index gather + vertex coordinates + local solution + one write of every CSR value and
     of every rhs entry (no source table, no transient term in this workload)."""
     n_loc = pb.adrU.shape[1] + pb.adrP.shape[1]
+    transient = 0
+    if pb.chns is not None:                # + Phi, Mu tables and the time-derivative vector of the transient form
+        n_loc += pb.adrF.shape[1] + pb.adrM.shape[1]
+        transient = 1
     nE = pb.mesh.n_cells
-    return 4 * n_loc + 8 * pb.dim * (pb.dim + 1) + 8 * n_loc + 8 * nnz / nE + 8 * pb.n_inc / nE
+    return 4 * n_loc + 8 * pb.dim * (pb.dim + 1) + 8 * n_loc * (1 + transient) + 8 * nnz / nE + 8 * pb.n_inc / nE
 
 
-def cpu_reference_baseline(n_cpu, reps, threads=None):
+def chns_model():
+    from feng_b200 import problems as PB
+    return PB.ChnsModel(rhoA=1.0, rhoB=0.8, viscA=0.02, viscB=0.05, mobility=1e-3, sigma=0.1, epsilon=0.05, force=(0.0, -0.5))
+
+
+def chns_state(pb):
+    """BDF-like transient state of the CHNS workload: perturbed unknowns, a time-derivative vector and c0 = 1.5 / dt."""
+    from feng_b200 import problems as PB
+    sol = PB.perturb_unknowns(pb)
+    dot = np.random.default_rng(11).uniform(-1.0, 1.0, pb.n_dof)
+    return sol, dot, 150.0
+
+
+def cpu_reference_baseline(n_cpu, reps, threads=None, chns=False):
     """The reference's own CPU assembly (oracle/_ref = unmodified feNG compiled here) on a bounded sample."""
     from feng_b200 import mesh as M, problems as PB
     from oracle import ref
@@ -126,6 +151,24 @@ def cpu_reference_baseline(n_cpu, reps, threads=None):
     M.write_msh(m, path)
     if threads:
         ref.set_threads(threads)
+    if chns:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_chns import _oracle_problem
+        pb = PB.chns(m, chns_model(), 8, 1, MU, RHO, build_pattern=False)
+        P = ref.RefProblem(path, "chns", 2, 8, 1, MU, RHO, chns=_oracle_problem(pb).prm.as_array())
+        os.remove(path)
+        sol, dot, c0 = chns_state(pb)
+        P.set_solution(sol, dot, c0, 0.0)
+        P.assemble()
+        times = []
+        for _ in range(reps):
+            _, _, sec = P.assemble()
+            times.append(float(sec[0] + sec[1]))
+        nE = m.n_cells
+        P.close()
+        return {"times": times, "n_elm": nE, "cores": ref.max_threads(),
+                "sample": f"T2D({n_cpu}) = {nE} triangles, CHNS_Abels residual + finite-difference Jacobian through "
+                          f"feBilinearForm::computeMatrixFiniteDifference, {reps} passes"}
     P = ref.RefProblem(path, "ns_div", 2, 8, field=1, mu=MU, rho=RHO, p_essential=False)
     os.remove(path)
     pb = PB.taylor_hood(m, "ns_div", 8, 1, MU, RHO, build_pattern=False, with_source=True)
@@ -171,7 +214,8 @@ def run_reference(args, rank, world):
         base = cpu_port_baseline(args.cpu_n3, max(args.steps, 1) + args.warmup)
         kind, timing = "port", "oracle/fe_oracle.py element loops (numpy) + sorted scatter, host perf_counter"
     else:
-        base = cpu_reference_baseline(args.cpu_n, max(args.steps, 1) + args.warmup)
+        base = cpu_reference_baseline(args.cpu_n_chns if args.workload == "chns" else args.cpu_n, max(args.steps, 1) + args.warmup,
+                                      chns=args.workload == "chns")
         kind, timing = "reference", ("reference's own colour loop over computeMatrix/computeResidual + restated "
                                      "Pardiso-style scatter, OpenMP, host steady_clock")
     if base is None:
@@ -197,10 +241,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="t3d", choices=["t2d", "t3d"],
+    ap.add_argument("--workload", default="t3d", choices=["t2d", "t3d", "chns"],
                     help="t3d: the ~20 M-DOF tetrahedral cube BASELINE.json quotes the metric on (default); t2d: refined triangles")
     ap.add_argument("--n", "--size", dest="n", type=int, default=0)
     ap.add_argument("--cpu-n", type=int, default=256, help="T2D size of the reference CPU sample")
+    ap.add_argument("--cpu-n-chns", type=int, default=96, help="T2D size of the reference CPU sample of the CHNS workload")
     ap.add_argument("--cpu-n3", type=int, default=8, help="T3D size of the oracle-port CPU sample")
     ap.add_argument("--solve-maxit", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")
@@ -214,7 +259,11 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
-    n = args.n or (1024 if args.workload == "t2d" else 92)
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    n = args.n or {"t2d": 1024, "t3d": 92, "chns": 512}[args.workload]
 
     import torch
     import torch.distributed as dist
@@ -234,7 +283,14 @@ def main():
     patch = gather and S.gather_plan_kind() == 2
     nE = pb.mesh.n_cells
     host_sol = torch.from_numpy(sol).pin_memory().numpy()        # pinned host buffer of the caller
-    S.set_solution(host_sol)
+    chns = pb.chns is not None
+    if chns:
+        _, dot, c0 = chns_state(pb)
+        host_dot = torch.from_numpy(dot).pin_memory().numpy()
+        upload = lambda: S.set_solution(host_sol, host_dot, c0, 0.0)
+    else:
+        upload = lambda: S.set_solution(host_sol)
+    upload()
 
     def barrier():
         S.sync()
@@ -267,14 +323,14 @@ def main():
     clocks = sampler.stop()
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------
     for _ in range(2):
-        S.set_solution(host_sol)
+        upload()
         S.set_to_zero(3)
         S.assemble(3)
         S.rhs_max_norm()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        S.set_solution(host_sol)
+        upload()
         S.set_to_zero(3)
         S.assemble(3)
         rn = S.rhs_max_norm()
@@ -291,7 +347,7 @@ def main():
     tot_owned = float(owned_all[0])
 
     extra = {}
-    if not args.no_solve:
+    if not args.no_solve and not chns:
         extra["newton_step"] = newton_step(ls, sol, pb, args.solve_maxit)
 
     if rank == 0:
@@ -315,19 +371,23 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_name, "elements_per_gpu": int(owned), "ghost_elements_per_gpu": int(nE - owned),
                        "n_dof_per_gpu": int(pb.n_dof), "n_unknowns_per_gpu": int(pb.n_inc), "nnz_per_gpu": int(S.nnz),
-                       "assembly": ("patch kernel: block-slot owners over Morton patches of elements, element state staged "
+                       "assembly": ("chns_kernel: one warp per element, lane j = residual of the state perturbed in local "
+                                    "column j (finite-difference Jacobian), red.global.add.f64 into the CSR arrays after "
+                                    "a memset") if chns else
+                                   ("patch kernel: block-slot owners over Morton patches of elements, element state staged "
                                     "in shared memory, pre-contracted reference tensors; every CSR value written once, "
                                     "no memset, no atomics") if patch else
                                    ("row-owner gather on pre-contracted reference tensors: every CSR row written once, "
                                     "no memset, no atomics") if gather else
                                    "quadrature-loop kernel + atomic (red.global.add.f64) scatter into precomputed CSR slots",
                        "cache": "inputs larger than L2 (CSR values written per pass = %.1f GB)" % (S.nnz * 8 / 1e9),
-                       "partition": ("strips, owner-computes with one ghost layer of elements (no collective in assembly); "
+                       "partition": ("strips / slabs, owner-computes with one ghost layer of elements (no collective in assembly); "
                                      "SpMV input halo over NCCL send/recv, Krylov dots all-reduced") if world > 1
                        else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
-                         "kernel": ("patch_kernel (one launch per assembly pass) + patch_zero_kernel" if patch else
+                         "kernel": "chns_kernel (+ memsets of val and rhs)" if chns else
+                                   ("patch_kernel (one launch per assembly pass) + patch_zero_kernel" if patch else
                                     "gather kernels (one assembly pass = several launches, timed together)"
                                     if gather else "th_kernel fused Jacobian+residual+scatter"),
                          "kernel_ms": k_ms, "algorithmic_bytes_per_element": bpe, "peak_source": peak_src,
@@ -336,14 +396,14 @@ def main():
             "spmv": {"ms": spmv_ms, "achieved_gbs": spmv_bytes / (spmv_ms * 1e-3) / 1e9,
                      "frac": spmv_bytes / (spmv_ms * 1e-3) / 1e9 / peak, "bytes": spmv_bytes},
             "e2e": {"value": tot_owned / (e2e_ms / args.steps * 1e-3) / 1e6, "unit": UNIT,
-                    "h2d_bytes_per_step": int(pb.n_dof * 8), "d2h_bytes_per_step": 8,
+                    "h2d_bytes_per_step": int(pb.n_dof * 8 * (2 if chns else 1)), "d2h_bytes_per_step": 8,
                     "ms_per_step": e2e_ms / args.steps, "rhs_max_norm": rn},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         line.update(extra)
         if world == 1 and not args.no_cpu:
-            ref2d = cpu_reference_baseline(args.cpu_n, 3)
-            base = ref2d if args.workload == "t2d" else cpu_port_baseline(args.cpu_n3, 3)
+            ref2d = cpu_reference_baseline(args.cpu_n, 3) if not chns else cpu_reference_baseline(args.cpu_n_chns, 3, chns=True)
+            base = ref2d if args.workload != "t3d" else cpu_port_baseline(args.cpu_n3, 3)
             if base is not None:
                 per = sum(base["times"]) / len(base["times"])
                 line["cpu_baseline"] = {"value": base["n_elm"] / per / 1e6, "unit": UNIT, "cores": base["cores"],
@@ -356,7 +416,8 @@ def main():
                 per = sum(ref2d["times"]) / len(ref2d["times"])
                 line["cpu_reference_2d"] = {"value": ref2d["n_elm"] / per / 1e6, "unit": UNIT, "cores": ref2d["cores"],
                                             "kind": "reference", "sample": ref2d["sample"]}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

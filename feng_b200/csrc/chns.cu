@@ -47,7 +47,7 @@ template <int NSF> struct ChnsT {
   __host__ __device__ static int len(int nq) { return nq + nq * CHNS_NSU * 3 + nq * CHNS_NSP + nq * NSF * 3; }
 };
 
-template <int NSF> __global__ void __launch_bounds__(CHNS_WPB * 32) chns_kernel(const ChnsArgs a)
+template <int NSF> __global__ void __launch_bounds__(CHNS_WPB * 32, 4) chns_kernel(const ChnsArgs a)
 {
   using T = ChnsT<NSF>;
   constexpr int M = T::M, NU = T::NU, NSU = CHNS_NSU, NSP = CHNS_NSP;
