@@ -630,6 +630,40 @@ int analyze_forms(System *S)
   return B200_OK;
 }
 
+// CSR slot of every local entry, for the scatter kernels (th_kernel / sc_kernel).  4 nElm M^2 bytes (21.6 GB at T3D(92)):
+// built at finalize only when no write-once plan exists, otherwise on the first scatter-mode assembly.
+static int build_slot_map(System *S)
+{
+  const Space &U  = S->spaces[S->su];
+  const int    NU = U.nS * U.nc, NP = S->sp >= 0 ? S->spaces[S->sp].nS : 0;
+  const int    M  = S->M;
+  int          mask = 0;
+  for(int bi = 0; bi < 2; ++bi)
+    for(int bj = 0; bj < 2; ++bj)
+      if(S->has_matrix_block[bi][bj]) mask |= 1 << (bi * 2 + bj);
+  if(S->d_slot) cudaFree(S->d_slot);
+  S->d_slot = nullptr;
+  B200_CUDA(cudaMalloc(&S->d_slot, (size_t)S->nElm * M * M * sizeof(int32_t)));
+  int *d_err;
+  B200_CUDA(cudaMalloc(&d_err, sizeof(int)));
+  B200_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), S->stream));
+  slot_map_kernel<<<148 * 8, 256, 0, S->stream>>>(S->nElm, M, NU, U.d_adr, S->sp >= 0 ? S->spaces[S->sp].d_adr : nullptr, NP, S->d_ia,
+                                                  S->d_ja, S->nInc, mask, S->d_slot, d_err);
+  count_launch();
+  int h_err = 0;
+  B200_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, S->stream));
+  B200_CUDA(cudaStreamSynchronize(S->stream));
+  cudaFree(d_err);
+  if(h_err) {
+    cudaFree(S->d_slot);
+    S->d_slot = nullptr;
+    set_error("b200_finalize: a local (row, col) pair is missing from the CSR pattern");
+    return B200_ERR_ARG;
+  }
+  log_stage("plan: slot map");
+  return B200_OK;
+}
+
 int build_plan(System *S)
 {
   if(S->d_ia == nullptr) {
@@ -665,33 +699,8 @@ int build_plan(System *S)
     B200_CUDA(cudaStreamSynchronize(S->stream));
   }
 
-  // slot map
-  {
-    const Space &U  = S->spaces[S->su];
-    const int    NU = U.nS * U.nc, NP = S->sp >= 0 ? S->spaces[S->sp].nS : 0;
-    const int    M  = S->M;
-    int          mask = 0;
-    for(int bi = 0; bi < 2; ++bi)
-      for(int bj = 0; bj < 2; ++bj)
-        if(S->has_matrix_block[bi][bj]) mask |= 1 << (bi * 2 + bj);
-    if(S->d_slot) cudaFree(S->d_slot);
-    B200_CUDA(cudaMalloc(&S->d_slot, (size_t)S->nElm * M * M * sizeof(int32_t)));
-    int *d_err;
-    B200_CUDA(cudaMalloc(&d_err, sizeof(int)));
-    B200_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), S->stream));
-    slot_map_kernel<<<148 * 8, 256, 0, S->stream>>>(S->nElm, M, NU, U.d_adr, S->sp >= 0 ? S->spaces[S->sp].d_adr : nullptr, NP, S->d_ia,
-                                                    S->d_ja, S->nInc, mask, S->d_slot, d_err);
-    count_launch();
-    int h_err = 0;
-    B200_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, S->stream));
-    B200_CUDA(cudaStreamSynchronize(S->stream));
-    cudaFree(d_err);
-    if(h_err) {
-      set_error("b200_finalize: a local (row, col) pair is missing from the CSR pattern");
-      return B200_ERR_ARG;
-    }
-  }
-  log_stage("plan: slot map");
+  if(S->d_slot) cudaFree(S->d_slot);
+  S->d_slot = nullptr;
   // row-owner gather plan where the problem qualifies
   gather_free(S);
   if(S->plan == PLAN_TAYLOR_HOOD && S->assembly_mode != B200_ASSEMBLY_SCATTER) {
@@ -701,6 +710,8 @@ int build_plan(System *S)
     set_error("b200_finalize: the gather assembly needs the fused Taylor-Hood system");
     return B200_ERR_UNSUPP;
   }
+  // the write-once plans validate the pattern themselves; without one the scatter kernels run and need their slot map now
+  if(S->gather == nullptr) return build_slot_map(S);
   return B200_OK;
 }
 
@@ -820,6 +831,10 @@ int launch_assemble(System *S, int what, int only_transient)
   {
     const int zrc = flush_zero(S, 3);
     if(zrc != B200_OK) return zrc;
+  }
+  if(S->plan != PLAN_CHNS && S->d_slot == nullptr) {
+    const int src = build_slot_map(S);
+    if(src != B200_OK) return src;
   }
   if(S->plan == PLAN_CHNS) {
     // the monolithic form is not a "transient matrix" form (feBilinearForm::isTransientMatrix is false for it)
