@@ -35,6 +35,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <type_traits>
 #include <cstdio>
 #include <fstream>
 #include <map>
@@ -47,6 +48,8 @@ struct feB200Options {
   bool devicePattern = false;          // build the EZCRS pattern on the device instead of taking the host one
   bool alwaysUpload  = false;          // re-upload the state in assembleMatrices even right after assembleResiduals
 };
+
+extern std::vector<double> solAtTimeN; // src/feNonLinearSolver.cpp:35
 
 namespace feB200detail
 {
@@ -70,19 +73,23 @@ namespace feB200detail
   template <class T> struct DiffPeek : public T {
     static const feFunction *diff(const T *s) { return s->*(&DiffPeek::_diffusivity); }
   };
-  // CHNS_Abels<2> keeps its property callbacks and constants protected (src/feSysElm.h:1272-1284)
-  struct ChnsPeek : public CHNS_Abels<2> {
-    static const feFunction *density(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_density); }
-    static const feFunction *drhodphi(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_drhodphi); }
-    static const feFunction *viscosity(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_viscosity); }
-    static const feFunction *mobility(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_mobility); }
-    static const feVectorFunction *volumeForce(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_volumeForce); }
-    static const feVectorFunction *sourceU(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_sourceU); }
-    static const feFunction *sourceP(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_sourceP); }
-    static const feFunction *sourcePhi(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_sourcePhi); }
-    static const feFunction *sourceMu(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_sourceMu); }
-    static double surfaceTension(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_surfaceTension); }
-    static double epsilon(const CHNS_Abels<2> *s) { return s->*(&ChnsPeek::_epsilon); }
+  // CHNS_Abels<2> / CHNS_MassAveraged<2> keep their property callbacks and constants protected
+  // (src/feSysElm.h:1272-1284, :1355-1368)
+  template <class C> struct ChnsPeekT : public C {
+    static const feFunction *density(const C *s) { return s->*(&ChnsPeekT::_density); }
+    static const feFunction *drhodphi(const C *s) { return s->*(&ChnsPeekT::_drhodphi); }
+    static const feFunction *viscosity(const C *s) { return s->*(&ChnsPeekT::_viscosity); }
+    static const feFunction *mobility(const C *s) { return s->*(&ChnsPeekT::_mobility); }
+    static const feVectorFunction *volumeForce(const C *s) { return s->*(&ChnsPeekT::_volumeForce); }
+    static const feVectorFunction *sourceU(const C *s) { return s->*(&ChnsPeekT::_sourceU); }
+    static const feFunction *sourceP(const C *s) { return s->*(&ChnsPeekT::_sourceP); }
+    static const feFunction *sourcePhi(const C *s) { return s->*(&ChnsPeekT::_sourcePhi); }
+    static const feFunction *sourceMu(const C *s) { return s->*(&ChnsPeekT::_sourceMu); }
+    static double surfaceTension(const C *s) { return s->*(&ChnsPeekT::_surfaceTension); }
+    static double epsilon(const C *s) { return s->*(&ChnsPeekT::_epsilon); }
+  };
+  struct MassAveragedPeek : public CHNS_MassAveraged<2> {
+    static double alpha(const CHNS_MassAveraged<2> *s) { return s->*(&MassAveragedPeek::_alpha); }
   };
 } // namespace feB200detail
 
@@ -98,6 +105,7 @@ protected:
   int           _dim = 0, _nElm = 0, _nQuad = 0;
   std::vector<feSpace *> _spaceList; // engine space id -> host space
   bool          _stateFresh = false;
+  bool          _needSolutionN = false;
   bool          _constraintInit = false;
   b200_solve_info _lastInfo{};
   int           _numSolves = 0;
@@ -247,12 +255,16 @@ protected:
     out[2] = 0.;
     return true;
   }
-  bool addChnsForm(feBilinearForm *f, feSysElm *se)
+  template <class C> bool addChnsForm(feBilinearForm *f, feSysElm *se, int kind)
   {
-    auto *s = dynamic_cast<const CHNS_Abels<2> *>(se);
-    if(!s || f->_intSpaces.size() != 4) return fail("CHNS_ABELS form must be a CHNS_Abels<2> on {U, P, Phi, Mu}");
-    using Pk = feB200detail::ChnsPeek;
+    auto *s = dynamic_cast<const C *>(se);
+    if(!s || f->_intSpaces.size() != 4) return fail("CHNS form must be a CHNS_Abels<2> / CHNS_MassAveraged<2> on {U, P, Phi, Mu}");
+    using Pk = feB200detail::ChnsPeekT<C>;
     b200_chns_params prm{};
+    if constexpr(std::is_same<C, CHNS_MassAveraged<2>>::value) {
+      prm.mass_alpha = feB200detail::MassAveragedPeek::alpha(s);
+      _needSolutionN = true; // phi at the previous time step: the global solAtTimeN goes to the device with the state
+    }
     bool limRho = false, limVisc = false;
     if(!probeLinearLaw(Pk::density(s), prm.rho_a, prm.rho_b, limRho) || !probeLinearLaw(Pk::viscosity(s), prm.visc_a, prm.visc_b, limVisc) ||
        limRho != limVisc)
@@ -283,7 +295,7 @@ protected:
     int sp[4];
     for(int k = 0; k < 4; ++k)
       if((sp[k] = spaceId(f->_intSpaces[k])) < 0) return false;
-    return ok(b200_add_form_chns(_sys, B200_FORM_CHNS_ABELS, sp[0], sp[1], sp[2], sp[3], &prm), "b200_add_form_chns");
+    return ok(b200_add_form_chns(_sys, kind, sp[0], sp[1], sp[2], sp[3], &prm), "b200_add_form_chns");
   }
 
   template <class T> bool addCoeffForm(feBilinearForm *f, feSysElm *se, int kind, int su, int sp, const feFunction *param)
@@ -357,7 +369,8 @@ protected:
         _sources.push_back(sf);
         return true;
       }
-      case CHNS_ABELS: return addChnsForm(f, se);
+      case CHNS_ABELS: return addChnsForm<CHNS_Abels<2>>(f, se, B200_FORM_CHNS_ABELS);
+      case CHNS_MASS_AVERAGED: return addChnsForm<CHNS_MassAveraged<2>>(f, se, B200_FORM_CHNS_MASS_AVERAGED);
       case TRANSIENT_MASS: return addCoeffForm<feSysElm_TransientMass>(f, se, id, s0, -1, nullptr);
       case DIFFUSION:
         // diffusivity is the form's only callback: kind DIFFUSION uses coeff x param with param = 1
@@ -386,6 +399,9 @@ protected:
     refreshSources(sol);
     ok(b200_set_solution(_sys, sol->getSolution().data(), sol->getSolutionDot().data(), sol->getC0(), sol->getCurrentTime()),
        "b200_set_solution");
+    // feBilinearForm::initialize reads the previous time step from the global solAtTimeN (src/feBilinearForm.cpp:277,347)
+    if(_needSolutionN)
+      ok(b200_set_solution_n(_sys, (feInt)solAtTimeN.size() == _nDOF ? solAtTimeN.data() : nullptr), "b200_set_solution_n");
   }
 
   // rows of essential vector components, as src/feLinearSystemMklPardiso.cpp:998-1041

@@ -19,7 +19,7 @@ SYMBOLS = [
     "b200_set_mesh", "b200_set_quadrature", "b200_add_space", "b200_add_form", "b200_set_source", "b200_set_pattern",
     "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode", "b200_set_assembly_mode", "b200_has_gather_plan", "b200_add_form_chns",
     "b200_set_constraints", "b200_set_blocks", "b200_finalize", "b200_system_size", "b200_set_solution",
-    "b200_set_to_zero", "b200_assemble", "b200_rhs_max_norm", "b200_du_max_norm", "b200_constrain",
+    "b200_set_solution_n", "b200_set_to_zero", "b200_assemble", "b200_rhs_max_norm", "b200_du_max_norm", "b200_constrain",
     "b200_apply_periodicity", "b200_solve", "b200_correct_solution", "b200_get_rhs", "b200_axpy_rhs",
     "b200_get_matrix_values", "b200_get_du", "b200_get_solution", "b200_spmv", "b200_last_assemble_ms",
     "b200_last_solve_ms", "b200_time_spmv", "b200_sync", "b200_time_begin", "b200_time_end",
@@ -42,10 +42,10 @@ class ChnsParams(C.Structure):
                 ("mobility", C.c_double), ("surface_tension", C.c_double), ("epsilon", C.c_double),
                 ("force", C.c_double * 3), ("source_u", C.c_double * 3), ("source_p", C.c_double),
                 ("source_phi", C.c_double), ("source_mu", C.c_double), ("limiter", C.c_int),
-                ("degenerate_mobility", C.c_int)]
+                ("degenerate_mobility", C.c_int), ("mass_alpha", C.c_double)]
 
 
-FORM_CHNS_ABELS = 35
+FORM_CHNS_ABELS, FORM_CHNS_MASS_AVERAGED = 35, 36
 
 
 class SolveInfo(C.Structure):
@@ -148,12 +148,14 @@ class System:
         return check(self.L.b200_add_form(self.h, kind, su, sp, C.c_double(coeff), C.c_double(param), _d(src)),
                      "b200_add_form")
 
-    def add_form_chns(self, su, sp, sf, sm, model, kind=FORM_CHNS_ABELS):
+    def add_form_chns(self, su, sp, sf, sm, model, kind=None):
         """model: any object with the attributes of feng_b200.problems.ChnsModel"""
+        if kind is None:
+            kind = FORM_CHNS_MASS_AVERAGED if getattr(model, "formulation", "abels") == "mass_averaged" else FORM_CHNS_ABELS
         prm = ChnsParams(model.rhoA, model.rhoB, model.viscA, model.viscB, model.mobility, model.sigma, model.epsilon,
                          (C.c_double * 3)(model.force[0], model.force[1], 0.0),
                          (C.c_double * 3)(model.src_u[0], model.src_u[1], 0.0), model.src_p, model.src_phi,
-                         model.src_mu, int(model.limiter), int(model.degenerate_mobility))
+                         model.src_mu, int(model.limiter), int(model.degenerate_mobility), float(getattr(model, "alpha", 0.0)))
         return check(self.L.b200_add_form_chns(self.h, kind, su, sp, sf, sm, C.byref(prm)), "b200_add_form_chns")
 
     def set_source(self, form_id, source):
@@ -234,6 +236,14 @@ class System:
         sol = np.ascontiguousarray(sol, np.float64)
         sd = None if sol_dot is None else np.ascontiguousarray(sol_dot, np.float64)
         check(self.L.b200_set_solution(self.h, _d(sol), _d(sd), C.c_double(c0), C.c_double(t)), "b200_set_solution")
+
+    def set_solution_n(self, sol_n):
+        """state at the previous time step (the reference's global solAtTimeN); None = the current solution"""
+        if sol_n is None:
+            check(self.L.b200_set_solution_n(self.h, None), "b200_set_solution_n")
+        else:
+            a = np.ascontiguousarray(sol_n, np.float64)
+            check(self.L.b200_set_solution_n(self.h, _d(a)), "b200_set_solution_n")
 
     def set_to_zero(self, what=3):
         check(self.L.b200_set_to_zero(self.h, what), "b200_set_to_zero")

@@ -117,6 +117,7 @@ static void free_system(System *S)
   cudaFree(S->d_du);
   cudaFree(S->d_sol);
   cudaFree(S->d_soldot);
+  cudaFree(S->d_soln);
   cudaFree(S->d_slot);
   cudaFree(S->d_tab);
   cudaFree(S->d_color_elems);
@@ -141,6 +142,9 @@ static int alloc_linear_system(System *S)
   cudaFree(S->d_du);
   cudaFree(S->d_sol);
   cudaFree(S->d_soldot);
+  cudaFree(S->d_soln);
+  S->d_soln    = nullptr;
+  S->have_soln = false;
   B200_CUDA(cudaMalloc(&S->d_val, (size_t)S->nnz * sizeof(double)));
   B200_CUDA(cudaMalloc(&S->d_rhs, nb));
   B200_CUDA(cudaMalloc(&S->d_du, nb));
@@ -324,8 +328,8 @@ int b200_add_form_chns(b200_system *s, int kind, int space_u, int space_p, int s
       set_error("b200_add_form_chns: unknown space id");
       return B200_ERR_ARG;
     }
-  if(kind != B200_FORM_CHNS_ABELS || !params) {
-    set_error("b200_add_form_chns: only B200_FORM_CHNS_ABELS is built (the other CHNS formulations are not)");
+  if((kind != B200_FORM_CHNS_ABELS && kind != B200_FORM_CHNS_MASS_AVERAGED) || !params) {
+    set_error("b200_add_form_chns: CHNS_Abels and CHNS_MassAveraged are built (CHNS_Khanwale and CHNS_VolumeAveragedGeneric are not)");
     return B200_ERR_UNSUPP;
   }
   Form f;
@@ -335,7 +339,8 @@ int b200_add_form_chns(b200_system *s, int kind, int space_u, int space_p, int s
   s->forms.push_back(f);
   s->chns_active = true;
   for(int k = 0; k < 4; ++k) s->chns_space[k] = sp[k];
-  s->chns_prm = *params;
+  s->chns_prm   = *params;
+  s->chns_model = kind == B200_FORM_CHNS_MASS_AVERAGED ? 1 : 0;
   chns_free(s);
   s->plan = PLAN_NONE;
   return (int)s->forms.size() - 1;
@@ -536,6 +541,21 @@ int b200_set_solution(b200_system *s, const double *sol, const double *sol_dot, 
   s->c0 = c0;
   s->t  = t;
   B200_CUDA(cudaStreamSynchronize(s->stream)); // the host buffers may be pageable and reused by the caller
+  return B200_OK;
+}
+
+int b200_set_solution_n(b200_system *s, const double *sol_n)
+{
+  CHECK_S(s);
+  if(!s->d_sol) {
+    set_error("b200_set_solution_n: set the pattern first");
+    return B200_ERR_ARG;
+  }
+  s->have_soln = sol_n != nullptr;
+  if(!sol_n) return B200_OK;
+  if(!s->d_soln) B200_CUDA(cudaMalloc(&s->d_soln, (size_t)s->nDOF * sizeof(double)));
+  B200_CUDA(cudaMemcpyAsync(s->d_soln, sol_n, (size_t)s->nDOF * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  B200_CUDA(cudaStreamSynchronize(s->stream));
   return B200_OK;
 }
 

@@ -1,6 +1,8 @@
 // Monolithic Cahn-Hilliard Navier-Stokes weak form with finite-difference Jacobian.
 //
-// Reference: CHNS_Abels<2>::computeBe (src/feSysElmCHNS.cpp:66-273) evaluated N+1 times per element by
+// Reference: CHNS_Abels<2>::computeBe (src/feSysElmCHNS.cpp:66-273, MODEL 0) and CHNS_MassAveraged<2>::computeBe
+// (src/feSysElmCHNS.cpp:347-602, MODEL 1: mass-averaged velocity, pressure-dependent diffusive flux, time-averaged double
+// well with phi at the previous time step from b200_set_solution_n) evaluated N+1 times per element by
 // feBilinearForm::computeMatrixFiniteDifference (src/feBilinearForm.cpp:388-428), one weak form on the fields
 // [U (vector P2), P (P1), Phi, Mu (P1 or P2)] (layout src/feSysElmCHNS.cpp:13-14), property laws of CHNS_Solver
 // (src/CHNS_Solver.cpp:124-235) as enums instead of host callbacks.
@@ -24,7 +26,7 @@ struct ChnsArgs {
   int64_t         nElm;
   const double   *xyz;
   const int32_t  *conn, *adr; // adr: [nElm][M] local DOFs in field order U | P | Phi | Mu
-  const double   *sol, *soldot, *tab;
+  const double   *sol, *soldot, *soln, *tab;
   const int64_t  *ia;
   const int32_t  *ja;
   double         *val, *rhs;
@@ -34,30 +36,34 @@ struct ChnsArgs {
   b200_chns_params prm;
 };
 
-constexpr int CHNS_NSU = 6, CHNS_NSP = 3, CHNS_WPB = 4, CHNS_NFLD = 16;
+constexpr int CHNS_NSU = 6, CHNS_NSP = 3, CHNS_WPB = 4;
+// fields per quadrature node: 16 for CHNS_Abels; + grad p (2) + phi at the previous time step for CHNS_MassAveraged
+__host__ __device__ constexpr int chns_nfld(int model) { return model == 0 ? 16 : 20; }
 
 template <int NSF> struct ChnsT {
   static constexpr int NU = CHNS_NSU * 2, M = NU + CHNS_NSP + 2 * NSF;
-  // table layout (doubles): w[nq] | LU[nq][6] | dLU[nq][6][2] | LP[nq][3] | LF[nq][NSF] | dLF[nq][NSF][2]
+  // table layout (doubles): w[nq] | LU[nq][6] | dLU[nq][6][2] | LP[nq][3] | LF[nq][NSF] | dLF[nq][NSF][2] | dLP[nq][3][2]
   __host__ __device__ static int o_lu(int nq) { return nq; }
   __host__ __device__ static int o_dlu(int nq) { return nq + nq * CHNS_NSU; }
   __host__ __device__ static int o_lp(int nq) { return nq + nq * CHNS_NSU * 3; }
   __host__ __device__ static int o_lf(int nq) { return nq + nq * CHNS_NSU * 3 + nq * CHNS_NSP; }
   __host__ __device__ static int o_dlf(int nq) { return nq + nq * CHNS_NSU * 3 + nq * CHNS_NSP + nq * NSF; }
-  __host__ __device__ static int len(int nq) { return nq + nq * CHNS_NSU * 3 + nq * CHNS_NSP + nq * NSF * 3; }
+  __host__ __device__ static int o_dlp(int nq) { return nq + nq * CHNS_NSU * 3 + nq * CHNS_NSP + nq * NSF * 3; }
+  __host__ __device__ static int len(int nq) { return o_dlp(nq) + nq * CHNS_NSP * 2; }
 };
 
-template <int NSF> __global__ void __launch_bounds__(CHNS_WPB * 32, 4) chns_kernel(const ChnsArgs a)
+template <int NSF, int MODEL> __global__ void __launch_bounds__(CHNS_WPB * 32, MODEL == 0 ? 4 : 3) chns_kernel(const ChnsArgs a)
 {
   using T = ChnsT<NSF>;
-  constexpr int M = T::M, NU = T::NU, NSU = CHNS_NSU, NSP = CHNS_NSP;
+  constexpr int M = T::M, NU = T::NU, NSU = CHNS_NSU, NSP = CHNS_NSP, CHNS_NFLD = chns_nfld(MODEL);
   static_assert(M + 1 <= 32, "one lane per local column plus the base lane");
   extern __shared__ double sm[];
   double *s_tab = sm;                                    // ntab
   double *s_loc = s_tab + a.ntab;                        // [WPB][M]
   double *s_dot = s_loc + CHNS_WPB * M;                  // [WPB][M]
   double *s_fld = s_dot + CHNS_WPB * M;                  // [WPB][nq][NFLD]
-  int32_t *s_adr = reinterpret_cast<int32_t *>(s_fld + (size_t)CHNS_WPB * a.nq * CHNS_NFLD); // [WPB][M]
+  double *s_ln  = s_fld + (size_t)CHNS_WPB * a.nq * CHNS_NFLD; // [WPB][8] Phi DOFs at the previous time step (MODEL 1)
+  int32_t *s_adr = reinterpret_cast<int32_t *>(s_ln + CHNS_WPB * 8); // [WPB][M]
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nq = a.nq;
   for(int i = tid; i < a.ntab; i += CHNS_WPB * 32) s_tab[i] = a.tab[i];
@@ -65,7 +71,8 @@ template <int NSF> __global__ void __launch_bounds__(CHNS_WPB * 32, 4) chns_kern
   const int64_t e = blockIdx.x * (int64_t)CHNS_WPB + wid;
   if(e >= a.nElm) return;
   const double *w = s_tab, *LU = s_tab + T::o_lu(nq), *dLU = s_tab + T::o_dlu(nq), *LP = s_tab + T::o_lp(nq), *LF = s_tab + T::o_lf(nq),
-               *dLF = s_tab + T::o_dlf(nq);
+               *dLF = s_tab + T::o_dlf(nq), *dLP = s_tab + T::o_dlp(nq);
+  double *locn = s_ln + wid * 8;
   double  *loc = s_loc + wid * M, *dot = s_dot + wid * M, *fld = s_fld + (size_t)wid * nq * CHNS_NFLD;
   int32_t *adr = s_adr + wid * M;
   for(int i = lane; i < M; i += 32) {
@@ -73,6 +80,9 @@ template <int NSF> __global__ void __launch_bounds__(CHNS_WPB * 32, 4) chns_kern
     adr[i] = d;
     loc[i] = a.sol[d];
     dot[i] = a.soldot ? a.soldot[d] : 0.;
+    // feBilinearForm::initialize fills _solAtTimeN from the global solAtTimeN (src/feBilinearForm.cpp:347); without
+    // b200_set_solution_n it is the current solution, as in a stationary solve
+    if(MODEL == 1 && i >= NU + NSP && i < NU + NSP + NSF) locn[i - NU - NSP] = a.soln ? a.soln[d] : a.sol[d];
   }
   double G[4], J;
   {
@@ -102,7 +112,16 @@ template <int NSF> __global__ void __launch_bounds__(CHNS_WPB * 32, 4) chns_kern
       f[10] += gy * Ul[b * 2];     // d_y u_0
       f[11] += gy * Ul[b * 2 + 1]; // d_y u_1
     }
-    for(int q = 0; q < NSP; ++q) f[2] += LP[k * NSP + q] * Pl[q];
+    for(int q = 0; q < NSP; ++q) {
+      f[2] += LP[k * NSP + q] * Pl[q];
+      if(MODEL == 1) {
+        const double dr = dLP[(k * NSP + q) * 2], ds = dLP[(k * NSP + q) * 2 + 1];
+        f[16] += (dr * G[0] + ds * G[2]) * Pl[q];
+        f[17] += (dr * G[1] + ds * G[3]) * Pl[q];
+      }
+    }
+    if(MODEL == 1)
+      for(int i = 0; i < NSF; ++i) f[18] += LF[k * NSF + i] * locn[i];
     for(int i = 0; i < NSF; ++i) {
       const double L = LF[k * NSF + i], dr = dLF[(k * NSF + i) * 2], ds = dLF[(k * NSF + i) * 2 + 1];
       const double gx = dr * G[0] + ds * G[2], gy = dr * G[1] + ds * G[3];
@@ -157,6 +176,12 @@ template <int NSF> __global__ void __launch_bounds__(CHNS_WPB * 32, 4) chns_kern
       const double *f = fld + k * CHNS_NFLD;
       double u0 = f[0], u1 = f[1], p = f[2], phi = f[3], mu = f[4], dt0 = f[5], dt1 = f[6], dphidt = f[7];
       double gu00 = f[8], gu01 = f[9], gu10 = f[10], gu11 = f[11], gp0 = f[12], gp1 = f[13], gm0 = f[14], gm1 = f[15];
+      double gpr0 = 0., gpr1 = 0., phin = 0.; // grad p and phi at the previous time step (MODEL 1)
+      if(MODEL == 1) {
+        gpr0 = f[16];
+        gpr1 = f[17];
+        phin = f[18];
+      }
       // test functions and their physical gradients at this node
       double lu[NSU], gux[NSU], guy[NSU], lf[NSF], gfx[NSF], gfy[NSF];
 #pragma unroll
@@ -186,6 +211,11 @@ template <int NSF> __global__ void __launch_bounds__(CHNS_WPB * 32, 4) chns_kern
         gu10 += du0 * gy;
         gu11 += du1 * gy;
         p += dp * LP[k * NSP + qP];
+        if(MODEL == 1) {
+          const double pr_ = dLP[(k * NSP + qP) * 2], ps_ = dLP[(k * NSP + qP) * 2 + 1];
+          gpr0 += dp * (pr_ * G[0] + ps_ * G[2]);
+          gpr1 += dp * (pr_ * G[1] + ps_ * G[3]);
+        }
         const double Lf = LF[k * NSF + iF], fr = dLF[(k * NSF + iF) * 2], fs = dLF[(k * NSF + iF) * 2 + 1];
         phi += dphi * Lf;
         dphidt += dphi * a.c0 * Lf;
@@ -201,29 +231,64 @@ template <int NSF> __global__ void __launch_bounds__(CHNS_WPB * 32, 4) chns_kern
       const double rho = drho * pc + (pr.rho_a + pr.rho_b) * 0.5;
       const double eta = (pr.visc_a - pr.visc_b) * 0.5 * pc + (pr.visc_a + pr.visc_b) * 0.5;
       const double Mob = pr.degenerate_mobility ? pr.mobility * fabs(1. - phi * phi) : pr.mobility;
-      // src/feSysElmCHNS.cpp:158-171
       const double ugu0 = u0 * gu00 + u1 * gu10, ugu1 = u0 * gu01 + u1 * gu11;
-      const double gmgu0 = gm0 * gu00 + gm1 * gu10, gmgu1 = gm0 * gu01 + gm1 * gu11;
       const double S00 = gu00 + gu00, S01 = gu01 + gu10, S11 = gu11 + gu11;
       const double divu = gu00 + gu11, ugphi = u0 * gp0 + u1 * gp1;
-      // momentum (:192-219): test function i = 2a + c is phi_a e_c
-      const double v0 = rho * (dt0 + ugu0 - pr.force[0]) - drho * Mob * gmgu0 + phi * gm0 + pr.source_u[0];
-      const double v1 = rho * (dt1 + ugu1 - pr.force[1]) - drho * Mob * gmgu1 + phi * gm1 + pr.source_u[1];
+      if(MODEL == 0) {
+        // CHNS_Abels, src/feSysElmCHNS.cpp:158-171
+        const double gmgu0 = gm0 * gu00 + gm1 * gu10, gmgu1 = gm0 * gu01 + gm1 * gu11;
+        // momentum (:192-219): test function i = 2a + c is phi_a e_c
+        const double v0 = rho * (dt0 + ugu0 - pr.force[0]) - drho * Mob * gmgu0 + phi * gm0 + pr.source_u[0];
+        const double v1 = rho * (dt1 + ugu1 - pr.force[1]) - drho * Mob * gmgu1 + phi * gm1 + pr.source_u[1];
 #pragma unroll
-      for(int b = 0; b < NSU; ++b) {
-        R[2 * b] -= jw * (v0 * lu[b] - p * gux[b] + eta * (gux[b] * S00 + guy[b] * S01));
-        R[2 * b + 1] -= jw * (v1 * lu[b] - p * guy[b] + eta * (gux[b] * S01 + guy[b] * S11));
-      }
-      // continuity (:224-227)
+        for(int b = 0; b < NSU; ++b) {
+          R[2 * b] -= jw * (v0 * lu[b] - p * gux[b] + eta * (gux[b] * S00 + guy[b] * S01));
+          R[2 * b + 1] -= jw * (v1 * lu[b] - p * guy[b] + eta * (gux[b] * S01 + guy[b] * S11));
+        }
+        // continuity (:224-227)
 #pragma unroll
-      for(int q = 0; q < NSP; ++q) R[NU + q] -= jw * (divu + pr.source_p) * LP[k * NSP + q];
-      // tracer (:232-250) and potential (:255-271)
-      const double tf = dphidt + ugphi + pr.source_phi;
-      const double tm = mu - dw * phi * (phi * phi - 1.) + pr.source_mu;
+        for(int q = 0; q < NSP; ++q) R[NU + q] -= jw * (divu + pr.source_p) * LP[k * NSP + q];
+        // tracer (:232-250) and potential (:255-271)
+        const double tf = dphidt + ugphi + pr.source_phi;
+        const double tm = mu - dw * phi * (phi * phi - 1.) + pr.source_mu;
 #pragma unroll
-      for(int i = 0; i < NSF; ++i) {
-        R[NU + NSP + i] -= jw * (tf * lf[i] + Mob * (gm0 * gfx[i] + gm1 * gfy[i]));
-        R[NU + NSP + NSF + i] -= jw * (tm * lf[i] - lam * (gp0 * gfx[i] + gp1 * gfy[i]));
+        for(int i = 0; i < NSF; ++i) {
+          R[NU + NSP + i] -= jw * (tf * lf[i] + Mob * (gm0 * gfx[i] + gm1 * gfy[i]));
+          R[NU + NSP + NSF + i] -= jw * (tm * lf[i] - lam * (gp0 * gfx[i] + gp1 * gfy[i]));
+        }
+      } else {
+        // CHNS_MassAveraged, src/feSysElmCHNS.cpp:446-466: div(rho u), time-averaged double well (Simpson in time)
+        const double alpha = pr.mass_alpha;
+        const double beta  = 3. / (2. * sqrt(2.)) * pr.surface_tension / pr.epsilon; // src/feSysElm.h:1425
+        const double divRhoU = rho * divu + drho * ugphi;
+        const double pavg = 0.5 * (phi + phin);
+        const double well = (phi * (phi * phi - 1.) + 4. * pavg * (pavg * pavg - 1.) + phin * (phin * phin - 1.)) * beta / 6.;
+        // momentum (:486-513)
+        const double mc = 0.5 * (drho * dphidt + divRhoU);
+        const double v0 = rho * (dt0 + ugu0 - pr.force[0]) + mc * u0 + phi * gm0 + pr.source_u[0];
+        const double v1 = rho * (dt1 + ugu1 - pr.force[1]) + mc * u1 + phi * gm1 + pr.source_u[1];
+        const double pe = p + eta * divu; // - p div(phi_i) - eta (2/dim) div u div(phi_i), dim = 2
+#pragma unroll
+        for(int b = 0; b < NSU; ++b) {
+          R[2 * b] -= jw * (v0 * lu[b] - pe * gux[b] + eta * (gux[b] * S00 + guy[b] * S01));
+          R[2 * b + 1] -= jw * (v1 * lu[b] - pe * guy[b] + eta * (gux[b] * S01 + guy[b] * S11));
+        }
+        // continuity (:518-541): div u + alpha div(M grad(mu + alpha p)); P1 test-function gradients
+        const double fx = Mob * (gm0 + alpha * gpr0), fy = Mob * (gm1 + alpha * gpr1);
+#pragma unroll
+        for(int q = 0; q < NSP; ++q) {
+          const double dr = dLP[(k * NSP + q) * 2], ds = dLP[(k * NSP + q) * 2 + 1];
+          const double gx = dr * G[0] + ds * G[2], gy = dr * G[1] + ds * G[3];
+          R[NU + q] -= jw * ((divu + pr.source_p) * LP[k * NSP + q] + alpha * (fx * gx + fy * gy));
+        }
+        // tracer (:546-574, conservative convective term) and potential (:579-600)
+        const double tf = dphidt + pr.source_phi;
+        const double tm = mu - well + pr.source_mu;
+#pragma unroll
+        for(int i = 0; i < NSF; ++i) {
+          R[NU + NSP + i] -= jw * (tf * lf[i] - phi * (u0 * gfx[i] + u1 * gfy[i]) + fx * gfx[i] + fy * gfy[i]);
+          R[NU + NSP + NSF + i] -= jw * (tm * lf[i] - lam * (gp0 * gfx[i] + gp1 * gfy[i]));
+        }
       }
     }
   }
@@ -323,6 +388,7 @@ int chns_build_plan(System *S)
   tab.insert(tab.end(), P.L.begin(), P.L.end());
   tab.insert(tab.end(), F.L.begin(), F.L.end());
   tab.insert(tab.end(), F.dL.begin(), F.dL.end());
+  tab.insert(tab.end(), P.dL.begin(), P.dL.end());
   const int expect = F.nS == 3 ? ChnsT<3>::len(S->nq) : ChnsT<6>::len(S->nq);
   if((int)tab.size() != expect) {
     set_error("CHNS kernel: basis tables have unexpected sizes");
@@ -361,15 +427,25 @@ int chns_launch(System *S, int what)
   a.prm    = S->chns_prm;
   const int    nsf  = S->spaces[S->chns_space[2]].nS;
   const int    M    = S->M;
-  const size_t smem = ((size_t)a.ntab + 2 * CHNS_WPB * M + (size_t)CHNS_WPB * a.nq * CHNS_NFLD) * sizeof(double) + (size_t)CHNS_WPB * M * sizeof(int32_t);
+  const int    model = S->chns_model;
+  a.soln = (model == 1 && S->have_soln) ? S->d_soln : nullptr;
+  const size_t smem = ((size_t)a.ntab + 2 * CHNS_WPB * M + (size_t)CHNS_WPB * a.nq * chns_nfld(model) + CHNS_WPB * 8) * sizeof(double) +
+                      (size_t)CHNS_WPB * M * sizeof(int32_t);
   const unsigned grid = (unsigned)((S->nElm + CHNS_WPB - 1) / CHNS_WPB);
-  if(nsf == 3) {
-    B200_CUDA(cudaFuncSetAttribute(chns_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chns_kernel<3><<<grid, CHNS_WPB * 32, smem, S->stream>>>(a);
-  } else {
-    B200_CUDA(cudaFuncSetAttribute(chns_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chns_kernel<6><<<grid, CHNS_WPB * 32, smem, S->stream>>>(a);
-  }
+#define B200_LAUNCH_CHNS(NSF, MODEL)                                                                                                     \
+  do {                                                                                                                                   \
+    B200_CUDA(cudaFuncSetAttribute(chns_kernel<NSF, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+    chns_kernel<NSF, MODEL><<<grid, CHNS_WPB * 32, smem, S->stream>>>(a);                                                                \
+  } while(0)
+  if(nsf == 3 && model == 0)
+    B200_LAUNCH_CHNS(3, 0);
+  else if(nsf == 6 && model == 0)
+    B200_LAUNCH_CHNS(6, 0);
+  else if(nsf == 3)
+    B200_LAUNCH_CHNS(3, 1);
+  else
+    B200_LAUNCH_CHNS(6, 1);
+#undef B200_LAUNCH_CHNS
   count_launch();
   B200_CUDA(cudaGetLastError());
   return B200_OK;

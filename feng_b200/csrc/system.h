@@ -129,6 +129,9 @@ struct System {
   bool             chns_active = false;
   int              chns_space[4] = {-1, -1, -1, -1};
   b200_chns_params chns_prm = {};
+  int              chns_model = 0;       // 0 CHNS_Abels, 1 CHNS_MassAveraged
+  double          *d_soln = nullptr;     // state at the previous time step (b200_set_solution_n)
+  bool             have_soln = false;
   int32_t         *chns_adr = nullptr;
   double          *chns_tab = nullptr;
   int              chns_tab_len = 0;

@@ -284,6 +284,10 @@ class ChnsModel:
     limiter: bool = False
     degenerate_mobility: bool = False
     phi_order: int = 1
+    # "abels" = CHNS_Abels<2>; "mass_averaged" = CHNS_MassAveraged<2> with alpha = (rho_2 - rho_1) / (rho_1 + rho_2)
+    # (src/feSysElm.h:1352-1430, src/CHNS_Solver.cpp:398-416)
+    formulation: str = "abels"
+    alpha: float = 0.0
 
 
 def phi_init(x):

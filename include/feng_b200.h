@@ -51,8 +51,11 @@ enum {
   B200_FORM_DIV_NEWTONIAN_STRESS           = 25, /* feSysElm_DivergenceNewtonianStress,    src/feVectorSysElm.cpp:1454-1532 */
   B200_FORM_MIXED_GRADIENT                 = 26, /* feSysElm_MixedGradient<dim>,           src/feVectorSysElm.cpp:528-578 */
   B200_FORM_MIXED_DIVERGENCE               = 31, /* feSysElm_MixedDivergence<dim>,         src/feVectorSysElm.cpp:685-749 */
-  B200_FORM_CHNS_ABELS                     = 35  /* CHNS_Abels<2> (volume-averaged CHNS),  src/feSysElmCHNS.cpp:66-273; Jacobian by
+  B200_FORM_CHNS_ABELS                     = 35, /* CHNS_Abels<2> (volume-averaged CHNS),  src/feSysElmCHNS.cpp:66-273; Jacobian by
                                                     finite differences, src/feBilinearForm.cpp:388-428 */
+  B200_FORM_CHNS_MASS_AVERAGED             = 36  /* CHNS_MassAveraged<2>,                  src/feSysElmCHNS.cpp:347-602; needs the Phi
+                                                    DOFs of the previous time step (b200_set_solution_n) and the gradient
+                                                    table of the pressure space */
 };
 
 /* Parameters of the monolithic Cahn-Hilliard Navier-Stokes weak form.  The reference passes host callbacks
@@ -65,6 +68,7 @@ typedef struct {
   double rho_a, rho_b, visc_a, visc_b, mobility, surface_tension, epsilon;
   double force[3], source_u[3], source_p, source_phi, source_mu;
   int    limiter, degenerate_mobility;
+  double mass_alpha; /* CHNS_MassAveraged only: alpha = (rho_2 - rho_1) / (rho_1 + rho_2), CHNSparameters[0] (src/feSysElm.h:1419) */
 } b200_chns_params;
 
 /* Scatter strategies for the race-free add into the CSR matrix (north-star subsystem 3). */
@@ -145,6 +149,10 @@ int b200_add_form(b200_system *s, int kind, int space_u, int space_p, double coe
  * Jacobian (N+1 residual evaluations per element) run on the device. */
 int b200_add_form_chns(b200_system *s, int kind, int space_u, int space_p, int space_phi, int space_mu,
                        const b200_chns_params *params);
+/* state vector at the previous time step, nDOF doubles: what feBilinearForm::initialize copies into _solAtTimeN from the
+ * global solAtTimeN (src/feBilinearForm.cpp:277,347; set by the time integrators through src/feNonLinearSolver.cpp:35).
+ * Read by B200_FORM_CHNS_MASS_AVERAGED only; NULL (or never called) means "equal to the current solution". */
+int b200_set_solution_n(b200_system *s, const double *sol_n);
 /* replace the tabulated source of form `form_id` (returned by b200_add_form): time-dependent source callbacks are
  * re-tabulated by the adapter when feSolution::getCurrentTime() changes (the reference evaluates the callback with
  * args.t = tn on every element visit, src/feBilinearForm.cpp:291-295) */

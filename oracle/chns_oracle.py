@@ -21,6 +21,7 @@ import numpy as np
 from .fe_oracle import geometry, phys_grad
 
 CHNS_ABELS = 35          # elementSystemType, src/feSysElm.h:59
+CHNS_MASS_AVERAGED = 36  # src/feSysElm.h:60
 H0 = float(np.sqrt(np.finfo(np.float64).eps))
 
 
@@ -41,11 +42,14 @@ class ChnsParams:
     limiter: bool = False
     degenerate_mobility: bool = False
     phi_order: int = 1
+    formulation: str = "abels"     # or "mass_averaged" (CHNS_MassAveraged<2>, src/feSysElmCHNS.cpp:347-602)
+    alpha: float = 0.0             # CHNS_MassAveraged: (rho_2 - rho_1) / (rho_1 + rho_2), src/feSysElm.h:1419
 
     def as_array(self):
         return np.array([self.rhoA, self.rhoB, self.viscA, self.viscB, self.mobility, self.sigma, self.epsilon,
                          self.force[0], self.force[1], self.src_u[0], self.src_u[1], self.src_p, self.src_phi,
-                         self.src_mu, float(self.limiter), float(self.degenerate_mobility), float(self.phi_order)])
+                         self.src_mu, float(self.limiter), float(self.degenerate_mobility), float(self.phi_order),
+                         1.0 if self.formulation == "mass_averaged" else 0.0, self.alpha])
 
     @property
     def lam(self):
@@ -65,9 +69,9 @@ class ChnsProblem:
     prm: ChnsParams = field(default_factory=ChnsParams)
 
 
-def residual(pb: ChnsProblem, geo, loc, dot, prm: ChnsParams):
-    """Be[e, M] of CHNS_Abels on every element; loc = [U (nE, nSU, d), P (nE, nSP), Phi, Mu], dot likewise (P, Mu
-    entries unused)."""
+def residual(pb: ChnsProblem, geo, loc, dot, prm: ChnsParams, phi_n_loc=None):
+    """Be[e, M] of CHNS_Abels / CHNS_MassAveraged on every element; loc = [U (nE, nSU, d), P (nE, nSP), Phi, Mu], dot
+    likewise (P, Mu entries unused); phi_n_loc = Phi DOFs at the previous time step (mass-averaged form only)."""
     d = pb.dim
     LU, LP, LF, LM = pb.L
     jw = geo.detJ[:, None] * pb.w[None, :]
@@ -95,6 +99,9 @@ def residual(pb: ChnsProblem, geo, loc, dot, prm: ChnsParams):
     divu = np.einsum("ekmm->ek", gu)
     ugphi = np.einsum("ekm,ekm->ek", u, gphi)
     lam = prm.lam
+    if prm.formulation == "mass_averaged":
+        return _residual_mass_averaged(pb, geo, prm, jw, (gU, gF, gM), (u, p, phi, mu, dudt, dphidt, gu, gphi, gmu),
+                                       (rho, drho, eta, Mob, f, Su), (ugu, S, divu, ugphi), loc, phi_n_loc)
     # momentum: test function i = a*d + c
     vec = (rho[..., None] * (dudt + ugu - f) - (drho * Mob)[..., None] * gmgu + phi[..., None] * gmu + Su)   # . phi_a e_c
     Bu = np.einsum("ekc,ka,ek->eac", vec, LU, jw)
@@ -108,8 +115,40 @@ def residual(pb: ChnsProblem, geo, loc, dot, prm: ChnsParams):
     return -np.concatenate([Bu.reshape(nE, -1), Bp, Bf, Bm], 1)
 
 
-def element_systems(pb: ChnsProblem, sol, soldot=None, c0=0.0, matrix=True):
-    """(Ae[e, M, M] by finite differences or None, Be[e, M], adr[e, M])."""
+def _residual_mass_averaged(pb, geo, prm, jw, grads, flds, props, derived, loc, phi_n_loc):
+    """CHNS_MassAveraged<2>::computeBe, src/feSysElmCHNS.cpp:347-602 (tau = lambda, beta = 3/(2 sqrt 2) sigma / epsilon,
+    src/feSysElm.h:1425-1426)."""
+    LU, LP, LF, LM = pb.L
+    gU, gF, gM = grads
+    u, p, phi, mu, dudt, dphidt, gu, gphi, gmu = flds
+    rho, drho, eta, Mob, f, Su = props
+    ugu, S, divu, ugphi = derived
+    gP = phys_grad(pb.dL[1], geo)
+    gp = np.einsum("ekam,ea->ekm", gP, loc[1])
+    phi_n = np.einsum("kq,eq->ek", LF, loc[2] if phi_n_loc is None else phi_n_loc)
+    alpha, tau = prm.alpha, prm.lam
+    beta = 3.0 / (2.0 * np.sqrt(2.0)) * prm.sigma / prm.epsilon
+    div_rho_u = rho * divu + drho * ugphi                                     # :458-461
+    phi_avg = 0.5 * (phi + phi_n)
+    well = (phi * (phi * phi - 1.0) + 4.0 * phi_avg * (phi_avg * phi_avg - 1.0) + phi_n * (phi_n * phi_n - 1.0)) * beta / 6.0
+    # momentum (:486-513)
+    vec = rho[..., None] * (dudt + ugu - f) + (0.5 * (drho * dphidt + div_rho_u))[..., None] * u + phi[..., None] * gmu + Su
+    Bu = np.einsum("ekc,ka,ek->eac", vec, LU, jw)
+    Bu += np.einsum("ek,ekac,ek->eac", -(p + eta * (2.0 / pb.dim) * divu), gU, jw)   # - p div(phi_i) - eta 2/dim div u div(phi_i)
+    Bu += np.einsum("ek,ekam,ekmc,ek->eac", eta, gU, S, jw)
+    flux = Mob[..., None] * (gmu + alpha * gp)
+    # continuity (:518-541), tracer (:546-574), potential (:579-600)
+    Bp = np.einsum("ek,kq,ek->eq", divu + prm.src_p, LP, jw) + alpha * np.einsum("ekm,ekqm,ek->eq", flux, gP, jw)
+    Bf = np.einsum("ek,kq,ek->eq", dphidt + prm.src_phi, LF, jw) - np.einsum("ek,ekm,ekqm,ek->eq", phi, u, gF, jw) \
+        + np.einsum("ekm,ekqm,ek->eq", flux, gF, jw)
+    Bm = np.einsum("ek,kq,ek->eq", mu - well + prm.src_mu, LM, jw) - tau * np.einsum("ekm,ekqm,ek->eq", gphi, gM, jw)
+    nE = loc[0].shape[0]
+    return -np.concatenate([Bu.reshape(nE, -1), Bp, Bf, Bm], 1)
+
+
+def element_systems(pb: ChnsProblem, sol, soldot=None, c0=0.0, matrix=True, sol_n=None):
+    """(Ae[e, M, M] by finite differences or None, Be[e, M], adr[e, M]).  sol_n: state at the previous time step (the
+    reference's global solAtTimeN, never perturbed by the finite differences); None = the current solution."""
     geo = geometry(pb.xyz, pb.cells, pb.dim)
     nE = pb.cells.shape[0]
     d = pb.dim
@@ -124,7 +163,8 @@ def element_systems(pb: ChnsProblem, sol, soldot=None, c0=0.0, matrix=True):
             out.append(v.reshape(shapes[0]) if s == 0 else v)
         return out
     loc, dot = gather(sol), gather(soldot)
-    R0 = residual(pb, geo, loc, dot, pb.prm)
+    phi_n = (sol if sol_n is None else sol_n)[pb.adr[2]].copy()
+    R0 = residual(pb, geo, loc, dot, pb.prm, phi_n)
     adr = np.concatenate(pb.adr, 1)
     if not matrix:
         return None, R0, adr
@@ -139,7 +179,7 @@ def element_systems(pb: ChnsProblem, sol, soldot=None, c0=0.0, matrix=True):
             delta = H0 * np.maximum(np.abs(t), 1.0)
             flat[:, j] = t + delta
             flatd[:, j] = td + delta * c0
-            Rh = residual(pb, geo, loc, dot, pb.prm)
+            Rh = residual(pb, geo, loc, dot, pb.prm, phi_n)
             Ae[:, :, col] = -(Rh - R0) * (1.0 / delta)[:, None]
             flat[:, j] = t
             flatd[:, j] = td
@@ -147,9 +187,9 @@ def element_systems(pb: ChnsProblem, sol, soldot=None, c0=0.0, matrix=True):
     return Ae, R0, adr
 
 
-def assemble(pb: ChnsProblem, ia, ja, sol, soldot=None, c0=0.0, matrix=True, residual_=True):
+def assemble(pb: ChnsProblem, ia, ja, sol, soldot=None, c0=0.0, matrix=True, residual_=True, sol_n=None):
     """Global CSR values and rhs (scatter of src/feLinearSystemMklPardiso.cpp:524-663, :699-741)."""
-    Ae, Be, adr = element_systems(pb, sol, soldot, c0, matrix)
+    Ae, Be, adr = element_systems(pb, sol, soldot, c0, matrix, sol_n)
     n = np.int64(pb.n_inc)
     vals = np.zeros(ja.shape[0])
     rhs = np.zeros(pb.n_inc)

@@ -154,6 +154,14 @@ class RefProblem:
             dp = _p(sol_dot)
         self.L.ref_set_solution(self.h, _p(sol), dp, C.c_double(c0), C.c_double(t))
 
+    def set_solution_n(self, sol_n):
+        """state at the previous time step (the reference's global solAtTimeN); None = the current solution"""
+        if sol_n is None:
+            self.L.ref_set_solution_n(self.h, None)
+        else:
+            a = np.ascontiguousarray(sol_n, np.float64)
+            self.L.ref_set_solution_n(self.h, _p(a))
+
     # ---- hot path -------------------------------------------------------------------------
     def form_info(self, f) -> FormInfo:
         out = np.zeros(8, np.int64)

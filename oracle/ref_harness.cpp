@@ -383,10 +383,10 @@ public:
 
 // ---- CHNS (config 5): parameters and property callbacks ------------------------------------------------
 // g_chns = {rhoA, rhoB, viscA, viscB, mobility, sigma, epsilon, fx, fy, Su0, Su1, Sp, Sphi, Smu, limiter, degenerateMobility,
-//           phiOrder}; set by ref_set_chns_params before ref_create(kind = 5).  The property laws are the ones
+//           phiOrder, formulation (0 CHNS_Abels, 1 CHNS_MassAveraged), alpha}; set by ref_set_chns_params before ref_create(kind = 5).  The property laws are the ones
 // CHNS_Solver hands to its weak form (src/CHNS_Solver.cpp:124-235): linear mixing in phi, optional clipping of phi to
 // [-1, 1], constant or degenerate mobility M |1 - phi^2|.
-double g_chns[17] = {1., 1., 1., 1., 1., 1., 0.1, 0., 0., 0., 0., 0., 0., 0., 0., 0., 1.};
+double g_chns[19] = {1., 1., 1., 1., 1., 1., 0.1, 0., 0., 0., 0., 0., 0., 0., 0., 0., 1., 0., 0.};
 
 double chnsLinearCb(const feFunctionArguments &args, const std::vector<double> &par)
 {
@@ -432,6 +432,10 @@ struct RefProblem {
   feSpace                      *uSpace = nullptr, *pSpace = nullptr;
   feVectorFunction             *uExact = nullptr;
   feFunction                   *pExact = nullptr, *sExact = nullptr;
+  // state at the previous time step handed to feBilinearForm::initialize through the global solAtTimeN
+  // (ref_set_solution_n); empty = the current solution
+  std::vector<double>           solN;
+  const std::vector<double>    &stateN() const { return solN.empty() ? sol->getSolution() : solN; }
 
   ~RefProblem()
   {
@@ -480,7 +484,8 @@ int ref_error_norms(void *h, const double *sol, double *out);
 // CHNS parameter block for the next ref_create(kind = 5); see g_chns
 void ref_set_chns_params(const double *p, int n)
 {
-  for(int i = 0; i < n && i < 17; ++i) g_chns[i] = p[i];
+  g_chns[17] = g_chns[18] = 0.;
+  for(int i = 0; i < n && i < 19; ++i) g_chns[i] = p[i];
 }
 
 int ref_max_threads()
@@ -578,10 +583,17 @@ void *ref_create(const char *meshFile, const ref_recipe_t *rc)
     feFunction       *srcP  = mkS(P, constantCallback, {g[11]});
     feFunction       *srcF  = mkS(P, constantCallback, {g[12]});
     feFunction       *srcM  = mkS(P, constantCallback, {g[13]});
-    std::vector<double> prm = {g[5], g[6]};
     feBilinearForm     *chns = nullptr;
-    CHK(createBilinearForm(chns, {u, p, phi, mu},
-                           new CHNS_Abels<2>(rho, drho, visc, dvisc, mob, force, srcP, srcU, srcF, srcM, prm)));
+    if(g[17] == 1.) {
+      // src/CHNS_Solver.cpp:398-416: {mass_alpha, surfaceTension, epsilon}
+      std::vector<double> prm = {g[18], g[5], g[6]};
+      CHK(createBilinearForm(chns, {u, p, phi, mu},
+                             new CHNS_MassAveraged<2>(rho, drho, visc, dvisc, mob, force, srcP, srcU, srcF, srcM, prm)));
+    } else {
+      std::vector<double> prm = {g[5], g[6]};
+      CHK(createBilinearForm(chns, {u, p, phi, mu},
+                             new CHNS_Abels<2>(rho, drho, visc, dvisc, mob, force, srcP, srcU, srcF, srcM, prm)));
+    }
     P->forms.push_back(chns);
   } else {
     // (Navier-)Stokes Taylor-Hood: tests/withLinearSolver/navier_stokes.cpp:63-99, stokes.cpp
@@ -648,7 +660,7 @@ void *ref_create(const char *meshFile, const ref_recipe_t *rc)
   }
 
   P->sol->initialize(P->mesh);
-  solAtTimeN = P->sol->getSolution();
+  solAtTimeN = P->stateN();
   P->sys     = new feLinearSystemStub(P->forms, P->numbering);
   return P;
 }
@@ -805,7 +817,18 @@ int ref_set_solution(void *h, const double *sol, const double *solDot, double c0
   if(solDot) std::memcpy(P->sol->getSolutionDot().data(), solDot, n * sizeof(double));
   P->sol->setC0(c0);
   P->sol->setCurrentTime(t);
-  solAtTimeN = P->sol->getSolution();
+  solAtTimeN = P->stateN();
+  return 0;
+}
+
+// state at the previous time step (NULL: back to "equal to the current solution")
+int ref_set_solution_n(void *h, const double *solN)
+{
+  RefProblem *P = (RefProblem *)h;
+  if(solN)
+    P->solN.assign(solN, solN + P->sol->getNumDOFs());
+  else
+    P->solN.clear();
   return 0;
 }
 
@@ -828,7 +851,7 @@ int ref_element(void *h, int f, int elem, double *Ae, double *Be, int64_t *adrI,
   RefProblem     *P = (RefProblem *)h;
   feBilinearForm *F = P->forms[f];
   const feInt     M = F->getLocalMatrixM(), N = F->getLocalMatrixN();
-  solAtTimeN        = P->sol->getSolution();
+  solAtTimeN        = P->stateN();
   if(F->hasMatrix()) {
     F->computeMatrix(P->sol, elem);
     const double *const *A = F->getAe();
@@ -848,7 +871,7 @@ int ref_element(void *h, int f, int elem, double *Ae, double *Be, int64_t *adrI,
 int ref_assemble(void *h, int what, double *values, double *rhs, double *seconds)
 {
   RefProblem *P = (RefProblem *)h;
-  solAtTimeN    = P->sol->getSolution();
+  solAtTimeN    = P->stateN();
   double t0m = P->sys->_tAsmMat, t0r = P->sys->_tAsmRes;
   if(what & 2) {
     P->sys->setMatrixToZero();
@@ -984,7 +1007,7 @@ int ref_assemble_b200(void *h, int what, int devicePattern, double *values, doub
   o.devicePattern = devicePattern != 0;
   feLinearSystem *sys = nullptr;
   if(createLinearSystemB200(sys, P->forms, P->numbering, o) != FE_STATUS_OK) return -1;
-  solAtTimeN = P->sol->getSolution();
+  solAtTimeN = P->stateN();
   sys->setToZero();
   if(what & 1) sys->assembleResiduals(P->sol);
   if(what & 2) sys->assembleMatrices(P->sol, false);

@@ -33,6 +33,15 @@ def _oracle_problem(pb):
                           [pb.LU, pb.LP, pb.LF, pb.LF], [pb.dLU, pb.dLP, pb.dLF, pb.dLF], pb.n_inc, prm)
 
 
+def _params_from_fixture(cls, a):
+    """ChnsParams / ChnsModel from the fixture's parameter block (oracle/chns_oracle.ChnsParams.as_array)"""
+    kw = dict(force=tuple(a[7:9]), src_u=tuple(a[9:11]), src_p=a[11], src_phi=a[12], src_mu=a[13], limiter=bool(a[14]),
+              degenerate_mobility=bool(a[15]), phi_order=int(a[16]))
+    if len(a) > 17 and a[17] == 1.0:
+        kw.update(formulation="mass_averaged", alpha=float(a[18]))
+    return cls(*a[:7], **kw)
+
+
 def _state(pb, seed=5):
     from feng_b200 import problems as PB
     sol = PB.perturb_unknowns(pb, 1e-2, seed=seed)
@@ -40,8 +49,9 @@ def _state(pb, seed=5):
     return sol, sd, 3.5
 
 
-@pytest.mark.parametrize("model,phi_order", [("plain", 1), ("full", 1), ("full", 2)])
-def test_oracle_and_host_tables_vs_compiled_reference(model, phi_order, tmp_path, have_ref):
+@pytest.mark.parametrize("model,phi_order,formulation", [("plain", 1, "abels"), ("full", 1, "abels"), ("full", 2, "abels"),
+                                                         ("plain", 1, "mass_averaged"), ("full", 2, "mass_averaged")])
+def test_oracle_and_host_tables_vs_compiled_reference(model, phi_order, formulation, tmp_path, have_ref):
     if not have_ref:
         pytest.skip("oracle/_ref not built")
     from feng_b200 import mesh as M, problems as PB
@@ -49,7 +59,8 @@ def test_oracle_and_host_tables_vs_compiled_reference(model, phi_order, tmp_path
     m = M.rect_mesh(5, 4, 1.3, 0.9, -0.2, 0.1)
     path = str(tmp_path / "m.msh")
     M.write_msh(m, path)
-    mdl = PB.ChnsModel(phi_order=phi_order, **MODELS[model])
+    mdl = PB.ChnsModel(phi_order=phi_order, formulation=formulation, alpha=-0.3 if formulation != "abels" else 0.0,
+                       **MODELS[model])
     pb = PB.chns(m, mdl, 8, 1, 0.05, 1.3)
     opb = _oracle_problem(pb)
     P = ref.RefProblem(path, "chns", 2, 8, 1, 0.05, 1.3, chns=opb.prm.as_array())
@@ -63,24 +74,28 @@ def test_oracle_and_host_tables_vs_compiled_reference(model, phi_order, tmp_path
     assert np.abs(rsol - pb.sol).max() <= 1e-14
     sol, sd, c0 = _state(pb)
     P.set_solution(sol, sd, c0, 0.0)
+    sol_n = None
+    if formulation != "abels":     # state at the previous time step (the reference's global solAtTimeN) != current state
+        sol_n = sol + np.random.default_rng(9).uniform(-0.05, 0.05, sol.shape)
+        P.set_solution_n(sol_n)
     fi = P.form_info(0)
-    assert fi.sys_id == CO.CHNS_ABELS and fi.M == opb.adr[0].shape[1] + 3 + 2 * pb.LF.shape[1]
+    assert fi.sys_id == (CO.CHNS_ABELS if formulation == "abels" else CO.CHNS_MASS_AVERAGED)
+    assert fi.M == opb.adr[0].shape[1] + 3 + 2 * pb.LF.shape[1]
     v, r, _ = P.assemble()
-    ov, orr = CO.assemble(opb, pb.ia, pb.ja, sol, sd, c0)
+    ov, orr = CO.assemble(opb, pb.ia, pb.ja, sol, sd, c0, sol_n=sol_n)
     assert_close_vec(orr, r, 1e-13, "rhs")
     assert_close_rows(ov, v, pb.ia, FD_TOL, "FD matrix")
     P.close()
 
 
-@pytest.mark.parametrize("name", ["ref_square1_chns_abels_p1", "ref_square1_chns_abels_p2"])
+@pytest.mark.parametrize("name", ["ref_square1_chns_abels_p1", "ref_square1_chns_abels_p2",
+                                  "ref_square1_chns_mass_averaged_p1"])
 def test_oracle_vs_golden_fixture(name):
     """Fixture = inputs as the reference tabulated them + outputs of its own CPU path (tests/golden/make_golden.py)."""
     from oracle import chns_oracle as CO
     g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
-    prm_a = g["chns_params"]
-    prm = CO.ChnsParams(*prm_a[:7], force=tuple(prm_a[7:9]), src_u=tuple(prm_a[9:11]), src_p=prm_a[11], src_phi=prm_a[12],
-                        src_mu=prm_a[13], limiter=bool(prm_a[14]), degenerate_mobility=bool(prm_a[15]),
-                        phi_order=int(prm_a[16]))
+    prm = _params_from_fixture(CO.ChnsParams, g["chns_params"])
+    sol_n = g["sol_n"] if "sol_n" in g else None
     LU = np.ascontiguousarray(g["L0"][:, 0::2, 0])
     dLU = np.ascontiguousarray(np.stack([g["dLdr0"][:, 0::2, 0], g["dLds0"][:, 0::2, 0]], 2))
     Ls, dLs = [LU], [dLU]
@@ -88,11 +103,11 @@ def test_oracle_vs_golden_fixture(name):
         Ls.append(g[f"L{s}"])
         dLs.append(np.ascontiguousarray(np.stack([g[f"dLdr{s}"], g[f"dLds{s}"]], 2)))
     pb = CO.ChnsProblem(2, g["xyz"], g["cells"], [g[f"adr{s}"] for s in range(4)], g["w"], Ls, dLs, int(g["n_inc"]), prm)
-    Ae, Be, adr = CO.element_systems(pb, g["sol"], g["sol_dot"], float(g["c0"]))
+    Ae, Be, adr = CO.element_systems(pb, g["sol"], g["sol_dot"], float(g["c0"]), sol_n=sol_n)
     for i, e in enumerate(g["elements"]):
         assert np.abs(Be[e] - g["Be"][i]).max() <= 1e-13 * np.abs(g["Be"][i]).max()
         assert np.abs(Ae[e] - g["Ae"][i]).max() <= FD_TOL * np.abs(g["Ae"][i]).max()
-    ov, orr = CO.assemble(pb, g["ia"], g["ja"], g["sol"], g["sol_dot"], float(g["c0"]))
+    ov, orr = CO.assemble(pb, g["ia"], g["ja"], g["sol"], g["sol_dot"], float(g["c0"]), sol_n=sol_n)
     assert_close_vec(orr, g["rhs"], 1e-13, "rhs")
     assert_close_rows(ov, g["values"], g["ia"], FD_TOL, "FD matrix")
 
@@ -121,16 +136,24 @@ def test_fd_jacobian_is_the_derivative_of_the_residual():
 
 # ---- GPU -------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("model,phi_order,device_pattern", [("plain", 1, False), ("full", 1, True), ("full", 2, False)])
-def test_cuda_chns_vs_oracle(model, phi_order, device_pattern):
+@pytest.mark.parametrize("model,phi_order,device_pattern,formulation",
+                         [("plain", 1, False, "abels"), ("full", 1, True, "abels"), ("full", 2, False, "abels"),
+                          ("plain", 1, True, "mass_averaged"), ("full", 1, False, "mass_averaged"),
+                          ("full", 2, False, "mass_averaged")])
+def test_cuda_chns_vs_oracle(model, phi_order, device_pattern, formulation):
     from feng_b200 import mesh as M, problems as PB
     from feng_b200.linear_system import LinearSystemB200
     from oracle import chns_oracle as CO
     m = M.square_mesh(10)
-    pb = PB.chns(m, PB.ChnsModel(phi_order=phi_order, **MODELS[model]), 8, 1, 0.05, 1.3)
+    mdl = PB.ChnsModel(phi_order=phi_order, formulation=formulation, alpha=-0.3 if formulation != "abels" else 0.0,
+                       **MODELS[model])
+    pb = PB.chns(m, mdl, 8, 1, 0.05, 1.3)
     sol, sd, c0 = _state(pb)
-    ov, orr = CO.assemble(_oracle_problem(pb), pb.ia, pb.ja, sol, sd, c0)
+    sol_n = None if formulation == "abels" else sol + np.random.default_rng(9).uniform(-0.05, 0.05, sol.shape)
+    ov, orr = CO.assemble(_oracle_problem(pb), pb.ia, pb.ja, sol, sd, c0, sol_n=sol_n)
     ls = LinearSystemB200(pb, device_pattern=device_pattern)
+    if sol_n is not None:
+        ls.sys.set_solution_n(sol_n)
     if device_pattern:
         ia, ja = ls.sys.get_pattern()
         assert np.array_equal(ia, pb.ia) and np.array_equal(ja, pb.ja)
@@ -147,14 +170,13 @@ def test_cuda_chns_vs_oracle(model, phi_order, device_pattern):
 
 
 @pytest.mark.gpu
-def test_cuda_chns_vs_golden_fixture():
+@pytest.mark.parametrize("name", ["ref_square1_chns_abels_p1", "ref_square1_chns_mass_averaged_p1"])
+def test_cuda_chns_vs_golden_fixture(name):
     """the CUDA path on the reference's OWN tables (fixture) against the reference's own outputs"""
     from feng_b200 import capi
     from feng_b200 import problems as PB
-    g = dict(np.load(os.path.join(GOLDEN_DIR, "ref_square1_chns_abels_p1.npz"), allow_pickle=False))
-    a = g["chns_params"]
-    mdl = PB.ChnsModel(*a[:7], force=tuple(a[7:9]), src_u=tuple(a[9:11]), src_p=a[11], src_phi=a[12], src_mu=a[13],
-                       limiter=bool(a[14]), degenerate_mobility=bool(a[15]), phi_order=int(a[16]))
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+    mdl = _params_from_fixture(PB.ChnsModel, g["chns_params"])
     S = capi.System(0)
     S.set_mesh(2, g["xyz"], g["cells"])
     S.set_quadrature(g["w"])
@@ -168,6 +190,8 @@ def test_cuda_chns_vs_golden_fixture():
     S.add_form_chns(*ids, mdl)
     S.finalize()
     S.set_solution(g["sol"], g["sol_dot"], float(g["c0"]), 0.0)
+    if "sol_n" in g:
+        S.set_solution_n(g["sol_n"])
     S.set_to_zero(3)
     S.assemble(3, False)
     assert_close_vec(S.get_rhs(), g["rhs"], 1e-12, "rhs")
@@ -175,16 +199,19 @@ def test_cuda_chns_vs_golden_fixture():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("phi_order,device_pattern", [(1, False), (2, True)])
-def test_chns_through_the_cpp_adapter(phi_order, device_pattern):
-    """The reference's own host objects (mesh reader, feSpace, feMetaNumber, CHNS_Abels<2> with its property CALLBACKS)
+@pytest.mark.parametrize("phi_order,device_pattern,formulation", [(1, False, "abels"), (2, True, "abels"),
+                                                                  (1, True, "mass_averaged"), (2, False, "mass_averaged")])
+def test_chns_through_the_cpp_adapter(phi_order, device_pattern, formulation):
+    """The reference's own host objects (mesh reader, feSpace, feMetaNumber, CHNS_Abels<2> / CHNS_MassAveraged<2> with
+    their property CALLBACKS, the global solAtTimeN)
     drive the CUDA backend through adapter/feLinearSystemB200.h: the adapter probes the callbacks, recognises the laws
     of CHNS_Solver (src/CHNS_Solver.cpp:124-235) and registers the monolithic form; the result must match the
     reference's own CPU assembly of the same state (both computed here, in the same process)."""
     from oracle import chns_oracle as CO, ref
     if not ref.available_b200():
         pytest.skip("oracle/_ref/libfeng_ref_b200.so not built (make -C oracle)")
-    prm = CO.ChnsParams(phi_order=phi_order, **MODELS["full"])
+    prm = CO.ChnsParams(phi_order=phi_order, formulation=formulation, alpha=-0.3 if formulation != "abels" else 0.0,
+                        **MODELS["full"])
     P = ref.RefProblem(os.path.join(ref.DATA_DIR, "square2.msh"), "chns", 2, 8, 1, 0.05, 1.3, b200=True,
                        chns=prm.as_array())
     sol, _ = P.solution()
@@ -192,6 +219,8 @@ def test_chns_through_the_cpp_adapter(phi_order, device_pattern):
     sol[:P.n_inc] += rng.uniform(-1e-2, 1e-2, P.n_inc)
     sd = rng.standard_normal(P.n_dof)
     P.set_solution(sol, sd, 2.5, 0.0)
+    if formulation != "abels":
+        P.set_solution_n(sol + rng.uniform(-5e-2, 5e-2, P.n_dof))
     v, r, _ = P.assemble()                        # reference CPU path (colour loop + FD Jacobian + scatter)
     gv, gr = P.assemble_b200(device_pattern=device_pattern)
     ia, _ = P.pattern()
