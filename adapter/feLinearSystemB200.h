@@ -91,6 +91,33 @@ namespace feB200detail
   struct MassAveragedPeek : public CHNS_MassAveraged<2> {
     static double alpha(const CHNS_MassAveraged<2> *s) { return s->*(&MassAveragedPeek::_alpha); }
   };
+  // CHNS_Khanwale<2> has no surface tension / epsilon members: Re, Pe, Cn, We, Fr, rhoA, rhoB (src/feSysElm.h:1449)
+  struct KhanwalePeek : public CHNS_Khanwale<2> {
+    using C = CHNS_Khanwale<2>;
+    static const feFunction *density(const C *s) { return s->*(&KhanwalePeek::_density); }
+    static const feFunction *drhodphi(const C *s) { return s->*(&KhanwalePeek::_drhodphi); }
+    static const feFunction *viscosity(const C *s) { return s->*(&KhanwalePeek::_viscosity); }
+    static const feFunction *mobility(const C *s) { return s->*(&KhanwalePeek::_mobility); }
+    static const feVectorFunction *volumeForce(const C *s) { return s->*(&KhanwalePeek::_volumeForce); }
+    static const feVectorFunction *sourceU(const C *s) { return s->*(&KhanwalePeek::_sourceU); }
+    static const feFunction *sourceP(const C *s) { return s->*(&KhanwalePeek::_sourceP); }
+    static const feFunction *sourcePhi(const C *s) { return s->*(&KhanwalePeek::_sourcePhi); }
+    static const feFunction *sourceMu(const C *s) { return s->*(&KhanwalePeek::_sourceMu); }
+    static double surfaceTension(const C *) { return 0.; }
+    static double epsilon(const C *) { return 1.; }
+    static void numbers(const C *s, double *out)
+    {
+      out[0] = s->*(&KhanwalePeek::_Re);
+      out[1] = s->*(&KhanwalePeek::_Pe);
+      out[2] = s->*(&KhanwalePeek::_Cn);
+      out[3] = s->*(&KhanwalePeek::_We);
+      out[4] = s->*(&KhanwalePeek::_Fr);
+      out[5] = s->*(&KhanwalePeek::_rhoA);
+      out[6] = s->*(&KhanwalePeek::_rhoB);
+    }
+  };
+  template <class C> struct ChnsPeekOf { using type = ChnsPeekT<C>; };
+  template <> struct ChnsPeekOf<CHNS_Khanwale<2>> { using type = KhanwalePeek; };
 } // namespace feB200detail
 
 class feLinearSystemB200 : public feLinearSystem
@@ -259,11 +286,15 @@ protected:
   {
     auto *s = dynamic_cast<const C *>(se);
     if(!s || f->_intSpaces.size() != 4) return fail("CHNS form must be a CHNS_Abels<2> / CHNS_MassAveraged<2> on {U, P, Phi, Mu}");
-    using Pk = feB200detail::ChnsPeekT<C>;
+    using Pk = typename feB200detail::ChnsPeekOf<C>::type;
     b200_chns_params prm{};
     if constexpr(std::is_same<C, CHNS_MassAveraged<2>>::value) {
       prm.mass_alpha = feB200detail::MassAveragedPeek::alpha(s);
       _needSolutionN = true; // phi at the previous time step: the global solAtTimeN goes to the device with the state
+    }
+    if constexpr(std::is_same<C, CHNS_Khanwale<2>>::value) {
+      feB200detail::KhanwalePeek::numbers(s, prm.khanwale);
+      _needSolutionN = true; // every field at the previous time step and the time step
     }
     bool limRho = false, limVisc = false;
     if(!probeLinearLaw(Pk::density(s), prm.rho_a, prm.rho_b, limRho) || !probeLinearLaw(Pk::viscosity(s), prm.visc_a, prm.visc_b, limVisc) ||
@@ -371,6 +402,7 @@ protected:
       }
       case CHNS_ABELS: return addChnsForm<CHNS_Abels<2>>(f, se, B200_FORM_CHNS_ABELS);
       case CHNS_MASS_AVERAGED: return addChnsForm<CHNS_MassAveraged<2>>(f, se, B200_FORM_CHNS_MASS_AVERAGED);
+      case CHNS_KHANWALE: return addChnsForm<CHNS_Khanwale<2>>(f, se, B200_FORM_CHNS_KHANWALE);
       case TRANSIENT_MASS: return addCoeffForm<feSysElm_TransientMass>(f, se, id, s0, -1, nullptr);
       case DIFFUSION:
         // diffusivity is the form's only callback: kind DIFFUSION uses coeff x param with param = 1
@@ -401,7 +433,8 @@ protected:
        "b200_set_solution");
     // feBilinearForm::initialize reads the previous time step from the global solAtTimeN (src/feBilinearForm.cpp:277,347)
     if(_needSolutionN)
-      ok(b200_set_solution_n(_sys, (feInt)solAtTimeN.size() == _nDOF ? solAtTimeN.data() : nullptr), "b200_set_solution_n");
+      ok(b200_set_solution_n(_sys, (feInt)solAtTimeN.size() == _nDOF ? solAtTimeN.data() : nullptr, sol->getTimeStep()),
+         "b200_set_solution_n");
   }
 
   // rows of essential vector components, as src/feLinearSystemMklPardiso.cpp:998-1041

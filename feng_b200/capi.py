@@ -42,10 +42,10 @@ class ChnsParams(C.Structure):
                 ("mobility", C.c_double), ("surface_tension", C.c_double), ("epsilon", C.c_double),
                 ("force", C.c_double * 3), ("source_u", C.c_double * 3), ("source_p", C.c_double),
                 ("source_phi", C.c_double), ("source_mu", C.c_double), ("limiter", C.c_int),
-                ("degenerate_mobility", C.c_int), ("mass_alpha", C.c_double)]
+                ("degenerate_mobility", C.c_int), ("mass_alpha", C.c_double), ("khanwale", C.c_double * 7)]
 
 
-FORM_CHNS_ABELS, FORM_CHNS_MASS_AVERAGED = 35, 36
+FORM_CHNS_ABELS, FORM_CHNS_MASS_AVERAGED, FORM_CHNS_KHANWALE = 35, 36, 38
 
 
 class SolveInfo(C.Structure):
@@ -151,11 +151,13 @@ class System:
     def add_form_chns(self, su, sp, sf, sm, model, kind=None):
         """model: any object with the attributes of feng_b200.problems.ChnsModel"""
         if kind is None:
-            kind = FORM_CHNS_MASS_AVERAGED if getattr(model, "formulation", "abels") == "mass_averaged" else FORM_CHNS_ABELS
+            kind = {"abels": FORM_CHNS_ABELS, "mass_averaged": FORM_CHNS_MASS_AVERAGED,
+                    "khanwale": FORM_CHNS_KHANWALE}[getattr(model, "formulation", "abels")]
         prm = ChnsParams(model.rhoA, model.rhoB, model.viscA, model.viscB, model.mobility, model.sigma, model.epsilon,
                          (C.c_double * 3)(model.force[0], model.force[1], 0.0),
                          (C.c_double * 3)(model.src_u[0], model.src_u[1], 0.0), model.src_p, model.src_phi,
-                         model.src_mu, int(model.limiter), int(model.degenerate_mobility), float(getattr(model, "alpha", 0.0)))
+                         model.src_mu, int(model.limiter), int(model.degenerate_mobility), float(getattr(model, "alpha", 0.0)),
+                         (C.c_double * 7)(*[float(x) for x in getattr(model, "khanwale", (1.,) * 7)]))
         return check(self.L.b200_add_form_chns(self.h, kind, su, sp, sf, sm, C.byref(prm)), "b200_add_form_chns")
 
     def set_source(self, form_id, source):
@@ -237,13 +239,14 @@ class System:
         sd = None if sol_dot is None else np.ascontiguousarray(sol_dot, np.float64)
         check(self.L.b200_set_solution(self.h, _d(sol), _d(sd), C.c_double(c0), C.c_double(t)), "b200_set_solution")
 
-    def set_solution_n(self, sol_n):
-        """state at the previous time step (the reference's global solAtTimeN); None = the current solution"""
+    def set_solution_n(self, sol_n, dt=0.0):
+        """state at the previous time step (the reference's global solAtTimeN; None = the current solution) and the time
+        step (feSolution::getTimeStep)"""
         if sol_n is None:
-            check(self.L.b200_set_solution_n(self.h, None), "b200_set_solution_n")
+            check(self.L.b200_set_solution_n(self.h, None, C.c_double(dt)), "b200_set_solution_n")
         else:
             a = np.ascontiguousarray(sol_n, np.float64)
-            check(self.L.b200_set_solution_n(self.h, _d(a)), "b200_set_solution_n")
+            check(self.L.b200_set_solution_n(self.h, _d(a), C.c_double(dt)), "b200_set_solution_n")
 
     def set_to_zero(self, what=3):
         check(self.L.b200_set_to_zero(self.h, what), "b200_set_to_zero")

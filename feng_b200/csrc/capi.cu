@@ -328,8 +328,8 @@ int b200_add_form_chns(b200_system *s, int kind, int space_u, int space_p, int s
       set_error("b200_add_form_chns: unknown space id");
       return B200_ERR_ARG;
     }
-  if((kind != B200_FORM_CHNS_ABELS && kind != B200_FORM_CHNS_MASS_AVERAGED) || !params) {
-    set_error("b200_add_form_chns: CHNS_Abels and CHNS_MassAveraged are built (CHNS_Khanwale and CHNS_VolumeAveragedGeneric are not)");
+  if((kind != B200_FORM_CHNS_ABELS && kind != B200_FORM_CHNS_MASS_AVERAGED && kind != B200_FORM_CHNS_KHANWALE) || !params) {
+    set_error("b200_add_form_chns: CHNS_Abels, CHNS_MassAveraged and CHNS_Khanwale are built (CHNS_VolumeAveragedGeneric is not)");
     return B200_ERR_UNSUPP;
   }
   Form f;
@@ -340,7 +340,7 @@ int b200_add_form_chns(b200_system *s, int kind, int space_u, int space_p, int s
   s->chns_active = true;
   for(int k = 0; k < 4; ++k) s->chns_space[k] = sp[k];
   s->chns_prm   = *params;
-  s->chns_model = kind == B200_FORM_CHNS_MASS_AVERAGED ? 1 : 0;
+  s->chns_model = kind == B200_FORM_CHNS_MASS_AVERAGED ? 1 : (kind == B200_FORM_CHNS_KHANWALE ? 2 : 0);
   chns_free(s);
   s->plan = PLAN_NONE;
   return (int)s->forms.size() - 1;
@@ -544,13 +544,14 @@ int b200_set_solution(b200_system *s, const double *sol, const double *sol_dot, 
   return B200_OK;
 }
 
-int b200_set_solution_n(b200_system *s, const double *sol_n)
+int b200_set_solution_n(b200_system *s, const double *sol_n, double dt)
 {
   CHECK_S(s);
   if(!s->d_sol) {
     set_error("b200_set_solution_n: set the pattern first");
     return B200_ERR_ARG;
   }
+  s->dt        = dt;
   s->have_soln = sol_n != nullptr;
   if(!sol_n) return B200_OK;
   if(!s->d_soln) B200_CUDA(cudaMalloc(&s->d_soln, (size_t)s->nDOF * sizeof(double)));

@@ -2,7 +2,9 @@
 //
 // Reference: CHNS_Abels<2>::computeBe (src/feSysElmCHNS.cpp:66-273, MODEL 0) and CHNS_MassAveraged<2>::computeBe
 // (src/feSysElmCHNS.cpp:347-602, MODEL 1: mass-averaged velocity, pressure-dependent diffusive flux, time-averaged double
-// well with phi at the previous time step from b200_set_solution_n) evaluated N+1 times per element by
+// well with phi at the previous time step from b200_set_solution_n) and CHNS_Khanwale<2>::computeBe
+// (src/feSysElmCHNS.cpp:678-938, MODEL 2: non-dimensional, every field averaged with the previous time step) evaluated N+1
+// times per element by
 // feBilinearForm::computeMatrixFiniteDifference (src/feBilinearForm.cpp:388-428), one weak form on the fields
 // [U (vector P2), P (P1), Phi, Mu (P1 or P2)] (layout src/feSysElmCHNS.cpp:13-14), property laws of CHNS_Solver
 // (src/CHNS_Solver.cpp:124-235) as enums instead of host callbacks.
@@ -32,13 +34,14 @@ struct ChnsArgs {
   double         *val, *rhs;
   int64_t         nInc;
   int             nq, ntab, what;
-  double          c0, h0;
+  double          c0, h0, dt;
   b200_chns_params prm;
 };
 
 constexpr int CHNS_NSU = 6, CHNS_NSP = 3, CHNS_WPB = 4;
-// fields per quadrature node: 16 for CHNS_Abels; + grad p (2) + phi at the previous time step for CHNS_MassAveraged
-__host__ __device__ constexpr int chns_nfld(int model) { return model == 0 ? 16 : 20; }
+// fields per quadrature node: 16 for CHNS_Abels; + grad p (2) + phi at the previous time step for CHNS_MassAveraged;
+// + the 13 fields of the previous time step {u, p, phi, mu, grad u, grad phi, grad mu} for CHNS_Khanwale
+__host__ __device__ constexpr int chns_nfld(int model) { return model == 0 ? 16 : (model == 1 ? 20 : 30); }
 
 template <int NSF> struct ChnsT {
   static constexpr int NU = CHNS_NSU * 2, M = NU + CHNS_NSP + 2 * NSF;
@@ -62,8 +65,8 @@ template <int NSF, int MODEL> __global__ void __launch_bounds__(CHNS_WPB * 32, M
   double *s_loc = s_tab + a.ntab;                        // [WPB][M]
   double *s_dot = s_loc + CHNS_WPB * M;                  // [WPB][M]
   double *s_fld = s_dot + CHNS_WPB * M;                  // [WPB][nq][NFLD]
-  double *s_ln  = s_fld + (size_t)CHNS_WPB * a.nq * CHNS_NFLD; // [WPB][8] Phi DOFs at the previous time step (MODEL 1)
-  int32_t *s_adr = reinterpret_cast<int32_t *>(s_ln + CHNS_WPB * 8); // [WPB][M]
+  double *s_ln  = s_fld + (size_t)CHNS_WPB * a.nq * CHNS_NFLD; // [WPB][32] local DOFs at the previous time step (MODEL 1: Phi only)
+  int32_t *s_adr = reinterpret_cast<int32_t *>(s_ln + CHNS_WPB * 32); // [WPB][M]
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nq = a.nq;
   for(int i = tid; i < a.ntab; i += CHNS_WPB * 32) s_tab[i] = a.tab[i];
@@ -72,7 +75,7 @@ template <int NSF, int MODEL> __global__ void __launch_bounds__(CHNS_WPB * 32, M
   if(e >= a.nElm) return;
   const double *w = s_tab, *LU = s_tab + T::o_lu(nq), *dLU = s_tab + T::o_dlu(nq), *LP = s_tab + T::o_lp(nq), *LF = s_tab + T::o_lf(nq),
                *dLF = s_tab + T::o_dlf(nq), *dLP = s_tab + T::o_dlp(nq);
-  double *locn = s_ln + wid * 8;
+  double *locn = s_ln + wid * 32;
   double  *loc = s_loc + wid * M, *dot = s_dot + wid * M, *fld = s_fld + (size_t)wid * nq * CHNS_NFLD;
   int32_t *adr = s_adr + wid * M;
   for(int i = lane; i < M; i += 32) {
@@ -83,6 +86,7 @@ template <int NSF, int MODEL> __global__ void __launch_bounds__(CHNS_WPB * 32, M
     // feBilinearForm::initialize fills _solAtTimeN from the global solAtTimeN (src/feBilinearForm.cpp:347); without
     // b200_set_solution_n it is the current solution, as in a stationary solve
     if(MODEL == 1 && i >= NU + NSP && i < NU + NSP + NSF) locn[i - NU - NSP] = a.soln ? a.soln[d] : a.sol[d];
+    if(MODEL == 2) locn[i] = a.soln ? a.soln[d] : a.sol[d];
   }
   double G[4], J;
   {
@@ -133,6 +137,31 @@ template <int NSF, int MODEL> __global__ void __launch_bounds__(CHNS_WPB * 32, M
       f[14] += gx * Ml[i];
       f[15] += gy * Ml[i];
     }
+    if(MODEL == 2) {
+      // previous time step: f[16..28] = {u_n (2), p_n, phi_n, mu_n, grad u_n (4), grad phi_n (2), grad mu_n (2)}
+      const double *Un = locn, *Pn = locn + NU, *Fn = locn + NU + NSP, *Mn = locn + NU + NSP + NSF;
+      for(int b = 0; b < NSU; ++b) {
+        const double L = LU[k * NSU + b], dr = dLU[(k * NSU + b) * 2], ds = dLU[(k * NSU + b) * 2 + 1];
+        const double gx = dr * G[0] + ds * G[2], gy = dr * G[1] + ds * G[3];
+        f[16] += L * Un[b * 2];
+        f[17] += L * Un[b * 2 + 1];
+        f[21] += gx * Un[b * 2];
+        f[22] += gx * Un[b * 2 + 1];
+        f[23] += gy * Un[b * 2];
+        f[24] += gy * Un[b * 2 + 1];
+      }
+      for(int q = 0; q < NSP; ++q) f[18] += LP[k * NSP + q] * Pn[q];
+      for(int i = 0; i < NSF; ++i) {
+        const double L = LF[k * NSF + i], dr = dLF[(k * NSF + i) * 2], ds = dLF[(k * NSF + i) * 2 + 1];
+        const double gx = dr * G[0] + ds * G[2], gy = dr * G[1] + ds * G[3];
+        f[19] += L * Fn[i];
+        f[25] += gx * Fn[i];
+        f[26] += gy * Fn[i];
+        f[20] += L * Mn[i];
+        f[27] += gx * Mn[i];
+        f[28] += gy * Mn[i];
+      }
+    }
 #pragma unroll
     for(int i = 0; i < CHNS_NFLD; ++i) fld[k * CHNS_NFLD + i] = f[i];
   }
@@ -182,6 +211,7 @@ template <int NSF, int MODEL> __global__ void __launch_bounds__(CHNS_WPB * 32, M
         gpr1 = f[17];
         phin = f[18];
       }
+      (void)gpr0, (void)gpr1, (void)phin;
       // test functions and their physical gradients at this node
       double lu[NSU], gux[NSU], guy[NSU], lf[NSF], gfx[NSF], gfy[NSF];
 #pragma unroll
@@ -255,6 +285,52 @@ template <int NSF, int MODEL> __global__ void __launch_bounds__(CHNS_WPB * 32, M
         for(int i = 0; i < NSF; ++i) {
           R[NU + NSP + i] -= jw * (tf * lf[i] + Mob * (gm0 * gfx[i] + gm1 * gfy[i]));
           R[NU + NSP + NSF + i] -= jw * (tm * lf[i] - lam * (gp0 * gfx[i] + gp1 * gfy[i]));
+        }
+      } else if(MODEL == 2) {
+        // CHNS_Khanwale, src/feSysElmCHNS.cpp:717-800: every field averaged with the previous time step
+        const double *kw = pr.khanwale; // Re, Pe, Cn, We, Fr, rhoA, rhoB
+        const double Re = kw[0], Pe = kw[1], Cn = kw[2], We = kw[3], Fr = kw[4], rA = kw[5], rB = kw[6];
+        const double ua0 = 0.5 * (u0 + f[16]), ua1 = 0.5 * (u1 + f[17]), pa = 0.5 * (p + f[18]), fa = 0.5 * (phi + f[19]),
+                     ma = 0.5 * (mu + f[20]);
+        const double ga00 = 0.5 * (gu00 + f[21]), ga01 = 0.5 * (gu01 + f[22]), ga10 = 0.5 * (gu10 + f[23]), ga11 = 0.5 * (gu11 + f[24]);
+        const double gfa0 = 0.5 * (gp0 + f[25]), gfa1 = 0.5 * (gp1 + f[26]), gma0 = 0.5 * (gm0 + f[27]), gma1 = 0.5 * (gm1 + f[28]);
+        const double phin_ = f[19];
+        auto lin = [&](double x, double va, double vb) {
+          const double c = pr.limiter ? fmax(-1., fmin(1., x)) : x;
+          return (va - vb) * 0.5 * c + (va + vb) * 0.5;
+        };
+        const double rho_n = lin(phin_, pr.rho_a, pr.rho_b), rho_a = lin(fa, pr.rho_a, pr.rho_b), eta_a = lin(fa, pr.visc_a, pr.visc_b);
+        const double well = fa * (fa * fa - 1.);
+        const double divua = ga00 + ga11;
+        const double ug0 = ua0 * ga00 + ua1 * ga10, ug1 = ua0 * ga01 + ua1 * ga11;
+        const double T00 = ga00 + ga00, T01 = ga01 + ga10, T11 = ga11 + ga11;
+        const double jc = (rB - rA) / (2. * rA * Cn), j0 = jc * gma0, j1 = jc * gma1;
+        const double jg0 = j0 * ga00 + j1 * ga10, jg1 = j0 * ga01 + j1 * ga11;
+        const double div_rau = drho * (gfa0 * ua0 + gfa1 * ua1) + rho_a * divua;
+        // momentum (:838-858); the volume force of this class is the constant (0, -1) (:623)
+        const double v0 = rho_a * (dt0 + ug0) + jg0 / Pe - rho_a * 0. / Fr + pr.source_u[0];
+        const double v1 = rho_a * (dt1 + ug1) + jg1 / Pe - rho_a * (-1.) / Fr + pr.source_u[1];
+        const double ck = Cn / We, cp = pa / We, ce = eta_a / Re;
+#pragma unroll
+        for(int b = 0; b < NSU; ++b) {
+          R[2 * b] -= jw * (v0 * lu[b] - ck * (gux[b] * gfa0 * gfa0 + guy[b] * gfa1 * gfa0) - cp * gux[b] + ce * (gux[b] * T00 + guy[b] * T01));
+          R[2 * b + 1] -= jw * (v1 * lu[b] - ck * (gux[b] * gfa0 * gfa1 + guy[b] * gfa1 * gfa1) - cp * guy[b] + ce * (gux[b] * T01 + guy[b] * T11));
+        }
+        // continuity (:863-888)
+        const double tc = divu + (rho - rho_n) / a.dt + div_rau + pr.source_p;
+#pragma unroll
+        for(int q = 0; q < NSP; ++q) {
+          const double dr = dLP[(k * NSP + q) * 2], ds = dLP[(k * NSP + q) * 2 + 1];
+          const double gx = dr * G[0] + ds * G[2], gy = dr * G[1] + ds * G[3];
+          R[NU + q] -= jw * (tc * LP[k * NSP + q] - (j0 * gx + j1 * gy) / Pe);
+        }
+        // tracer (:893-913) and potential (:918-936)
+        const double tf = dphidt + pr.source_phi, dm = 1. / (Pe * Cn);
+        const double tm = ma - well + pr.source_mu;
+#pragma unroll
+        for(int i = 0; i < NSF; ++i) {
+          R[NU + NSP + i] -= jw * (tf * lf[i] - fa * (ua0 * gfx[i] + ua1 * gfy[i]) + dm * (gma0 * gfx[i] + gma1 * gfy[i]));
+          R[NU + NSP + NSF + i] -= jw * (tm * lf[i] - Cn * Cn * (gfa0 * gfx[i] + gfa1 * gfy[i]));
         }
       } else {
         // CHNS_MassAveraged, src/feSysElmCHNS.cpp:446-466: div(rho u), time-averaged double well (Simpson in time)
@@ -428,8 +504,13 @@ int chns_launch(System *S, int what)
   const int    nsf  = S->spaces[S->chns_space[2]].nS;
   const int    M    = S->M;
   const int    model = S->chns_model;
-  a.soln = (model == 1 && S->have_soln) ? S->d_soln : nullptr;
-  const size_t smem = ((size_t)a.ntab + 2 * CHNS_WPB * M + (size_t)CHNS_WPB * a.nq * chns_nfld(model) + CHNS_WPB * 8) * sizeof(double) +
+  a.soln = (model != 0 && S->have_soln) ? S->d_soln : nullptr;
+  a.dt   = S->dt;
+  if(model == 2 && !(S->dt > 0.)) {
+    set_error("CHNS_Khanwale needs the time step: call b200_set_solution_n(s, sol_n, dt) with dt > 0");
+    return B200_ERR_ARG;
+  }
+  const size_t smem = ((size_t)a.ntab + 2 * CHNS_WPB * M + (size_t)CHNS_WPB * a.nq * chns_nfld(model) + CHNS_WPB * 32) * sizeof(double) +
                       (size_t)CHNS_WPB * M * sizeof(int32_t);
   const unsigned grid = (unsigned)((S->nElm + CHNS_WPB - 1) / CHNS_WPB);
 #define B200_LAUNCH_CHNS(NSF, MODEL)                                                                                                     \
@@ -441,10 +522,14 @@ int chns_launch(System *S, int what)
     B200_LAUNCH_CHNS(3, 0);
   else if(nsf == 6 && model == 0)
     B200_LAUNCH_CHNS(6, 0);
-  else if(nsf == 3)
+  else if(nsf == 3 && model == 1)
     B200_LAUNCH_CHNS(3, 1);
-  else
+  else if(nsf == 6 && model == 1)
     B200_LAUNCH_CHNS(6, 1);
+  else if(nsf == 3)
+    B200_LAUNCH_CHNS(3, 2);
+  else
+    B200_LAUNCH_CHNS(6, 2);
 #undef B200_LAUNCH_CHNS
   count_launch();
   B200_CUDA(cudaGetLastError());

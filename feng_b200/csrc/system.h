@@ -129,7 +129,8 @@ struct System {
   bool             chns_active = false;
   int              chns_space[4] = {-1, -1, -1, -1};
   b200_chns_params chns_prm = {};
-  int              chns_model = 0;       // 0 CHNS_Abels, 1 CHNS_MassAveraged
+  int              chns_model = 0;       // 0 CHNS_Abels, 1 CHNS_MassAveraged, 2 CHNS_Khanwale
+  double           dt = 0.;              // time step (b200_set_solution_n)
   double          *d_soln = nullptr;     // state at the previous time step (b200_set_solution_n)
   bool             have_soln = false;
   int32_t         *chns_adr = nullptr;

@@ -286,8 +286,11 @@ class ChnsModel:
     phi_order: int = 1
     # "abels" = CHNS_Abels<2>; "mass_averaged" = CHNS_MassAveraged<2> with alpha = (rho_2 - rho_1) / (rho_1 + rho_2)
     # (src/feSysElm.h:1352-1430, src/CHNS_Solver.cpp:398-416)
+    # "khanwale" = CHNS_Khanwale<2> with khanwale = (Re, Pe, Cn, We, Fr, rhoA, rhoB) (src/feSysElm.h:1434-1512,
+    # src/CHNS_Solver.cpp:418-446)
     formulation: str = "abels"
     alpha: float = 0.0
+    khanwale: tuple = (1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0)
 
 
 def phi_init(x):

@@ -53,9 +53,12 @@ enum {
   B200_FORM_MIXED_DIVERGENCE               = 31, /* feSysElm_MixedDivergence<dim>,         src/feVectorSysElm.cpp:685-749 */
   B200_FORM_CHNS_ABELS                     = 35, /* CHNS_Abels<2> (volume-averaged CHNS),  src/feSysElmCHNS.cpp:66-273; Jacobian by
                                                     finite differences, src/feBilinearForm.cpp:388-428 */
-  B200_FORM_CHNS_MASS_AVERAGED             = 36  /* CHNS_MassAveraged<2>,                  src/feSysElmCHNS.cpp:347-602; needs the Phi
+  B200_FORM_CHNS_MASS_AVERAGED             = 36, /* CHNS_MassAveraged<2>,                  src/feSysElmCHNS.cpp:347-602; needs the Phi
                                                     DOFs of the previous time step (b200_set_solution_n) and the gradient
                                                     table of the pressure space */
+  B200_FORM_CHNS_KHANWALE                  = 38  /* CHNS_Khanwale<2> (non-dimensional, time-averaged fields),
+                                                    src/feSysElmCHNS.cpp:678-938; needs the whole state of the previous time
+                                                    step and the time step (b200_set_solution_n) */
 };
 
 /* Parameters of the monolithic Cahn-Hilliard Navier-Stokes weak form.  The reference passes host callbacks
@@ -69,6 +72,8 @@ typedef struct {
   double force[3], source_u[3], source_p, source_phi, source_mu;
   int    limiter, degenerate_mobility;
   double mass_alpha; /* CHNS_MassAveraged only: alpha = (rho_2 - rho_1) / (rho_1 + rho_2), CHNSparameters[0] (src/feSysElm.h:1419) */
+  double khanwale[7]; /* CHNS_Khanwale only: Re, Pe, Cn, We, Fr, rhoA, rhoB = CHNSparameters[0..6] (src/feSysElm.h:1501-1507); its
+                         volume force is the constant (0, -1) of src/feSysElmCHNS.cpp:623, mobility and force[] are unused */
 } b200_chns_params;
 
 /* Scatter strategies for the race-free add into the CSR matrix (north-star subsystem 3). */
@@ -150,9 +155,11 @@ int b200_add_form(b200_system *s, int kind, int space_u, int space_p, double coe
 int b200_add_form_chns(b200_system *s, int kind, int space_u, int space_p, int space_phi, int space_mu,
                        const b200_chns_params *params);
 /* state vector at the previous time step, nDOF doubles: what feBilinearForm::initialize copies into _solAtTimeN from the
- * global solAtTimeN (src/feBilinearForm.cpp:277,347; set by the time integrators through src/feNonLinearSolver.cpp:35).
- * Read by B200_FORM_CHNS_MASS_AVERAGED only; NULL (or never called) means "equal to the current solution". */
-int b200_set_solution_n(b200_system *s, const double *sol_n);
+ * global solAtTimeN (src/feBilinearForm.cpp:277,347; set by the time integrators through src/feNonLinearSolver.cpp:35),
+ * and the time step feBilinearForm::initialize takes from feSolution::getTimeStep() (src/feBilinearForm.cpp:293).
+ * Read by B200_FORM_CHNS_MASS_AVERAGED (Phi) and B200_FORM_CHNS_KHANWALE (every field, dt); sol_n = NULL (or never
+ * called) means "equal to the current solution". */
+int b200_set_solution_n(b200_system *s, const double *sol_n, double dt);
 /* replace the tabulated source of form `form_id` (returned by b200_add_form): time-dependent source callbacks are
  * re-tabulated by the adapter when feSolution::getCurrentTime() changes (the reference evaluates the callback with
  * args.t = tn on every element visit, src/feBilinearForm.cpp:291-295) */

@@ -22,6 +22,7 @@ from .fe_oracle import geometry, phys_grad
 
 CHNS_ABELS = 35          # elementSystemType, src/feSysElm.h:59
 CHNS_MASS_AVERAGED = 36  # src/feSysElm.h:60
+CHNS_KHANWALE = 38       # src/feSysElm.h:62
 H0 = float(np.sqrt(np.finfo(np.float64).eps))
 
 
@@ -42,14 +43,17 @@ class ChnsParams:
     limiter: bool = False
     degenerate_mobility: bool = False
     phi_order: int = 1
-    formulation: str = "abels"     # or "mass_averaged" (CHNS_MassAveraged<2>, src/feSysElmCHNS.cpp:347-602)
+    formulation: str = "abels"     # or "mass_averaged" (CHNS_MassAveraged<2>, src/feSysElmCHNS.cpp:347-602),
+    #                                   "khanwale" (CHNS_Khanwale<2>, src/feSysElmCHNS.cpp:678-938)
     alpha: float = 0.0             # CHNS_MassAveraged: (rho_2 - rho_1) / (rho_1 + rho_2), src/feSysElm.h:1419
+    khanwale: tuple = (1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0)   # Re, Pe, Cn, We, Fr, rhoA, rhoB (src/feSysElm.h:1501-1507)
 
     def as_array(self):
         return np.array([self.rhoA, self.rhoB, self.viscA, self.viscB, self.mobility, self.sigma, self.epsilon,
                          self.force[0], self.force[1], self.src_u[0], self.src_u[1], self.src_p, self.src_phi,
                          self.src_mu, float(self.limiter), float(self.degenerate_mobility), float(self.phi_order),
-                         1.0 if self.formulation == "mass_averaged" else 0.0, self.alpha])
+                         {"abels": 0.0, "mass_averaged": 1.0, "khanwale": 2.0}[self.formulation], self.alpha,
+                         *self.khanwale])
 
     @property
     def lam(self):
@@ -69,9 +73,10 @@ class ChnsProblem:
     prm: ChnsParams = field(default_factory=ChnsParams)
 
 
-def residual(pb: ChnsProblem, geo, loc, dot, prm: ChnsParams, phi_n_loc=None):
-    """Be[e, M] of CHNS_Abels / CHNS_MassAveraged on every element; loc = [U (nE, nSU, d), P (nE, nSP), Phi, Mu], dot
-    likewise (P, Mu entries unused); phi_n_loc = Phi DOFs at the previous time step (mass-averaged form only)."""
+def residual(pb: ChnsProblem, geo, loc, dot, prm: ChnsParams, phi_n_loc=None, loc_n=None, dt=0.0):
+    """Be[e, M] of CHNS_Abels / CHNS_MassAveraged / CHNS_Khanwale on every element; loc = [U (nE, nSU, d), P (nE, nSP),
+    Phi, Mu], dot likewise (P, Mu entries unused); phi_n_loc = Phi DOFs at the previous time step (mass-averaged form),
+    loc_n = all local DOFs at the previous time step and dt = time step (Khanwale form)."""
     d = pb.dim
     LU, LP, LF, LM = pb.L
     jw = geo.detJ[:, None] * pb.w[None, :]
@@ -99,6 +104,8 @@ def residual(pb: ChnsProblem, geo, loc, dot, prm: ChnsParams, phi_n_loc=None):
     divu = np.einsum("ekmm->ek", gu)
     ugphi = np.einsum("ekm,ekm->ek", u, gphi)
     lam = prm.lam
+    if prm.formulation == "khanwale":
+        return _residual_khanwale(pb, geo, prm, jw, loc, dot, loc if loc_n is None else loc_n, dt)
     if prm.formulation == "mass_averaged":
         return _residual_mass_averaged(pb, geo, prm, jw, (gU, gF, gM), (u, p, phi, mu, dudt, dphidt, gu, gphi, gmu),
                                        (rho, drho, eta, Mob, f, Su), (ugu, S, divu, ugphi), loc, phi_n_loc)
@@ -146,7 +153,57 @@ def _residual_mass_averaged(pb, geo, prm, jw, grads, flds, props, derived, loc, 
     return -np.concatenate([Bu.reshape(nE, -1), Bp, Bf, Bm], 1)
 
 
-def element_systems(pb: ChnsProblem, sol, soldot=None, c0=0.0, matrix=True, sol_n=None):
+def _residual_khanwale(pb, geo, prm, jw, loc, dot, loc_n, dt):
+    """CHNS_Khanwale<2>::computeBe, src/feSysElmCHNS.cpp:678-938: non-dimensional form on fields averaged with the
+    previous time step; the volume force is the constant (0, -1) of :623."""
+    d = pb.dim
+    LU, LP, LF, LM = pb.L
+    gU, gP, gF, gM = (phys_grad(pb.dL[i], geo) for i in range(4))
+    Re, Pe, Cn, We, Fr, rA, rB = prm.khanwale
+
+    def fields(l):
+        U, P, F, Mu = l
+        return (np.einsum("ka,eac->ekc", LU, U), np.einsum("kq,eq->ek", LP, P), np.einsum("kq,eq->ek", LF, F),
+                np.einsum("kq,eq->ek", LM, Mu), np.einsum("ekam,eac->ekmc", gU, U), np.einsum("ekam,ea->ekm", gF, F),
+                np.einsum("ekam,ea->ekm", gM, Mu))
+    u, p, phi, mu, gu, gphi, gmu = fields(loc)
+    un, pn, phin, mun, gun, gphin, gmun = fields(loc_n)
+    ua, pa, fa, ma = 0.5 * (u + un), 0.5 * (p + pn), 0.5 * (phi + phin), 0.5 * (mu + mun)
+    gua, gfa, gma = 0.5 * (gu + gun), 0.5 * (gphi + gphin), 0.5 * (gmu + gmun)
+    dudt = np.einsum("ka,eac->ekc", LU, dot[0])
+    dphidt = np.einsum("kq,eq->ek", LF, dot[2])
+
+    def lin(x, a, b):
+        c = np.clip(x, -1.0, 1.0) if prm.limiter else x
+        return (a - b) / 2.0 * c + (a + b) / 2.0
+    rho_n, rho_a, eta_a, rho = lin(phin, prm.rhoA, prm.rhoB), lin(fa, prm.rhoA, prm.rhoB), lin(fa, prm.viscA, prm.viscB), \
+        lin(phi, prm.rhoA, prm.rhoB)
+    drho = (prm.rhoA - prm.rhoB) / 2.0
+    well = fa * (fa * fa - 1.0)
+    divu, divua = np.einsum("ekmm->ek", gu), np.einsum("ekmm->ek", gua)
+    ugu = np.einsum("ekn,eknc->ekc", ua, gua)
+    S = gua + np.swapaxes(gua, 2, 3)
+    jflux = (rB - rA) / (2.0 * rA * Cn) * gma
+    jgu = np.einsum("ekn,eknc->ekc", jflux, gua)
+    gg = gfa[..., :, None] * gfa[..., None, :]
+    div_rau = drho * np.einsum("ekm,ekm->ek", gfa, ua) + rho_a * divua
+    f = np.array([0.0, -1.0])[:d]
+    Su = np.asarray(prm.src_u, float)[:d]
+    vec = rho_a[..., None] * (dudt + ugu) + jgu / Pe - rho_a[..., None] * f / Fr + Su
+    Bu = np.einsum("ekc,ka,ek->eac", vec, LU, jw)
+    Bu += np.einsum("ekam,ekmc,ek->eac", gU, gg, jw) * (-Cn / We)
+    Bu += np.einsum("ek,ekac,ek->eac", -pa / We, gU, jw)
+    Bu += np.einsum("ek,ekam,ekmc,ek->eac", eta_a / Re, gU, S, jw)
+    Bp = np.einsum("ek,kq,ek->eq", divu + (rho - rho_n) / dt + div_rau + prm.src_p, LP, jw) \
+        - np.einsum("ekm,ekqm,ek->eq", jflux, gP, jw) / Pe
+    Bf = np.einsum("ek,kq,ek->eq", dphidt + prm.src_phi, LF, jw) - np.einsum("ek,ekm,ekqm,ek->eq", fa, ua, gF, jw) \
+        + np.einsum("ekm,ekqm,ek->eq", gma, gF, jw) / (Pe * Cn)
+    Bm = np.einsum("ek,kq,ek->eq", ma - well + prm.src_mu, LM, jw) - Cn * Cn * np.einsum("ekm,ekqm,ek->eq", gfa, gM, jw)
+    nE = loc[0].shape[0]
+    return -np.concatenate([Bu.reshape(nE, -1), Bp, Bf, Bm], 1)
+
+
+def element_systems(pb: ChnsProblem, sol, soldot=None, c0=0.0, matrix=True, sol_n=None, dt=0.0):
     """(Ae[e, M, M] by finite differences or None, Be[e, M], adr[e, M]).  sol_n: state at the previous time step (the
     reference's global solAtTimeN, never perturbed by the finite differences); None = the current solution."""
     geo = geometry(pb.xyz, pb.cells, pb.dim)
@@ -164,7 +221,8 @@ def element_systems(pb: ChnsProblem, sol, soldot=None, c0=0.0, matrix=True, sol_
         return out
     loc, dot = gather(sol), gather(soldot)
     phi_n = (sol if sol_n is None else sol_n)[pb.adr[2]].copy()
-    R0 = residual(pb, geo, loc, dot, pb.prm, phi_n)
+    loc_n = [v.copy() for v in gather(sol if sol_n is None else sol_n)]
+    R0 = residual(pb, geo, loc, dot, pb.prm, phi_n, loc_n, dt)
     adr = np.concatenate(pb.adr, 1)
     if not matrix:
         return None, R0, adr
@@ -179,7 +237,7 @@ def element_systems(pb: ChnsProblem, sol, soldot=None, c0=0.0, matrix=True, sol_
             delta = H0 * np.maximum(np.abs(t), 1.0)
             flat[:, j] = t + delta
             flatd[:, j] = td + delta * c0
-            Rh = residual(pb, geo, loc, dot, pb.prm, phi_n)
+            Rh = residual(pb, geo, loc, dot, pb.prm, phi_n, loc_n, dt)
             Ae[:, :, col] = -(Rh - R0) * (1.0 / delta)[:, None]
             flat[:, j] = t
             flatd[:, j] = td
@@ -187,9 +245,9 @@ def element_systems(pb: ChnsProblem, sol, soldot=None, c0=0.0, matrix=True, sol_
     return Ae, R0, adr
 
 
-def assemble(pb: ChnsProblem, ia, ja, sol, soldot=None, c0=0.0, matrix=True, residual_=True, sol_n=None):
+def assemble(pb: ChnsProblem, ia, ja, sol, soldot=None, c0=0.0, matrix=True, residual_=True, sol_n=None, dt=0.0):
     """Global CSR values and rhs (scatter of src/feLinearSystemMklPardiso.cpp:524-663, :699-741)."""
-    Ae, Be, adr = element_systems(pb, sol, soldot, c0, matrix, sol_n)
+    Ae, Be, adr = element_systems(pb, sol, soldot, c0, matrix, sol_n, dt)
     n = np.int64(pb.n_inc)
     vals = np.zeros(ja.shape[0])
     rhs = np.zeros(pb.n_inc)

@@ -154,13 +154,14 @@ class RefProblem:
             dp = _p(sol_dot)
         self.L.ref_set_solution(self.h, _p(sol), dp, C.c_double(c0), C.c_double(t))
 
-    def set_solution_n(self, sol_n):
-        """state at the previous time step (the reference's global solAtTimeN); None = the current solution"""
+    def set_solution_n(self, sol_n, dt=0.0):
+        """state at the previous time step (the reference's global solAtTimeN; None = the current solution) and the time
+        step (feSolution::setTimeStep)"""
         if sol_n is None:
-            self.L.ref_set_solution_n(self.h, None)
+            self.L.ref_set_solution_n(self.h, None, C.c_double(dt))
         else:
             a = np.ascontiguousarray(sol_n, np.float64)
-            self.L.ref_set_solution_n(self.h, _p(a))
+            self.L.ref_set_solution_n(self.h, _p(a), C.c_double(dt))
 
     # ---- hot path -------------------------------------------------------------------------
     def form_info(self, f) -> FormInfo:

@@ -383,10 +383,11 @@ public:
 
 // ---- CHNS (config 5): parameters and property callbacks ------------------------------------------------
 // g_chns = {rhoA, rhoB, viscA, viscB, mobility, sigma, epsilon, fx, fy, Su0, Su1, Sp, Sphi, Smu, limiter, degenerateMobility,
-//           phiOrder, formulation (0 CHNS_Abels, 1 CHNS_MassAveraged), alpha}; set by ref_set_chns_params before ref_create(kind = 5).  The property laws are the ones
+//           phiOrder, formulation (0 CHNS_Abels, 1 CHNS_MassAveraged, 2 CHNS_Khanwale), alpha, Re, Pe, Cn, We, Fr, rhoA, rhoB};
+//           set by ref_set_chns_params before ref_create(kind = 5).  The property laws are the ones
 // CHNS_Solver hands to its weak form (src/CHNS_Solver.cpp:124-235): linear mixing in phi, optional clipping of phi to
 // [-1, 1], constant or degenerate mobility M |1 - phi^2|.
-double g_chns[19] = {1., 1., 1., 1., 1., 1., 0.1, 0., 0., 0., 0., 0., 0., 0., 0., 0., 1., 0., 0.};
+double g_chns[26] = {1., 1., 1., 1., 1., 1., 0.1, 0., 0., 0., 0., 0., 0., 0., 0., 0., 1., 0., 0., 1., 1., 1., 1., 1., 1., 1.};
 
 double chnsLinearCb(const feFunctionArguments &args, const std::vector<double> &par)
 {
@@ -485,7 +486,8 @@ int ref_error_norms(void *h, const double *sol, double *out);
 void ref_set_chns_params(const double *p, int n)
 {
   g_chns[17] = g_chns[18] = 0.;
-  for(int i = 0; i < n && i < 19; ++i) g_chns[i] = p[i];
+  for(int i = 19; i < 26; ++i) g_chns[i] = 1.;
+  for(int i = 0; i < n && i < 26; ++i) g_chns[i] = p[i];
 }
 
 int ref_max_threads()
@@ -589,6 +591,11 @@ void *ref_create(const char *meshFile, const ref_recipe_t *rc)
       std::vector<double> prm = {g[18], g[5], g[6]};
       CHK(createBilinearForm(chns, {u, p, phi, mu},
                              new CHNS_MassAveraged<2>(rho, drho, visc, dvisc, mob, force, srcP, srcU, srcF, srcM, prm)));
+    } else if(g[17] == 2.) {
+      // src/CHNS_Solver.cpp:418-446: {Re, Pe, Cn, We, Fr, rhoA, rhoB}
+      std::vector<double> prm = {g[19], g[20], g[21], g[22], g[23], g[24], g[25]};
+      CHK(createBilinearForm(chns, {u, p, phi, mu},
+                             new CHNS_Khanwale<2>(rho, drho, visc, dvisc, mob, force, srcP, srcU, srcF, srcM, prm)));
     } else {
       std::vector<double> prm = {g[5], g[6]};
       CHK(createBilinearForm(chns, {u, p, phi, mu},
@@ -821,10 +828,16 @@ int ref_set_solution(void *h, const double *sol, const double *solDot, double c0
   return 0;
 }
 
-// state at the previous time step (NULL: back to "equal to the current solution")
-int ref_set_solution_n(void *h, const double *solN)
+// state at the previous time step (NULL: back to "equal to the current solution") and the time step
+int ref_set_solution_n(void *h, const double *solN, double dt)
 {
   RefProblem *P = (RefProblem *)h;
+  {
+    // feSolution::_dt has no setter of its own: initializeTemporalSolution (src/feSolution.cpp:97-104) sets it
+    const double t = P->sol->getCurrentTime();
+    if(dt > 0.) P->sol->initializeTemporalSolution(t, t + dt, 1);
+    P->sol->setCurrentTime(t);
+  }
   if(solN)
     P->solN.assign(solN, solN + P->sol->getNumDOFs());
   else

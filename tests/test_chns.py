@@ -18,6 +18,16 @@ import pytest
 from conftest import GOLDEN_DIR, assert_close_rows, assert_close_vec
 
 FD_TOL = 1e-6
+KHANWALE = (40., 25., 0.07, 3.0, 1.7, 1.3, 0.7)      # Re, Pe, Cn, We, Fr, rhoA, rhoB
+DT = 0.02
+
+
+def _variant(formulation):
+    """extra ChnsModel / ChnsParams fields of a formulation"""
+    return dict(formulation=formulation, alpha=-0.3 if formulation == "mass_averaged" else 0.0,
+                khanwale=KHANWALE if formulation == "khanwale" else (1.,) * 7)
+
+
 MODELS = {
     "plain": dict(rhoA=1.3, rhoB=0.7, viscA=0.05, viscB=0.02, mobility=0.01, sigma=0.5, epsilon=0.07),
     "full": dict(rhoA=1.3, rhoB=0.7, viscA=0.05, viscB=0.02, mobility=0.01, sigma=0.5, epsilon=0.07, force=(0.1, -0.98),
@@ -39,6 +49,8 @@ def _params_from_fixture(cls, a):
               degenerate_mobility=bool(a[15]), phi_order=int(a[16]))
     if len(a) > 17 and a[17] == 1.0:
         kw.update(formulation="mass_averaged", alpha=float(a[18]))
+    if len(a) > 17 and a[17] == 2.0:
+        kw.update(formulation="khanwale", khanwale=tuple(float(x) for x in a[19:26]))
     return cls(*a[:7], **kw)
 
 
@@ -50,7 +62,8 @@ def _state(pb, seed=5):
 
 
 @pytest.mark.parametrize("model,phi_order,formulation", [("plain", 1, "abels"), ("full", 1, "abels"), ("full", 2, "abels"),
-                                                         ("plain", 1, "mass_averaged"), ("full", 2, "mass_averaged")])
+                                                         ("plain", 1, "mass_averaged"), ("full", 2, "mass_averaged"),
+                                                         ("plain", 1, "khanwale"), ("full", 2, "khanwale")])
 def test_oracle_and_host_tables_vs_compiled_reference(model, phi_order, formulation, tmp_path, have_ref):
     if not have_ref:
         pytest.skip("oracle/_ref not built")
@@ -59,8 +72,7 @@ def test_oracle_and_host_tables_vs_compiled_reference(model, phi_order, formulat
     m = M.rect_mesh(5, 4, 1.3, 0.9, -0.2, 0.1)
     path = str(tmp_path / "m.msh")
     M.write_msh(m, path)
-    mdl = PB.ChnsModel(phi_order=phi_order, formulation=formulation, alpha=-0.3 if formulation != "abels" else 0.0,
-                       **MODELS[model])
+    mdl = PB.ChnsModel(phi_order=phi_order, **_variant(formulation), **MODELS[model])
     pb = PB.chns(m, mdl, 8, 1, 0.05, 1.3)
     opb = _oracle_problem(pb)
     P = ref.RefProblem(path, "chns", 2, 8, 1, 0.05, 1.3, chns=opb.prm.as_array())
@@ -77,25 +89,26 @@ def test_oracle_and_host_tables_vs_compiled_reference(model, phi_order, formulat
     sol_n = None
     if formulation != "abels":     # state at the previous time step (the reference's global solAtTimeN) != current state
         sol_n = sol + np.random.default_rng(9).uniform(-0.05, 0.05, sol.shape)
-        P.set_solution_n(sol_n)
+        P.set_solution_n(sol_n, DT)
     fi = P.form_info(0)
-    assert fi.sys_id == (CO.CHNS_ABELS if formulation == "abels" else CO.CHNS_MASS_AVERAGED)
+    assert fi.sys_id == {"abels": CO.CHNS_ABELS, "mass_averaged": CO.CHNS_MASS_AVERAGED, "khanwale": CO.CHNS_KHANWALE}[formulation]
     assert fi.M == opb.adr[0].shape[1] + 3 + 2 * pb.LF.shape[1]
     v, r, _ = P.assemble()
-    ov, orr = CO.assemble(opb, pb.ia, pb.ja, sol, sd, c0, sol_n=sol_n)
+    ov, orr = CO.assemble(opb, pb.ia, pb.ja, sol, sd, c0, sol_n=sol_n, dt=DT)
     assert_close_vec(orr, r, 1e-13, "rhs")
     assert_close_rows(ov, v, pb.ia, FD_TOL, "FD matrix")
     P.close()
 
 
 @pytest.mark.parametrize("name", ["ref_square1_chns_abels_p1", "ref_square1_chns_abels_p2",
-                                  "ref_square1_chns_mass_averaged_p1"])
+                                  "ref_square1_chns_mass_averaged_p1", "ref_square1_chns_khanwale_p1"])
 def test_oracle_vs_golden_fixture(name):
     """Fixture = inputs as the reference tabulated them + outputs of its own CPU path (tests/golden/make_golden.py)."""
     from oracle import chns_oracle as CO
     g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
     prm = _params_from_fixture(CO.ChnsParams, g["chns_params"])
     sol_n = g["sol_n"] if "sol_n" in g else None
+    dt = float(g["dt"]) if "dt" in g else 0.0
     LU = np.ascontiguousarray(g["L0"][:, 0::2, 0])
     dLU = np.ascontiguousarray(np.stack([g["dLdr0"][:, 0::2, 0], g["dLds0"][:, 0::2, 0]], 2))
     Ls, dLs = [LU], [dLU]
@@ -103,11 +116,11 @@ def test_oracle_vs_golden_fixture(name):
         Ls.append(g[f"L{s}"])
         dLs.append(np.ascontiguousarray(np.stack([g[f"dLdr{s}"], g[f"dLds{s}"]], 2)))
     pb = CO.ChnsProblem(2, g["xyz"], g["cells"], [g[f"adr{s}"] for s in range(4)], g["w"], Ls, dLs, int(g["n_inc"]), prm)
-    Ae, Be, adr = CO.element_systems(pb, g["sol"], g["sol_dot"], float(g["c0"]), sol_n=sol_n)
+    Ae, Be, adr = CO.element_systems(pb, g["sol"], g["sol_dot"], float(g["c0"]), sol_n=sol_n, dt=dt)
     for i, e in enumerate(g["elements"]):
         assert np.abs(Be[e] - g["Be"][i]).max() <= 1e-13 * np.abs(g["Be"][i]).max()
         assert np.abs(Ae[e] - g["Ae"][i]).max() <= FD_TOL * np.abs(g["Ae"][i]).max()
-    ov, orr = CO.assemble(pb, g["ia"], g["ja"], g["sol"], g["sol_dot"], float(g["c0"]), sol_n=sol_n)
+    ov, orr = CO.assemble(pb, g["ia"], g["ja"], g["sol"], g["sol_dot"], float(g["c0"]), sol_n=sol_n, dt=dt)
     assert_close_vec(orr, g["rhs"], 1e-13, "rhs")
     assert_close_rows(ov, g["values"], g["ia"], FD_TOL, "FD matrix")
 
@@ -139,21 +152,21 @@ def test_fd_jacobian_is_the_derivative_of_the_residual():
 @pytest.mark.parametrize("model,phi_order,device_pattern,formulation",
                          [("plain", 1, False, "abels"), ("full", 1, True, "abels"), ("full", 2, False, "abels"),
                           ("plain", 1, True, "mass_averaged"), ("full", 1, False, "mass_averaged"),
-                          ("full", 2, False, "mass_averaged")])
+                          ("full", 2, False, "mass_averaged"), ("plain", 1, False, "khanwale"),
+                          ("full", 1, True, "khanwale"), ("full", 2, False, "khanwale")])
 def test_cuda_chns_vs_oracle(model, phi_order, device_pattern, formulation):
     from feng_b200 import mesh as M, problems as PB
     from feng_b200.linear_system import LinearSystemB200
     from oracle import chns_oracle as CO
     m = M.square_mesh(10)
-    mdl = PB.ChnsModel(phi_order=phi_order, formulation=formulation, alpha=-0.3 if formulation != "abels" else 0.0,
-                       **MODELS[model])
+    mdl = PB.ChnsModel(phi_order=phi_order, **_variant(formulation), **MODELS[model])
     pb = PB.chns(m, mdl, 8, 1, 0.05, 1.3)
     sol, sd, c0 = _state(pb)
     sol_n = None if formulation == "abels" else sol + np.random.default_rng(9).uniform(-0.05, 0.05, sol.shape)
-    ov, orr = CO.assemble(_oracle_problem(pb), pb.ia, pb.ja, sol, sd, c0, sol_n=sol_n)
+    ov, orr = CO.assemble(_oracle_problem(pb), pb.ia, pb.ja, sol, sd, c0, sol_n=sol_n, dt=DT)
     ls = LinearSystemB200(pb, device_pattern=device_pattern)
     if sol_n is not None:
-        ls.sys.set_solution_n(sol_n)
+        ls.sys.set_solution_n(sol_n, DT)
     if device_pattern:
         ia, ja = ls.sys.get_pattern()
         assert np.array_equal(ia, pb.ia) and np.array_equal(ja, pb.ja)
@@ -170,7 +183,8 @@ def test_cuda_chns_vs_oracle(model, phi_order, device_pattern, formulation):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["ref_square1_chns_abels_p1", "ref_square1_chns_mass_averaged_p1"])
+@pytest.mark.parametrize("name", ["ref_square1_chns_abels_p1", "ref_square1_chns_mass_averaged_p1",
+                                  "ref_square1_chns_khanwale_p1"])
 def test_cuda_chns_vs_golden_fixture(name):
     """the CUDA path on the reference's OWN tables (fixture) against the reference's own outputs"""
     from feng_b200 import capi
@@ -191,7 +205,7 @@ def test_cuda_chns_vs_golden_fixture(name):
     S.finalize()
     S.set_solution(g["sol"], g["sol_dot"], float(g["c0"]), 0.0)
     if "sol_n" in g:
-        S.set_solution_n(g["sol_n"])
+        S.set_solution_n(g["sol_n"], float(g["dt"]))
     S.set_to_zero(3)
     S.assemble(3, False)
     assert_close_vec(S.get_rhs(), g["rhs"], 1e-12, "rhs")
@@ -200,7 +214,8 @@ def test_cuda_chns_vs_golden_fixture(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("phi_order,device_pattern,formulation", [(1, False, "abels"), (2, True, "abels"),
-                                                                  (1, True, "mass_averaged"), (2, False, "mass_averaged")])
+                                                                  (1, True, "mass_averaged"), (2, False, "mass_averaged"),
+                                                                  (1, False, "khanwale"), (2, True, "khanwale")])
 def test_chns_through_the_cpp_adapter(phi_order, device_pattern, formulation):
     """The reference's own host objects (mesh reader, feSpace, feMetaNumber, CHNS_Abels<2> / CHNS_MassAveraged<2> with
     their property CALLBACKS, the global solAtTimeN)
@@ -210,8 +225,7 @@ def test_chns_through_the_cpp_adapter(phi_order, device_pattern, formulation):
     from oracle import chns_oracle as CO, ref
     if not ref.available_b200():
         pytest.skip("oracle/_ref/libfeng_ref_b200.so not built (make -C oracle)")
-    prm = CO.ChnsParams(phi_order=phi_order, formulation=formulation, alpha=-0.3 if formulation != "abels" else 0.0,
-                        **MODELS["full"])
+    prm = CO.ChnsParams(phi_order=phi_order, **_variant(formulation), **MODELS["full"])
     P = ref.RefProblem(os.path.join(ref.DATA_DIR, "square2.msh"), "chns", 2, 8, 1, 0.05, 1.3, b200=True,
                        chns=prm.as_array())
     sol, _ = P.solution()
@@ -220,7 +234,7 @@ def test_chns_through_the_cpp_adapter(phi_order, device_pattern, formulation):
     sd = rng.standard_normal(P.n_dof)
     P.set_solution(sol, sd, 2.5, 0.0)
     if formulation != "abels":
-        P.set_solution_n(sol + rng.uniform(-5e-2, 5e-2, P.n_dof))
+        P.set_solution_n(sol + rng.uniform(-5e-2, 5e-2, P.n_dof), DT)
     v, r, _ = P.assemble()                        # reference CPU path (colour loop + FD Jacobian + scatter)
     gv, gr = P.assemble_b200(device_pattern=device_pattern)
     ia, _ = P.pattern()
