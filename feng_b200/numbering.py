@@ -110,6 +110,15 @@ def build_numbering(mesh: Mesh, spaces: list[SpaceSpec]) -> Numbering:
     else:
         tri_e = mesh.bfacets[:, [[0, 1], [1, 2], [2, 0]]].reshape(-1, 2)
         bedges = _edge_lookup(edges, nV, tri_e)
+    # sub-meshes of a partition (feng_b200/partition.py): vertices / edges of the ghost layer that lie on the physical
+    # boundary of the WHOLE mesh although no boundary facet of this sub-mesh holds them
+    xv = getattr(mesh, "extra_boundary_vertices", None)
+    if xv is not None and len(xv):
+        bverts = np.union1d(bverts, np.asarray(xv, np.int64))
+    xe = getattr(mesh, "extra_boundary_edges", None)
+    if xe is not None and len(xe):
+        extra = _edge_lookup(edges, nV, np.asarray(xe, np.int64).reshape(-1, 2))
+        bedges = np.concatenate([bedges, extra[~np.isin(extra, bedges)]])
 
     names = []
     for s in spaces:

@@ -156,3 +156,118 @@ def slab_problem(n: int, rank: int, world: int, kind: str = "ns_div", quad_degre
             dist.all_gather_object(out, obj)
             return out
     return pb, build_halo(keys, owner, rank, world, allgather, owned_cells)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# General meshes: recursive coordinate bisection of the elements (METIS is not in this image; any element -> part map
+# can be passed instead), topological row keys
+# ---------------------------------------------------------------------------------------------------------------
+def rcb_partition(mesh: M.Mesh, world: int) -> np.ndarray:
+    """part[nE]: recursive coordinate bisection of the element centroids into `world` parts of (almost) equal size;
+    every cut is perpendicular to the longest extent of the piece it splits."""
+    cen = mesh.xyz[mesh.cells].mean(1)[:, :mesh.dim]
+    part = np.zeros(mesh.n_cells, np.int32)
+
+    def split(idx, p0, n):
+        if n == 1:
+            part[idx] = p0
+            return
+        c = cen[idx]
+        ax = int(np.argmax(c.max(0) - c.min(0)))
+        nl = n // 2
+        k = (idx.size * nl) // n
+        order = np.argsort(c[:, ax], kind="stable")
+        split(idx[order[:k]], p0, nl)
+        split(idx[order[k:]], p0 + nl, n - nl)
+    split(np.arange(mesh.n_cells), 0, world)
+    return part
+
+
+def _sorted_key(v: np.ndarray, n: int) -> np.ndarray:
+    s = np.sort(v.astype(np.int64), axis=1)
+    key = s[:, 0]
+    for c in range(1, s.shape[1]):
+        key = key * np.int64(n) + s[:, c]
+    return key
+
+
+def topological_keys(pb: PB.HostProblem, gvert: np.ndarray, n_vertices_global: int) -> np.ndarray:
+    """Global identity of every DOF of a (sub-)problem: (field, component, vertex | edge of the WHOLE mesh).  gvert maps
+    the vertices of pb.mesh to vertices of the whole mesh."""
+    num = pb.num
+    keys = np.full(pb.n_dof, -1, np.int64)
+    ge = gvert[num.edges]
+    ekey = np.minimum(ge[:, 0], ge[:, 1]).astype(np.int64) * np.int64(n_vertices_global) + np.maximum(ge[:, 0], ge[:, 1])
+    for f, fn in enumerate(num.fields.values()):
+        for c in range(fn.ncomp):
+            tag = np.int64((f * 4 + c)) << np.int64(58)
+            vd = fn.vertex_dof[:, c]
+            ok = vd >= 0
+            keys[vd[ok]] = tag | gvert[ok].astype(np.int64)
+            ed = fn.edge_dof[:, c]
+            ok = ed >= 0
+            keys[ed[ok]] = tag | (np.int64(1) << np.int64(57)) | ekey[ok]
+    return keys
+
+
+def submesh_problem(mesh: M.Mesh, part: np.ndarray, rank: int, world: int, kind: str = "ns_div", quad_degree: int = 8,
+                    field_id: int = 1, mu: float = 1.0 / 40.0, rho: float = 1.0, allgather=None,
+                    build_pattern: bool = False, with_source: bool = False):
+    """(HostProblem, Partition, gvert) of part `rank` of an arbitrary simplicial mesh held by every rank (as the reference
+    does, src/feLinearSystemPETSc.cpp:626-640).  A node (vertex or edge) belongs to the lowest part among its adjacent
+    elements; the sub-mesh holds every element adjacent to an owned node (owner-computes, one ghost layer), its physical
+    boundary facets, and the ghost-layer vertices / edges of the physical boundary as essential entities."""
+    from . import numbering as NB
+    nVg = mesh.n_vertices
+    edges_g, cell_edges_g = NB.build_edges(mesh)
+    vo = np.full(nVg, world, np.int64)
+    np.minimum.at(vo, mesh.cells.reshape(-1), np.repeat(part.astype(np.int64), mesh.cells.shape[1]))
+    eo = np.full(edges_g.shape[0], world, np.int64)
+    np.minimum.at(eo, cell_edges_g.reshape(-1), np.repeat(part.astype(np.int64), cell_edges_g.shape[1]))
+    local = np.nonzero((vo[mesh.cells] == rank).any(1) | (eo[cell_edges_g] == rank).any(1))[0]
+    gvert = np.unique(mesh.cells[local])
+    g2l = np.full(nVg, -1, np.int64)
+    g2l[gvert] = np.arange(gvert.size)
+    cells = g2l[mesh.cells[local]].astype(np.int32)
+    # physical boundary facets of the sub-mesh = its one-sided facets that are boundary facets of the whole mesh
+    bkey_g = np.sort(_sorted_key(mesh.bfacets, nVg))
+    bf = M.boundary_facets(cells)
+    bf = np.ascontiguousarray(bf[np.isin(_sorted_key(gvert[bf], nVg), bkey_g)]).astype(np.int32)
+    pp = None
+    if mesh.point_pressure is not None and g2l[mesh.point_pressure] >= 0:
+        pp = int(g2l[mesh.point_pressure])
+    sub = M.Mesh(mesh.dim, np.ascontiguousarray(mesh.xyz[gvert]), cells, bf, pp)
+    # ghost-layer entities on the physical boundary of the whole mesh
+    bv_g = np.unique(mesh.bfacets)
+    sub.extra_boundary_vertices = np.nonzero(np.isin(gvert, bv_g))[0]
+    be_g = mesh.bfacets if mesh.dim == 2 else mesh.bfacets[:, [[0, 1], [1, 2], [2, 0]]].reshape(-1, 2)
+    bekey_g = np.unique(_sorted_key(be_g, nVg))
+    edges_l, _ = NB.build_edges(sub)
+    on_b = np.isin(_sorted_key(gvert[edges_l], nVg), bekey_g)
+    sub.extra_boundary_edges = edges_l[on_b]
+    pb = PB.taylor_hood(sub, kind, quad_degree, field_id, mu, rho, build_pattern=build_pattern, with_source=with_source)
+    keys = topological_keys(pb, gvert, nVg)
+    # owner of every DOF = owner of its node
+    owner = np.zeros(pb.n_dof, np.int64)
+    ekey_sorted_idx = np.argsort(_sorted_key(edges_g, nVg))
+    ekey_sorted = _sorted_key(edges_g, nVg)[ekey_sorted_idx]
+    ge = ekey_sorted_idx[np.searchsorted(ekey_sorted, _sorted_key(gvert[pb.num.edges], nVg))]   # local edge -> global edge
+    for fn in pb.num.fields.values():
+        for c in range(fn.ncomp):
+            vd = fn.vertex_dof[:, c]
+            ok = vd >= 0
+            owner[vd[ok]] = vo[gvert[ok]]
+            ed = fn.edge_dof[:, c]
+            ok = ed >= 0
+            owner[ed[ok]] = eo[ge[ok]]
+    if world == 1:
+        return pb, None, gvert
+    if allgather is None:
+        import torch.distributed as dist
+
+        def allgather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+    owned_cells = int((part == rank).sum())
+    return pb, build_halo(keys[:pb.n_inc], owner[:pb.n_inc], rank, world, allgather, owned_cells), gvert

@@ -22,6 +22,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", dest="n", type=int, default=6)
     ap.add_argument("--dim", type=int, default=2, help="2: strips of triangles cut along y; 3: slabs of tetrahedra cut along z")
+    ap.add_argument("--partition", default="structured", choices=["structured", "rcb"],
+                    help="rcb: recursive coordinate bisection of an unstructured mesh (jittered vertices, shuffled element "
+                         "order) held by every rank, rows matched through topological keys")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -32,22 +35,38 @@ def main():
     from feng_b200.linear_system import LinearSystemB200, NLSolverOptions, solve_newton_raphson
     n = args.n
     mu, rho = 1.0, 1.0
-    if args.dim == 2:
+    mg = None
+    if args.partition == "rcb":
+        # the same unstructured mesh on every rank: interior vertices jittered, elements in random order
+        mg = M.rect_mesh(n, n * world, 1.0, float(world)) if args.dim == 2 else M.box_mesh(n, n, n * world, float(world))
+        r0 = np.random.default_rng(11)
+        interior = np.setdiff1d(np.arange(mg.n_vertices), np.unique(mg.bfacets))
+        mg.xyz[interior, :args.dim] += r0.uniform(-0.15 / n, 0.15 / n, (interior.size, args.dim))
+        mg.cells = np.ascontiguousarray(mg.cells[r0.permutation(mg.n_cells)])
+        mg.bfacets = M.boundary_facets(mg.cells)
+        mg.point_pressure = 0
+        deg, fld = (8, 1) if args.dim == 2 else (6, 3)
+        pb, part, gvert = PT.submesh_problem(mg, PT.rcb_partition(mg, world), rank, world, "ns_div", deg, fld, mu, rho)
+    elif args.dim == 2:
         pb, part = PT.strip_problem(n, rank, world, "ns_div", 8, 1, mu, rho, with_source=False)
     else:
         pb, part = PT.slab_problem(n, rank, world, "ns_div", 6, 3, mu, rho, with_source=False)
     ls = LinearSystemB200(pb, device=local, device_pattern=True, partition=part)
     # halo exchange: ghost entries must come back as the owners' values
     rng = np.random.default_rng(5)
-    if args.dim == 2:
+    if args.partition == "rcb":
+        pg = PB.taylor_hood(mg, "ns_div", deg, fld, mu, rho, with_source=False)
+        gkeys = PT.topological_keys(pg, np.arange(mg.n_vertices), mg.n_vertices)[:pg.n_inc]
+    elif args.dim == 2:
         mg = M.rect_mesh(n, n * world, 1.0, float(world))
         mg.point_pressure = 0
         pg = PB.taylor_hood(mg, "ns_div", 8, 1, mu, rho, with_source=False)
+        gkeys, _ = PT.dof_keys_and_owner(pg, n, 1)
     else:
         mg = M.box_mesh(n, n, n * world, float(world))
         mg.point_pressure = 0
         pg = PB.taylor_hood(mg, "ns_div", 6, 3, mu, rho, with_source=False)
-    gkeys, _ = PT.dof_keys_and_owner(pg, n, 1)
+        gkeys, _ = PT.dof_keys_and_owner(pg, n, 1)
     order = np.argsort(gkeys)
     pos = order[np.searchsorted(gkeys[order], part.keys)]
     xg = rng.standard_normal(pg.n_inc)
@@ -80,7 +99,7 @@ def main():
     t = torch.tensor([err, errg], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"multi_gpu_check dim={args.dim} world={world} n={n}: newton its {len(hist)} (single GPU {len(hist2)}), "
+        print(f"multi_gpu_check dim={args.dim} partition={args.partition} world={world} n={n}: newton its {len(hist)} (single GPU {len(hist2)}), "
               f"krylov its {[h['linearIter'] for h in hist]} vs {[h['linearIter'] for h in hist2]}, "
               f"max |du_dist - du_single| owned {t[0].item():.3e} all {t[1].item():.3e} (scale {scale:.3e})")
     assert t[0].item() <= 1e-5 * scale and t[1].item() <= 1e-5 * scale, t
