@@ -185,10 +185,9 @@ def cpu_reference_baseline(n_cpu, reps, threads=None, chns=False):
                       f"Jacobian+residual, {reps} passes"}
 
 
-def cpu_port_baseline(n_cpu, reps):
-    """3-D workload: the reference has no vector-valued space on tetrahedra (src/feSpace.cpp:762-767 instantiates the 2-D
-    ones only), so its CPU arm is the oracle port (oracle/fe_oracle.py, numpy restatement of the same weak forms and of
-    the sorted scatter, pinned on the compiled reference in 2-D) on a bounded sample of the same workload."""
+def _port_worker(job):
+    """One host process: `reps` oracle assemblies of its own copy of the T3D(n_cpu) sample (numpy threads pinned to 1)."""
+    n_cpu, reps = job
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from conftest import to_oracle_problem
     from feng_b200 import mesh as M, problems as PB
@@ -202,9 +201,30 @@ def cpu_port_baseline(n_cpu, reps):
         t0 = time.perf_counter()
         O.assemble(op, pb.ia, pb.ja, sol)
         times.append(time.perf_counter() - t0)
-    return {"times": times, "n_elm": m.n_cells, "cores": 1, "kind": "port",
-            "sample": f"T3D({n_cpu}) = {m.n_cells} tetrahedra, same forms, Jacobian+residual + sorted scatter, numpy oracle "
-                      f"port (the reference has no 3-D vector spaces), {reps} passes"}
+    return times, m.n_cells
+
+
+def cpu_port_baseline(n_cpu, reps, procs=None):
+    """3-D workload: the reference has no vector-valued space on tetrahedra (src/feSpace.cpp:762-767 instantiates the 2-D
+    ones only), so its CPU arm is the oracle port (oracle/fe_oracle.py, numpy restatement of the same weak forms and of
+    the sorted scatter, pinned on the compiled reference in 2-D) on a bounded sample of the same workload.  Every host core
+    runs its own copy of the sample in its own process (the element loop has no shared state); the reported rate is the sum
+    over the processes, each pass as slow as the slowest process."""
+    import multiprocessing as mp
+    procs = procs or max(1, os.cpu_count() or 1)
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.setdefault(k, "1")
+    if procs == 1:
+        res = [_port_worker((n_cpu, reps))]
+    else:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            res = pool.map(_port_worker, [(n_cpu, reps)] * procs)
+    n_elm = res[0][1]
+    times = [max(r[0][i] for r in res) for i in range(reps)]
+    return {"times": times, "n_elm": n_elm * procs, "cores": procs, "kind": "port",
+            "sample": f"{procs} x T3D({n_cpu}) = {procs} x {n_elm} tetrahedra (one copy per host core, one process each), "
+                      f"same forms, Jacobian+residual + sorted scatter, numpy oracle port (the reference has no 3-D vector "
+                      f"spaces), {reps} passes"}
 
 
 def run_reference(args, rank, world):
