@@ -28,6 +28,7 @@ struct ChnsArgs {
   int64_t         nElm;
   const double   *xyz;
   const int32_t  *conn, *adr; // adr: [nElm][M] local DOFs in field order U | P | Phi | Mu
+  const uint16_t *off;        // [nElm][M][M] row-local CSR offset of local entry (i, j), 0xFFFF = not assembled
   const double   *sol, *soldot, *soln, *tab;
   const int64_t  *ia;
   const int32_t  *ja;
@@ -261,45 +262,72 @@ template <int NSF, int MODEL> __global__ void __launch_bounds__(CHNS_WPB * 32, M
       const double rho = drho * pc + (pr.rho_a + pr.rho_b) * 0.5;
       const double eta = (pr.visc_a - pr.visc_b) * 0.5 * pc + (pr.visc_a + pr.visc_b) * 0.5;
       const double Mob = pr.degenerate_mobility ? pr.mobility * fabs(1. - phi * phi) : pr.mobility;
-      const double ugu0 = u0 * gu00 + u1 * gu10, ugu1 = u0 * gu01 + u1 * gu11;
-      const double S00 = gu00 + gu00, S01 = gu01 + gu10, S11 = gu11 + gu11;
-      const double divu = gu00 + gu11, ugphi = u0 * gp0 + u1 * gp1;
+      const double divu = gu00 + gu11;
+      // Every block of the residual has the form  -jw (c phi_i + X d_x phi_i + Y d_y phi_i): the formulation only decides
+      // the coefficients, which carry the quadrature weight so that each test function costs three FMAs.
+      double a0, a1, X0, Y0, X1, Y1; // momentum rows (components 0, 1) of velocity test function phi_b
+      double cP, PX = 0., PY = 0.;   // continuity rows
+      double cF, FX, FY, cM, MX, MY; // tracer and potential rows
       if(MODEL == 0) {
-        // CHNS_Abels, src/feSysElmCHNS.cpp:158-171
+        // CHNS_Abels, src/feSysElmCHNS.cpp:158-271
+        const double ugu0 = u0 * gu00 + u1 * gu10, ugu1 = u0 * gu01 + u1 * gu11;
         const double gmgu0 = gm0 * gu00 + gm1 * gu10, gmgu1 = gm0 * gu01 + gm1 * gu11;
-        // momentum (:192-219): test function i = 2a + c is phi_a e_c
-        const double v0 = rho * (dt0 + ugu0 - pr.force[0]) - drho * Mob * gmgu0 + phi * gm0 + pr.source_u[0];
-        const double v1 = rho * (dt1 + ugu1 - pr.force[1]) - drho * Mob * gmgu1 + phi * gm1 + pr.source_u[1];
-#pragma unroll
-        for(int b = 0; b < NSU; ++b) {
-          R[2 * b] -= jw * (v0 * lu[b] - p * gux[b] + eta * (gux[b] * S00 + guy[b] * S01));
-          R[2 * b + 1] -= jw * (v1 * lu[b] - p * guy[b] + eta * (gux[b] * S01 + guy[b] * S11));
-        }
-        // continuity (:224-227)
-#pragma unroll
-        for(int q = 0; q < NSP; ++q) R[NU + q] -= jw * (divu + pr.source_p) * LP[k * NSP + q];
-        // tracer (:232-250) and potential (:255-271)
-        const double tf = dphidt + ugphi + pr.source_phi;
-        const double tm = mu - dw * phi * (phi * phi - 1.) + pr.source_mu;
-#pragma unroll
-        for(int i = 0; i < NSF; ++i) {
-          R[NU + NSP + i] -= jw * (tf * lf[i] + Mob * (gm0 * gfx[i] + gm1 * gfy[i]));
-          R[NU + NSP + NSF + i] -= jw * (tm * lf[i] - lam * (gp0 * gfx[i] + gp1 * gfy[i]));
-        }
-      } else if(MODEL == 2) {
-        // CHNS_Khanwale, src/feSysElmCHNS.cpp:717-800: every field averaged with the previous time step
+        const double S00 = gu00 + gu00, S01 = gu01 + gu10, S11 = gu11 + gu11;
+        a0 = jw * (rho * (dt0 + ugu0 - pr.force[0]) - drho * Mob * gmgu0 + phi * gm0 + pr.source_u[0]);
+        a1 = jw * (rho * (dt1 + ugu1 - pr.force[1]) - drho * Mob * gmgu1 + phi * gm1 + pr.source_u[1]);
+        const double je = jw * eta;
+        X0 = je * S00 - jw * p;
+        Y0 = je * S01;
+        X1 = Y0;
+        Y1 = je * S11 - jw * p;
+        cP = jw * (divu + pr.source_p);
+        cF = jw * (dphidt + u0 * gp0 + u1 * gp1 + pr.source_phi);
+        FX = jw * Mob * gm0;
+        FY = jw * Mob * gm1;
+        cM = jw * (mu - dw * phi * (phi * phi - 1.) + pr.source_mu);
+        MX = -jw * lam * gp0;
+        MY = -jw * lam * gp1;
+      } else if(MODEL == 1) {
+        // CHNS_MassAveraged, src/feSysElmCHNS.cpp:446-600: div(rho u), time-averaged double well (Simpson in time)
+        const double alpha = pr.mass_alpha;
+        const double beta  = 3. / (2. * sqrt(2.)) * pr.surface_tension / pr.epsilon; // src/feSysElm.h:1425
+        const double ugu0 = u0 * gu00 + u1 * gu10, ugu1 = u0 * gu01 + u1 * gu11;
+        const double S00 = gu00 + gu00, S01 = gu01 + gu10, S11 = gu11 + gu11;
+        const double divRhoU = rho * divu + drho * (u0 * gp0 + u1 * gp1);
+        const double pavg = 0.5 * (phi + phin);
+        const double well = (phi * (phi * phi - 1.) + 4. * pavg * (pavg * pavg - 1.) + phin * (phin * phin - 1.)) * beta / 6.;
+        const double mc = 0.5 * (drho * dphidt + divRhoU);
+        a0 = jw * (rho * (dt0 + ugu0 - pr.force[0]) + mc * u0 + phi * gm0 + pr.source_u[0]);
+        a1 = jw * (rho * (dt1 + ugu1 - pr.force[1]) + mc * u1 + phi * gm1 + pr.source_u[1]);
+        const double je = jw * eta, jpe = jw * (p + eta * divu); // - p div(phi_i) - eta (2/dim) div u div(phi_i), dim = 2
+        X0 = je * S00 - jpe;
+        Y0 = je * S01;
+        X1 = Y0;
+        Y1 = je * S11 - jpe;
+        const double fx = Mob * (gm0 + alpha * gpr0), fy = Mob * (gm1 + alpha * gpr1);
+        cP = jw * (divu + pr.source_p);
+        PX = jw * alpha * fx;
+        PY = jw * alpha * fy;
+        cF = jw * (dphidt + pr.source_phi);
+        FX = jw * (fx - phi * u0);
+        FY = jw * (fy - phi * u1);
+        cM = jw * (mu - well + pr.source_mu);
+        MX = -jw * lam * gp0;
+        MY = -jw * lam * gp1;
+      } else {
+        // CHNS_Khanwale, src/feSysElmCHNS.cpp:717-936: every field averaged with the previous time step; the volume
+        // force of this class is the constant (0, -1) (:623)
         const double *kw = pr.khanwale; // Re, Pe, Cn, We, Fr, rhoA, rhoB
         const double Re = kw[0], Pe = kw[1], Cn = kw[2], We = kw[3], Fr = kw[4], rA = kw[5], rB = kw[6];
         const double ua0 = 0.5 * (u0 + f[16]), ua1 = 0.5 * (u1 + f[17]), pa = 0.5 * (p + f[18]), fa = 0.5 * (phi + f[19]),
                      ma = 0.5 * (mu + f[20]);
         const double ga00 = 0.5 * (gu00 + f[21]), ga01 = 0.5 * (gu01 + f[22]), ga10 = 0.5 * (gu10 + f[23]), ga11 = 0.5 * (gu11 + f[24]);
         const double gfa0 = 0.5 * (gp0 + f[25]), gfa1 = 0.5 * (gp1 + f[26]), gma0 = 0.5 * (gm0 + f[27]), gma1 = 0.5 * (gm1 + f[28]);
-        const double phin_ = f[19];
         auto lin = [&](double x, double va, double vb) {
-          const double c = pr.limiter ? fmax(-1., fmin(1., x)) : x;
-          return (va - vb) * 0.5 * c + (va + vb) * 0.5;
+          const double cl = pr.limiter ? fmax(-1., fmin(1., x)) : x;
+          return (va - vb) * 0.5 * cl + (va + vb) * 0.5;
         };
-        const double rho_n = lin(phin_, pr.rho_a, pr.rho_b), rho_a = lin(fa, pr.rho_a, pr.rho_b), eta_a = lin(fa, pr.visc_a, pr.visc_b);
+        const double rho_n = lin(f[19], pr.rho_a, pr.rho_b), rho_a = lin(fa, pr.rho_a, pr.rho_b), eta_a = lin(fa, pr.visc_a, pr.visc_b);
         const double well = fa * (fa * fa - 1.);
         const double divua = ga00 + ga11;
         const double ug0 = ua0 * ga00 + ua1 * ga10, ug1 = ua0 * ga01 + ua1 * ga11;
@@ -307,88 +335,89 @@ template <int NSF, int MODEL> __global__ void __launch_bounds__(CHNS_WPB * 32, M
         const double jc = (rB - rA) / (2. * rA * Cn), j0 = jc * gma0, j1 = jc * gma1;
         const double jg0 = j0 * ga00 + j1 * ga10, jg1 = j0 * ga01 + j1 * ga11;
         const double div_rau = drho * (gfa0 * ua0 + gfa1 * ua1) + rho_a * divua;
-        // momentum (:838-858); the volume force of this class is the constant (0, -1) (:623)
-        const double v0 = rho_a * (dt0 + ug0) + jg0 / Pe - rho_a * 0. / Fr + pr.source_u[0];
-        const double v1 = rho_a * (dt1 + ug1) + jg1 / Pe - rho_a * (-1.) / Fr + pr.source_u[1];
-        const double ck = Cn / We, cp = pa / We, ce = eta_a / Re;
+        a0 = jw * (rho_a * (dt0 + ug0) + jg0 / Pe + pr.source_u[0]);
+        a1 = jw * (rho_a * (dt1 + ug1) + jg1 / Pe + rho_a / Fr + pr.source_u[1]);
+        const double jk = jw * Cn / We, jp = jw * pa / We, je = jw * eta_a / Re;
+        X0 = je * T00 - jp - jk * gfa0 * gfa0;
+        Y0 = je * T01 - jk * gfa1 * gfa0;
+        X1 = je * T01 - jk * gfa0 * gfa1;
+        Y1 = je * T11 - jp - jk * gfa1 * gfa1;
+        cP = jw * (divu + (rho - rho_n) / a.dt + div_rau + pr.source_p);
+        PX = -jw * j0 / Pe;
+        PY = -jw * j1 / Pe;
+        const double dm = 1. / (Pe * Cn);
+        cF = jw * (dphidt + pr.source_phi);
+        FX = jw * (dm * gma0 - fa * ua0);
+        FY = jw * (dm * gma1 - fa * ua1);
+        cM = jw * (ma - well + pr.source_mu);
+        MX = -jw * Cn * Cn * gfa0;
+        MY = -jw * Cn * Cn * gfa1;
+        (void)eta, (void)Mob;
+      }
 #pragma unroll
-        for(int b = 0; b < NSU; ++b) {
-          R[2 * b] -= jw * (v0 * lu[b] - ck * (gux[b] * gfa0 * gfa0 + guy[b] * gfa1 * gfa0) - cp * gux[b] + ce * (gux[b] * T00 + guy[b] * T01));
-          R[2 * b + 1] -= jw * (v1 * lu[b] - ck * (gux[b] * gfa0 * gfa1 + guy[b] * gfa1 * gfa1) - cp * guy[b] + ce * (gux[b] * T01 + guy[b] * T11));
-        }
-        // continuity (:863-888)
-        const double tc = divu + (rho - rho_n) / a.dt + div_rau + pr.source_p;
+      for(int b = 0; b < NSU; ++b) {
+        R[2 * b]     = fma(-a0, lu[b], fma(-X0, gux[b], fma(-Y0, guy[b], R[2 * b])));
+        R[2 * b + 1] = fma(-a1, lu[b], fma(-X1, gux[b], fma(-Y1, guy[b], R[2 * b + 1])));
+      }
 #pragma unroll
-        for(int q = 0; q < NSP; ++q) {
+      for(int q = 0; q < NSP; ++q) {
+        double r = fma(-cP, LP[k * NSP + q], R[NU + q]);
+        if(MODEL != 0) {
           const double dr = dLP[(k * NSP + q) * 2], ds = dLP[(k * NSP + q) * 2 + 1];
-          const double gx = dr * G[0] + ds * G[2], gy = dr * G[1] + ds * G[3];
-          R[NU + q] -= jw * (tc * LP[k * NSP + q] - (j0 * gx + j1 * gy) / Pe);
+          r = fma(-PX, dr * G[0] + ds * G[2], fma(-PY, dr * G[1] + ds * G[3], r));
         }
-        // tracer (:893-913) and potential (:918-936)
-        const double tf = dphidt + pr.source_phi, dm = 1. / (Pe * Cn);
-        const double tm = ma - well + pr.source_mu;
+        R[NU + q] = r;
+      }
 #pragma unroll
-        for(int i = 0; i < NSF; ++i) {
-          R[NU + NSP + i] -= jw * (tf * lf[i] - fa * (ua0 * gfx[i] + ua1 * gfy[i]) + dm * (gma0 * gfx[i] + gma1 * gfy[i]));
-          R[NU + NSP + NSF + i] -= jw * (tm * lf[i] - Cn * Cn * (gfa0 * gfx[i] + gfa1 * gfy[i]));
-        }
-      } else {
-        // CHNS_MassAveraged, src/feSysElmCHNS.cpp:446-466: div(rho u), time-averaged double well (Simpson in time)
-        const double alpha = pr.mass_alpha;
-        const double beta  = 3. / (2. * sqrt(2.)) * pr.surface_tension / pr.epsilon; // src/feSysElm.h:1425
-        const double divRhoU = rho * divu + drho * ugphi;
-        const double pavg = 0.5 * (phi + phin);
-        const double well = (phi * (phi * phi - 1.) + 4. * pavg * (pavg * pavg - 1.) + phin * (phin * phin - 1.)) * beta / 6.;
-        // momentum (:486-513)
-        const double mc = 0.5 * (drho * dphidt + divRhoU);
-        const double v0 = rho * (dt0 + ugu0 - pr.force[0]) + mc * u0 + phi * gm0 + pr.source_u[0];
-        const double v1 = rho * (dt1 + ugu1 - pr.force[1]) + mc * u1 + phi * gm1 + pr.source_u[1];
-        const double pe = p + eta * divu; // - p div(phi_i) - eta (2/dim) div u div(phi_i), dim = 2
-#pragma unroll
-        for(int b = 0; b < NSU; ++b) {
-          R[2 * b] -= jw * (v0 * lu[b] - pe * gux[b] + eta * (gux[b] * S00 + guy[b] * S01));
-          R[2 * b + 1] -= jw * (v1 * lu[b] - pe * guy[b] + eta * (gux[b] * S01 + guy[b] * S11));
-        }
-        // continuity (:518-541): div u + alpha div(M grad(mu + alpha p)); P1 test-function gradients
-        const double fx = Mob * (gm0 + alpha * gpr0), fy = Mob * (gm1 + alpha * gpr1);
-#pragma unroll
-        for(int q = 0; q < NSP; ++q) {
-          const double dr = dLP[(k * NSP + q) * 2], ds = dLP[(k * NSP + q) * 2 + 1];
-          const double gx = dr * G[0] + ds * G[2], gy = dr * G[1] + ds * G[3];
-          R[NU + q] -= jw * ((divu + pr.source_p) * LP[k * NSP + q] + alpha * (fx * gx + fy * gy));
-        }
-        // tracer (:546-574, conservative convective term) and potential (:579-600)
-        const double tf = dphidt + pr.source_phi;
-        const double tm = mu - well + pr.source_mu;
-#pragma unroll
-        for(int i = 0; i < NSF; ++i) {
-          R[NU + NSP + i] -= jw * (tf * lf[i] - phi * (u0 * gfx[i] + u1 * gfy[i]) + fx * gfx[i] + fy * gfy[i]);
-          R[NU + NSP + NSF + i] -= jw * (tm * lf[i] - lam * (gp0 * gfx[i] + gp1 * gfy[i]));
-        }
+      for(int i = 0; i < NSF; ++i) {
+        R[NU + NSP + i]       = fma(-cF, lf[i], fma(-FX, gfx[i], fma(-FY, gfy[i], R[NU + NSP + i])));
+        R[NU + NSP + NSF + i] = fma(-cM, lf[i], fma(-MX, gfx[i], fma(-MY, gfy[i], R[NU + NSP + NSF + i])));
       }
     }
   }
   // ---- Jacobian column: Ae[i][j] = -(Rh[i] - R0[i]) / delta (src/feBilinearForm.cpp:419-422); residual = R0
   const double inv = column ? 1. / delta : 0.;
-  const int32_t J_ = column ? adr[j] : 0x7fffffff;
 #pragma unroll
   for(int i = 0; i < M; ++i) {
     const double  r0 = __shfl_sync(0xffffffffu, R[i], M);
     const int32_t I  = adr[i];
     if(I >= a.nInc) continue;
     if(j == M && (a.what & 1)) atomicAdd(a.rhs + I, r0);
-    if(column && (a.what & 2) && J_ < a.nInc) {
-      const double v  = -(R[i] - r0) * inv;
-      int64_t      lo = a.ia[I], hi = a.ia[I + 1] - 1;
+    if(column && (a.what & 2)) {
+      // the reference scans the row for the column (src/feLinearSystemMklPardiso.cpp:648-658); here the row-local offset of
+      // every local entry was found once at plan time (chns_offsets_kernel)
+      const uint32_t o = a.off[((int64_t)e * M + i) * M + j];
+      if(o != 0xFFFFu) atomicAdd(a.val + a.ia[I] + o, -(R[i] - r0) * inv);
+    }
+  }
+}
+
+// row-local CSR offsets of the M x M local entries of every element (binary search of the column in the row, once)
+__global__ void chns_offsets_kernel(int64_t nElm, int M, const int32_t *adr, const int64_t *ia, const int32_t *ja, int64_t nInc, uint16_t *off,
+                                    int *err)
+{
+  const int64_t tot = nElm * M * (int64_t)M;
+  for(int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = idx / (M * M);
+    const int     r = (int)(idx - e * M * M), i = r / M, j = r - i * M;
+    const int32_t I = adr[e * M + i], Jc = adr[e * M + j];
+    uint16_t      o = 0xFFFF;
+    if(I < nInc && Jc < nInc) {
+      int64_t lo = ia[I], hi = ia[I + 1] - 1;
+      const int64_t beg = lo, end = hi + 1;
       while(lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if(a.ja[mid] < J_)
+        if(ja[mid] < Jc)
           lo = mid + 1;
         else
           hi = mid;
       }
-      if(a.ja[lo] == J_) atomicAdd(a.val + lo, v);
+      if(lo < end && ja[lo] == Jc && lo - beg < 0xFFFF)
+        o = (uint16_t)(lo - beg);
+      else
+        atomicExch(err, 1);
     }
+    off[idx] = o;
   }
 }
 
@@ -419,8 +448,10 @@ void chns_free(System *S)
 {
   cudaFree(S->chns_adr);
   cudaFree(S->chns_tab);
+  cudaFree(S->chns_off);
   S->chns_adr = nullptr;
   S->chns_tab = nullptr;
+  S->chns_off = nullptr;
 }
 
 // Validates the CHNS registration and builds the concatenated element->DOF table (also used by the pattern builder).
@@ -475,7 +506,23 @@ int chns_build_plan(System *S)
   S->chns_tab_len = (int)tab.size();
   B200_CUDA(cudaMalloc(&S->chns_tab, tab.size() * sizeof(double)));
   B200_CUDA(cudaMemcpyAsync(S->chns_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, S->stream));
+  // row-local offsets of the local entries
+  cudaFree(S->chns_off);
+  S->chns_off = nullptr;
+  B200_CUDA(cudaMalloc(&S->chns_off, (size_t)S->nElm * S->M * S->M * sizeof(uint16_t)));
+  int *d_err;
+  B200_CUDA(cudaMalloc(&d_err, sizeof(int)));
+  B200_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), S->stream));
+  chns_offsets_kernel<<<148 * 8, 256, 0, S->stream>>>(S->nElm, S->M, S->chns_adr, S->d_ia, S->d_ja, S->nInc, S->chns_off, d_err);
+  count_launch();
+  int h_err = 0;
+  B200_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, S->stream));
   B200_CUDA(cudaStreamSynchronize(S->stream));
+  cudaFree(d_err);
+  if(h_err) {
+    set_error("b200_finalize: a local (row, col) pair of the CHNS form is missing from the CSR pattern");
+    return B200_ERR_ARG;
+  }
   return B200_OK;
 }
 
@@ -487,6 +534,7 @@ int chns_launch(System *S, int what)
   a.xyz    = S->d_xyz;
   a.conn   = S->d_conn;
   a.adr    = S->chns_adr;
+  a.off    = S->chns_off;
   a.sol    = S->d_sol;
   a.soldot = S->have_soldot ? S->d_soldot : nullptr;
   a.tab    = S->chns_tab;

@@ -134,6 +134,7 @@ struct System {
   double          *d_soln = nullptr;     // state at the previous time step (b200_set_solution_n)
   bool             have_soln = false;
   int32_t         *chns_adr = nullptr;
+  uint16_t        *chns_off = nullptr;   // [nElm][M][M] row-local CSR offsets of the local entries
   double          *chns_tab = nullptr;
   int              chns_tab_len = 0;
 
