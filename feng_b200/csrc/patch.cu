@@ -94,7 +94,9 @@ template <int D, int NS, int NP> struct PT {
 
 struct PatchPlan {
   int32_t    nPatch = 0, nNodes = 0;
-  int        PE = 0, maxE = 0, NT = 256, max_smem_doubles = 0;
+  int        PE = 0, maxE = 0, NT = 256, max_smem_doubles = 0, max_nb = 0, max_np = 0, max_nn = 0;
+  bool       slice = false;        // B200_PATCH_KERNEL=slice: row-slice kernel (slice.cuh, 2-D only)
+  const double *d_gt = nullptr;    // GT-layout reference tensors (owned by the gather plan)
   int64_t    nBlocks = 0, nCtr = 0, nPairs = 0, nElemsTot = 0;
   PatchDesc *desc = nullptr;
   int32_t   *elems = nullptr;
@@ -482,6 +484,10 @@ __global__ void __launch_bounds__(NT, MINB) patch_kernel(const PatchArgs a)
   }
 }
 
+} // namespace b200
+#include "slice.cuh"
+namespace b200 {
+
 __global__ void patch_zero_kernel(int64_t n, const int64_t *idx, double *val)
 {
   for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) val[idx[i]] = 0.;
@@ -815,6 +821,15 @@ struct IsZeroOp {
 struct DescNe {
   __host__ __device__ int32_t operator()(const PatchDesc &d) const { return d.ne; }
 };
+struct DescNb {
+  __host__ __device__ int32_t operator()(const PatchDesc &d) const { return d.nb; }
+};
+struct DescNp {
+  __host__ __device__ int32_t operator()(const PatchDesc &d) const { return d.np; }
+};
+struct DescNn {
+  __host__ __device__ int32_t operator()(const PatchDesc &d) const { return d.nn; }
+};
 
 void patch_free(System *S)
 {
@@ -859,6 +874,11 @@ template <int D, int NS, int NP> static int build_patch_plan_t(System *S, const 
   PatchPlan    *P    = new PatchPlan;
   S->patch           = P;
   P->d_geo           = gt.d_geo;
+  P->d_gt            = gt.d_tab;
+  {
+    const char *k = getenv("B200_PATCH_KERNEL");
+    P->slice      = k && std::string(k) == "slice";
+  }
   {
     const char *k = getenv("B200_PATCH_ELEMS");
     P->PE         = k ? atoi(k) : (D == 2 ? 64 : 32);
@@ -1069,6 +1089,9 @@ template <int D, int NS, int NP> static int build_patch_plan_t(System *S, const 
   {
     thrust::device_ptr<PatchDesc> dp(P->desc);
     P->maxE = thrust::transform_reduce(pol, dp, dp + nPatch, DescNe(), 0, thrust::maximum<int32_t>());
+    P->max_nb = thrust::transform_reduce(pol, dp, dp + nPatch, DescNb(), 0, thrust::maximum<int32_t>());
+    P->max_np = thrust::transform_reduce(pol, dp, dp + nPatch, DescNp(), 0, thrust::maximum<int32_t>());
+    P->max_nn = thrust::transform_reduce(pol, dp, dp + nPatch, DescNn(), 0, thrust::maximum<int32_t>());
   }
   const size_t smem = ((size_t)((P->tab_len_src + 1) & ~1) + (size_t)P->max_smem_doubles) * sizeof(double);
   if(smem > 224 * 1024) {
@@ -1147,10 +1170,61 @@ template <int D, int NS, int NP, int NT, int MINB> static int launch_patch_t(Sys
   return B200_OK;
 }
 
+// row-slice kernel: B200_ERR_UNSUPP when the pass needs something it does not do (transient residual, sources, oversized
+// patches); the caller then runs the patch kernel
+static int launch_slice_2d(System *S, int what, const THCoeffs &c)
+{
+  constexpr int NT = 256, MAXS = 12;
+  PatchPlan *P = static_cast<PatchPlan *>(S->patch);
+  if((c.c_mass != 0. && S->have_soldot && (what & 1)) || c.c_src != 0. || P->max_nb > NT * MAXS || P->maxE > NT) return B200_ERR_UNSUPP;
+  PatchArgs a;
+  a.desc   = P->desc;
+  a.elems  = P->elems;
+  a.nodes  = P->nodes;
+  a.pairs  = P->pairs;
+  a.blocks = P->blocks;
+  a.ctr    = P->ctr;
+  a.adrU   = S->spaces[S->su].d_adr;
+  a.adrP   = S->spaces[S->sp].d_adr;
+  a.sol    = S->d_sol;
+  a.soldot = nullptr;
+  a.source = nullptr;
+  a.geo    = P->d_geo;
+  a.tab    = P->d_tab;
+  a.val    = S->d_val;
+  a.rhs    = S->d_rhs;
+  a.nInc   = S->nInc;
+  a.nq     = S->nq;
+  a.ntab   = P->tab_len;
+  a.c      = c;
+  a.c0     = S->c0;
+  B200_CUDA(cudaMemcpyToSymbolAsync(c_gt, P->d_gt, sizeof(double) * GT<2, 6, 3>::O_W, 0, cudaMemcpyDeviceToDevice, S->stream));
+  const size_t smem = (size_t)P->maxE * (PS<2, 6, 3>::W + 32 + 16) * sizeof(double) + (size_t)(((P->max_np + 3) & ~3) + P->max_nn + 8) * sizeof(uint16_t);
+  if(smem > 224 * 1024) return B200_ERR_UNSUPP;
+  if(what & 1) {
+    B200_CUDA(cudaFuncSetAttribute(slice_kernel_2d<NT, MAXS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    slice_kernel_2d<NT, MAXS, true><<<P->nPatch, NT, smem, S->stream>>>(a);
+  } else {
+    B200_CUDA(cudaFuncSetAttribute(slice_kernel_2d<NT, MAXS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    slice_kernel_2d<NT, MAXS, false><<<P->nPatch, NT, smem, S->stream>>>(a);
+  }
+  count_launch();
+  if(P->nZero > 0) {
+    patch_zero_kernel<<<(unsigned)std::min<int64_t>((P->nZero + 255) / 256, 148 * 8), 256, 0, S->stream>>>(P->nZero, P->zero_idx, S->d_val);
+    count_launch();
+  }
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
 // what: bit 0 residual, bit 1 matrix; OVERWRITES val / rhs (every unknown row is written exactly once)
 int launch_patch(System *S, int what, const THCoeffs &c)
 {
   const PatchPlan *P = static_cast<const PatchPlan *>(S->patch);
+  if(S->dim == 2 && P->slice && (what & 2)) {
+    const int rc = launch_slice_2d(S, what, c);
+    if(rc != B200_ERR_UNSUPP) return rc;
+  }
   if(S->dim == 2) {
     if(P->NT == 128) return launch_patch_t<2, 6, 3, 128, 4>(S, what, c);
     if(P->NT == 512) return launch_patch_t<2, 6, 3, 512, 1>(S, what, c);

@@ -106,3 +106,23 @@ def test_patch_against_reference_fixtures(name, patch_kernel):
     S.assemble(3)
     assert_close_rows(S.get_matrix_values(), g["vals"], g["ia"], 1e-12, "matrix vs reference")
     assert_close_vec(S.get_rhs(), g["rhs"], 1e-12, "rhs vs reference")
+
+
+@pytest.mark.parametrize("kind", ["ns_div", "ns_lap", "stokes_div"])
+@pytest.mark.parametrize("patch_elems", [9, 64])
+def test_row_slice_kernel_2d_vs_oracle(kind, patch_elems, patch_kernel, monkeypatch):
+    """B200_PATCH_KERNEL=slice (csrc/slice.cuh): element-centric producers with constant-bank reference tensors, slot owners
+    that keep their sums in registers across the row slices; same plan, same numbers."""
+    from feng_b200 import mesh as M, problems as PB
+    from oracle import fe_oracle as O
+    monkeypatch.setenv("B200_PATCH_KERNEL", "slice")
+    m = M.square_mesh(13)
+    pb = PB.taylor_hood(m, kind, 8, 0, 0.025, 1.3, with_source=False)
+    sol = PB.perturb_unknowns(pb)
+    ov, orr = O.assemble(to_oracle_problem(pb), pb.ia, pb.ja, sol)
+    ls, v, r = _assemble(pb, sol, patch_elems=patch_elems, monkeypatch=monkeypatch)
+    assert_close_rows(v, ov, pb.ia, 1e-12, "matrix")
+    assert_close_vec(r, orr, 1e-12, "rhs")
+    ls.sys.set_to_zero(3)
+    ls.sys.assemble(2, False)                       # matrix-only pass: same numbers, rhs untouched (lazy zero -> zeros)
+    assert np.array_equal(ls.sys.get_matrix_values(), v)
