@@ -319,12 +319,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput -------------------------------------------------------------------
+    # clocks / throttle reasons are sampled from the warm-up to the end of the end-to-end loop (nvidia-smi needs ~0.2 s to
+    # deliver its first sample; the device-timed region alone is a fraction of a second)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         S.set_to_zero(3)
         S.assemble(3)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     capi.reset_kernel_launches()
     kern_ms = []
     barrier()
@@ -340,7 +342,6 @@ def main():
         S.set_to_zero(3)
         S.assemble(3)
         kern_ms.append(S.last_assemble_ms())
-    clocks = sampler.stop()
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------
     for _ in range(2):
         upload()
@@ -357,6 +358,7 @@ def main():
     S.sync()
     e2e_s = time.perf_counter() - t0
     spmv_ms = S.time_spmv(20)
+    clocks = sampler.stop()
 
     t_all = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     owned_all = torch.tensor([float(owned)], dtype=torch.float64, device="cuda")
