@@ -159,22 +159,6 @@ def test_gather_is_deterministic_and_lazy_zero_is_exact():
     assert np.array_equal(ls.sys.get_matrix_values(), v1) and np.array_equal(ls.sys.get_rhs(), r1)
 
 
-def _greedy_colors(cells, n_vertices):
-    """Host colouring with the rule of feCncGeo::colorElements(1) (src/feCncGeo.cpp:752-794): sweep the uncoloured
-    elements in order and take those whose vertices were not touched earlier in the sweep."""
-    nE = cells.shape[0]
-    color = -np.ones(nE, np.int32)
-    c = 0
-    while (color < 0).any():
-        touched = np.zeros(n_vertices, bool)
-        for e in np.nonzero(color < 0)[0]:
-            if not touched[cells[e]].any():
-                color[e] = c
-                touched[cells[e]] = True
-        c += 1
-    return color
-
-
 def test_colored_scatter_matches_atomic():
     from feng_b200 import mesh as M, problems as PB
     from oracle import fe_oracle as O
@@ -182,7 +166,8 @@ def test_colored_scatter_matches_atomic():
     pb = PB.taylor_hood(m, "ns_div", 8, 0, 0.05, 1.0)
     sol = PB.perturb_unknowns(pb)
     ov, orr = O.assemble(to_oracle_problem(pb), pb.ia, pb.ja, sol)
-    colors = _greedy_colors(m.cells, m.n_vertices)
+    from feng_b200.coloring import color_elements
+    colors = color_elements(m.cells, m.n_vertices)        # feCncGeo::colorElements(1), src/feCncGeo.cpp:752-794
     _, v, r = _cuda_assemble(pb, sol, colors=colors, mode=1)
     assert_close_rows(v, ov, pb.ia, 1e-12, "matrix (coloured)")
     assert_close_vec(r, orr, 1e-12, "rhs (coloured)")
