@@ -28,7 +28,8 @@ def test_taylor_hood_2d_all_elements(kind, transient, tmp_path, have_ref):
     ov, orr = O.assemble(opb, pb.ia, pb.ja, sol, sd, c0)
     assert_close_rows(ov, v, pb.ia, 1e-13, "matrix")
     assert_close_vec(orr, r, 1e-13, "rhs")
-    assert np.array_equal(P.colors(), __import__("test_gpu_parity")._greedy_colors(m.cells, m.n_vertices))
+    from feng_b200.coloring import color_elements
+    assert np.array_equal(P.colors(), color_elements(m.cells, m.n_vertices))     # feCncGeo::colorElements(1)
     P.close()
 
 
