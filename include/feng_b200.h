@@ -149,8 +149,8 @@ int b200_add_space(b200_system *s, int n_scalar_functions, int n_components, con
  * quadrature node[, component]) or NULL. */
 int b200_add_form(b200_system *s, int kind, int space_u, int space_p, double coeff, double param,
                   const double *source);
-/* the monolithic CHNS weak form on the spaces {U, P, Phi, Mu} (createBilinearForm(..., {u, p, phi, mu}, new CHNS_Abels<2>),
- * src/CHNS_Solver.cpp:236-420).  It must be the only form of the system; both the residual and the finite-difference
+/* the monolithic CHNS weak form on the spaces {U, P, Phi, Mu} (createBilinearForm(..., {u, p, phi, mu}, new CHNS_Abels<2> |
+ * CHNS_MassAveraged<2> | CHNS_Khanwale<2>), src/CHNS_Solver.cpp:370-446); kind = B200_FORM_CHNS_*.  It must be the only form of the system; both the residual and the finite-difference
  * Jacobian (N+1 residual evaluations per element) run on the device. */
 int b200_add_form_chns(b200_system *s, int kind, int space_u, int space_p, int space_phi, int space_mu,
                        const b200_chns_params *params);
