@@ -1,0 +1,1020 @@
+// Aggregation multigrid on the device: the approximate inverse of an elliptic field block inside the preconditioners
+// of the Newton linear solve (north-star subsystem 4).
+//
+// The reference delegates the solve to PETSc's KSP (GMRES(30) + ILU(0) on one rank, block-Jacobi on n ranks,
+// src/feLinearSystem.h:196-199, src/feLinearSystemPETSc.cpp:337) or to Pardiso LU
+// (src/feLinearSystemMklPardiso.cpp:893-965).  A triangular-solve-based ILU is a poor fit for the GPU and a
+// single-level method needs O(1/h) iterations; this hierarchy is built from sort / scan / SpMV primitives only:
+//
+//   level 0   the assembled CSR matrix itself (a row mask selects the field: velocity rows of a Taylor-Hood system, or
+//             every row of a scalar problem); nothing is copied
+//   level 1   for P2 spaces: the P1 sub-space on the same mesh (vertex unknowns keep their value, a mid-edge unknown
+//             is the mean of its two end vertices) -- Galerkin product P^T A P of the component-diagonal blocks
+//   level 2+  plain aggregation on a distance-2 maximal independent set of the matrix graph (Bell, Dalton, Olson,
+//             SIAM J. Sci. Comput. 34 (2012)): roots = MIS(2), every unknown joins the nearest root, Galerkin product =
+//             sum of the entries of an aggregate pair
+//   coarsest  dense inverse (Gauss-Jordan in one CTA)
+//
+// Cycle: V(2,2) with Chebyshev-accelerated Jacobi (spectral radius of D^-1 A from a few power iterations).  The symbolic
+// part (parents, aggregates, coarse patterns) depends on the mesh and the pattern only and is built once; the numeric
+// part (Galerkin values, inverse diagonals, spectral radii, coarse inverse) is redone whenever the matrix changed.
+// On several GPUs the hierarchy is rank-local (ghost rows are masked out): block-Jacobi across ranks, as PETSc's
+// parallel default.
+#include <thrust/binary_search.h>
+#include <thrust/device_ptr.h>
+#include <thrust/execution_policy.h>
+#include <thrust/scan.h>
+#include <thrust/sort.h>
+#include <thrust/unique.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "amg.h"
+
+namespace b200 {
+
+static const int GRID = 148 * 8;
+
+// ----------------------------------------------------------------------------------------------------------
+// field map / P2 -> P1 parents
+// ----------------------------------------------------------------------------------------------------------
+// fld[dof] = base + component of the local function (function a*nc + c is phi_a e_c, src/feSpace_2D.cpp:41-55)
+__global__ void amg_field_kernel(int64_t nElm, const int32_t *__restrict__ adr, int nloc, int nc, int64_t nInc, int base, uint8_t *fld)
+{
+  const int64_t tot = nElm * nloc;
+  for(int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int     k = (int)(idx % nloc);
+    const int64_t dof = adr[idx];
+    if(dof < nInc) fld[dof] = (uint8_t)(base + k % nc);
+  }
+}
+
+__global__ void amg_mask_ghost_kernel(int64_t n, const double *__restrict__ owned, uint8_t *fld)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if(owned[i] == 0.) fld[i] = AMG_FLD_NONE;
+}
+
+__global__ void amg_vertex_flag_kernel(int64_t nElm, const int32_t *__restrict__ adr, int nloc, int nvc, int64_t nInc,
+                                       const uint8_t *__restrict__ fld, int fld_lo, int fld_hi, int32_t *isvert)
+{
+  const int64_t tot = nElm * nvc;
+  for(int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = idx / nvc;
+    const int     k = (int)(idx - e * nvc);
+    const int64_t dof = adr[e * nloc + k];
+    if(dof < nInc && fld[dof] >= fld_lo && fld[dof] < fld_hi) isvert[dof] = 1;
+  }
+}
+
+// local edge -> end vertices of the P2 Lagrange bases of the reference: triangle edges (0,1),(1,2),(2,0)
+// (src/feSpace_2D.cpp:536-544), tetrahedron edges in the order of _edgesOrder (src/feTetrahedron.h:31).  The host
+// checks the table against the basis tabulation it was given (amg_check_p2_edges).
+__constant__ int c_edge_tri[3][2] = {{0, 1}, {1, 2}, {2, 0}};
+__constant__ int c_edge_tet[6][2] = {{0, 2}, {2, 1}, {1, 0}, {1, 3}, {3, 0}, {3, 2}};
+static const int h_edge_tri[3][2] = {{0, 1}, {1, 2}, {2, 0}};
+static const int h_edge_tet[6][2] = {{0, 2}, {2, 1}, {1, 0}, {1, 3}, {3, 0}, {3, 2}};
+
+// kind: 0 inactive, 1 one parent with weight 1, 2 mid-edge unknown: up to two parents with weight 1/2 each (a missing
+// parent is an essential / foreign vertex: its coarse function does not exist)
+__global__ void amg_p2_parent_kernel(int64_t nElm, const int32_t *__restrict__ adr, int nloc, int nv, int nc, int dim, int64_t nInc,
+                                     const uint8_t *__restrict__ fld, int fld_lo, int fld_hi, const int32_t *__restrict__ isvert,
+                                     const int32_t *__restrict__ cid, int32_t *par0, int32_t *par1, uint8_t *pkind)
+{
+  const int     nS = nloc / nc;
+  const int64_t tot = nElm * nloc;
+  for(int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = idx / nloc;
+    const int     k = (int)(idx - e * nloc);
+    const int     a = k / nc, c = k - a * nc;
+    const int64_t dof = adr[idx];
+    if(dof >= nInc || fld[dof] < fld_lo || fld[dof] >= fld_hi) continue;
+    if(a < nv) {
+      par0[dof]  = cid[dof];
+      par1[dof]  = -1;
+      pkind[dof] = 1;
+    } else if(a < nS) {
+      const int     ed = a - nv;
+      const int     va = dim == 2 ? c_edge_tri[ed][0] : c_edge_tet[ed][0], vb = dim == 2 ? c_edge_tri[ed][1] : c_edge_tet[ed][1];
+      const int64_t da = adr[e * nloc + va * nc + c], db = adr[e * nloc + vb * nc + c];
+      int32_t       pa = (da < nInc && isvert[da]) ? cid[da] : -1;
+      int32_t       pb = (db < nInc && isvert[db]) ? cid[db] : -1;
+      // canonical order so that every element sharing the edge writes the same pair
+      if(pa < pb) {
+        const int32_t t = pa;
+        pa = pb;
+        pb = t;
+      }
+      par0[dof]  = pa;
+      par1[dof]  = pb;
+      pkind[dof] = 2;
+    }
+  }
+}
+
+// keys of the P1 element pattern of the coarse unknowns: (I, J) for every pair of vertex functions of an element
+// (same component only when decoupled)
+__global__ void amg_p1_keys_kernel(int64_t nElm, const int32_t *__restrict__ adr, int nloc, int nvc, int nc, int64_t nInc,
+                                   const int32_t *__restrict__ isvert, const int32_t *__restrict__ cid, int64_t ncoarse, int decoupled,
+                                   uint64_t *keys)
+{
+  const int64_t per = (int64_t)nvc * nvc, tot = nElm * per;
+  for(int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = idx / per;
+    const int     r = (int)(idx - e * per);
+    const int     i = r / nvc, j = r - i * nvc;
+    uint64_t      key = ~0ull;
+    if(!decoupled || (i % nc) == (j % nc)) {
+      const int64_t di = adr[e * nloc + i], dj = adr[e * nloc + j];
+      if(di < nInc && dj < nInc && isvert[di] && isvert[dj]) key = (uint64_t)cid[di] * (uint64_t)ncoarse + (uint64_t)cid[dj];
+    }
+    keys[idx] = key;
+  }
+}
+
+// keys of the aggregated pattern: (parent(i), parent(j)) for every stored entry
+__global__ void amg_agg_keys_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja, const int32_t *__restrict__ par0,
+                                    int64_t ncoarse, uint64_t *keys)
+{
+  const int     lane = threadIdx.x & 7;
+  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3, ng = (gridDim.x * (int64_t)blockDim.x) >> 3;
+  for(int64_t i = g0; i < n; i += ng) {
+    const int32_t I = par0[i];
+    for(int64_t k = ia[i] + lane; k < ia[i + 1]; k += 8) {
+      const int32_t J = par0[ja[k]];
+      keys[k] = (I >= 0 && J >= 0) ? (uint64_t)I * (uint64_t)ncoarse + (uint64_t)J : ~0ull;
+    }
+  }
+}
+
+__global__ void amg_row_start_keys_kernel(int64_t n, uint64_t *q)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x) q[i] = (uint64_t)i * (uint64_t)n;
+}
+
+__global__ void amg_split_keys_kernel(int64_t nnz, int64_t n, const uint64_t *keys, int32_t *ja)
+{
+  for(int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x)
+    ja[k] = (int32_t)(keys[k] % (uint64_t)n);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Galerkin product  Ac(I, J) += w_iI w_jJ A(i, j)
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void amg_add_coarse(const int64_t *__restrict__ iac, const int32_t *__restrict__ jac, double *valc, int32_t I, int32_t J,
+                                               double v)
+{
+  int64_t lo = iac[I], hi = iac[I + 1] - 1;
+  while(lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if(jac[mid] < J)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  if(jac[lo] == J) atomicAdd(valc + lo, v);
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) amg_galerkin_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
+                                                           const double *__restrict__ val, const uint8_t *__restrict__ fld,
+                                                           const int32_t *__restrict__ par0, const int32_t *__restrict__ par1,
+                                                           const uint8_t *__restrict__ pkind, const int64_t *__restrict__ iac,
+                                                           const int32_t *__restrict__ jac, double *valc)
+{
+  const int     lane = threadIdx.x % LPR;
+  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR, ng = (gridDim.x * (int64_t)blockDim.x) / LPR;
+  for(int64_t i = g0; i < n; i += ng) {
+    const int ki = pkind[i];
+    if(ki == 0) continue;
+    const int32_t I0 = par0[i], I1 = par1 ? par1[i] : -1;
+    const double  wi = ki == 2 ? 0.5 : 1.;
+    const int     fi = fld ? fld[i] : 0;
+    for(int64_t k = ia[i] + lane; k < ia[i + 1]; k += LPR) {
+      const int32_t j = ja[k];
+      const int     kj = pkind[j];
+      if(kj == 0 || (fld && fld[j] != fi)) continue;
+      const double  v = val[k] * wi * (kj == 2 ? 0.5 : 1.);
+      const int32_t J0 = par0[j], J1 = par1 ? par1[j] : -1;
+      if(I0 >= 0) {
+        if(J0 >= 0) amg_add_coarse(iac, jac, valc, I0, J0, v);
+        if(J1 >= 0) amg_add_coarse(iac, jac, valc, I0, J1, v);
+      }
+      if(I1 >= 0) {
+        if(J0 >= 0) amg_add_coarse(iac, jac, valc, I1, J0, v);
+        if(J1 >= 0) amg_add_coarse(iac, jac, valc, I1, J1, v);
+      }
+    }
+  }
+}
+
+// inverse diagonal of the active rows (0 elsewhere: inactive rows never change)
+__global__ void amg_dinv_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja, const double *__restrict__ val,
+                                const uint8_t *__restrict__ pkind, double *__restrict__ dinv)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double d = 0.;
+    if(!pkind || pkind[i]) {
+      for(int64_t k = ia[i]; k < ia[i + 1]; ++k)
+        if(ja[k] == i) d = val[k];
+    }
+    dinv[i] = d != 0. ? 1. / d : 0.;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// MIS(2) aggregation
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t amg_hash(uint32_t x)
+{
+  x ^= x >> 16;
+  x *= 0x7feb352dU;
+  x ^= x >> 15;
+  x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
+
+// key = state (2 bits: 0 decided-out, 1 undecided, 2 root) | hash (30 bits) | index (32 bits); `active` (nullable) is
+// the row mask of the graph: inactive rows neither take part nor relay
+__global__ void amg_mis_init_kernel(int64_t n, const uint8_t *__restrict__ active, uint64_t *key)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    key[i] = (active && !active[i]) ? 0ull : ((1ull << 62) | ((uint64_t)(amg_hash((uint32_t)i) & 0x3fffffffu) << 32) | (uint64_t)i);
+}
+
+__global__ void amg_mis_prop_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja, const uint8_t *__restrict__ active,
+                                    const uint64_t *__restrict__ in, uint64_t *__restrict__ out)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t m = 0ull;
+    if(!active || active[i]) {
+      m = in[i];
+      for(int64_t k = ia[i]; k < ia[i + 1]; ++k) {
+        const uint64_t v = in[ja[k]];
+        m = v > m ? v : m;
+      }
+    }
+    out[i] = m;
+  }
+}
+
+__global__ void amg_mis_update_kernel(int64_t n, uint64_t *key, const uint64_t *__restrict__ m2, int *undecided)
+{
+  int cnt = 0;
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t k = key[i];
+    if((k >> 62) == 1ull) {
+      if(m2[i] == k)
+        key[i] = (k & ~(3ull << 62)) | (2ull << 62); // largest undecided key of its 2-ring: new root
+      else if((m2[i] >> 62) == 2ull)
+        key[i] = 0ull;                               // a root within distance 2: covered
+      else
+        ++cnt;
+    }
+  }
+  if(cnt) atomicAdd(undecided, cnt);
+}
+
+__global__ void amg_root_flag_kernel(int64_t n, const uint64_t *__restrict__ key, int32_t *isroot)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    isroot[i] = (key[i] >> 62) == 2ull ? 1 : 0;
+}
+
+__global__ void amg_agg_root_kernel(int64_t n, const uint64_t *__restrict__ key, const int32_t *__restrict__ rid, int32_t *agg)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    agg[i] = (key[i] >> 62) == 2ull ? rid[i] : -1;
+}
+
+// one ring of growth: an unassigned active unknown joins the aggregate of its most strongly connected assigned neighbour
+__global__ void amg_agg_grow_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja, const double *__restrict__ val,
+                                    const uint8_t *__restrict__ active, const int32_t *__restrict__ in, int32_t *__restrict__ out)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int32_t a = in[i];
+    if(a < 0 && (!active || active[i])) {
+      double best = -1.;
+      for(int64_t k = ia[i]; k < ia[i + 1]; ++k) {
+        const int32_t b = in[ja[k]];
+        const double  w = val ? fabs(val[k]) : 1.;
+        if(b >= 0 && (w > best || (w == best && b > a))) {
+          best = w;
+          a    = b;
+        }
+      }
+    }
+    out[i] = a;
+  }
+}
+
+__global__ void amg_orphan_flag_kernel(int64_t n, const uint8_t *__restrict__ active, const int32_t *__restrict__ agg, int32_t *flag)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    flag[i] = ((!active || active[i]) && agg[i] < 0) ? 1 : 0;
+}
+
+__global__ void amg_orphan_assign_kernel(int64_t n, const int32_t *__restrict__ flag, const int32_t *__restrict__ oid, int32_t base, int32_t *agg)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if(flag[i]) agg[i] = base + oid[i];
+}
+
+__global__ void amg_kind_from_agg_kernel(int64_t n, const int32_t *__restrict__ agg, uint8_t *pkind)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) pkind[i] = agg[i] >= 0 ? 1 : 0;
+}
+
+__global__ void amg_in_range_kernel(int64_t n, const uint8_t *__restrict__ fld, int lo, int hi, uint8_t *act)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    act[i] = (fld[i] >= lo && fld[i] < hi) ? 1 : 0;
+}
+
+__global__ void amg_norm2_kernel(int64_t n, const double *__restrict__ x, double *nrm2)
+{
+  double s = 0.;
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += x[i] * x[i];
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if((threadIdx.x & 31) == 0 && s != 0.) atomicAdd(nrm2, s);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// cycle kernels
+// ----------------------------------------------------------------------------------------------------------
+// generic CSR product (coarse levels), LPR lanes per row
+template <int LPR>
+__global__ void __launch_bounds__(256) amg_spmv_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
+                                                       const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+  const int     lane = threadIdx.x % LPR;
+  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR, ng = (gridDim.x * (int64_t)blockDim.x) / LPR;
+  for(int64_t i = g0; i < n; i += ng) {
+    double s = 0.;
+    for(int64_t k = ia[i] + lane; k < ia[i + 1]; k += LPR) s += val[k] * x[ja[k]];
+#pragma unroll
+    for(int o = LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LPR);
+    if(lane == 0) y[i] = s;
+  }
+}
+
+// Chebyshev step: r = b - t (t = A x, or 0 when first); d = c1 d + c2 dinv r; x (+)= d
+__global__ void amg_cheb_kernel(int64_t n, const double *__restrict__ b, const double *__restrict__ t, const double *__restrict__ dinv, double c1,
+                                double c2, double *__restrict__ d, double *__restrict__ x, int first_zero)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double r  = t ? b[i] - t[i] : b[i];
+    const double dn = (c1 != 0. ? c1 * d[i] : 0.) + c2 * dinv[i] * r;
+    d[i] = dn;
+    x[i] = first_zero ? dn : x[i] + dn;
+  }
+}
+
+// rc[parent] += w (b - t)
+__global__ void amg_restrict_kernel(int64_t n, const double *__restrict__ b, const double *__restrict__ t, const int32_t *__restrict__ par0,
+                                    const int32_t *__restrict__ par1, const uint8_t *__restrict__ pkind, double *rc)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = pkind[i];
+    if(k == 0) continue;
+    const double  r = (b[i] - t[i]) * (k == 2 ? 0.5 : 1.);
+    const int32_t p0 = par0[i], p1 = par1 ? par1[i] : -1;
+    if(p0 >= 0) atomicAdd(rc + p0, r);
+    if(p1 >= 0) atomicAdd(rc + p1, r);
+  }
+}
+
+__global__ void amg_prolong_kernel(int64_t n, const double *__restrict__ xc, const int32_t *__restrict__ par0, const int32_t *__restrict__ par1,
+                                   const uint8_t *__restrict__ pkind, double *__restrict__ x)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = pkind[i];
+    if(k == 0) continue;
+    const int32_t p0 = par0[i], p1 = par1 ? par1[i] : -1;
+    double        s = 0.;
+    if(p0 >= 0) s += xc[p0];
+    if(p1 >= 0) s += xc[p1];
+    x[i] += (k == 2 ? 0.5 : 1.) * s;
+  }
+}
+
+// power iteration helpers: y = dinv * t, accumulate |y|^2
+__global__ void amg_scale_norm_kernel(int64_t n, const double *__restrict__ dinv, const double *__restrict__ t, double *__restrict__ y, double *nrm2)
+{
+  double s = 0.;
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = dinv[i] * t[i];
+    y[i] = v;
+    s += v * v;
+  }
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if((threadIdx.x & 31) == 0 && s != 0.) atomicAdd(nrm2, s);
+}
+
+__global__ void amg_normalize_kernel(int64_t n, const double *nrm2, double *__restrict__ y)
+{
+  const double a = *nrm2 > 0. ? 1. / sqrt(*nrm2) : 0.;
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] *= a;
+}
+
+__global__ void amg_seed_kernel(int64_t n, const double *__restrict__ dinv, double *__restrict__ y)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = dinv[i] != 0. ? 0.5 + (double)(amg_hash((uint32_t)i) & 0xffffu) / 65536. : 0.;
+}
+
+// coarsest level: dense copy [A | I] and Gauss-Jordan with partial pivoting in one CTA (n <= AMG_MAX_DENSE)
+__global__ void amg_dense_fill_kernel(int n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja, const double *__restrict__ val, double *M)
+{
+  const int ld = 2 * n;
+  for(int i = blockIdx.x; i < n; i += gridDim.x) {
+    for(int j = threadIdx.x; j < ld; j += blockDim.x) M[(size_t)i * ld + j] = (j == n + i) ? 1. : 0.;
+    __syncthreads();
+    for(int64_t k = ia[i] + threadIdx.x; k < ia[i + 1]; k += blockDim.x) M[(size_t)i * ld + ja[k]] = val[k];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(1024) amg_gauss_jordan_kernel(int n, double *M, double *inv)
+{
+  const int   ld = 2 * n;
+  __shared__ int    s_piv;
+  __shared__ double s_red[32];
+  __shared__ int    s_idx[32];
+  for(int p = 0; p < n; ++p) {
+    // pivot search in column p, rows p..n-1
+    double best = -1.;
+    int    bi = p;
+    for(int r = p + threadIdx.x; r < n; r += blockDim.x) {
+      const double v = fabs(M[(size_t)r * ld + p]);
+      if(v > best) {
+        best = v;
+        bi   = r;
+      }
+    }
+    for(int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_down_sync(0xffffffffu, best, o);
+      const int    oi = __shfl_down_sync(0xffffffffu, bi, o);
+      if(ob > best) {
+        best = ob;
+        bi   = oi;
+      }
+    }
+    if((threadIdx.x & 31) == 0) {
+      s_red[threadIdx.x >> 5] = best;
+      s_idx[threadIdx.x >> 5] = bi;
+    }
+    __syncthreads();
+    if(threadIdx.x == 0) {
+      double b = -1.;
+      int    i = p;
+      for(int w = 0; w < (int)(blockDim.x >> 5); ++w)
+        if(s_red[w] > b) {
+          b = s_red[w];
+          i = s_idx[w];
+        }
+      s_piv = i;
+      if(b <= 0.) { // empty column (an aggregate of decoupled zero rows): identity
+        M[(size_t)p * ld + p] = 1.;
+        s_piv = p;
+      }
+    }
+    __syncthreads();
+    const int piv = s_piv;
+    if(piv != p) {
+      for(int j = threadIdx.x; j < ld; j += blockDim.x) {
+        const double t = M[(size_t)p * ld + j];
+        M[(size_t)p * ld + j]   = M[(size_t)piv * ld + j];
+        M[(size_t)piv * ld + j] = t;
+      }
+    }
+    __syncthreads();
+    const double ip = 1. / M[(size_t)p * ld + p];
+    __syncthreads();
+    for(int j = threadIdx.x; j < ld; j += blockDim.x) M[(size_t)p * ld + j] *= ip;
+    __syncthreads();
+    // eliminate column p from every other row: thread tile over (row, col)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for(int r = warp; r < n; r += nw) {
+      if(r == p) continue;
+      const double f = M[(size_t)r * ld + p];
+      if(f == 0.) continue;
+      for(int j = lane; j < ld; j += 32)
+        if(j != p) M[(size_t)r * ld + j] -= f * M[(size_t)p * ld + j];
+    }
+    __syncthreads();
+    for(int r = threadIdx.x; r < n; r += blockDim.x)
+      if(r != p) M[(size_t)r * ld + p] = 0.;
+    __syncthreads();
+  }
+  for(int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int i = idx / n, j = idx - i * n;
+    inv[idx] = M[(size_t)i * ld + n + j];
+  }
+}
+
+__global__ void amg_dense_apply_kernel(int n, const double *__restrict__ inv, const double *__restrict__ b, double *__restrict__ x)
+{
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+  for(int i = warp; i < n; i += nw) {
+    double s = 0.;
+    for(int j = lane; j < n; j += 32) s += inv[(size_t)i * n + j] * b[j];
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if(lane == 0) x[i] = s;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------------
+static void free_level(AmgLevel &L)
+{
+  cudaFree(L.ia_own);
+  cudaFree(L.ja_own);
+  cudaFree(L.val_own);
+  cudaFree(L.dinv);
+  cudaFree(L.par0);
+  cudaFree(L.par1);
+  cudaFree(L.pkind);
+  cudaFree(L.x);
+  cudaFree(L.b);
+  cudaFree(L.t);
+  cudaFree(L.d);
+  cudaFree(L.ev);
+  L = AmgLevel();
+}
+
+void amg_free(Amg *A)
+{
+  if(!A) return;
+  for(auto &L : A->L) free_level(L);
+  A->L.clear();
+  cudaFree(A->dense);
+  cudaFree(A->cinv);
+  cudaFree(A->d_nrm);
+  cudaFree(A->d_active0);
+  A->dense = A->cinv = A->d_nrm = nullptr;
+  A->d_active0 = nullptr;
+  A->symbolic = false;
+}
+
+static int csr_product(System *S, const AmgLevel &L, const double *x, double *y)
+{
+  if(L.n <= 0) return B200_OK;
+  if(L.is_system) return spmv(S, x, y);
+  const double avg = (double)L.nnz / (double)L.n;
+  const int64_t blocks8 = (L.n * 8 + 255) / 256, blocks2 = (L.n * 2 + 255) / 256;
+  if(avg > 12.)
+    amg_spmv_kernel<8><<<(unsigned)std::min<int64_t>(blocks8, 148 * 32), 256, 0, S->stream>>>(L.n, L.ia, L.ja, L.val, x, y);
+  else
+    amg_spmv_kernel<2><<<(unsigned)std::min<int64_t>(blocks2, 148 * 32), 256, 0, S->stream>>>(L.n, L.ia, L.ja, L.val, x, y);
+  count_launch();
+  return B200_OK;
+}
+
+static inline unsigned grid_for(int64_t n, int per_block = 256)
+{
+  const int64_t b = (n + per_block - 1) / per_block;
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(b, GRID));
+}
+
+// sorted unique keys (sentinel ~0 dropped) -> CSR of an n x n matrix
+static int keys_to_csr(System *S, uint64_t *keys, int64_t nkeys, int64_t n, AmgLevel &C)
+{
+  auto pol = thrust::cuda::par.on(S->stream);
+  thrust::device_ptr<uint64_t> kp(keys);
+  // thrust::sort on 64-bit keys is a radix sort; chunking is not needed below 2^31 keys
+  thrust::sort(pol, kp, kp + nkeys);
+  int64_t nu = thrust::unique(pol, kp, kp + nkeys) - kp;
+  if(nu > 0) {
+    uint64_t last = 0;
+    cudaMemcpyAsync(&last, keys + nu - 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, S->stream);
+    cudaStreamSynchronize(S->stream);
+    if(last == ~0ull) --nu;
+  }
+  C.n   = n;
+  C.nnz = nu;
+  B200_CUDA(cudaMalloc(&C.ia_own, (size_t)(n + 1) * sizeof(int64_t)));
+  B200_CUDA(cudaMalloc(&C.ja_own, (size_t)std::max<int64_t>(nu, 1) * sizeof(int32_t)));
+  B200_CUDA(cudaMalloc(&C.val_own, (size_t)std::max<int64_t>(nu, 1) * sizeof(double)));
+  uint64_t *q = nullptr;
+  B200_CUDA(cudaMalloc(&q, (size_t)(n + 1) * sizeof(uint64_t)));
+  amg_row_start_keys_kernel<<<grid_for(n + 1), 256, 0, S->stream>>>(n, q);
+  thrust::device_ptr<uint64_t> qp(q);
+  thrust::lower_bound(pol, kp, kp + nu, qp, qp + n + 1, thrust::device_pointer_cast(C.ia_own));
+  amg_split_keys_kernel<<<grid_for(nu), 256, 0, S->stream>>>(nu, n, keys, C.ja_own);
+  count_launch(2);
+  B200_CUDA(cudaStreamSynchronize(S->stream));
+  cudaFree(q);
+  C.ia  = C.ia_own;
+  C.ja  = C.ja_own;
+  C.val = C.val_own;
+  return B200_OK;
+}
+
+static int alloc_vectors(AmgLevel &L, bool own_xb)
+{
+  const size_t nb = (size_t)std::max<int64_t>(L.n, 1) * sizeof(double);
+  if(own_xb) {
+    B200_CUDA(cudaMalloc(&L.x, nb));
+    B200_CUDA(cudaMalloc(&L.b, nb));
+  }
+  B200_CUDA(cudaMalloc(&L.t, nb));
+  B200_CUDA(cudaMalloc(&L.d, nb));
+  B200_CUDA(cudaMalloc(&L.dinv, nb));
+  return B200_OK;
+}
+
+// checks the hard-wired local edge tables against the P2 tabulation: with lambda_v = phi_v + 1/2 sum_{e contains v} phi_e
+// every mid-edge function must equal 4 lambda_a lambda_b at every quadrature node
+static bool check_p2_edges(const Space &sp, int dim, int nq)
+{
+  const int nv = dim + 1, ne = dim == 2 ? 3 : 6;
+  if(sp.nS != nv + ne) return false;
+  for(int k = 0; k < nq; ++k) {
+    double lam[4] = {0., 0., 0., 0.};
+    for(int v = 0; v < nv; ++v) lam[v] = sp.L[(size_t)k * sp.nS + v];
+    for(int e = 0; e < ne; ++e) {
+      const int a = dim == 2 ? h_edge_tri[e][0] : h_edge_tet[e][0], b = dim == 2 ? h_edge_tri[e][1] : h_edge_tet[e][1];
+      lam[a] += 0.5 * sp.L[(size_t)k * sp.nS + nv + e];
+      lam[b] += 0.5 * sp.L[(size_t)k * sp.nS + nv + e];
+    }
+    for(int e = 0; e < ne; ++e) {
+      const int a = dim == 2 ? h_edge_tri[e][0] : h_edge_tet[e][0], b = dim == 2 ? h_edge_tri[e][1] : h_edge_tet[e][1];
+      if(fabs(sp.L[(size_t)k * sp.nS + nv + e] - 4. * lam[a] * lam[b]) > 1e-10) return false;
+    }
+  }
+  return true;
+}
+
+// aggregation of level `l` (symbolic): MIS(2) roots, two rings of growth, orphans as singletons
+static int aggregate_level(System *S, Amg *A, int l, int64_t *ncoarse)
+{
+  AmgLevel     &L = A->L[l];
+  const int64_t n = L.n;
+  auto          pol = thrust::cuda::par.on(S->stream);
+  uint64_t     *key = nullptr, *m1 = nullptr, *m2 = nullptr;
+  int32_t      *tmp = nullptr, *tmp2 = nullptr;
+  int          *d_cnt = nullptr;
+  B200_CUDA(cudaMalloc(&key, n * sizeof(uint64_t)));
+  B200_CUDA(cudaMalloc(&m1, n * sizeof(uint64_t)));
+  B200_CUDA(cudaMalloc(&m2, n * sizeof(uint64_t)));
+  B200_CUDA(cudaMalloc(&tmp, n * sizeof(int32_t)));
+  B200_CUDA(cudaMalloc(&tmp2, n * sizeof(int32_t)));
+  B200_CUDA(cudaMalloc(&d_cnt, sizeof(int)));
+  B200_CUDA(cudaMalloc(&L.par0, n * sizeof(int32_t)));
+  B200_CUDA(cudaMalloc(&L.pkind, n));
+  const uint8_t *active = l == 0 ? A->d_active0 : nullptr;
+  const double  *gval = l == 0 ? L.val : nullptr; // coarse values do not exist yet at symbolic time
+  amg_mis_init_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, active, key);
+  count_launch();
+  for(int round = 0; round < 200; ++round) {
+    amg_mis_prop_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, L.ia, L.ja, active, key, m1);
+    amg_mis_prop_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, L.ia, L.ja, active, m1, m2);
+    B200_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int), S->stream));
+    amg_mis_update_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, key, m2, d_cnt);
+    count_launch(3);
+    int cnt = 0;
+    B200_CUDA(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    if(cnt == 0) break;
+  }
+  // number the roots
+  amg_root_flag_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, key, tmp);
+  thrust::device_ptr<int32_t> tp(tmp), t2(tmp2);
+  int32_t last_flag = 0, last_id = 0;
+  thrust::exclusive_scan(pol, tp, tp + n, t2);
+  B200_CUDA(cudaMemcpyAsync(&last_flag, tmp + n - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, S->stream));
+  B200_CUDA(cudaMemcpyAsync(&last_id, tmp2 + n - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, S->stream));
+  B200_CUDA(cudaStreamSynchronize(S->stream));
+  int32_t nroots = last_flag + last_id;
+  amg_agg_root_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, key, tmp2, L.par0);
+  // two rings (every unknown is within distance 2 of a root)
+  amg_agg_grow_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, L.ia, L.ja, gval, active, L.par0, tmp);
+  amg_agg_grow_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, L.ia, L.ja, gval, active, tmp, L.par0);
+  count_launch(4);
+  // orphans (cannot happen with a symmetric pattern; a non-symmetric one may leave some): singletons
+  amg_orphan_flag_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, active, L.par0, tmp);
+  thrust::exclusive_scan(pol, tp, tp + n, t2);
+  B200_CUDA(cudaMemcpyAsync(&last_flag, tmp + n - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, S->stream));
+  B200_CUDA(cudaMemcpyAsync(&last_id, tmp2 + n - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, S->stream));
+  B200_CUDA(cudaStreamSynchronize(S->stream));
+  const int32_t norph = last_flag + last_id;
+  if(norph > 0) amg_orphan_assign_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, tmp, tmp2, nroots, L.par0);
+  amg_kind_from_agg_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, L.par0, L.pkind);
+  count_launch(3);
+  B200_CUDA(cudaStreamSynchronize(S->stream));
+  *ncoarse = (int64_t)nroots + norph;
+  cudaFree(key);
+  cudaFree(m1);
+  cudaFree(m2);
+  cudaFree(tmp);
+  cudaFree(tmp2);
+  cudaFree(d_cnt);
+  return B200_OK;
+}
+
+// Symbolic set-up.  fld_lo..fld_hi-1 = the field ids (AmgFieldMap) of the rows the hierarchy acts on; space = the
+// interpolation space of that field (P2 -> P1 level when it has mid-edge functions).
+int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int fld_hi, int space)
+{
+  amg_free(A);
+  const int64_t n = S->nInc;
+  const Space  &sp = S->spaces[space];
+  const int     nv = S->nv, nloc = sp.nS * sp.nc;
+  auto          pol = thrust::cuda::par.on(S->stream);
+  A->verbose = getenv("B200_VERBOSE") != nullptr;
+  A->L.emplace_back();
+  {
+    AmgLevel &L0 = A->L[0];
+    L0.n = n;
+    L0.nnz = S->nnz;
+    L0.ia = S->d_ia;
+    L0.ja = S->d_ja;
+    L0.val = S->d_val;
+    L0.is_system = true;
+    int rc = alloc_vectors(L0, false);
+    if(rc != B200_OK) return rc;
+  }
+  A->d_fld = d_fld;
+  B200_CUDA(cudaMalloc(&A->d_nrm, 4 * sizeof(double)));
+  int64_t ncoarse = 0;
+  const bool p2 = sp.nS > nv;
+  if(p2) {
+    if(!check_p2_edges(sp, S->dim, S->nq)) {
+      set_error("amg: the basis tabulation is not the P2 Lagrange basis with the reference's local edge order");
+      return B200_ERR_UNSUPP;
+    }
+    AmgLevel &L0 = A->L[0];
+    int32_t  *isvert = nullptr, *cid = nullptr;
+    B200_CUDA(cudaMalloc(&isvert, n * sizeof(int32_t)));
+    B200_CUDA(cudaMalloc(&cid, n * sizeof(int32_t)));
+    B200_CUDA(cudaMemsetAsync(isvert, 0, n * sizeof(int32_t), S->stream));
+    amg_vertex_flag_kernel<<<GRID, 256, 0, S->stream>>>(S->nElm, sp.d_adr, nloc, nv * sp.nc, n, d_fld, fld_lo, fld_hi, isvert);
+    thrust::device_ptr<int32_t> ip(isvert), cp(cid);
+    thrust::exclusive_scan(pol, ip, ip + n, cp);
+    int32_t lf = 0, li = 0;
+    B200_CUDA(cudaMemcpyAsync(&lf, isvert + n - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaMemcpyAsync(&li, cid + n - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    ncoarse = (int64_t)lf + li;
+    B200_CUDA(cudaMalloc(&L0.par0, n * sizeof(int32_t)));
+    B200_CUDA(cudaMalloc(&L0.par1, n * sizeof(int32_t)));
+    B200_CUDA(cudaMalloc(&L0.pkind, n));
+    B200_CUDA(cudaMemsetAsync(L0.pkind, 0, n, S->stream));
+    B200_CUDA(cudaMemsetAsync(L0.par0, 0xff, n * sizeof(int32_t), S->stream));
+    B200_CUDA(cudaMemsetAsync(L0.par1, 0xff, n * sizeof(int32_t), S->stream));
+    amg_p2_parent_kernel<<<GRID, 256, 0, S->stream>>>(S->nElm, sp.d_adr, nloc, nv, sp.nc, S->dim, n, d_fld, fld_lo, fld_hi, isvert, cid, L0.par0,
+                                                      L0.par1, L0.pkind);
+    count_launch(2);
+    // coarse pattern = P1 element pattern of the vertex unknowns
+    A->L.emplace_back();
+    if(ncoarse > 0) {
+      const int     nvc = nv * sp.nc;
+      const int64_t nkeys = S->nElm * (int64_t)nvc * nvc;
+      uint64_t     *keys = nullptr;
+      B200_CUDA(cudaMalloc(&keys, (size_t)nkeys * sizeof(uint64_t)));
+      amg_p1_keys_kernel<<<GRID * 2, 256, 0, S->stream>>>(S->nElm, sp.d_adr, nloc, nvc, sp.nc, n, isvert, cid, ncoarse, 1, keys);
+      count_launch();
+      int rc = keys_to_csr(S, keys, nkeys, ncoarse, A->L[1]);
+      cudaFree(keys);
+      if(rc != B200_OK) return rc;
+    } else
+      A->L[1].n = 0;
+    A->L[0].decoupled = true;
+    cudaFree(isvert);
+    cudaFree(cid);
+    int rc = alloc_vectors(A->L[1], true);
+    if(rc != B200_OK) return rc;
+  } else {
+    // P1 space: level 0 is aggregated directly; the row mask of the graph is the field range
+    B200_CUDA(cudaMalloc(&A->d_active0, n));
+    amg_in_range_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, d_fld, fld_lo, fld_hi, A->d_active0);
+    count_launch();
+    A->L[0].decoupled = true;
+  }
+  // aggregation levels
+  for(int l = (int)A->L.size() - 1; l < AMG_MAX_LEVELS - 1; ++l) {
+    if(l > 0 && A->L[l].n <= AMG_MAX_DENSE) break;
+    int64_t nc2 = 0;
+    int     rc = aggregate_level(S, A, l, &nc2);
+    if(rc != B200_OK) return rc;
+    if(nc2 <= 0 || nc2 * 10 > A->L[l].n * 9) { // coarsening stalled: stop here
+      cudaFree(A->L[l].par0);
+      cudaFree(A->L[l].pkind);
+      A->L[l].par0  = nullptr;
+      A->L[l].pkind = nullptr;
+      break;
+    }
+    A->L.emplace_back();
+    AmgLevel &F = A->L[l];
+    uint64_t *keys = nullptr;
+    B200_CUDA(cudaMalloc(&keys, (size_t)std::max<int64_t>(F.nnz, 1) * sizeof(uint64_t)));
+    amg_agg_keys_kernel<<<grid_for(F.n * 8), 256, 0, S->stream>>>(F.n, F.ia, F.ja, F.par0, nc2, keys);
+    count_launch();
+    rc = keys_to_csr(S, keys, F.nnz, nc2, A->L[l + 1]);
+    cudaFree(keys);
+    if(rc != B200_OK) return rc;
+    rc = alloc_vectors(A->L[l + 1], true);
+    if(rc != B200_OK) return rc;
+  }
+  // coarsest level
+  const AmgLevel &C = A->L.back();
+  A->dense_n = (C.n <= AMG_MAX_DENSE && !C.is_system) ? (int)C.n : 0;
+  if(A->dense_n > 0) {
+    B200_CUDA(cudaMalloc(&A->dense, (size_t)A->dense_n * 2 * A->dense_n * sizeof(double)));
+    B200_CUDA(cudaMalloc(&A->cinv, (size_t)A->dense_n * A->dense_n * sizeof(double)));
+  }
+  if(A->verbose) {
+    fprintf(stderr, "[feng_b200] amg hierarchy:");
+    for(auto &L : A->L) fprintf(stderr, " (%lld rows, %lld nnz)", (long long)L.n, (long long)L.nnz);
+    fprintf(stderr, " dense %d\n", A->dense_n);
+  }
+  A->symbolic = true;
+  return B200_OK;
+}
+
+// spectral radius of D^-1 A by power iteration (warm-started from the previous set-up's vector)
+static int power_iteration(System *S, Amg *A, int l, int iters)
+{
+  AmgLevel &L = A->L[l];
+  L.lam = 1.;
+  if(L.n <= 0) return B200_OK;
+  if(!L.ev) B200_CUDA(cudaMalloc(&L.ev, (size_t)L.n * sizeof(double)));
+  if(!L.have_eig) {
+    amg_seed_kernel<<<grid_for(L.n), 256, 0, S->stream>>>(L.n, L.dinv, L.ev);
+    B200_CUDA(cudaMemsetAsync(A->d_nrm, 0, sizeof(double), S->stream));
+    amg_norm2_kernel<<<grid_for(L.n), 256, 0, S->stream>>>(L.n, L.ev, A->d_nrm);
+    amg_normalize_kernel<<<grid_for(L.n), 256, 0, S->stream>>>(L.n, A->d_nrm, L.ev);
+    count_launch(3);
+  }
+  for(int it = 0; it < iters; ++it) {
+    int rc = csr_product(S, L, L.ev, L.t);
+    if(rc != B200_OK) return rc;
+    B200_CUDA(cudaMemsetAsync(A->d_nrm, 0, sizeof(double), S->stream));
+    amg_scale_norm_kernel<<<grid_for(L.n), 256, 0, S->stream>>>(L.n, L.dinv, L.t, L.ev, A->d_nrm); // ev = D^-1 A ev, |ev|^2
+    if(it == iters - 1) B200_CUDA(cudaMemcpyAsync(S->h_scratch, A->d_nrm, sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+    amg_normalize_kernel<<<grid_for(L.n), 256, 0, S->stream>>>(L.n, A->d_nrm, L.ev);
+    count_launch(2);
+  }
+  B200_CUDA(cudaStreamSynchronize(S->stream));
+  const double lam = sqrt(S->h_scratch[0]);
+  L.have_eig = true;
+  L.lam = (lam > 0. && std::isfinite(lam)) ? 1.1 * lam : 1.;
+  return B200_OK;
+}
+
+// Numeric set-up: Galerkin values level by level, inverse diagonals, spectral radii, coarsest inverse.
+int amg_setup_numeric(System *S, Amg *A)
+{
+  if(!A->symbolic) {
+    set_error("amg: symbolic set-up missing");
+    return B200_ERR_ARG;
+  }
+  const int nl = (int)A->L.size();
+  for(int l = 0; l < nl; ++l) {
+    AmgLevel &L = A->L[l];
+    if(L.n <= 0) continue;
+    // inverse diagonal of the active rows
+    const uint8_t *mask = L.pkind;
+    if(l == 0 && !L.pkind) mask = A->d_active0; // single-level corner case
+    amg_dinv_kernel<<<grid_for(L.n), 256, 0, S->stream>>>(L.n, L.ia, L.ja, L.val, l == 0 ? mask : nullptr, L.dinv);
+    count_launch();
+    if(l + 1 < nl) {
+      AmgLevel &C = A->L[l + 1];
+      if(C.n > 0) {
+        B200_CUDA(cudaMemsetAsync(C.val_own, 0, (size_t)C.nnz * sizeof(double), S->stream));
+        const int64_t blocks = (L.n * 8 + 255) / 256;
+        amg_galerkin_kernel<8><<<(unsigned)std::min<int64_t>(blocks, 148 * 32), 256, 0, S->stream>>>(
+          L.n, L.ia, L.ja, L.val, (l == 0 && L.decoupled) ? A->d_fld : nullptr, L.par0, L.par1, L.pkind, C.ia, C.ja, C.val_own);
+        count_launch();
+      }
+    }
+    B200_CUDA(cudaGetLastError());
+  }
+  for(int l = 0; l < nl; ++l) {
+    if(l == nl - 1 && A->dense_n > 0) break;
+    const bool warm = A->L[l].have_eig;
+    int        rc = power_iteration(S, A, l, warm ? 3 : (l == 0 ? 8 : 12));
+    if(rc != B200_OK) return rc;
+  }
+  if(A->dense_n > 0) {
+    const AmgLevel &C = A->L.back();
+    amg_dense_fill_kernel<<<std::min(A->dense_n, 148 * 4), 128, 0, S->stream>>>(A->dense_n, C.ia, C.ja, C.val, A->dense);
+    amg_gauss_jordan_kernel<<<1, 1024, 0, S->stream>>>(A->dense_n, A->dense, A->cinv);
+    count_launch(2);
+  }
+  B200_CUDA(cudaGetLastError());
+  if(A->verbose) {
+    cudaStreamSynchronize(S->stream);
+    fprintf(stderr, "[feng_b200] amg numeric: lambda_max(D^-1 A) =");
+    for(auto &L : A->L) fprintf(stderr, " %.3f", L.lam);
+    fprintf(stderr, "\n");
+  }
+  return B200_OK;
+}
+
+// Chebyshev smoother of degree AMG_CHEB_DEGREE on [lam / AMG_CHEB_RATIO, lam]; zero_guess: x is not read
+static int smooth(System *S, Amg *A, int l, const double *b, double *x, bool zero_guess)
+{
+  AmgLevel    &L = A->L[l];
+  const double lmax = L.lam, lmin = L.lam / AMG_CHEB_RATIO;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  double       rho = 1. / sigma;
+  for(int k = 0; k < AMG_CHEB_DEGREE; ++k) {
+    const bool first = k == 0;
+    const double *t = nullptr;
+    if(!(first && zero_guess)) {
+      int rc = csr_product(S, L, x, L.t);
+      if(rc != B200_OK) return rc;
+      t = L.t;
+    }
+    double c1, c2;
+    if(first) {
+      c1 = 0.;
+      c2 = 1. / theta;
+    } else {
+      const double rho_n = 1. / (2. * sigma - rho);
+      c1 = rho_n * rho;
+      c2 = 2. * rho_n / delta;
+      rho = rho_n;
+    }
+    amg_cheb_kernel<<<grid_for(L.n), 256, 0, S->stream>>>(L.n, b, t, L.dinv, c1, c2, L.d, x, (first && zero_guess) ? 1 : 0);
+    count_launch();
+  }
+  return B200_OK;
+}
+
+static int cycle(System *S, Amg *A, int l, const double *b, double *x)
+{
+  AmgLevel &L = A->L[l];
+  const int nl = (int)A->L.size();
+  if(L.n <= 0) return B200_OK;
+  if(l == nl - 1) {
+    if(A->dense_n > 0) {
+      amg_dense_apply_kernel<<<std::max(1, std::min((A->dense_n + 7) / 8, 148 * 4)), 256, 0, S->stream>>>(A->dense_n, A->cinv, b, x);
+      count_launch();
+      return B200_OK;
+    }
+    // no dense solve (single level, or coarsening stalled above the dense limit): a few smoothing sweeps
+    int rc = smooth(S, A, l, b, x, true);
+    for(int s = 0; s < 2 && rc == B200_OK; ++s) rc = smooth(S, A, l, b, x, false);
+    return rc;
+  }
+  AmgLevel &C = A->L[l + 1];
+  int       rc = smooth(S, A, l, b, x, true);
+  if(rc != B200_OK) return rc;
+  if(C.n > 0) {
+    rc = csr_product(S, L, x, L.t);
+    if(rc != B200_OK) return rc;
+    B200_CUDA(cudaMemsetAsync(C.b, 0, (size_t)C.n * sizeof(double), S->stream));
+    amg_restrict_kernel<<<grid_for(L.n), 256, 0, S->stream>>>(L.n, b, L.t, L.par0, L.par1, L.pkind, C.b);
+    count_launch();
+    rc = cycle(S, A, l + 1, C.b, C.x);
+    if(rc != B200_OK) return rc;
+    amg_prolong_kernel<<<grid_for(L.n), 256, 0, S->stream>>>(L.n, C.x, L.par0, L.par1, L.pkind, x);
+    count_launch();
+  }
+  return smooth(S, A, l, b, x, false);
+}
+
+// x = one V-cycle applied to b (both n-vectors of the system; inactive rows of x come out 0)
+int amg_vcycle(System *S, Amg *A, const double *b, double *x)
+{
+  const int rc = cycle(S, A, 0, b, x);
+  if(rc != B200_OK) return rc;
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int amg_build_field_map(System *S, uint8_t **out)
+{
+  const int64_t n = S->nInc;
+  uint8_t      *fld = nullptr;
+  B200_CUDA(cudaMalloc(&fld, n));
+  B200_CUDA(cudaMemsetAsync(fld, AMG_FLD_NONE, n, S->stream));
+  const Space &U = S->spaces[S->su];
+  amg_field_kernel<<<GRID, 256, 0, S->stream>>>(S->nElm, U.d_adr, U.nS * U.nc, U.nc, n, 0, fld);
+  count_launch();
+  if(S->sp >= 0) {
+    const Space &P = S->spaces[S->sp];
+    amg_field_kernel<<<GRID, 256, 0, S->stream>>>(S->nElm, P.d_adr, P.nS * P.nc, P.nc, n, AMG_FLD_P, fld);
+    count_launch();
+  }
+  const double *owned = comm_mask(S);
+  if(owned) {
+    amg_mask_ghost_kernel<<<GRID, 256, 0, S->stream>>>(n, owned, fld);
+    count_launch();
+  }
+  B200_CUDA(cudaGetLastError());
+  *out = fld;
+  return B200_OK;
+}
+
+} // namespace b200

@@ -1,0 +1,56 @@
+// Aggregation multigrid hierarchy (amg.cu) and the preconditioners built on it (precond.cu).  Internal header.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "system.h"
+
+namespace b200 {
+
+constexpr int     AMG_MAX_LEVELS  = 12;
+constexpr int     AMG_MAX_DENSE   = 384; // coarsest level is inverted densely below this size
+constexpr int     AMG_CHEB_DEGREE = 2;
+constexpr double  AMG_CHEB_RATIO  = 4.;  // smoother targets [lambda_max / ratio, lambda_max] of D^-1 A
+constexpr uint8_t AMG_FLD_P       = 100; // field id of the pressure rows (velocity components are 0 .. dim-1)
+constexpr uint8_t AMG_FLD_NONE    = 255; // row outside every field / ghost row of another rank
+
+struct AmgLevel {
+  int64_t        n = 0, nnz = 0;
+  const int64_t *ia = nullptr;
+  const int32_t *ja = nullptr;
+  const double  *val = nullptr;
+  int64_t       *ia_own = nullptr; // coarse levels own their CSR arrays; level 0 aliases the system matrix
+  int32_t       *ja_own = nullptr;
+  double        *val_own = nullptr;
+  bool           is_system = false, decoupled = false;
+  double        *dinv = nullptr;
+  double         lam = 1.;
+  bool           have_eig = false;
+  // transfer to the next level: up to two parents per unknown (kind 1: weight 1; kind 2: weight 1/2 each; 0: inactive)
+  int32_t *par0 = nullptr, *par1 = nullptr;
+  uint8_t *pkind = nullptr;
+  // work vectors
+  double *x = nullptr, *b = nullptr, *t = nullptr, *d = nullptr, *ev = nullptr;
+};
+
+struct Amg {
+  std::vector<AmgLevel> L;
+  const uint8_t        *d_fld = nullptr;     // level-0 field id per row (owned by the preconditioner)
+  uint8_t              *d_active0 = nullptr; // level-0 row mask when level 0 is aggregated directly (P1 spaces)
+  int                   dense_n = 0;
+  double               *dense = nullptr, *cinv = nullptr, *d_nrm = nullptr;
+  bool                  symbolic = false, verbose = false;
+};
+
+void amg_free(Amg *A);
+int  amg_build_field_map(System *S, uint8_t **d_fld);
+int  amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int fld_hi, int space);
+int  amg_setup_numeric(System *S, Amg *A);
+int  amg_vcycle(System *S, Amg *A, const double *b, double *x);
+
+// precond.cu: B200_PC_AMG / B200_PC_SCHUR_AMG
+int  precond_setup(System *S, int pc);
+int  precond_apply(System *S, int pc, const double *r, double *z);
+void precond_free(System *S);
+
+} // namespace b200

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "amg.h"
 #include "system.h"
 
 namespace b200 {
@@ -103,6 +104,7 @@ static void free_system(System *S)
 {
   cudaSetDevice(S->device);
   krylov_free(S);
+  precond_free(S);
   gather_free(S);
   chns_free(S);
   comm_free(S);
@@ -567,6 +569,7 @@ int b200_set_to_zero(b200_system *s, int what)
     set_error("b200_set_to_zero: set the pattern first");
     return B200_ERR_ARG;
   }
+  if(what & 2) ++s->val_epoch;
   if(s->gather != nullptr && s->assembly_mode != B200_ASSEMBLY_SCATTER) {
     s->pending_zero |= (what & 3); // the gather kernels overwrite: memset only if something else touches the arrays
     return B200_OK;
@@ -581,6 +584,7 @@ int b200_assemble(b200_system *s, int what, int only_transient)
 {
   CHECK_S(s);
   B200_CUDA(cudaEventRecord(s->ev0, s->stream));
+  if(what & 2) ++s->val_epoch;
   const int rc = launch_assemble(s, what, only_transient);
   if(rc != B200_OK) return rc;
   B200_CUDA(cudaEventRecord(s->ev1, s->stream));
@@ -605,6 +609,7 @@ int b200_constrain(b200_system *s)
   CHECK_S(s);
   if(flush_zero(s, 3) != B200_OK) return B200_ERR_CUDA;
   if(s->n_crow == 0) return B200_OK;
+  ++s->val_epoch;
   constrain_kernel<<<GRID, 256, 0, s->stream>>>(s->nInc, s->d_ia, s->d_ja, s->d_val, s->d_rhs, s->d_cflag);
   count_launch();
   B200_CUDA(cudaGetLastError());
@@ -616,6 +621,7 @@ int b200_apply_periodicity(b200_system *s)
   CHECK_S(s);
   if(flush_zero(s, 3) != B200_OK) return B200_ERR_CUDA;
   if(s->n_per == 0) return B200_OK;
+  ++s->val_epoch;
   periodic_kernel<<<(unsigned)std::min<int64_t>((s->n_per + 127) / 128, GRID), 128, 0, s->stream>>>(s->n_per, s->d_master, s->d_slave, s->nInc,
                                                                                                  s->d_ia, s->d_ja, s->d_val, s->d_rhs);
   count_launch();

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "amg.h"
 #include "system.h"
 
 namespace b200 {
@@ -305,6 +306,9 @@ struct Krylov {
 };
 
 static const int GRID = 148 * 8;
+// the Hessenberg column travels through the pinned scratch buffer of b200_create (256 doubles) and multi_axpy_kernel keeps the
+// coefficients in shared memory
+constexpr int GMRES_MAX_RESTART = 250;
 
 void krylov_free(System *S)
 {
@@ -436,6 +440,8 @@ static int apply_pc(System *S, Krylov *K, int pc, const double *r, double *z)
     diag_scale_kernel<<<GRID, 256, 0, S->stream>>>(n, K->dinv, r, z);
     block_apply_kernel<<<(unsigned)((K->nb + 3) / 4), 128, 0, S->stream>>>(K->nb, K->bptr, K->brow, K->boff, K->binv, r, z);
     count_launch(2);
+  } else if(pc == B200_PC_AMG || pc == B200_PC_SCHUR_AMG) {
+    return precond_apply(S, pc, r, z);
   } else {
     B200_CUDA(cudaMemcpyAsync(z, r, n * sizeof(double), cudaMemcpyDeviceToDevice, S->stream));
   }
@@ -447,11 +453,20 @@ static int apply_pc(System *S, Krylov *K, int pc, const double *r, double *z)
 int gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info)
 {
   const int m = opt->restart > 0 ? opt->restart : 30;
-  int       rc = ensure_workspace(S, m);
+  if(m > GMRES_MAX_RESTART) {
+    set_error("b200_solve: restart length above " + std::to_string(GMRES_MAX_RESTART));
+    return B200_ERR_ARG;
+  }
+  int rc = ensure_workspace(S, m);
   if(rc != B200_OK) return rc;
   Krylov       *K = static_cast<Krylov *>(S->krylov);
   const int64_t n = K->n;
-  const int     pc = opt->pc;
+  int           pc = opt->pc;
+  if(pc == B200_PC_AUTO) pc = S->plan == PLAN_TAYLOR_HOOD && S->sp >= 0 ? B200_PC_SCHUR_AMG : (S->plan == PLAN_SCALAR ? B200_PC_AMG : B200_PC_JACOBI);
+  if(pc == B200_PC_AMG || pc == B200_PC_SCHUR_AMG) {
+    rc = precond_setup(S, pc);
+    if(rc != B200_OK) return rc;
+  }
   if(pc == B200_PC_ILU0) {
     set_error("B200_PC_ILU0 is not implemented yet");
     return B200_ERR_UNSUPP;

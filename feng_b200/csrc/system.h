@@ -112,6 +112,9 @@ struct System {
 
   // Krylov workspace (allocated lazily, krylov.cu)
   void *krylov = nullptr;
+  // multigrid / Schur-complement preconditioner state (precond.cu, amg.cu)
+  void    *precond = nullptr;
+  uint64_t val_epoch = 0; // bumped whenever the matrix values change: the numeric part of a preconditioner is redone lazily
 
   // multi-GPU communicator + halo plan (comm.cu)
   void *comm = nullptr;

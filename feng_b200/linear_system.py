@@ -80,7 +80,7 @@ class LinearSystemB200:
         self._recomputeMatrix = True
         self._rel_tol, self._abs_tol, self._div_tol, self._max_iter = 1e-8, 1e-14, 1e6, 10000
         self.restart = 30
-        self.pc = capi.PC_JACOBI
+        self.pc = capi.PC_AUTO
         self.last_info = None
 
     def sys_M(self) -> int:

@@ -97,7 +97,13 @@ enum {
   B200_PC_NONE         = 0,
   B200_PC_JACOBI       = 1, /* point Jacobi; zero diagonals (pressure rows of Taylor-Hood) are replaced by 1 */
   B200_PC_BLOCK_JACOBI = 2, /* dense LU of the diagonal blocks given by b200_set_blocks                      */
-  B200_PC_ILU0         = 3  /* ILU(0) on the CSR pattern (PETSc's sequential default, src/feLinearSystem.h:198) */
+  B200_PC_ILU0         = 3, /* ILU(0) on the CSR pattern (PETSc's sequential default, src/feLinearSystem.h:198) */
+  B200_PC_AMG          = 4, /* one multigrid V-cycle on the whole matrix (scalar diffusion-type systems): P2 -> P1 on the same
+                               mesh, then MIS(2) aggregation levels, Chebyshev-Jacobi smoothing (csrc/amg.cu)              */
+  B200_PC_SCHUR_AMG    = 5, /* Taylor-Hood saddle-point systems: block upper-triangular preconditioner, velocity block by
+                               the multigrid V-cycle, Schur complement by the scaled pressure mass diagonal with a rank-one
+                               term for a pinned pressure (csrc/precond.cu)                                                 */
+  B200_PC_AUTO         = 6  /* SCHUR_AMG for Taylor-Hood systems, AMG for scalar systems, JACOBI otherwise (CHNS)           */
 };
 
 typedef struct {
