@@ -160,6 +160,106 @@ __global__ void amg_split_keys_kernel(int64_t nnz, int64_t n, const uint64_t *ke
     ja[k] = (int32_t)(keys[k] % (uint64_t)n);
 }
 
+
+// ----------------------------------------------------------------------------------------------------------
+// level-0 single-precision working copy (same-field entries of the active rows)
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool amg_keep(const uint8_t *__restrict__ fld, const uint8_t *__restrict__ pkind, int fi, int32_t j)
+{
+  return pkind[j] != 0 && fld[j] == fi;
+}
+
+__global__ void __launch_bounds__(256) amg_dec_count_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
+                                                            const uint8_t *__restrict__ fld, const uint8_t *__restrict__ pkind, int64_t *cnt)
+{
+  const int     lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * (int64_t)blockDim.x) >> 5;
+  for(int64_t i = w0; i < n; i += nw) {
+    int c = 0;
+    if(pkind[i]) {
+      const int fi = fld[i];
+      for(int64_t k = ia[i] + lane; k < ia[i + 1]; k += 32) c += amg_keep(fld, pkind, fi, ja[k]) ? 1 : 0;
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if(lane == 0) cnt[i] = c;
+  }
+}
+
+template <bool WITH_JA>
+__global__ void __launch_bounds__(256) amg_dec_fill_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
+                                                           const double *__restrict__ val, const uint8_t *__restrict__ fld,
+                                                           const uint8_t *__restrict__ pkind, const int64_t *__restrict__ ias, int32_t *jas,
+                                                           float *vals)
+{
+  const int     lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * (int64_t)blockDim.x) >> 5;
+  for(int64_t i = w0; i < n; i += nw) {
+    if(!pkind[i]) continue;
+    const int     fi = fld[i];
+    int64_t       out = ias[i];
+    const int64_t beg = ia[i], end = ia[i + 1];
+    for(int64_t k0 = beg; k0 < end; k0 += 32) {
+      const int64_t  k = k0 + lane;
+      const int32_t  j = k < end ? ja[k] : 0;
+      const bool     keep = k < end && amg_keep(fld, pkind, fi, j);
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if(keep) {
+        const int64_t o = out + __popc(m & ((1u << lane) - 1u));
+        if(WITH_JA) jas[o] = j;
+        vals[o] = (float)val[k];
+      }
+      out += __popc(m);
+    }
+  }
+}
+
+template <int LPR, int RPG>
+__global__ void __launch_bounds__(256) amg_spmv_f32_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
+                                                           const float *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+{
+  const int     lane = threadIdx.x % LPR;
+  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR, ng = (gridDim.x * (int64_t)blockDim.x) / LPR;
+  for(int64_t row0 = g0 * RPG; row0 < n; row0 += ng * RPG) {
+    int64_t beg[RPG], end[RPG];
+#pragma unroll
+    for(int r = 0; r < RPG; ++r) {
+      const int64_t row = row0 + r;
+      beg[r] = row < n ? ia[row] : 0;
+      end[r] = row < n ? ia[row + 1] : 0;
+    }
+    double s[RPG];
+#pragma unroll
+    for(int r = 0; r < RPG; ++r) s[r] = 0.;
+    int64_t longest = 0;
+#pragma unroll
+    for(int r = 0; r < RPG; ++r) longest = max(longest, end[r] - beg[r]);
+    for(int64_t off = lane; off < longest; off += LPR) {
+      float   v[RPG];
+      int32_t c[RPG];
+#pragma unroll
+      for(int r = 0; r < RPG; ++r) {
+        const int64_t k = beg[r] + off;
+        const bool    ok = k < end[r];
+        v[r] = ok ? val[k] : 0.f;
+        c[r] = ok ? ja[k] : 0;
+      }
+#pragma unroll
+      for(int r = 0; r < RPG; ++r) s[r] += (double)v[r] * x[c[r]];
+    }
+#pragma unroll
+    for(int r = 0; r < RPG; ++r) {
+#pragma unroll
+      for(int o = LPR / 2; o > 0; o >>= 1) s[r] += __shfl_down_sync(0xffffffffu, s[r], o, LPR);
+    }
+    if(lane == 0) {
+#pragma unroll
+      for(int r = 0; r < RPG; ++r)
+        if(row0 + r < n) y[row0 + r] = s[r];
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------------------
 // Galerkin product  Ac(I, J) += w_iI w_jJ A(i, j)
 // ----------------------------------------------------------------------------------------------------------
@@ -177,9 +277,9 @@ __device__ __forceinline__ void amg_add_coarse(const int64_t *__restrict__ iac, 
   if(jac[lo] == J) atomicAdd(valc + lo, v);
 }
 
-template <int LPR>
+template <int LPR, typename VT>
 __global__ void __launch_bounds__(256) amg_galerkin_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
-                                                           const double *__restrict__ val, const uint8_t *__restrict__ fld,
+                                                           const VT *__restrict__ val, const uint8_t *__restrict__ fld,
                                                            const int32_t *__restrict__ par0, const int32_t *__restrict__ par1,
                                                            const uint8_t *__restrict__ pkind, const int64_t *__restrict__ iac,
                                                            const int32_t *__restrict__ jac, double *valc)
@@ -196,7 +296,7 @@ __global__ void __launch_bounds__(256) amg_galerkin_kernel(int64_t n, const int6
       const int32_t j = ja[k];
       const int     kj = pkind[j];
       if(kj == 0 || (fld && fld[j] != fi)) continue;
-      const double  v = val[k] * wi * (kj == 2 ? 0.5 : 1.);
+      const double  v = (double)val[k] * wi * (kj == 2 ? 0.5 : 1.);
       const int32_t J0 = par0[j], J1 = par1 ? par1[j] : -1;
       if(I0 >= 0) {
         if(J0 >= 0) amg_add_coarse(iac, jac, valc, I0, J0, v);
@@ -547,6 +647,9 @@ static void free_level(AmgLevel &L)
   cudaFree(L.t);
   cudaFree(L.d);
   cudaFree(L.ev);
+  cudaFree(L.ia_s);
+  cudaFree(L.ja_s);
+  cudaFree(L.val_s);
   L = AmgLevel();
 }
 
@@ -567,6 +670,18 @@ void amg_free(Amg *A)
 static int csr_product(System *S, const AmgLevel &L, const double *x, double *y)
 {
   if(L.n <= 0) return B200_OK;
+  if(L.val_s) {
+    const double  avg = (double)L.nnz_s / (double)L.n;
+    if(avg > 40.) {
+      const int64_t blocks = (L.n * 8 / 2 + 255) / 256;
+      amg_spmv_f32_kernel<8, 2><<<(unsigned)std::min<int64_t>(blocks, 148 * 32), 256, 0, S->stream>>>(L.n, L.ia_s, L.ja_s, L.val_s, x, y);
+    } else {
+      const int64_t blocks = (L.n * 4 / 2 + 255) / 256;
+      amg_spmv_f32_kernel<4, 2><<<(unsigned)std::min<int64_t>(blocks, 148 * 32), 256, 0, S->stream>>>(L.n, L.ia_s, L.ja_s, L.val_s, x, y);
+    }
+    count_launch();
+    return B200_OK;
+  }
   if(L.is_system) return spmv(S, x, y);
   const double avg = (double)L.nnz / (double)L.n;
   const int64_t blocks8 = (L.n * 8 + 255) / 256, blocks2 = (L.n * 2 + 255) / 256;
@@ -730,6 +845,10 @@ int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int 
   const int     nv = S->nv, nloc = sp.nS * sp.nc;
   auto          pol = thrust::cuda::par.on(S->stream);
   A->verbose = getenv("B200_VERBOSE") != nullptr;
+  if(const char *e = getenv("B200_AMG_DEGREE")) A->cheb_degree = std::max(1, atoi(e));
+  if(const char *e = getenv("B200_AMG_CYCLES")) A->cycles = std::max(1, atoi(e));
+  if(const char *e = getenv("B200_AMG_RATIO")) A->cheb_ratio = std::max(1.5, atof(e));
+  if(const char *e = getenv("B200_AMG_F32")) A->use_f32 = atoi(e) != 0;
   A->L.emplace_back();
   {
     AmgLevel &L0 = A->L[0];
@@ -824,6 +943,24 @@ int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int 
     rc = alloc_vectors(A->L[l + 1], true);
     if(rc != B200_OK) return rc;
   }
+  // single-precision working copy of level 0 (pattern now, values in the numeric phase)
+  if(A->use_f32 && A->L[0].pkind) {
+    AmgLevel &L0 = A->L[0];
+    int64_t  *cnt = nullptr;
+    B200_CUDA(cudaMalloc(&cnt, (size_t)(n + 1) * sizeof(int64_t)));
+    B200_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(n + 1) * sizeof(int64_t), S->stream));
+    amg_dec_count_kernel<<<GRID * 4, 256, 0, S->stream>>>(n, L0.ia, L0.ja, d_fld, L0.pkind, cnt);
+    count_launch();
+    thrust::device_ptr<int64_t> cp(cnt);
+    thrust::exclusive_scan(pol, cp, cp + n + 1, cp);
+    B200_CUDA(cudaMemcpyAsync(&L0.nnz_s, cnt + n, sizeof(int64_t), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    L0.ia_s = cnt;
+    B200_CUDA(cudaMalloc(&L0.ja_s, (size_t)std::max<int64_t>(L0.nnz_s, 1) * sizeof(int32_t)));
+    B200_CUDA(cudaMalloc(&L0.val_s, (size_t)std::max<int64_t>(L0.nnz_s, 1) * sizeof(float)));
+    amg_dec_fill_kernel<true><<<GRID * 4, 256, 0, S->stream>>>(n, L0.ia, L0.ja, L0.val, d_fld, L0.pkind, L0.ia_s, L0.ja_s, L0.val_s);
+    count_launch();
+  }
   // coarsest level
   const AmgLevel &C = A->L.back();
   A->dense_n = (C.n <= AMG_MAX_DENSE && !C.is_system) ? (int)C.n : 0;
@@ -878,6 +1015,11 @@ int amg_setup_numeric(System *S, Amg *A)
     return B200_ERR_ARG;
   }
   const int nl = (int)A->L.size();
+  if(A->L[0].val_s) {
+    AmgLevel &L0 = A->L[0];
+    amg_dec_fill_kernel<false><<<GRID * 4, 256, 0, S->stream>>>(L0.n, L0.ia, L0.ja, L0.val, A->d_fld, L0.pkind, L0.ia_s, nullptr, L0.val_s);
+    count_launch();
+  }
   for(int l = 0; l < nl; ++l) {
     AmgLevel &L = A->L[l];
     if(L.n <= 0) continue;
@@ -891,8 +1033,13 @@ int amg_setup_numeric(System *S, Amg *A)
       if(C.n > 0) {
         B200_CUDA(cudaMemsetAsync(C.val_own, 0, (size_t)C.nnz * sizeof(double), S->stream));
         const int64_t blocks = (L.n * 8 + 255) / 256;
-        amg_galerkin_kernel<8><<<(unsigned)std::min<int64_t>(blocks, 148 * 32), 256, 0, S->stream>>>(
-          L.n, L.ia, L.ja, L.val, (l == 0 && L.decoupled) ? A->d_fld : nullptr, L.par0, L.par1, L.pkind, C.ia, C.ja, C.val_own);
+        const unsigned gb = (unsigned)std::min<int64_t>(blocks, 148 * 32);
+        if(L.val_s)
+          amg_galerkin_kernel<8, float><<<gb, 256, 0, S->stream>>>(L.n, L.ia_s, L.ja_s, L.val_s, nullptr, L.par0, L.par1, L.pkind, C.ia, C.ja,
+                                                                   C.val_own);
+        else
+          amg_galerkin_kernel<8, double><<<gb, 256, 0, S->stream>>>(L.n, L.ia, L.ja, L.val, (l == 0 && L.decoupled) ? A->d_fld : nullptr, L.par0,
+                                                                    L.par1, L.pkind, C.ia, C.ja, C.val_own);
         count_launch();
       }
     }
@@ -924,10 +1071,10 @@ int amg_setup_numeric(System *S, Amg *A)
 static int smooth(System *S, Amg *A, int l, const double *b, double *x, bool zero_guess)
 {
   AmgLevel    &L = A->L[l];
-  const double lmax = L.lam, lmin = L.lam / AMG_CHEB_RATIO;
+  const double lmax = L.lam, lmin = L.lam / A->cheb_ratio;
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
   double       rho = 1. / sigma;
-  for(int k = 0; k < AMG_CHEB_DEGREE; ++k) {
+  for(int k = 0; k < A->cheb_degree; ++k) {
     const bool first = k == 0;
     const double *t = nullptr;
     if(!(first && zero_guess)) {
@@ -951,7 +1098,7 @@ static int smooth(System *S, Amg *A, int l, const double *b, double *x, bool zer
   return B200_OK;
 }
 
-static int cycle(System *S, Amg *A, int l, const double *b, double *x)
+static int cycle(System *S, Amg *A, int l, const double *b, double *x, bool zero_guess = true)
 {
   AmgLevel &L = A->L[l];
   const int nl = (int)A->L.size();
@@ -968,7 +1115,7 @@ static int cycle(System *S, Amg *A, int l, const double *b, double *x)
     return rc;
   }
   AmgLevel &C = A->L[l + 1];
-  int       rc = smooth(S, A, l, b, x, true);
+  int       rc = smooth(S, A, l, b, x, zero_guess);
   if(rc != B200_OK) return rc;
   if(C.n > 0) {
     rc = csr_product(S, L, x, L.t);
@@ -987,7 +1134,8 @@ static int cycle(System *S, Amg *A, int l, const double *b, double *x)
 // x = one V-cycle applied to b (both n-vectors of the system; inactive rows of x come out 0)
 int amg_vcycle(System *S, Amg *A, const double *b, double *x)
 {
-  const int rc = cycle(S, A, 0, b, x);
+  int rc = cycle(S, A, 0, b, x, true);
+  for(int c = 1; c < A->cycles && rc == B200_OK; ++c) rc = cycle(S, A, 0, b, x, false);
   if(rc != B200_OK) return rc;
   B200_CUDA(cudaGetLastError());
   return B200_OK;

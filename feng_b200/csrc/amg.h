@@ -23,6 +23,13 @@ struct AmgLevel {
   int32_t       *ja_own = nullptr;
   double        *val_own = nullptr;
   bool           is_system = false, decoupled = false;
+  // level 0 only: single-precision copy of the entries the hierarchy works on (active rows, columns of the same field):
+  // the smoother, the residual and the Galerkin product of level 0 stream 8 bytes per entry of a third of the matrix
+  // instead of 12 bytes of all of it
+  int64_t *ia_s = nullptr;
+  int32_t *ja_s = nullptr;
+  float   *val_s = nullptr;
+  int64_t  nnz_s = 0;
   double        *dinv = nullptr;
   double         lam = 1.;
   bool           have_eig = false;
@@ -40,6 +47,9 @@ struct Amg {
   int                   dense_n = 0;
   double               *dense = nullptr, *cinv = nullptr, *d_nrm = nullptr;
   bool                  symbolic = false, verbose = false;
+  int                   cheb_degree = AMG_CHEB_DEGREE, cycles = 1; // B200_AMG_DEGREE / B200_AMG_CYCLES
+  double                cheb_ratio = AMG_CHEB_RATIO;               // B200_AMG_RATIO
+  bool                  use_f32 = true;                            // B200_AMG_F32=0: level 0 works on the FP64 system matrix
 };
 
 void amg_free(Amg *A);
