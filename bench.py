@@ -283,7 +283,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=256, help="T2D size of the reference CPU sample")
     ap.add_argument("--cpu-n-chns", type=int, default=96, help="T2D size of the reference CPU sample of the CHNS workload")
     ap.add_argument("--cpu-n3", type=int, default=8, help="T3D size of the oracle-port CPU sample")
-    ap.add_argument("--solve-maxit", type=int, default=300)
+    ap.add_argument("--solve-maxit", type=int, default=2000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-solve", action="store_true", help="skip the Newton-step timing (assembly + GMRES)")
     ap.add_argument("--assembly", default="auto", choices=["auto", "scatter", "gather"])

@@ -1155,13 +1155,20 @@ int amg_build_field_map(System *S, uint8_t **out)
     amg_field_kernel<<<GRID, 256, 0, S->stream>>>(S->nElm, P.d_adr, P.nS * P.nc, P.nc, n, AMG_FLD_P, fld);
     count_launch();
   }
+  B200_CUDA(cudaGetLastError());
+  *out = fld;
+  return B200_OK;
+}
+
+// ghost rows (owned by another rank) leave every field: the hierarchy and the pressure scaling are rank-local
+int amg_mask_ghosts(System *S, uint8_t *fld)
+{
   const double *owned = comm_mask(S);
   if(owned) {
-    amg_mask_ghost_kernel<<<GRID, 256, 0, S->stream>>>(n, owned, fld);
+    amg_mask_ghost_kernel<<<GRID, 256, 0, S->stream>>>(S->nInc, owned, fld);
     count_launch();
   }
   B200_CUDA(cudaGetLastError());
-  *out = fld;
   return B200_OK;
 }
 

@@ -54,6 +54,7 @@ struct Amg {
 
 void amg_free(Amg *A);
 int  amg_build_field_map(System *S, uint8_t **d_fld);
+int  amg_mask_ghosts(System *S, uint8_t *d_fld);
 int  amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int fld_hi, int space);
 int  amg_setup_numeric(System *S, Amg *A);
 int  amg_vcycle(System *S, Amg *A, const double *b, double *x);

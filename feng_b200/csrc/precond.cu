@@ -49,6 +49,7 @@ struct Precond {
   const void *pattern_ia = nullptr;
   uint64_t numeric_epoch = ~0ull;
   double   schur_scale = 0.;
+  int64_t  pmin = 0, umax = 0; // first pressure unknown / last velocity unknown of the local numbering (ghost rows included)
 };
 
 __global__ void pc_pmass_kernel(int64_t nElm, int dim, const double *__restrict__ xyz, const int32_t *__restrict__ conn,
@@ -189,7 +190,6 @@ struct MaxOp {
 static int schur_symbolic(System *S, Precond *P)
 {
   const int64_t n = S->nInc;
-  auto          pol = thrust::cuda::par.on(S->stream);
   const Space  &PS = S->spaces[S->sp];
   // diagonal of the pressure mass matrix from the pressure tabulation: m_i = |J| sum_k w_k psi_i(k)^2
   std::vector<double> mloc(PS.nS, 0.);
@@ -239,14 +239,10 @@ static int schur_symbolic(System *S, Precond *P)
   B200_CUDA(cudaMalloc(&P->d_b, (size_t)n * sizeof(double)));
   // pressure unknowns numbered after every velocity unknown (the reference numbers field by field, src/feNumber.cpp:370-483)?
   // then G z_p only touches the tail of the velocity rows
-  thrust::counting_iterator<int64_t> c0(0);
-  const int64_t pmin = thrust::transform_reduce(pol, c0, c0 + n, FldIs{P->d_fld, AMG_FLD_P, AMG_FLD_P + 1, n, true}, n, MinOp());
-  const int64_t umax = thrust::transform_reduce(pol, c0, c0 + n, FldIs{P->d_fld, 0, AMG_FLD_P, -1, false}, (int64_t)-1, MaxOp());
   P->tail = false;
-  if(!comm_active(S) && pmin > umax && pmin < n) {
-    // (on several GPUs ghost rows lose their field id, so the test is restricted to the single-GPU numbering)
+  if(P->pmin > P->umax && P->pmin < n) {
     B200_CUDA(cudaMalloc(&P->d_pstart, (size_t)n * sizeof(int64_t)));
-    pc_pstart_kernel<<<GRID, 256, 0, S->stream>>>(n, S->d_ia, S->d_ja, P->d_fld, pmin, P->d_pstart);
+    pc_pstart_kernel<<<GRID, 256, 0, S->stream>>>(n, S->d_ia, S->d_ja, P->d_fld, P->pmin, P->d_pstart);
     count_launch();
     P->tail = true;
   }
@@ -276,6 +272,15 @@ int precond_setup(System *S, int pc)
     P->pattern_ia = S->d_ia;
     S->precond = P;
     int rc = amg_build_field_map(S, &P->d_fld);
+    if(rc != B200_OK) return rc;
+    {
+      auto                               pol = thrust::cuda::par.on(S->stream);
+      const int64_t                      n = S->nInc;
+      thrust::counting_iterator<int64_t> c0(0);
+      P->pmin = thrust::transform_reduce(pol, c0, c0 + n, FldIs{P->d_fld, AMG_FLD_P, AMG_FLD_P + 1, n, true}, n, MinOp());
+      P->umax = thrust::transform_reduce(pol, c0, c0 + n, FldIs{P->d_fld, 0, AMG_FLD_P, -1, false}, (int64_t)-1, MaxOp());
+    }
+    rc = amg_mask_ghosts(S, P->d_fld);
     if(rc != B200_OK) return rc;
     // B200_PC_AMG on a Taylor-Hood system would treat the pressure rows as part of the elliptic field: refuse
     const int fld_hi = pc == B200_PC_SCHUR_AMG ? S->dim : S->spaces[S->su].nc;

@@ -75,9 +75,7 @@ def main():
     x = ls.sys.halo_exchange_host(x)
     assert np.array_equal(x, xg[pos]), f"rank {rank}: halo exchange mismatch"
     # distributed Newton solve (Kovasznay boundary data, zero initial guess inside)
-    ls.setRelativeTol(1e-9)
-    ls.setMaxIter(400000)
-    ls.restart = 150
+    ls.setRelativeTol(1e-9)        # restart length, iteration cap and preconditioner: the defaults (GMRES(30), 1e4, AUTO)
     sol = pb.sol.copy()
     sol[:pb.n_inc] = 0.0
     status, hist = solve_newton_raphson(ls, sol, NLSolverOptions(1e-7, 1e-7, 1e4, 20, 3, 1e-1))
@@ -85,8 +83,6 @@ def main():
     # reference: the undecomposed problem on one GPU (every rank solves it redundantly on its own GPU; small mesh)
     lg = LinearSystemB200(pg, device=local, device_pattern=True)
     lg.setRelativeTol(1e-9)
-    lg.setMaxIter(400000)
-    lg.restart = 150
     solg = pg.sol.copy()
     solg[:pg.n_inc] = 0.0
     st2, hist2 = solve_newton_raphson(lg, solg, NLSolverOptions(1e-7, 1e-7, 1e4, 20, 3, 1e-1))
