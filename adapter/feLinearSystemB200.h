@@ -42,7 +42,7 @@
 
 struct feB200Options {
   int device       = 0;
-  int preconditioner = B200_PC_JACOBI; // B200_PC_*
+  int preconditioner = B200_PC_AUTO;   // B200_PC_*: Schur/multigrid for Taylor-Hood, multigrid for scalar systems, Jacobi for CHNS
   int restart      = 30;               // GMRES restart length (PETSc default)
   int scatter      = B200_SCATTER_ATOMIC;
   bool devicePattern = false;          // build the EZCRS pattern on the device instead of taking the host one
@@ -199,24 +199,30 @@ protected:
     return id;
   }
 
-  // value of a coefficient callback, which must not depend on position (sampled on a few elements) -- the engine's
-  // fused kernels take constants (include/feng_b200.h, b200_add_form)
+  // value of a coefficient callback.  The fused kernels take constants (include/feng_b200.h, b200_add_form): the callback is
+  // evaluated at EVERY (element, quadrature node) -- as the reference does on every element visit, src/feVectorSysElm.cpp:1183 --
+  // and again at a second time and a second value of args.u; any variation is reported (FE_STATUS_ERROR) instead of being
+  // frozen into one number.
   bool constantValue(const feFunction *f, feSpace *geoSpace, int cncGeoTag, double t, double &value)
   {
-    feFunctionArguments args(t);
     std::vector<double> coord(3 * _cnc->getNumVerticesPerElem(), 0.); // feMesh::getCoord does not resize (src/feMesh.cpp:119-134)
-    bool   first = true;
-    const int step = std::max(1, _nElm / 7);
-    for(int e = 0; e < _nElm; e += step) {
-      _mesh->getCoord(cncGeoTag, e, coord);
-      for(int k = 0; k < _nQuad; k += std::max(1, _nQuad / 3)) {
-        geoSpace->interpolateVectorFieldAtQuadNode(coord, k, args.pos);
-        const double v = f->eval(args);
-        if(first) {
-          value = v;
-          first = false;
-        } else if(std::fabs(v - value) > 1e-14 * std::max(1., std::fabs(value)))
-          return false;
+    bool first = true;
+    for(int pass = 0; pass < 2; ++pass) {
+      feFunctionArguments args(pass == 0 ? t : t + 0.37);
+      args.u = pass == 0 ? 0. : 0.61;
+      // second pass (time / solution dependence): a sample of the elements is enough, space dependence was settled by the first
+      const int step = pass == 0 ? 1 : std::max(1, _nElm / 16);
+      for(int e = 0; e < _nElm; e += step) {
+        _mesh->getCoord(cncGeoTag, e, coord);
+        for(int k = 0; k < _nQuad; ++k) {
+          geoSpace->interpolateVectorFieldAtQuadNode(coord, k, args.pos);
+          const double v = f->eval(args);
+          if(first) {
+            value = v;
+            first = false;
+          } else if(std::fabs(v - value) > 1e-14 * std::max(1., std::fabs(value)))
+            return false;
+        }
       }
     }
     return true;
@@ -459,14 +465,7 @@ protected:
     }
     std::sort(rows.begin(), rows.end());
     rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
-    std::vector<int64_t> master, slave;
-    for(const auto &pr : _numbering->PeriodicDOF()) {
-      master.push_back(pr.first);
-      slave.push_back(pr.second);
-    }
-    if(!rows.empty() || !master.empty())
-      ok(b200_set_constraints(_sys, (int64_t)rows.size(), rows.data(), (int64_t)master.size(), master.data(), slave.data()),
-         "b200_set_constraints");
+    if(!rows.empty()) ok(b200_set_constraints(_sys, (int64_t)rows.size(), rows.data(), 0, nullptr, nullptr), "b200_set_constraints");
   }
 
 public:
@@ -512,6 +511,15 @@ public:
     for(auto *f : forms)
       for(auto *s : f->_intSpaces)
         if(spaceId(s) < 0) return;
+    {
+      // periodic pairs first: the device pattern builder adds their (slave, master) entries (src/feCompressedRowStorage.cpp:96-107)
+      std::vector<int64_t> master, slave;
+      for(const auto &pr : numbering->PeriodicDOF()) {
+        master.push_back(pr.first);
+        slave.push_back(pr.second);
+      }
+      if(!master.empty() && !ok(b200_set_periodic(_sys, (int64_t)master.size(), master.data(), slave.data()), "b200_set_periodic")) return;
+    }
     if(!opt.devicePattern) {
       feB200detail::PatternPeek crs((int)_nInc, _formMatrices, _numMatrixForms, numbering);
       std::vector<int64_t> ia(crs.ia().begin(), crs.ia().end());

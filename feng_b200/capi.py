@@ -18,12 +18,12 @@ SYMBOLS = [
     "b200_last_error", "b200_kernel_launches", "b200_reset_kernel_launches", "b200_create", "b200_destroy",
     "b200_set_mesh", "b200_set_quadrature", "b200_add_space", "b200_add_form", "b200_set_source", "b200_set_pattern",
     "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode", "b200_set_assembly_mode", "b200_has_gather_plan", "b200_add_form_chns",
-    "b200_set_constraints", "b200_set_blocks", "b200_finalize", "b200_system_size", "b200_set_solution",
+    "b200_set_constraints", "b200_set_periodic", "b200_set_blocks", "b200_finalize", "b200_system_size", "b200_set_solution",
     "b200_set_solution_n", "b200_set_to_zero", "b200_assemble", "b200_rhs_max_norm", "b200_du_max_norm", "b200_constrain",
     "b200_apply_periodicity", "b200_solve", "b200_correct_solution", "b200_get_rhs", "b200_axpy_rhs",
     "b200_get_matrix_values", "b200_get_du", "b200_get_solution", "b200_spmv", "b200_last_assemble_ms",
     "b200_last_solve_ms", "b200_time_spmv", "b200_sync", "b200_time_begin", "b200_time_end",
-    "b200_measure_fp64_peak", "b200_comm_unique_id", "b200_comm_init", "b200_set_halo", "b200_halo_exchange_host",
+    "b200_measure_fp64_peak", "b200_measure_dmma_peak", "b200_comm_unique_id", "b200_comm_init", "b200_set_halo", "b200_halo_exchange_host",
 ]
 
 SCATTER_ATOMIC, SCATTER_COLORED = 0, 1
@@ -225,6 +225,11 @@ class System:
                                           C.c_int64(0 if m is None else m.shape[0]), _i64(m), _i64(s)),
               "b200_set_constraints")
 
+    def set_periodic(self, master, slave):
+        m = np.ascontiguousarray(master, np.int64)
+        s = np.ascontiguousarray(slave, np.int64)
+        check(self.L.b200_set_periodic(self.h, C.c_int64(m.shape[0]), _i64(m), _i64(s)), "b200_set_periodic")
+
     def set_blocks(self, block_ptr, block_rows):
         bp = np.ascontiguousarray(block_ptr, np.int64)
         br = np.ascontiguousarray(block_rows, np.int64)
@@ -343,6 +348,12 @@ class System:
 def measure_fp64_peak(device: int = 0) -> float:
     v = C.c_double()
     check(lib().b200_measure_fp64_peak(device, C.byref(v)), "b200_measure_fp64_peak")
+    return v.value
+
+
+def measure_dmma_peak(device: int = 0) -> float:
+    v = C.c_double()
+    check(lib().b200_measure_dmma_peak(device, C.byref(v)), "b200_measure_dmma_peak")
     return v.value
 
 

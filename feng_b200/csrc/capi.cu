@@ -62,6 +62,25 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// FP64 tensor-core micro-benchmark: 8 independent accumulator tiles of mma.sync.m8n8k4.f64 per warp (the only FP64 MMA shape of
+// sm_100a), so that the north-star's "tensor cores only if they beat the CUDA-core form" gate rests on a measured number
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double *out, int iters, double a)
+{
+  double c[8][2];
+#pragma unroll
+  for(int t = 0; t < 8; ++t) c[t][0] = c[t][1] = 0.;
+  const double av = a + 1e-9 * threadIdx.x, bv = 1.0 - 1e-9 * threadIdx.x;
+  for(int it = 0; it < iters; ++it) {
+#pragma unroll
+    for(int t = 0; t < 8; ++t)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[t][0]), "+d"(c[t][1]) : "d"(av), "d"(bv));
+  }
+  double s = 0.;
+#pragma unroll
+  for(int t = 0; t < 8; ++t) s += c[t][0] + c[t][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // constrainEssentialComponents (src/feLinearSystemMklPardiso.cpp:1092-1114): zero the column, zero the row, unit
 // diagonal, zero rhs.  One warp per matrix row.
 __global__ void constrain_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja, double *__restrict__ val,
@@ -83,19 +102,27 @@ __global__ void constrain_kernel(int64_t n, const int64_t *__restrict__ ia, cons
 }
 
 // applyPeriodicity (src/feLinearSystemMklPardiso.cpp:1119-1149)
+// *missing is raised when the pattern has no (slave, master) entry: the pattern was built without the periodic pairs
+// (src/feCompressedRowStorage.cpp:96-107 adds them) and the row would silently pin du_slave to 0
 __global__ void periodic_kernel(int64_t np, const int64_t *__restrict__ master, const int64_t *__restrict__ slave, int64_t nInc,
-                                const int64_t *__restrict__ ia, const int32_t *__restrict__ ja, double *__restrict__ val, double *__restrict__ rhs)
+                                const int64_t *__restrict__ ia, const int32_t *__restrict__ ja, double *__restrict__ val, double *__restrict__ rhs,
+                                double *missing)
 {
   for(int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < np; p += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = master[p], s = slave[p];
     if(s < nInc && m < nInc) {
+      bool found = false;
       for(int64_t k = ia[s]; k < ia[s + 1]; ++k) {
         double v = 0.;
         if(ja[k] == s) v = 1.;
-        if(ja[k] == m) v = -1.;
+        if(ja[k] == m) {
+          v     = -1.;
+          found = true;
+        }
         val[k] = v;
       }
       rhs[s] = 0.;
+      if(!found) *missing = 1.;
     }
   }
 }
@@ -474,9 +501,20 @@ int b200_set_constraints(b200_system *s, int64_t n_rows, const int64_t *rows, in
   cudaFree(s->d_cflag);
   B200_CUDA(cudaMalloc(&s->d_cflag, (size_t)s->nInc));
   B200_CUDA(cudaMemcpy(s->d_cflag, flag.data(), (size_t)s->nInc, cudaMemcpyHostToDevice));
+  if(n_periodic > 0 && master && slave) return b200_set_periodic(s, n_periodic, master, slave);
+  return B200_OK;
+}
+
+int b200_set_periodic(b200_system *s, int64_t n_periodic, const int64_t *master, const int64_t *slave)
+{
+  CHECK_S(s);
+  if(n_periodic < 0 || (n_periodic > 0 && (!master || !slave))) {
+    set_error("b200_set_periodic: bad arguments");
+    return B200_ERR_ARG;
+  }
   s->n_per = n_periodic;
-  s->per_master_host.assign(master, master + (master ? n_periodic : 0));
-  s->per_slave_host.assign(slave, slave + (slave ? n_periodic : 0));
+  s->per_master_host.assign(master, master + n_periodic);
+  s->per_slave_host.assign(slave, slave + n_periodic);
   cudaFree(s->d_master);
   cudaFree(s->d_slave);
   s->d_master = s->d_slave = nullptr;
@@ -622,10 +660,18 @@ int b200_apply_periodicity(b200_system *s)
   if(flush_zero(s, 3) != B200_OK) return B200_ERR_CUDA;
   if(s->n_per == 0) return B200_OK;
   ++s->val_epoch;
+  B200_CUDA(cudaMemsetAsync(s->d_scratch, 0, sizeof(double), s->stream));
   periodic_kernel<<<(unsigned)std::min<int64_t>((s->n_per + 127) / 128, GRID), 128, 0, s->stream>>>(s->n_per, s->d_master, s->d_slave, s->nInc,
-                                                                                                 s->d_ia, s->d_ja, s->d_val, s->d_rhs);
+                                                                                                 s->d_ia, s->d_ja, s->d_val, s->d_rhs, s->d_scratch);
   count_launch();
   B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(s->h_scratch, s->d_scratch, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  B200_CUDA(cudaStreamSynchronize(s->stream));
+  if(s->h_scratch[0] != 0.) {
+    set_error("b200_apply_periodicity: the pattern has no (slave, master) entry -- give the periodic pairs (b200_set_periodic) before "
+              "b200_set_pattern / b200_build_pattern");
+    return B200_ERR_ARG;
+  }
   return B200_OK;
 }
 
@@ -825,6 +871,40 @@ int b200_measure_fp64_peak(int device, double *tflops)
   }
   count_launch(6);
   const double flops = 2.0 * 16.0 * iters * 148.0 * 8.0 * 256.0;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_measure_dmma_peak(int device, double *tflops)
+{
+  if(!tflops || cudaSetDevice(device) != cudaSuccess) {
+    set_error("b200_measure_dmma_peak: bad device");
+    return B200_ERR_CUDA;
+  }
+  double *d = nullptr;
+  B200_CUDA(cudaMalloc(&d, 148 * 8 * 256 * sizeof(double)));
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0));
+  B200_CUDA(cudaEventCreate(&e1));
+  const int iters = 2048;
+  dmma_peak_kernel<<<148 * 8, 256>>>(d, iters, 1.000001);
+  float best = 1e30f;
+  for(int r = 0; r < 5; ++r) {
+    cudaEventRecord(e0);
+    dmma_peak_kernel<<<148 * 8, 256>>>(d, iters, 1.000001);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = ms < best ? ms : best;
+  }
+  count_launch(6);
+  // one m8n8k4 MMA = 8*8*4 FMA = 512 flop per warp
+  const double flops = 512.0 * 8.0 * iters * 148.0 * 8.0 * (256.0 / 32.0);
   *tflops = flops / (best * 1e-3) / 1e12;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);

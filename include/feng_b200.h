@@ -189,6 +189,10 @@ int b200_has_gather_plan(const b200_system *s);
  * pairs (feMetaNumber::PeriodicDOF, src/feNumber.h:234) */
 int b200_set_constraints(b200_system *s, int64_t n_rows, const int64_t *rows, int64_t n_periodic,
                          const int64_t *master, const int64_t *slave);
+/* periodic (master, slave) DOF pairs alone; may be called BEFORE the pattern exists, and must be when the pattern is built
+ * on the device (b200_build_pattern adds the (slave, master) entries of src/feCompressedRowStorage.cpp:96-107).
+ * b200_apply_periodicity fails if a pair has no (slave, master) entry in the pattern. */
+int b200_set_periodic(b200_system *s, int64_t n_periodic, const int64_t *master, const int64_t *slave);
 /* diagonal blocks for B200_PC_BLOCK_JACOBI: block_ptr[n_blocks+1] into block_rows[] */
 int b200_set_blocks(b200_system *s, int64_t n_blocks, const int64_t *block_ptr, const int64_t *block_rows);
 /* compile the fused assembly plan (coefficients, CSR slot map); must follow the set-up calls above */
@@ -254,6 +258,8 @@ int b200_time_end(b200_system *s, float *ms);
 /* DFMA micro-benchmark on `device`: measured FP64 FMA throughput in TFLOP/s (the assembly kernels' second roofline;
  * MEASURED_PEAKS.json only holds HBM and bf16 figures) */
 int b200_measure_fp64_peak(int device, double *tflops);
+/* same for the FP64 tensor-core path (mma.sync.m8n8k4.f64): the evidence behind the north-star's tensor-core gate */
+int b200_measure_dmma_peak(int device, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,8 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libfeng_ref.so")
 LIB_B200_PATH = os.path.join(_HERE, "_ref", "libfeng_ref_b200.so")
 DATA_DIR = os.path.join(_HERE, "_ref", "data")     # copies of the reference's regression meshes (oracle/Makefile: data)
 
-KIND = {"diffusion": 0, "stokes_div": 1, "ns_div": 2, "ns_lap": 3, "stokes_lap": 4, "chns": 5}
+KIND = {"diffusion": 0, "stokes_div": 1, "ns_div": 2, "ns_lap": 3, "stokes_lap": 4, "chns": 5, "poiseuille_div": 6,
+        "poiseuille_lap": 7, "periodic_diffusion": 8, "var_diffusion": 9}
 
 
 class Recipe(C.Structure):
@@ -215,7 +216,7 @@ class RefProblem:
             raise RuntimeError(f"reference Newton failed rc={rc}")
         return sol, out
 
-    def newton_b200(self, tol_res=1e-10, tol_cor=1e-10, max_iter=10, rel_tol=1e-8, pc=1, restart=30,
+    def newton_b200(self, tol_res=1e-10, tol_cor=1e-10, max_iter=10, rel_tol=1e-8, pc=6, restart=30,
                     lin_max_iter=10000, scatter=0, device_pattern=False):
         """The unmodified reference Newton loop driving the CUDA backend through adapter/feLinearSystemB200.h.
         -> (solution, dict(errU, errP, n_solves, krylov_iterations, norm_axb, converged))"""
@@ -239,6 +240,23 @@ class RefProblem:
         if rc != 0:
             raise RuntimeError(f"assembly through the B200 adapter failed rc={rc}")
         return vals, rhs
+
+    def constrain_b200(self, device_pattern=False):
+        """assemble + constrainEssentialComponents + applyPeriodicity by the CUDA backend through the adapter"""
+        vals = np.zeros(self.nnz)
+        rhs = np.zeros(self.n_inc)
+        rc = self.L.ref_constrain_b200(self.h, int(device_pattern), _p(vals), _p(rhs))
+        if rc != 0:
+            raise RuntimeError(f"constrained assembly through the B200 adapter failed rc={rc}")
+        return vals, rhs
+
+    def periodic_pairs(self):
+        n = C.c_int64(0)
+        self.L.ref_periodic_pairs(self.h, None, None, C.byref(n))
+        m = np.zeros(max(n.value, 1), np.int64)
+        s = np.zeros(max(n.value, 1), np.int64)
+        self.L.ref_periodic_pairs(self.h, _p(m, C.c_int64), _p(s, C.c_int64), C.byref(n))
+        return m[:n.value], s[:n.value]
 
     def error_norms(self, sol):
         sol = np.ascontiguousarray(sol, np.float64)

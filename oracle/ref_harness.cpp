@@ -22,6 +22,7 @@
 #include <Eigen/Sparse>
 #include <Eigen/SparseLU>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -40,7 +41,10 @@ extern int                 FE_VERBOSE;
 extern "C" {
 typedef struct {
   int    kind;        // 0 scalar diffusion+source, 1 Stokes div-form, 2 NS div-form, 3 NS Laplacian-form,
-                      // 4 Stokes Laplacian-form
+                      // 4 Stokes Laplacian-form, 5 CHNS, 6 / 7 Stokes Poiseuille channel, divergence / Laplacian form
+                      // (tests/withLinearSolver/stokes.cpp:183-275), 8 scalar diffusion periodic between the channel's
+                      // inlet and outlet (feSpace::setPeriodic*, src/GenericSolver.cpp:187-194), 9 scalar diffusion with a
+                      // space-dependent diffusivity callback
   int    order;       // polynomial order of the primary field (pressure uses order-1)
   int    quad_degree; // quadrature degree given to createFiniteElementSpace
   int    field;       // analytic field family: 0 polynomial MMS of the reference tests, 1 Kovasznay(Re=1/mu),
@@ -120,6 +124,37 @@ void uSrcCb(const feFunctionArguments &args, const std::vector<double> &par, std
     res[0] = 0.;
     res[1] = 0.;
   }
+}
+
+// Poiseuille channel flow, tests/withLinearSolver/stokes.cpp:165-181: par = {H or L, dpdx}
+void poiseuilleUCb(const feFunctionArguments &args, const std::vector<double> &par, std::vector<double> &res)
+{
+  const double y = args.pos[1];
+  res[0] = -par[1] / 2. * y * (par[0] - y);
+  res[1] = 0.;
+}
+double poiseuillePCb(const feFunctionArguments &args, const std::vector<double> &par)
+{
+  return -par[1] * (par[0] - args.pos[0]);
+}
+// periodic-in-x scalar field on the channel [0,5] x [0,1] and its source for -k lap(u) (kind 8)
+double periodicSolCb(const feFunctionArguments &args, const std::vector<double> &)
+{
+  const double x = args.pos[0], y = args.pos[1];
+  return sin(2. * PI * x / 5.) * y * (1. - y) + y * y;
+}
+double periodicSrcCb(const feFunctionArguments &args, const std::vector<double> &par)
+{
+  const double x = args.pos[0], y = args.pos[1], w = 2. * PI / 5.;
+  // -(u_xx + u_yy) k, sign convention of the reference's Source form (convergenceLaplace.cpp:25-32: source = +k lap u ... )
+  const double lap = -w * w * sin(w * x) * y * (1. - y) - 2. * sin(w * x) + 2.;
+  return par[0] * lap;
+}
+// space-dependent diffusivity of kind 9 (field-dependent coefficient forms, tests/withLinearSolver/scalarFE.cpp)
+double varDiffusivityCb(const feFunctionArguments &args, const std::vector<double> &par)
+{
+  const double x = args.pos[0], y = args.pos[1];
+  return par[0] * (1. + 0.5 * x + 0.25 * y * y);
 }
 
 double sSolCb(const feFunctionArguments &args, const std::vector<double> &par)
@@ -426,6 +461,7 @@ struct RefProblem {
   std::vector<feVectorFunction *> vfun;
 
   std::vector<feSpace *>        spaces, essentialSpaces, interior; // interior = spaces used by the forms
+  std::vector<feSpace *>        extra;                             // created but possibly not part of `spaces`
   feMetaNumber                 *numbering = nullptr;
   feSolution                   *sol       = nullptr;
   std::vector<feBilinearForm *> forms;
@@ -444,6 +480,8 @@ struct RefProblem {
     for(auto *f : forms) delete f;
     delete sol;
     delete numbering;
+    for(auto *s : extra)
+      if(std::find(spaces.begin(), spaces.end(), s) == spaces.end()) delete s;
     for(auto *s : spaces) delete s;
     for(auto *f : sfun) delete f;
     for(auto *f : vfun) delete f;
@@ -602,6 +640,92 @@ void *ref_create(const char *meshFile, const ref_recipe_t *rc)
                              new CHNS_Abels<2>(rho, drho, visc, dvisc, mob, force, srcP, srcU, srcF, srcM, prm)));
     }
     P->forms.push_back(chns);
+  } else if(rc->kind == 6 || rc->kind == 7) {
+    // Stokes Poiseuille, tests/withLinearSolver/stokes.cpp:183-275; data/poiseuille0.msh names its entities
+    // Domain/Inlet/Outlet/NoSlip, data/poiseuille1.msh Domaine/Entree/Sortie/NoSlip
+    const bool        divForm = rc->kind == 6;
+    const std::string dom = hasEntity(P->mesh, "Domain") ? "Domain" : "Domaine";
+    const std::string in  = hasEntity(P->mesh, "Inlet") ? "Inlet" : "Entree";
+    const std::string out = hasEntity(P->mesh, "Outlet") ? "Outlet" : "Sortie";
+    const double      H = 1., L = 5., dpdx = -1.0;
+    feVectorFunction *uSol = mkV(P, poiseuilleUCb, {H, dpdx});
+    feFunction       *pSol = mkS(P, poiseuillePCb, {L, dpdx});
+    P->uExact              = uSol;
+    P->pExact              = pSol;
+    feSpace *u = nullptr, *p = nullptr, *uInlet = nullptr, *uOutlet = nullptr, *uNoSlip = nullptr;
+    CHK(createFiniteElementSpace(u, P->mesh, elementType::VECTOR_LAGRANGE, rc->order, "U", dom, rc->quad_degree, &vectorConstant::zero));
+    CHK(createFiniteElementSpace(uInlet, P->mesh, elementType::VECTOR_LAGRANGE, rc->order, "U", in, rc->quad_degree, uSol));
+    CHK(createFiniteElementSpace(uOutlet, P->mesh, elementType::VECTOR_LAGRANGE, rc->order, "U", out, rc->quad_degree, &vectorConstant::zero));
+    CHK(createFiniteElementSpace(uNoSlip, P->mesh, elementType::VECTOR_LAGRANGE, rc->order, "U", "NoSlip", rc->quad_degree, &vectorConstant::zero));
+    CHK(createFiniteElementSpace(p, P->mesh, elementType::LAGRANGE, rc->order - 1, "P", dom, rc->quad_degree, &scalarConstant::zero));
+    P->spaces          = {uInlet, uNoSlip, u, p};
+    P->essentialSpaces = {uNoSlip, uInlet};
+    if(divForm) {
+      P->spaces.push_back(uOutlet);
+      uOutlet->setEssentialComponent(1, true);
+    }
+    P->extra     = {uOutlet};
+    P->interior  = {u, p};
+    P->uSpace    = u;
+    P->pSpace    = p;
+    P->numbering = new feMetaNumber(P->mesh, P->spaces, P->essentialSpaces);
+    P->sol       = new feSolution(P->numbering->getNbDOFs(), P->spaces, P->essentialSpaces);
+    feBilinearForm *divSigma = nullptr, *diffU = nullptr, *gradP = nullptr, *divU = nullptr;
+    CHK(createBilinearForm(divU, {p, u}, new feSysElm_MixedDivergence<2>(&scalarConstant::one)));
+    P->forms = {divU};
+    if(divForm) {
+      CHK(createBilinearForm(divSigma, {u, p}, new feSysElm_DivergenceNewtonianStress<2>(&scalarConstant::one, &scalarConstant::one)));
+      P->forms.push_back(divSigma);
+    } else {
+      CHK(createBilinearForm(gradP, {u, p}, new feSysElm_MixedGradient<2>(&scalarConstant::minusOne)));
+      CHK(createBilinearForm(diffU, {u}, new feSysElm_VectorDiffusion<2>(&scalarConstant::minusOne, &scalarConstant::one)));
+      P->forms.push_back(diffU);
+      P->forms.push_back(gradP);
+    }
+  } else if(rc->kind == 8 || rc->kind == 9) {
+    // kind 8: scalar diffusion on the channel mesh, essential on the walls, PERIODIC between inlet (master) and outlet
+    //         (slave, offset (5, 0, 0)): exercises the pattern extras of feEZCompressedRowStorage
+    //         (src/feCompressedRowStorage.cpp:96-107) and applyPeriodicity (src/feLinearSystemMklPardiso.cpp:1119-1149)
+    // kind 9: scalar diffusion with a space-dependent diffusivity callback on any mesh with Domaine / Bord
+    const bool        periodic = rc->kind == 8;
+    const std::string dom = hasEntity(P->mesh, "Domain") ? "Domain" : "Domaine";
+    feFunction *sol = periodic ? mkS(P, periodicSolCb, {}) : mkS(P, sSolCb, {fld});
+    feFunction *src = periodic ? mkS(P, periodicSrcCb, {rc->mu}) : mkS(P, sSrcCb, {fld, rc->mu});
+    feFunction *k   = periodic ? mkS(P, constantCallback, {rc->mu}) : mkS(P, varDiffusivityCb, {rc->mu});
+    P->sExact       = sol;
+    feSpace *u = nullptr;
+    CHK(createFiniteElementSpace(u, P->mesh, elementType::LAGRANGE, rc->order, "U", dom, rc->quad_degree, &scalarConstant::zero));
+    if(periodic) {
+      const std::string in  = hasEntity(P->mesh, "Inlet") ? "Inlet" : "Entree";
+      const std::string out = hasEntity(P->mesh, "Outlet") ? "Outlet" : "Sortie";
+      feSpace *uW = nullptr, *uIn = nullptr, *uOut = nullptr;
+      CHK(createFiniteElementSpace(uW, P->mesh, elementType::LAGRANGE, rc->order, "U", "NoSlip", rc->quad_degree, sol));
+      CHK(createFiniteElementSpace(uIn, P->mesh, elementType::LAGRANGE, rc->order, "U", in, rc->quad_degree, &scalarConstant::zero));
+      CHK(createFiniteElementSpace(uOut, P->mesh, elementType::LAGRANGE, rc->order, "U", out, rc->quad_degree, &scalarConstant::zero));
+      uIn->setPeriodic(true);
+      uOut->setPeriodic(true);
+      uIn->setPeriodicMaster(true);
+      uOut->setPeriodicSlave(true);
+      uIn->setMatchingPeriodicSpace(uOut);
+      uOut->setMatchingPeriodicSpace(uIn);
+      uIn->setPeriodicOffset({5., 0., 0.});
+      uOut->setPeriodicOffset({5., 0., 0.});
+      P->spaces          = {u, uW, uIn, uOut};
+      P->essentialSpaces = {uW};
+    } else {
+      feSpace *uB = nullptr;
+      CHK(createFiniteElementSpace(uB, P->mesh, elementType::LAGRANGE, rc->order, "U", "Bord", rc->quad_degree, sol));
+      P->spaces          = {u, uB};
+      P->essentialSpaces = {uB};
+    }
+    P->interior  = {u};
+    P->uSpace    = u;
+    P->numbering = new feMetaNumber(P->mesh, P->spaces, P->essentialSpaces);
+    P->sol       = new feSolution(P->numbering->getNbDOFs(), P->spaces, P->essentialSpaces);
+    feBilinearForm *diff = nullptr, *source = nullptr;
+    CHK(createBilinearForm(diff, {u}, new feSysElm_Diffusion<2>(k)));
+    CHK(createBilinearForm(source, {u}, new feSysElm_Source(src)));
+    P->forms = {diff, source};
   } else {
     // (Navier-)Stokes Taylor-Hood: tests/withLinearSolver/navier_stokes.cpp:63-99, stokes.cpp
     const bool withConv = (rc->kind == 2 || rc->kind == 3);
@@ -1034,6 +1158,35 @@ int ref_assemble_b200(void *h, int what, int devicePattern, double *values, doub
 }
 #endif
 
+#ifdef WITH_B200_ADAPTER
+// assemble + constrainEssentialComponents + applyPeriodicity of the CURRENT state through the adapter: the constrained system
+// of the CUDA backend, to be compared entry by entry with ref_constrain (same pattern, same numbering)
+int ref_constrain_b200(void *h, int devicePattern, double *values, double *rhs)
+{
+  RefProblem   *P = (RefProblem *)h;
+  feB200Options o;
+  o.devicePattern = devicePattern != 0;
+  feLinearSystem *sys = nullptr;
+  if(createLinearSystemB200(sys, P->forms, P->numbering, o) != FE_STATUS_OK) return -1;
+  solAtTimeN = P->stateN();
+  sys->setToZero();
+  sys->assembleResiduals(P->sol);
+  sys->assembleMatrices(P->sol, false);
+  sys->constrainEssentialComponents(P->sol);
+  sys->applyPeriodicity();
+  feLinearSystemB200 *b  = static_cast<feLinearSystemB200 *>(sys);
+  int                 rc = 0;
+  int64_t             n = 0, nnz = 0;
+  b200_get_pattern_size(b->getHandle(), &n, &nnz);
+  if(nnz != P->sys->_nnz) rc = -5; // the device pattern must have the periodic extras of the reference's
+  if(rc == 0 && b200_get_matrix_values(b->getHandle(), values) != B200_OK) rc = -2;
+  if(rc == 0 && b200_get_rhs(b->getHandle(), rhs) != B200_OK) rc = -3;
+  if(b->getStatus() != FE_STATUS_OK) rc = -4;
+  delete sys;
+  return rc;
+}
+#endif
+
 // L2 error norms of an arbitrary nDOF solution vector against the recipe's analytic fields (feNorm).
 int ref_error_norms(void *h, const double *sol, double *out)
 {
@@ -1056,6 +1209,20 @@ int ref_error_norms(void *h, const double *sol, double *out)
     delete eU;
   }
   P->sol->getSolution() = save;
+  return 0;
+}
+
+// periodic (master, slave) DOF pairs of the numbering (feMetaNumber::PeriodicDOF, src/feNumber.h:234)
+int ref_periodic_pairs(void *h, int64_t *master, int64_t *slave, int64_t *n)
+{
+  RefProblem *P = (RefProblem *)h;
+  int64_t     k = 0;
+  for(const auto &pr : P->numbering->PeriodicDOF()) {
+    if(master) master[k] = pr.first;
+    if(slave) slave[k] = pr.second;
+    ++k;
+  }
+  *n = k;
   return 0;
 }
 
