@@ -63,5 +63,7 @@ int  amg_vcycle(System *S, Amg *A, const double *b, double *x);
 int  precond_setup(System *S, int pc);
 int  precond_apply(System *S, int pc, const double *r, double *z);
 void precond_free(System *S);
+// degrade the smoother (Chebyshev -> damped Jacobi) after GMRES stagnation; false if there is nothing left to degrade
+bool precond_fallback(System *S);
 
 } // namespace b200

@@ -508,7 +508,8 @@ int gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info
   rc = norm2_of(K->r, &rnorm0);
   if(rc != B200_OK) return rc;
   double    rnorm = rnorm0;
-  const double tol = fmax(opt->rel_tol * rnorm0, opt->abs_tol);
+  double    tol = fmax(opt->rel_tol * rnorm0, opt->abs_tol), cycle_start = rnorm0;
+  int       slow_cycles = 0;
   int       its = 0;
   bool      converged = rnorm0 <= opt->abs_tol, diverged = false;
 
@@ -609,6 +610,28 @@ int gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info
     rc = norm2_of(K->r, &rnorm);
     if(rc != B200_OK) return rc;
     if(rnorm <= tol) converged = true;
+    // stagnation guard of the multigrid preconditioners: two restart cycles in a row that gain less than 30 % mean the
+    // Chebyshev smoother is amplifying a convection-dominated level (cell Peclet number above one: coarse meshes at high
+    // Reynolds number); fall back to plain damped Jacobi smoothing, which is slower per cycle but safe, and re-base the
+    // convergence test on the new preconditioned norm
+    if(!converged && (pc == B200_PC_AMG || pc == B200_PC_SCHUR_AMG)) {
+      slow_cycles = rnorm > 0.7 * cycle_start ? slow_cycles + 1 : 0;
+      cycle_start = rnorm;
+      if(slow_cycles >= 2 && precond_fallback(S)) {
+        slow_cycles = 0;
+        rc = apply_pc(S, K, pc, S->d_rhs, K->r);
+        if(rc != B200_OK) return rc;
+        rc = norm2_of(K->r, &rnorm0);
+        if(rc != B200_OK) return rc;
+        tol = fmax(opt->rel_tol * rnorm0, opt->abs_tol);
+        rc = apply_pc(S, K, pc, K->z, K->r);
+        if(rc != B200_OK) return rc;
+        rc = norm2_of(K->r, &rnorm);
+        if(rc != B200_OK) return rc;
+        cycle_start = rnorm;
+        if(rnorm <= tol) converged = true;
+      }
+    }
   }
 
   // du = x; norms reported to the Newton loop are max-norms (src/feLinearSystemMklPardiso.cpp:960-961)

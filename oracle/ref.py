@@ -217,12 +217,13 @@ class RefProblem:
         return sol, out
 
     def newton_b200(self, tol_res=1e-10, tol_cor=1e-10, max_iter=10, rel_tol=1e-8, pc=6, restart=30,
-                    lin_max_iter=10000, scatter=0, device_pattern=False):
+                    lin_max_iter=10000, scatter=0, device_pattern=False, abs_tol=None):
         """The unmodified reference Newton loop driving the CUDA backend through adapter/feLinearSystemB200.h.
         -> (solution, dict(errU, errP, n_solves, krylov_iterations, norm_axb, converged))"""
         sol = np.zeros(self.n_dof)
         out = np.zeros(8)
         opts = np.array([pc, restart, lin_max_iter, scatter, int(device_pattern)], np.int32)
+        self.L.ref_set_b200_abs_tol(C.c_double(-1.0 if abs_tol is None else abs_tol))
         rc = self.L.ref_newton_b200(self.h, C.c_double(tol_res), C.c_double(tol_cor), max_iter, C.c_double(rel_tol),
                                     _p(opts, C.c_int32), _p(sol), _p(out))
         if rc != 0:

@@ -1098,6 +1098,9 @@ int ref_newton(void *h, double tolRes, double tolCor, int maxIter, double *sol_o
 // the one-line change of tests/withLinearSolver/navier_stokes.cpp:101-108.
 // opts: pc, restart, linear max_iter, scatter mode, device pattern (0/1).  out: errU, errP, nSolves, total Krylov
 // iterations, last |Ax-b|, converged flag of the last solve.
+static double g_b200_abs_tol = -1.; // < 0: keep feLinearSystem's default (1e-14, src/feLinearSystem.h:67)
+void ref_set_b200_abs_tol(double v) { g_b200_abs_tol = v; }
+
 int ref_newton_b200(void *h, double tolRes, double tolCor, int maxIter, double relTol, const int *opts, double *sol_out,
                     double *out)
 {
@@ -1111,6 +1114,7 @@ int ref_newton_b200(void *h, double tolRes, double tolCor, int maxIter, double r
   feLinearSystem *sys = nullptr;
   if(createLinearSystemB200(sys, P->forms, P->numbering, o) != FE_STATUS_OK) return -1;
   sys->setRelativeTol(relTol);
+  if(g_b200_abs_tol >= 0.) sys->setAbsoluteTol(g_b200_abs_tol);
   sys->setMaxIter(opts[2]);
   feNLSolverOptions     NL{tolRes, tolCor, 1e4, (double)maxIter, 4, 1e-1};
   std::vector<feNorm *> norms = {};
