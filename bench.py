@@ -201,46 +201,53 @@ def cpu_reference_baseline(n_cpu, reps, threads=None, chns=False):
                       f"Jacobian+residual, {reps} passes"}
 
 
-def _port_worker(job):
-    """One host process: `reps` oracle assemblies of its own copy of the T3D(n_cpu) sample (numpy threads pinned to 1)."""
-    n_cpu, reps = job
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from conftest import to_oracle_problem
-    from feng_b200 import mesh as M, problems as PB
-    from oracle import fe_oracle as O
+def cpu_port_baseline(n_cpu, reps, threads=None):
+    """3-D workload: the reference has no vector-valued space on tetrahedra (src/feSpace.cpp:762-767 instantiates the 2-D
+    ones only), so its CPU arm is oracle/port_cpp.cpp: a C++/OpenMP restatement of the reference's own assembly organisation
+    (one traversal per weak form, quadrature-point-major loops, colour loop + sorted scatter) generalised to dim = 3, pinned
+    on the numpy oracle and, in 2-D, on the compiled reference (tests/test_port_cpp.py).  All host threads, bounded sample."""
+    from feng_b200 import coloring, mesh as M, problems as PB
+    from oracle import port
+    if not port.available():
+        return None
+    if threads:
+        port.set_threads(threads)
     m = M.cube_mesh(n_cpu)
-    pb = PB.taylor_hood(m, "ns_div", 6, 3, MU, RHO, build_pattern=True, with_source=False)
+    pb = PB.taylor_hood(m, "ns_div", 6, 3, MU, RHO, build_pattern=False, with_source=False)
+    P = port.PortProblem(pb, coloring.color_elements(m.cells, m.n_vertices))
     sol = PB.perturb_unknowns(pb)
-    op = to_oracle_problem(pb)
+    P.assemble(sol)                                  # warm-up
+    times = [P.assemble(sol)[2] for _ in range(reps)]
+    return {"times": times, "n_elm": m.n_cells, "cores": port.max_threads(), "kind": "port-c++",
+            "sample": f"T3D({n_cpu}) = {m.n_cells} tetrahedra, same forms (convU+divU+divSigma), Jacobian+residual, colour loop + "
+                      f"sorted scatter, C++/OpenMP restatement of the reference's assembly path (the reference has no 3-D vector "
+                      f"spaces), {reps} passes"}
+
+
+def cpu_reference_3d_scalar(n_cpu, reps):
+    """Reference-code anchor in 3-D: the unmodified feSysElm_Diffusion<3> + Source on P2 tetrahedra (the only 3-D weak forms the
+    reference has, src/feSysElm.cpp:586-589), same colour loop and scatter, on a T3D(n) cube written as a .msh file."""
+    from feng_b200 import mesh as M
+    from oracle import ref
+    if not ref.available():
+        return None
+    import tempfile
+    m = M.cube_mesh(n_cpu)
+    path = os.path.join(tempfile.gettempdir(), f"bench_t3d_{n_cpu}_{os.getpid()}.msh")
+    M.write_msh(m, path)
+    P = ref.RefProblem(path, "diffusion", 2, 4, field=0, mu=1.0)
+    os.remove(path)
+    P.assemble()
     times = []
     for _ in range(reps):
-        t0 = time.perf_counter()
-        O.assemble(op, pb.ia, pb.ja, sol)
-        times.append(time.perf_counter() - t0)
-    return times, m.n_cells
-
-
-def cpu_port_baseline(n_cpu, reps, procs=None):
-    """3-D workload: the reference has no vector-valued space on tetrahedra (src/feSpace.cpp:762-767 instantiates the 2-D
-    ones only), so its CPU arm is the oracle port (oracle/fe_oracle.py, numpy restatement of the same weak forms and of
-    the sorted scatter, pinned on the compiled reference in 2-D) on a bounded sample of the same workload.  Every host core
-    runs its own copy of the sample in its own process (the element loop has no shared state); the reported rate is the sum
-    over the processes, each pass as slow as the slowest process."""
-    import multiprocessing as mp
-    procs = procs or max(1, os.cpu_count() or 1)
-    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-        os.environ.setdefault(k, "1")
-    if procs == 1:
-        res = [_port_worker((n_cpu, reps))]
-    else:
-        with mp.get_context("spawn").Pool(procs) as pool:
-            res = pool.map(_port_worker, [(n_cpu, reps)] * procs)
-    n_elm = res[0][1]
-    times = [max(r[0][i] for r in res) for i in range(reps)]
-    return {"times": times, "n_elm": n_elm * procs, "cores": procs, "kind": "port",
-            "sample": f"{procs} x T3D({n_cpu}) = {procs} x {n_elm} tetrahedra (one copy per host core, one process each), "
-                      f"same forms, Jacobian+residual + sorted scatter, numpy oracle port (the reference has no 3-D vector "
-                      f"spaces), {reps} passes"}
+        _, _, sec = P.assemble()
+        times.append(float(sec[0] + sec[1]))
+    nE = m.n_cells
+    P.close()
+    per = sum(times) / len(times)
+    return {"value": nE / per / 1e6, "unit": UNIT, "cores": ref.max_threads(), "kind": "reference",
+            "sample": f"T3D({n_cpu}) = {nE} tetrahedra, scalar P2 feSysElm_Diffusion<3> + Source (10 x 10 local system, quad deg 4), "
+                      f"Jacobian+residual, {reps} passes"}
 
 
 def run_reference(args, rank, world):
@@ -248,7 +255,7 @@ def run_reference(args, rank, world):
         return
     if args.workload == "t3d":
         base = cpu_port_baseline(args.cpu_n3, max(args.steps, 1) + args.warmup)
-        kind, timing = "port", "oracle/fe_oracle.py element loops (numpy) + sorted scatter, host perf_counter"
+        kind, timing = "port-c++", "oracle/port_cpp.cpp (C++/OpenMP, all host threads), host steady_clock around the assembly"
     else:
         base = cpu_reference_baseline(args.cpu_n_chns if args.workload == "chns" else args.cpu_n, max(args.steps, 1) + args.warmup,
                                       chns=args.workload == "chns")
@@ -282,7 +289,7 @@ def main():
     ap.add_argument("--n", "--size", dest="n", type=int, default=0)
     ap.add_argument("--cpu-n", type=int, default=256, help="T2D size of the reference CPU sample")
     ap.add_argument("--cpu-n-chns", type=int, default=96, help="T2D size of the reference CPU sample of the CHNS workload")
-    ap.add_argument("--cpu-n3", type=int, default=8, help="T3D size of the oracle-port CPU sample")
+    ap.add_argument("--cpu-n3", type=int, default=24, help="T3D size of the C++ port CPU sample")
     ap.add_argument("--solve-maxit", type=int, default=2000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-solve", action="store_true", help="skip the Newton-step timing (assembly + GMRES)")
@@ -449,6 +456,10 @@ def main():
             else:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                         "sample": "oracle/_ref missing"}
+            if args.workload == "t3d":
+                anchor = cpu_reference_3d_scalar(12, 3)
+                if anchor is not None:
+                    line["cpu_reference_3d_scalar"] = anchor
             if args.workload == "t3d" and ref2d is not None:
                 # for context: the unmodified reference on its own (2-D) implementation of the same forms
                 per = sum(ref2d["times"]) / len(ref2d["times"])
