@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfeng_b200.so")
-SOURCES = ["capi.cu", "assemble.cu", "krylov.cu", "pattern.cu", "gather.cu", "comm.cu", "chns.cu", "patch.cu", "amg.cu", "precond.cu"]
+SOURCES = ["capi.cu", "assemble.cu", "krylov.cu", "pattern.cu", "gather.cu", "comm.cu", "chns.cu", "amg.cu", "precond.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-I/usr/include"]
@@ -25,7 +25,7 @@ def _stale(target, deps):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "system.h"), os.path.join(CSRC, "device_common.cuh"), os.path.join(CSRC, "gather_lane.cuh"), os.path.join(CSRC, "slice.cuh"), os.path.join(CSRC, "amg.h"),
+    headers = [os.path.join(CSRC, "system.h"), os.path.join(CSRC, "device_common.cuh"), os.path.join(CSRC, "gather_lane.cuh"), os.path.join(CSRC, "amg.h"),
                os.path.join(HERE, "..", "include", "feng_b200.h")]
     objs, jobs = [], []
     for src in SOURCES:

@@ -1054,7 +1054,6 @@ bool gather_tables(const System *S, GatherTables *out)
 
 void gather_free(System *S)
 {
-  patch_free(S);
   GatherPlan *G = static_cast<GatherPlan *>(S->gather);
   if(!G) return;
   G->U.release();
@@ -1100,9 +1099,7 @@ int build_gather_plan(System *S)
     // lane-group kernels win 2.3x (the row images of one node are 2-5 KB, one thread per node leaves the SM empty)
     const char *k = getenv("B200_GATHER_KERNEL");
     G->lane       = k ? std::string(k) == "lane" : D == 3;
-    // default: the patch kernel (patch.cu, block-slot owners over Morton patches); "node" / "lane" select the row-owner
-    // kernels of this file, which also remain the fallback when the numbering does not have the regular node-block structure
-    G->patch      = k ? std::string(k) == "patch" : false;
+    G->patch      = false; // the round-1 patch / row-slice kernels were measured slower and moved to experiments/
   }
   if(G->lane) {
     const LaneCfg lc = lane_cfg(D, lane_default(D));
@@ -1122,14 +1119,6 @@ int build_gather_plan(System *S)
       geometry_kernel<3><<<148 * 8, 256, 0, S->stream>>>(S->nElm, S->d_xyz, S->d_conn, G->d_geo);
     count_launch();
     B200_CUDA(cudaStreamSynchronize(S->stream));
-    if(G->patch) {
-      if(build_patch_plan(S) == B200_OK) return B200_OK;
-      if(getenv("B200_GATHER_KERNEL")) { // explicitly requested: report why (b200_last_error)
-        gather_free(S);
-        return B200_ERR_UNSUPP;
-      }
-      G->patch = false;
-    }
     if(G->lane) {
       const size_t esw = (size_t)(NP * D * D + NS * NS + NS * D + NP + 1) / 2 * 2; // ES<D,NS,NP>::W
       B200_CUDA(cudaMalloc(&G->d_es, (size_t)S->nElm * esw * sizeof(double)));
@@ -1357,7 +1346,6 @@ template <int D, int NS, int NP, int NW, int L, int REGS> static int launch_gath
 int launch_gather(System *S, int what, const THCoeffs &c)
 {
   const GatherPlan *G = static_cast<const GatherPlan *>(S->gather);
-  if(G->patch && S->patch != nullptr) return launch_patch(S, what, c);
   if(G->lane) {
     if(S->dim == 2) {
       switch(G->lanes) {

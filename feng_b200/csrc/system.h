@@ -158,10 +158,6 @@ struct GatherTables {
   int           tab_len = 0, tab_len_src = 0;
 };
 bool gather_tables(const System *S, GatherTables *out);
-// patch.cu
-int  build_patch_plan(System *S);
-int  launch_patch(System *S, int what, const THCoeffs &c);
-void patch_free(System *S);
 // chns.cu
 int  chns_analyze(System *S);
 int  chns_build_plan(System *S);

@@ -22,6 +22,7 @@ def lib():
     if _lib is None:
         L = C.CDLL(LIB_PATH)
         L.port_assemble.restype = C.c_double
+        L.port_apply.restype = C.c_double
         L.port_pattern.restype = C.c_int64
         L.port_max_threads.restype = C.c_int
         _lib = L
@@ -55,7 +56,7 @@ def pattern(adrU, adrP, n_inc):
 class PortProblem:
     """Flat tables of one Taylor-Hood problem (feng_b200.problems.HostProblem) in the layout port_assemble takes."""
 
-    def __init__(self, pb, colors, ia=None, ja=None):
+    def __init__(self, pb, colors=None, ia=None, ja=None, pattern_free=False):
         self.dim = pb.dim
         self.xyz = np.ascontiguousarray(pb.mesh.xyz, np.float64)
         self.cells = np.ascontiguousarray(pb.mesh.cells, np.int32)
@@ -66,7 +67,9 @@ class PortProblem:
         self.dLU = np.ascontiguousarray(pb.dLU, np.float64)
         self.LP = np.ascontiguousarray(pb.LP, np.float64)
         self.n_inc = int(pb.n_inc)
-        if ia is None:
+        if pattern_free:                      # matrix-free use only (apply)
+            ia, ja = np.zeros(1, np.int64), np.zeros(0, np.int32)
+        elif ia is None:
             ia, ja = pattern(self.adrU, self.adrP, self.n_inc)
         self.ia = np.ascontiguousarray(ia, np.int64)
         self.ja = np.ascontiguousarray(ja, np.int32)
@@ -75,6 +78,9 @@ class PortProblem:
         self.kinds = np.array([f.kind for f in forms], np.int32)
         self.coeff = np.array([f.coeff for f in forms], np.float64)
         self.param = np.array([f.param for f in forms], np.float64)
+        if colors is None:
+            colors = np.zeros(self.cells.shape[0], np.int64)
+            assert pattern_free, "assemble() needs the element colours"
         colors = np.asarray(colors, np.int64)
         nc = int(colors.max()) + 1
         order = np.argsort(colors, kind="stable")
@@ -83,6 +89,7 @@ class PortProblem:
         self.n_colors = nc
         self.vals = np.zeros(self.ja.shape[0])
         self.rhs = np.zeros(self.n_inc)
+        self.pattern_free = pattern_free
 
     def assemble(self, sol, matrix=True, residual=True):
         """-> (vals, rhs, seconds)"""
@@ -96,3 +103,17 @@ class PortProblem:
                                   _p(self.param, C.c_double), self.n_colors, _p(self.color_ptr, C.c_int64),
                                   _p(self.color_elems, C.c_int32), what, _p(self.vals, C.c_double), _p(self.rhs, C.c_double))
         return self.vals, self.rhs, float(sec)
+
+    def apply(self, sol, xs):
+        """matrix-free y_v = A(sol) x_v for every vector of xs, and the rhs -> (ys, rhs, seconds)"""
+        sol = np.ascontiguousarray(sol, np.float64)
+        x = np.ascontiguousarray(np.stack(xs), np.float64)
+        y = np.zeros_like(x)
+        rhs = np.zeros(self.n_inc)
+        sec = lib().port_apply(self.dim, C.c_int64(self.cells.shape[0]), _p(self.xyz, C.c_double), _p(self.cells, C.c_int32),
+                               _p(self.adrU, C.c_int64), _p(self.adrP, C.c_int64), self.LU.shape[1], self.LP.shape[1], self.w.shape[0],
+                               _p(self.w, C.c_double), _p(self.LU, C.c_double), _p(self.dLU, C.c_double), _p(self.LP, C.c_double),
+                               C.c_int64(self.n_inc), _p(sol, C.c_double), int(self.kinds.shape[0]), _p(self.kinds, C.c_int32),
+                               _p(self.coeff, C.c_double), _p(self.param, C.c_double), int(x.shape[0]), _p(x, C.c_double),
+                               _p(y, C.c_double), _p(rhs, C.c_double))
+        return [y[i] for i in range(x.shape[0])], rhs, float(sec)

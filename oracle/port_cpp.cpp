@@ -301,4 +301,48 @@ double port_assemble(int dim, int64_t nE, const double *xyz, const int32_t *cell
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// Matrix-free application of the same operator: y += A(sol) x and rhs, element by element, without a CSR matrix -- the
+// size-independent checker of the GPU assembly at the bench size (tests/test_gpu_fullsize.py), where the assembled
+// matrix (15 GB of values) is not worth building on the host.  OpenMP over all elements, atomic row updates.
+double port_apply(int dim, int64_t nE, const double *xyz, const int32_t *cells, const int64_t *adrU, const int64_t *adrP, int nS, int nP, int nq,
+                  const double *w, const double *LU, const double *dLU, const double *LP, int64_t nInc, const double *sol, int nForms,
+                  const int32_t *kinds, const double *coeff, const double *param, int nVec, const double *x, double *y, double *rhs)
+{
+  const Mesh   mesh{dim, dim + 1, nE, xyz, cells};
+  const Tables T{nS, nP, nq, w, LU, dLU, LP};
+  const int    nU = nS * dim;
+  const auto   t0 = std::chrono::steady_clock::now();
+  std::memset(y, 0, (size_t)nInc * nVec * sizeof(double));
+  std::memset(rhs, 0, (size_t)nInc * sizeof(double));
+#pragma omp parallel
+  {
+    Local L;
+#pragma omp for schedule(dynamic, 64)
+    for(int64_t e = 0; e < nE; ++e) {
+      for(int f = 0; f < nForms; ++f) {
+        const int kind = kinds[f];
+        element_form(kind, coeff[f], param[f], mesh, T, e, adrU, adrP, sol, true, L);
+        const bool rowsP = kind == MIXED_DIVERGENCE;
+        for(int i = 0; i < L.M; ++i) {
+          const int64_t I = rowsP ? adrP[e * nP + i] : adrU[e * nU + i];
+          if(I >= nInc) continue;
+#pragma omp atomic
+          rhs[I] += L.Be[i];
+          for(int v = 0; v < nVec; ++v) {
+            const double *xv = x + (size_t)v * nInc;
+            double        s = 0.;
+            for(int j = 0; j < L.N; ++j) {
+              const int64_t Jc = kind == MIXED_GRADIENT ? adrP[e * nP + j] : (j < nU ? adrU[e * nU + j] : adrP[e * nP + (j - nU)]);
+              if(Jc < nInc) s += L.Ae[i][j] * xv[Jc];
+            }
+#pragma omp atomic
+            y[(size_t)v * nInc + I] += s;
+          }
+        }
+      }
+    }
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 } // extern "C"

@@ -1,10 +1,10 @@
-"""Parity at the sizes bench.py runs (the oracle does not finish there in seconds): size-independent cross-checks.
+"""Parity at the sizes bench.py runs: size-independent cross-checks against the CPU.
 
-Three independent CUDA implementations of the same assembly -- the row-owner kernels (thread per node in 2-D, lane groups
-in 3-D), the patch kernel (block-slot owners over Morton patches) and the quadrature-loop kernel with atomic scatter --
-must produce the same operator: A x for seeded random x (a checksum of every row), the rhs, and for the write-once kernels
-bitwise the same numbers on a second pass.  Each of them is pinned on the oracle at small sizes by test_gpu_parity.py /
-test_gpu_patch.py; tolerance 1e-12 relative to the largest entry of the compared vector."""
+The assembled operator of the CUDA row-owner kernels (thread per node in 2-D, lane groups in 3-D) is compared, on EVERY row,
+with the CPU restatement of the reference's element loops applied matrix-free (oracle/port_cpp.cpp: port_apply; pinned on the
+numpy oracle and on the compiled reference by tests/test_port_cpp.py): A x for seeded random x -- a checksum of every row of
+the 1.86 G-entry matrix -- and the rhs.  The independent CUDA quadrature-loop kernel with atomic scatter must agree as well,
+and the write-once kernels must repeat bitwise.  Tolerance 1e-12 relative to the largest entry of the compared vector."""
 import numpy as np
 import pytest
 
@@ -23,7 +23,7 @@ def _probe(pb, sol, xs, kernel, monkeypatch, scatter=False):
     if scatter:
         S.set_assembly_mode(capi.ASSEMBLY_SCATTER)
     else:
-        assert S.gather_plan_kind() == (2 if kernel == "patch" else 1)
+        assert S.gather_plan_kind() == 1
     S.set_solution(sol)
     S.set_to_zero(3)
     S.assemble(3)
@@ -52,7 +52,15 @@ def test_three_assembly_paths_agree_at_bench_size(workload, n, monkeypatch):
     for y, y2 in zip(ref_y, ref_again[0]):
         assert np.array_equal(y, y2)                                                  # write-once: bitwise repeatable
     assert np.array_equal(ref_r, ref_again[1])
-    for name, kw in (("patch", dict(kernel="patch")), ("scatter", dict(kernel=None, scatter=True))):
+    # CPU: the reference's element loops applied matrix-free (all host threads)
+    from oracle import port
+    if port.available():
+        cy, cr, sec = port.PortProblem(pb, pattern_free=True).apply(sol, xs[:1])
+        assert np.abs(cy[0] - ref_y[0]).max() <= 1e-12 * np.abs(cy[0]).max(), "GPU operator differs from the CPU element loops"
+        assert np.abs(cr - ref_r).max() <= 1e-12 * np.abs(cr).max(), "GPU rhs differs from the CPU element loops"
+    else:
+        pytest.skip("oracle/_ref/libfeng_port.so not built")
+    for name, kw in (("scatter", dict(kernel=None, scatter=True)),):
         ys, r, again = _probe(pb, sol, xs, kw.get("kernel"), monkeypatch, kw.get("scatter", False))
         for y, yr in zip(ys, ref_y):
             assert np.abs(y - yr).max() <= 1e-12 * np.abs(yr).max(), f"{name}: A x differs"
