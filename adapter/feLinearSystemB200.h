@@ -47,6 +47,13 @@ struct feB200Options {
   int scatter      = B200_SCATTER_ATOMIC;
   bool devicePattern = false;          // build the EZCRS pattern on the device instead of taking the host one
   bool alwaysUpload  = false;          // re-upload the state in assembleMatrices even right after assembleResiduals
+  // keep the state resident on the device.  After the first upload the device copy -- which correctSolution
+  // updates in place -- is authoritative for the UNKNOWNS; every later assemble only sends the essential-DOF tail of the host
+  // vector (entries >= nInc, rewritten by feSolution::initializeEssentialBC each time step, src/feTimeIntegration.cpp:523-536).
+  // Only valid for drivers that never write unknowns of feSolution between two assemblies other than through correctSolution
+  // (solveNewtonRaphson on a stationary problem does not); transient drivers keep it off because BDFContainer rewrites solDot
+  // on the host (src/feSolutionContainer.cpp:338-348) -- a B200-aware host calls b200_state_push / b200_state_bdf instead.
+  bool deviceResidentState = false;
 };
 
 extern std::vector<double> solAtTimeN; // src/feNonLinearSolver.cpp:35
@@ -134,6 +141,9 @@ protected:
   bool          _stateFresh = false;
   bool          _needSolutionN = false;
   bool          _constraintInit = false;
+  bool          _deviceCurrent = false;
+  int           _numUploads = 0;
+  std::vector<int64_t> _essIdx;
   b200_solve_info _lastInfo{};
   int           _numSolves = 0;
   long          _totalKrylovIterations = 0;
@@ -435,6 +445,15 @@ protected:
   void upload(const feSolution *sol)
   {
     refreshSources(sol);
+    if(_opt.deviceResidentState && _deviceCurrent && sol->getC0() == 0.) {
+      if(_essIdx.empty())
+        for(feInt i = _nInc; i < _nDOF; ++i) _essIdx.push_back((int64_t)i);
+      if(!_essIdx.empty())
+        ok(b200_set_essential(_sys, (int64_t)_essIdx.size(), _essIdx.data(), sol->getSolution().data() + _nInc), "b200_set_essential");
+      return;
+    }
+    _deviceCurrent = true;
+    ++_numUploads;
     ok(b200_set_solution(_sys, sol->getSolution().data(), sol->getSolutionDot().data(), sol->getC0(), sol->getCurrentTime()),
        "b200_set_solution");
     // feBilinearForm::initialize reads the previous time step from the global solAtTimeN (src/feBilinearForm.cpp:277,347)
@@ -543,6 +562,7 @@ public:
   feStatus getStatus() const { return _status; }
   const b200_solve_info &getLastSolveInfo() const { return _lastInfo; }
   int  getNumSolves() const { return _numSolves; }
+  int  getNumStateUploads() const { return _numUploads; }
   long getTotalKrylovIterations() const { return _totalKrylovIterations; }
   b200_system *getHandle() { return _sys; }
 

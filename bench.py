@@ -379,16 +379,39 @@ def main():
         S.assemble(3)
         rn = S.rhs_max_norm()
     S.sync()
-    e2e_s = time.perf_counter() - t0
+    e2e_full_s = time.perf_counter() - t0
+    # the same step with the state RESIDENT on the device: what a time step / Newton iteration needs from
+    # the host is the essential-DOF values of the new level (feSolution::initializeEssentialBC, src/feTimeIntegration.cpp:523-536;
+    # pinned host buffer -> b200_set_essential) -- the unknowns are already there, b200_correct_solution keeps them current
+    ess_idx = np.arange(pb.n_inc, pb.n_dof, dtype=np.int64)
+    ess_val = torch.from_numpy(np.ascontiguousarray(sol[pb.n_inc:])).pin_memory().numpy()
+    resident = not chns                      # the CHNS workload supplies a host-side time derivative every step
+    if resident:
+        for _ in range(2):
+            S.set_essential(ess_idx, ess_val)
+            S.set_to_zero(3)
+            S.assemble(3)
+            S.rhs_max_norm()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            S.set_essential(ess_idx, ess_val)
+            S.set_to_zero(3)
+            S.assemble(3)
+            rn = S.rhs_max_norm()
+        S.sync()
+        e2e_s = time.perf_counter() - t0
+    else:
+        e2e_s = e2e_full_s
     spmv_ms = S.time_spmv(20)
     clocks = sampler.stop()
 
-    t_all = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t_all = torch.tensor([total_ms, e2e_s * 1e3, e2e_full_s * 1e3], dtype=torch.float64, device="cuda")
     owned_all = torch.tensor([float(owned)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
         dist.all_reduce(owned_all, op=dist.ReduceOp.SUM)
-    total_ms, e2e_ms = float(t_all[0]), float(t_all[1])
+    total_ms, e2e_ms, e2e_full_ms = float(t_all[0]), float(t_all[1]), float(t_all[2])
     tot_owned = float(owned_all[0])
 
     extra = {}
@@ -441,8 +464,15 @@ def main():
             "spmv": {"ms": spmv_ms, "achieved_gbs": spmv_bytes / (spmv_ms * 1e-3) / 1e9,
                      "frac": spmv_bytes / (spmv_ms * 1e-3) / 1e9 / peak, "bytes": spmv_bytes},
             "e2e": {"value": tot_owned / (e2e_ms / args.steps * 1e-3) / 1e6, "unit": UNIT,
-                    "h2d_bytes_per_step": int(pb.n_dof * 8 * (2 if chns else 1)), "d2h_bytes_per_step": 8,
-                    "ms_per_step": e2e_ms / args.steps, "rhs_max_norm": rn},
+                    "h2d_bytes_per_step": int((pb.n_dof - pb.n_inc) * 8) if resident else int(pb.n_dof * 8 * 2),
+                    "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms / args.steps, "rhs_max_norm": rn,
+                    "state": ("device-resident: per step the host sends the essential-DOF values of the new level from a pinned "
+                              "buffer (b200_set_essential; index list uploaded once) and reads the rhs max-norm back") if resident
+                             else "host-resident: solution and time derivative uploaded every step",
+                    "full_upload": {"value": tot_owned / (e2e_full_ms / args.steps * 1e-3) / 1e6,
+                                    "h2d_bytes_per_step": int(pb.n_dof * 8 * (2 if chns else 1)),
+                                    "ms_per_step": e2e_full_ms / args.steps,
+                                    "note": "the unmodified host loop: whole state vector uploaded every step (b200_set_solution)"}},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         line.update(extra)

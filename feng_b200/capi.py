@@ -19,7 +19,7 @@ SYMBOLS = [
     "b200_set_mesh", "b200_set_quadrature", "b200_add_space", "b200_add_form", "b200_set_source", "b200_set_pattern",
     "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode", "b200_set_assembly_mode", "b200_has_gather_plan", "b200_add_form_chns",
     "b200_set_constraints", "b200_set_periodic", "b200_set_blocks", "b200_finalize", "b200_system_size", "b200_set_solution",
-    "b200_set_solution_n", "b200_set_to_zero", "b200_assemble", "b200_rhs_max_norm", "b200_du_max_norm", "b200_constrain",
+    "b200_set_solution_n", "b200_set_essential", "b200_state_push", "b200_state_bdf", "b200_set_to_zero", "b200_assemble", "b200_rhs_max_norm", "b200_du_max_norm", "b200_constrain",
     "b200_apply_periodicity", "b200_solve", "b200_correct_solution", "b200_get_rhs", "b200_axpy_rhs",
     "b200_get_matrix_values", "b200_get_du", "b200_get_solution", "b200_spmv", "b200_last_assemble_ms",
     "b200_last_solve_ms", "b200_time_spmv", "b200_sync", "b200_time_begin", "b200_time_end",
@@ -229,6 +229,18 @@ class System:
         m = np.ascontiguousarray(master, np.int64)
         s = np.ascontiguousarray(slave, np.int64)
         check(self.L.b200_set_periodic(self.h, C.c_int64(m.shape[0]), _i64(m), _i64(s)), "b200_set_periodic")
+
+    def set_essential(self, dofs, values):
+        """essential-BC refresh on the device copy; pass the SAME dofs array every step (it is uploaded once)"""
+        assert dofs.dtype == np.int64 and dofs.flags.c_contiguous and values.dtype == np.float64
+        check(self.L.b200_set_essential(self.h, C.c_int64(dofs.shape[0]), _i64(dofs), _d(values)), "b200_set_essential")
+
+    def state_push(self):
+        check(self.L.b200_state_push(self.h), "b200_state_push")
+
+    def state_bdf(self, coef, t=0.0, dt=0.0):
+        c = np.ascontiguousarray(coef, np.float64)
+        check(self.L.b200_state_bdf(self.h, int(c.shape[0]), _d(c), C.c_double(t), C.c_double(dt)), "b200_state_bdf")
 
     def set_blocks(self, block_ptr, block_rows):
         bp = np.ascontiguousarray(block_ptr, np.int64)

@@ -147,6 +147,10 @@ static void free_system(System *S)
   cudaFree(S->d_sol);
   cudaFree(S->d_soldot);
   cudaFree(S->d_soln);
+  cudaFree(S->d_hist[0]);
+  cudaFree(S->d_hist[1]);
+  cudaFree(S->d_ess_idx);
+  cudaFree(S->d_ess_val);
   cudaFree(S->d_slot);
   cudaFree(S->d_tab);
   cudaFree(S->d_color_elems);
@@ -174,6 +178,9 @@ static int alloc_linear_system(System *S)
   cudaFree(S->d_soln);
   S->d_soln    = nullptr;
   S->have_soln = false;
+  cudaFree(S->d_hist[0]);
+  cudaFree(S->d_hist[1]);
+  S->d_hist[0] = S->d_hist[1] = nullptr;
   B200_CUDA(cudaMalloc(&S->d_val, (size_t)S->nnz * sizeof(double)));
   B200_CUDA(cudaMalloc(&S->d_rhs, nb));
   B200_CUDA(cudaMalloc(&S->d_du, nb));
@@ -597,6 +604,94 @@ int b200_set_solution_n(b200_system *s, const double *sol_n, double dt)
   if(!s->d_soln) B200_CUDA(cudaMalloc(&s->d_soln, (size_t)s->nDOF * sizeof(double)));
   B200_CUDA(cudaMemcpyAsync(s->d_soln, sol_n, (size_t)s->nDOF * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   B200_CUDA(cudaStreamSynchronize(s->stream));
+  return B200_OK;
+}
+
+// ---- device-resident time stepping: the state never leaves the GPU between Newton iterations / time steps ----
+__global__ void set_entries_kernel(int64_t n, const int64_t *__restrict__ idx, const double *__restrict__ v, int64_t nDOF, double *x)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if(idx[i] >= 0 && idx[i] < nDOF) x[idx[i]] = v[i];
+}
+
+// solDot = sum_j c[j] hist_j (hist_0 = the current state)
+__global__ void bdf_kernel(int64_t n, int nc, double c0, double c1, double c2, const double *__restrict__ u0, const double *__restrict__ u1,
+                           const double *__restrict__ u2, double *__restrict__ dot)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double s = c0 * u0[i];
+    if(nc > 1) s += c1 * u1[i];
+    if(nc > 2) s += c2 * u2[i];
+    dot[i] = s;
+  }
+}
+
+int b200_set_essential(b200_system *s, int64_t n, const int64_t *dofs, const double *values)
+{
+  CHECK_S(s);
+  if(!s->d_sol || n < 0 || (n > 0 && (!dofs || !values))) {
+    set_error("b200_set_essential: bad arguments / no state");
+    return B200_ERR_ARG;
+  }
+  if(n == 0) return B200_OK;
+  if(s->ess_cap < n) {
+    cudaFree(s->d_ess_idx);
+    cudaFree(s->d_ess_val);
+    B200_CUDA(cudaMalloc(&s->d_ess_idx, (size_t)n * sizeof(int64_t)));
+    B200_CUDA(cudaMalloc(&s->d_ess_val, (size_t)n * sizeof(double)));
+    s->ess_cap = n;
+    s->ess_idx_host = nullptr;
+  }
+  // the index list is usually the same array at every time step: it crosses the bus once
+  if(s->ess_idx_host != dofs || s->ess_n != n) {
+    B200_CUDA(cudaMemcpyAsync(s->d_ess_idx, dofs, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
+    s->ess_idx_host = dofs;
+    s->ess_n        = n;
+  }
+  B200_CUDA(cudaMemcpyAsync(s->d_ess_val, values, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  set_entries_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, GRID), 256, 0, s->stream>>>(n, s->d_ess_idx, s->d_ess_val, s->nDOF, s->d_sol);
+  count_launch();
+  B200_CUDA(cudaStreamSynchronize(s->stream)); // the caller may reuse `values`
+  return B200_OK;
+}
+
+int b200_state_push(b200_system *s)
+{
+  CHECK_S(s);
+  if(!s->d_sol) {
+    set_error("b200_state_push: no state");
+    return B200_ERR_ARG;
+  }
+  const size_t nb = (size_t)s->nDOF * sizeof(double);
+  for(int k = 0; k < 2; ++k)
+    if(!s->d_hist[k]) {
+      B200_CUDA(cudaMalloc(&s->d_hist[k], nb));
+      B200_CUDA(cudaMemsetAsync(s->d_hist[k], 0, nb, s->stream));
+    }
+  std::swap(s->d_hist[0], s->d_hist[1]); // u_{n-1} <- u_n
+  B200_CUDA(cudaMemcpyAsync(s->d_hist[0], s->d_sol, nb, cudaMemcpyDeviceToDevice, s->stream));
+  // the state at time n of the time-averaged CHNS forms (the global solAtTimeN of src/feNonLinearSolver.cpp:60)
+  if(!s->d_soln) B200_CUDA(cudaMalloc(&s->d_soln, nb));
+  B200_CUDA(cudaMemcpyAsync(s->d_soln, s->d_sol, nb, cudaMemcpyDeviceToDevice, s->stream));
+  s->have_soln = true;
+  return B200_OK;
+}
+
+int b200_state_bdf(b200_system *s, int n_coef, const double *coef, double t, double dt)
+{
+  CHECK_S(s);
+  if(!s->d_sol || n_coef < 1 || n_coef > 3 || !coef || (n_coef > 1 && !s->d_hist[0]) || (n_coef > 2 && !s->d_hist[1])) {
+    set_error("b200_state_bdf: 1..3 coefficients, and b200_state_push once per past level");
+    return B200_ERR_ARG;
+  }
+  bdf_kernel<<<GRID, 256, 0, s->stream>>>(s->nDOF, n_coef, coef[0], n_coef > 1 ? coef[1] : 0., n_coef > 2 ? coef[2] : 0., s->d_sol, s->d_hist[0],
+                                         s->d_hist[1], s->d_soldot);
+  count_launch();
+  s->have_soldot = true;
+  s->c0          = coef[0];
+  s->t           = t;
+  s->dt          = dt;
+  B200_CUDA(cudaGetLastError());
   return B200_OK;
 }
 

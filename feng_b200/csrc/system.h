@@ -80,6 +80,12 @@ struct System {
   double  *d_val = nullptr, *d_rhs = nullptr, *d_du = nullptr, *d_sol = nullptr, *d_soldot = nullptr;
   double   c0 = 0., t = 0.;
   bool     have_soldot = false;
+  // device-resident time stepping (capi.cu: b200_state_push / b200_state_bdf / b200_set_essential)
+  double        *d_hist[2] = {nullptr, nullptr}; // u_n, u_{n-1}
+  int64_t       *d_ess_idx = nullptr;
+  double        *d_ess_val = nullptr;
+  int64_t        ess_cap = 0, ess_n = 0;
+  const int64_t *ess_idx_host = nullptr;
 
   // fused plan
   PlanKind     plan = PLAN_NONE;

@@ -82,6 +82,11 @@ class LinearSystemB200:
         self.restart = 30
         self.pc = capi.PC_AUTO
         self.last_info = None
+        # device-resident state (row N3): after the first upload the device copy, which correctSolution keeps current, is
+        # authoritative and assemble* no longer re-uploads the caller's vector
+        self.device_resident = False
+        self.uploads = 0
+        self._device_current = False
 
     def sys_M(self) -> int:
         """rows of the fused element system (15 for 2-D P2/P1, 34 for 3-D)"""
@@ -107,7 +112,11 @@ class LinearSystemB200:
     def setResidualToZero(self): self.sys.set_to_zero(1)
 
     def _upload(self, sol, sol_dot=None, c0=0.0, t=0.0):
+        if self.device_resident and self._device_current and sol_dot is None:
+            return
         self.sys.set_solution(sol, sol_dot, c0, t)
+        self.uploads += 1
+        self._device_current = True
 
     def assemble(self, sol, sol_dot=None, c0=0.0, t=0.0, assembleOnlyTransientMatrices=False):
         self._upload(sol, sol_dot, c0, t)

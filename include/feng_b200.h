@@ -204,6 +204,19 @@ int64_t b200_system_size(const b200_system *s);
 /* state upload: what feBilinearForm::initialize reads from feSolution (sol, solDot, c0, tn),
  * src/feBilinearForm.cpp:291-349; n_dof doubles each, sol_dot may be NULL */
 int b200_set_solution(b200_system *s, const double *sol, const double *sol_dot, double c0, double t);
+/* ---- device-resident time stepping: after b200_set_solution has been called ONCE, a B200-aware host keeps
+ *      the state on the device -- b200_correct_solution updates it in place -- and only these cross the bus per step:
+ *      the essential-DOF values of the new time level and a handful of scalars. ---- */
+/* essential-BC refresh, feSolution::initializeEssentialBC (src/feTimeIntegration.cpp:523-536): sol[dofs[i]] = values[i] on the
+ * device copy.  The index array is uploaded once as long as the same host array is passed again. */
+int b200_set_essential(b200_system *s, int64_t n, const int64_t *dofs, const double *values);
+/* start of a time step: shift the device history (u_{n-1} <- u_n <- current state; feSolutionContainer::rotate,
+ * src/feSolutionContainer.cpp:82-105) and record the state at time n that the time-averaged CHNS forms read
+ * (solAtTimeN, src/feNonLinearSolver.cpp:60) */
+int b200_state_push(b200_system *s);
+/* solDot = sum_j coef[j] u_{n+1-j} with u_{n+1} the current device state (BDFContainer::computeSolTimeDerivative,
+ * src/feSolutionContainer.cpp:338-348); c0 = coef[0], current time t and time step dt as b200_set_solution / _n take them */
+int b200_state_bdf(b200_system *s, int n_coef, const double *coef, double t, double dt);
 /* setToZero / setMatrixToZero / setResidualToZero (src/feLinearSystem.h:110-112): what = 1 rhs, 2 matrix, 3 both */
 int b200_set_to_zero(b200_system *s, int what);
 /* assemble / assembleMatrices / assembleResiduals (src/feLinearSystem.h:115-120): what = 1 residual, 2 matrix,
