@@ -238,6 +238,54 @@ protected:
     return true;
   }
 
+  // Space- / time-dependent coefficient of a scalar diffusion form: tabulated at every (element, quadrature node), where the
+  // reference evaluates it (src/feSysElm.cpp:538, :566), and re-tabulated when the time changes.  Solution-dependent callbacks
+  // (args.u) are rejected: the engine's Jacobian has no term for them.
+  struct CoeffForm {
+    int               formId;
+    const feFunction *f;
+    feSpace          *geoSpace;
+    int               cncGeoTag;
+    double            time;
+  };
+  std::vector<CoeffForm> _coeffs;
+
+  void tabulateCoefficient(const CoeffForm &cf, double t, double u, std::vector<double> &tab)
+  {
+    tab.resize((size_t)_nElm * _nQuad);
+    feFunctionArguments args(t);
+    args.u = u;
+    std::vector<double> coord(3 * _cnc->getNumVerticesPerElem(), 0.);
+    for(int e = 0; e < _nElm; ++e) {
+      _mesh->getCoord(cf.cncGeoTag, e, coord);
+      for(int k = 0; k < _nQuad; ++k) {
+        cf.geoSpace->interpolateVectorFieldAtQuadNode(coord, k, args.pos);
+        tab[(size_t)e * _nQuad + k] = cf.f->eval(args);
+      }
+    }
+  }
+
+  template <class T> bool addDiffusionForm(feBilinearForm *f, feSysElm *se, int kind, int su)
+  {
+    const T *s = dynamic_cast<const T *>(se);
+    if(!s) return fail("weak form class does not match its elementSystemType");
+    const feFunction *cb = feB200detail::SysPeek<T>::coeff(s);
+    double c = 1.;
+    if(constantValue(cb, f->_geoSpace, f->getCncGeoTag(), 0., c)) return ok(b200_add_form(_sys, kind, su, -1, c, 1., nullptr), "b200_add_form");
+    CoeffForm           cf{-1, cb, f->_geoSpace, f->getCncGeoTag(), 0.};
+    std::vector<double> t0, t1;
+    tabulateCoefficient(cf, 0., 0., t0);
+    tabulateCoefficient(cf, 0., 0.61, t1);
+    for(size_t i = 0; i < t0.size(); ++i)
+      if(std::fabs(t0[i] - t1[i]) > 1e-14 * std::max(1., std::fabs(t0[i])))
+        return fail("solution-dependent diffusivity callbacks are not supported (the Jacobian would miss d k / d u)");
+    cf.formId = b200_add_form(_sys, kind, su, -1, 1., 1., nullptr);
+    if(cf.formId < 0) return fail("b200_add_form");
+    if(!ok(b200_set_form_coefficient(_sys, cf.formId, t0.data()), "b200_set_form_coefficient")) return false;
+    _coeffs.push_back(cf);
+    return true;
+  }
+
   void tabulateSource(const SourceForm &sf, double t, std::vector<double> &tab)
   {
     const int nc = sf.vector ? _dim : 1;
@@ -422,8 +470,8 @@ protected:
       case TRANSIENT_MASS: return addCoeffForm<feSysElm_TransientMass>(f, se, id, s0, -1, nullptr);
       case DIFFUSION:
         // diffusivity is the form's only callback: kind DIFFUSION uses coeff x param with param = 1
-        if(_dim == 2) return addCoeffForm<feSysElm_Diffusion<2>>(f, se, id, s0, -1, nullptr);
-        return addCoeffForm<feSysElm_Diffusion<3>>(f, se, id, s0, -1, nullptr);
+        if(_dim == 2) return addDiffusionForm<feSysElm_Diffusion<2>>(f, se, id, s0);
+        return addDiffusionForm<feSysElm_Diffusion<3>>(f, se, id, s0);
       default: break;
     }
     if(_dim == 2) return addFormDim<2>(f, se);
@@ -439,6 +487,12 @@ protected:
       tabulateSource(sf, t, tab);
       ok(b200_set_source(_sys, sf.formId, tab.data()), "b200_set_source");
       sf.time = t;
+    }
+    for(auto &cf : _coeffs) {
+      if(cf.time == t) continue;
+      tabulateCoefficient(cf, t, 0., tab);
+      ok(b200_set_form_coefficient(_sys, cf.formId, tab.data()), "b200_set_form_coefficient");
+      cf.time = t;
     }
   }
 

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libfeng_b200.so")
 # every symbol include/feng_b200.h declares (tests/test_capi_symbols.py checks the list against the header)
 SYMBOLS = [
     "b200_last_error", "b200_kernel_launches", "b200_reset_kernel_launches", "b200_create", "b200_destroy",
-    "b200_set_mesh", "b200_set_quadrature", "b200_add_space", "b200_add_form", "b200_set_source", "b200_set_pattern",
+    "b200_set_mesh", "b200_set_quadrature", "b200_add_space", "b200_add_form", "b200_set_source", "b200_set_form_coefficient", "b200_set_pattern",
     "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode", "b200_set_assembly_mode", "b200_has_gather_plan", "b200_add_form_chns",
     "b200_set_constraints", "b200_set_periodic", "b200_set_blocks", "b200_finalize", "b200_system_size", "b200_set_solution",
     "b200_set_solution_n", "b200_set_essential", "b200_state_push", "b200_state_bdf", "b200_set_to_zero", "b200_assemble", "b200_rhs_max_norm", "b200_du_max_norm", "b200_constrain",
@@ -224,6 +224,10 @@ class System:
         check(self.L.b200_set_constraints(self.h, C.c_int64(rows.shape[0]), _i64(rows),
                                           C.c_int64(0 if m is None else m.shape[0]), _i64(m), _i64(s)),
               "b200_set_constraints")
+
+    def set_form_coefficient(self, form_id, table):
+        t = np.ascontiguousarray(table, np.float64)
+        check(self.L.b200_set_form_coefficient(self.h, int(form_id), _d(t)), "b200_set_form_coefficient")
 
     def set_periodic(self, master, slave):
         m = np.ascontiguousarray(master, np.int64)

@@ -846,6 +846,7 @@ int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int 
   auto          pol = thrust::cuda::par.on(S->stream);
   A->verbose = getenv("B200_VERBOSE") != nullptr;
   if(const char *e = getenv("B200_AMG_DEGREE")) A->cheb_degree = std::max(1, atoi(e));
+  if(const char *e = getenv("B200_AMG_PRE")) A->pre_degree = std::max(0, atoi(e));
   if(const char *e = getenv("B200_AMG_CYCLES")) A->cycles = std::max(1, atoi(e));
   if(const char *e = getenv("B200_AMG_RATIO")) A->cheb_ratio = std::max(1.5, atof(e));
   if(const char *e = getenv("B200_AMG_F32")) A->use_f32 = atoi(e) != 0;
@@ -1068,13 +1069,14 @@ int amg_setup_numeric(System *S, Amg *A)
 }
 
 // Chebyshev smoother of degree AMG_CHEB_DEGREE on [lam / AMG_CHEB_RATIO, lam]; zero_guess: x is not read
-static int smooth(System *S, Amg *A, int l, const double *b, double *x, bool zero_guess)
+static int smooth(System *S, Amg *A, int l, const double *b, double *x, bool zero_guess, int degree = 0)
 {
+  if(degree <= 0) degree = A->cheb_degree;
   AmgLevel    &L = A->L[l];
   const double lmax = L.lam, lmin = L.lam / A->cheb_ratio;
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
   double       rho = 1. / sigma;
-  for(int k = 0; k < A->cheb_degree; ++k) {
+  for(int k = 0; k < degree; ++k) {
     const bool first = k == 0;
     const double *t = nullptr;
     if(!(first && zero_guess)) {
@@ -1115,7 +1117,7 @@ static int cycle(System *S, Amg *A, int l, const double *b, double *x, bool zero
     return rc;
   }
   AmgLevel &C = A->L[l + 1];
-  int       rc = smooth(S, A, l, b, x, zero_guess);
+  int       rc = smooth(S, A, l, b, x, zero_guess, A->pre_degree);
   if(rc != B200_OK) return rc;
   if(C.n > 0) {
     rc = csr_product(S, L, x, L.t);

@@ -48,6 +48,7 @@ struct Amg {
   double               *dense = nullptr, *cinv = nullptr, *d_nrm = nullptr;
   bool                  symbolic = false, verbose = false;
   int                   cheb_degree = AMG_CHEB_DEGREE, cycles = 1; // B200_AMG_DEGREE / B200_AMG_CYCLES
+  int                   pre_degree = 0;                            // B200_AMG_PRE: degree of the pre-smoother (0 = cheb_degree)
   double                cheb_ratio = AMG_CHEB_RATIO;               // B200_AMG_RATIO
   bool                  use_f32 = true;                            // B200_AMG_F32=0: level 0 works on the FP64 system matrix
 };

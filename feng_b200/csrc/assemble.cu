@@ -291,6 +291,7 @@ struct SCArgs {
   const double  *xyz;
   const int32_t *conn, *adr;
   const double  *sol, *soldot, *source, *tab;
+  const double  *kcoef; // [nElm][nq] tabulated diffusivity (a space-dependent coefficient callback), or nullptr
   const int32_t *slot;
   double        *val, *rhs;
   const int32_t *elem_list;
@@ -305,7 +306,8 @@ template <int DIM, int NS> struct SCShape {
   static constexpr int F_GU = F_G + NS * DIM; // DIM  k*grad u
   static constexpr int F_R0 = F_GU + DIM;     // 1
   static constexpr int F_JW = F_R0 + 1;
-  static constexpr int NF = F_JW + 1;
+  static constexpr int F_KQ = F_JW + 1;       // diffusivity at the quadrature node
+  static constexpr int NF = F_KQ + 1;
   static constexpr int EL = DIM * DIM + 1 + NS + NS;
 };
 
@@ -390,9 +392,12 @@ __global__ void __launch_bounds__(EPB *NS) sc_kernel(const SCArgs a)
             gu[m] += v * U[b];
           }
         }
-#pragma unroll
-        for(int m = 0; m < DIM; ++m) s_qp[(S::F_GU + m) * NPAIR + pidx] = c.k * gu[m];
         const int64_t e  = a.elem_list ? (int64_t)a.elem_list[ei] : ei;
+        // the reference evaluates the coefficient callback at every quadrature node (src/feSysElm.cpp:538, :566)
+        const double  kq = a.kcoef ? c.k * a.kcoef[e * nq + k] : c.k;
+#pragma unroll
+        for(int m = 0; m < DIM; ++m) s_qp[(S::F_GU + m) * NPAIR + pidx] = kq * gu[m];
+        s_qp[S::F_KQ * NPAIR + pidx] = kq;
         double        r0 = -c.c_mass * ud;
         if(a.source) r0 -= c.c_src * a.source[e * nq + k];
         s_qp[S::F_R0 * NPAIR + pidx] = r0;
@@ -411,7 +416,7 @@ __global__ void __launch_bounds__(EPB *NS) sc_kernel(const SCArgs a)
 #pragma unroll
         for(int m = 0; m < DIM; ++m) ga[m] = qp[(S::F_G + i_me * DIM + m) * NPAIR];
         if(MAT) {
-          const double kj = jw * c.k, mj = jw * massc0 * phia;
+          const double kj = jw * qp[S::F_KQ * NPAIR], mj = jw * massc0 * phia;
 #pragma unroll
           for(int b = 0; b < NS; ++b) {
             double dot = 0.;
@@ -520,6 +525,7 @@ int analyze_forms(System *S)
   S->sc = ScalarCoeffs();
   S->sc_transient = ScalarCoeffs();
   S->d_source = nullptr;
+  S->d_kcoef  = nullptr;
   for(int bi = 0; bi < 2; ++bi)
     for(int bj = 0; bj < 2; ++bj) S->has_matrix_block[bi][bj] = false;
 
@@ -533,6 +539,13 @@ int analyze_forms(System *S)
         return B200_ERR_UNSUPP;
       }
       if(f.kind == B200_FORM_DIFFUSION) {
+        if(f.d_coeff_table) {
+          if(S->d_kcoef) {
+            set_error("b200_finalize: at most one diffusion form with a tabulated coefficient");
+            return B200_ERR_UNSUPP;
+          }
+          S->d_kcoef = f.d_coeff_table;
+        }
         S->sc.k += f.coeff * f.param; // diffusivity = coeff x param (the reference form has one callback: pass param = 1)
         S->has_matrix_block[0][0] = true;
       } else if(f.kind == B200_FORM_TRANSIENT_MASS) {
@@ -783,6 +796,7 @@ template <int DIM, int NS, int EPB, int CH> static int launch_sc(System *S, int 
   a.sol    = S->d_sol;
   a.soldot = S->have_soldot ? S->d_soldot : nullptr;
   a.source = (c.c_src != 0.) ? S->d_source : nullptr;
+  a.kcoef  = S->d_kcoef;
   a.tab    = S->d_tab;
   a.slot   = S->d_slot;
   a.val    = S->d_val;

@@ -136,7 +136,10 @@ static void free_system(System *S)
   chns_free(S);
   comm_free(S);
   for(auto &sp : S->spaces) cudaFree(sp.d_adr);
-  for(auto &f : S->forms) cudaFree(f.d_source);
+  for(auto &f : S->forms) {
+    cudaFree(f.d_source);
+    cudaFree(f.d_coeff_table);
+  }
   cudaFree(S->d_xyz);
   cudaFree(S->d_conn);
   cudaFree(S->d_ia);
@@ -396,6 +399,28 @@ int b200_set_source(b200_system *s, int form_id, const double *source)
   if(f.coeff != 1.)
     for(auto &v : scaled) v *= f.coeff;
   B200_CUDA(cudaMemcpy(f.d_source, scaled.data(), count * sizeof(double), cudaMemcpyHostToDevice));
+  return B200_OK;
+}
+
+int b200_set_form_coefficient(b200_system *s, int form_id, const double *table)
+{
+  CHECK_S(s);
+  if(form_id < 0 || form_id >= (int)s->forms.size() || !table) {
+    set_error("b200_set_form_coefficient: bad form id / null table");
+    return B200_ERR_ARG;
+  }
+  Form &f = s->forms[form_id];
+  if(f.kind != B200_FORM_DIFFUSION) {
+    set_error("b200_set_form_coefficient: tabulated coefficients are built for feSysElm_Diffusion (quadrature-loop kernel); the fused "
+              "Taylor-Hood kernels work on pre-contracted tensors and need constant coefficients");
+    return B200_ERR_UNSUPP;
+  }
+  const size_t count = (size_t)s->nElm * s->nq;
+  const bool   fresh = f.d_coeff_table == nullptr;
+  if(fresh) B200_CUDA(cudaMalloc(&f.d_coeff_table, count * sizeof(double)));
+  B200_CUDA(cudaMemcpy(f.d_coeff_table, table, count * sizeof(double), cudaMemcpyHostToDevice));
+  if(fresh) s->plan = PLAN_NONE; // picked up by the next b200_finalize
+  ++s->val_epoch;
   return B200_OK;
 }
 

@@ -34,6 +34,7 @@ struct Form {
   int     kind = 0, su = 0, sp = -1;
   double  coeff = 1., param = 1.;
   double *d_source = nullptr; // [nElm][nq][ncomp]
+  double *d_coeff_table = nullptr; // [nElm][nq] tabulated coefficient callback (b200_set_form_coefficient), or nullptr
 };
 
 // Coefficients of the fused Taylor-Hood kernel: sums over the registered forms, see assemble.cu
@@ -94,6 +95,7 @@ struct System {
   THCoeffs     th, th_transient;       // all forms / transient-matrix forms only
   ScalarCoeffs sc, sc_transient;
   double      *d_source = nullptr;     // source table of the (single) source form
+  const double *d_kcoef = nullptr;     // tabulated diffusivity of the scalar diffusion form (owned by its Form)
   int32_t     *d_slot = nullptr;       // [nElm][M][M] CSR slot or -1
   double      *d_tab = nullptr;        // packed basis tables + weights for the kernels
   int          tab_len = 0;

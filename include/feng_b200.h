@@ -170,6 +170,12 @@ int b200_set_solution_n(b200_system *s, const double *sol_n, double dt);
  * re-tabulated by the adapter when feSolution::getCurrentTime() changes (the reference evaluates the callback with
  * args.t = tn on every element visit, src/feBilinearForm.cpp:291-295) */
 int b200_set_source(b200_system *s, int form_id, const double *source);
+/* space- (and time-) dependent coefficient callback of form `form_id`, tabulated by the host at every (element, quadrature
+ * node) exactly where the reference evaluates it (feSysElm_Diffusion, src/feSysElm.cpp:538, :566); the form's constant coeff x
+ * param multiplies the table.  Built for B200_FORM_DIFFUSION (the quadrature-loop kernel); the fused Taylor-Hood kernels work on
+ * pre-contracted tensors and keep constant coefficients (B200_ERR_UNSUPP).  Call before b200_finalize; calling it again later
+ * replaces the values (time-dependent coefficients). */
+int b200_set_form_coefficient(b200_system *s, int form_id, const double *table);
 /* sparsity pattern of feEZCompressedRowStorage (src/feCompressedRowStorage.cpp:15-133), ia[n_inc+1], ja[nnz] */
 int b200_set_pattern(b200_system *s, int64_t n_inc, int64_t n_dof, const int64_t *ia, const int32_t *ja);
 /* same pattern built on the device from the spaces and forms registered so far; b200_get_pattern to read it back */

@@ -162,6 +162,7 @@ double sSolCb(const feFunctionArguments &args, const std::vector<double> &par)
   const double x = args.pos[0], y = args.pos[1], z = args.pos[2];
   const int field = (int)par[0];
   if(field == 0) return pow(x, 6) + pow(y, 6) + pow(z, 6);
+  if(field == 4) return sin(PI * x) * sin(PI * y); // tests/withLinearSolver/scalarFE.cpp:14-21
   return 0.;
 }
 
@@ -171,6 +172,7 @@ double sSrcCb(const feFunctionArguments &args, const std::vector<double> &par)
   const int    field = (int)par[0];
   const double k = par[1];
   if(field == 0) return k * 30. * (pow(x, 4) + pow(y, 4) + pow(z, 4));
+  if(field == 4) return -2. * k * PI * PI * sin(PI * x) * sin(PI * y); // tests/withLinearSolver/scalarFE.cpp:23-28
   return -1.;
 }
 

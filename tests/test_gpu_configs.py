@@ -100,3 +100,42 @@ def test_periodic_pairs_pattern_extras_and_apply_periodicity(device_pattern):
     assert np.abs(s_gpu - s_cpu).max() <= 1e-9 * np.abs(s_cpu).max()
     assert np.abs(s_gpu[master] - s_gpu[slave]).max() <= 1e-12
     P.close()
+
+
+# tests/withLinearSolver/scalarFE_diffusion.output:3-6 (P1) and :10-13 (P2): data/mmsMeshes/square{1..4}.msh, quadrature degree 8
+SCALARFE_DIFFUSION = {1: [7.907546e-02, 2.113277e-02, 5.377435e-03, 1.350436e-03],
+                      2: [4.327628e-03, 5.480619e-04, 6.873916e-05, 8.600535e-06]}
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_scalarfe_diffusion_goldens_through_the_adapter(order):
+    """P1 and P2 Poisson of the reference's scalarFE suite: the multigrid preconditioner on a P1 system (level 0 aggregated
+    directly) and on a P2 system (P2 -> P1 level first), 6 printed digits."""
+    ref = _ref()
+    for i, want in enumerate(SCALARFE_DIFFUSION[order], start=1):
+        P = ref.RefProblem(os.path.join(ref.DATA_DIR, f"mms_square{i}.msh"), "diffusion", order, 8, field=4, mu=1.0, b200=True)
+        sol, info = P.newton_b200(1e-10, 1e-10, 10, rel_tol=1e-12)
+        assert info["converged"] and info["krylov_iterations"] <= 40 * info["n_solves"], (order, i, info)
+        assert f"{info['errU']:.6e}" == f"{want:.6e}", (order, i, info, want)
+        P.close()
+
+
+def test_space_dependent_diffusivity_is_tabulated():
+    """feSysElm_Diffusion with a NON-constant coefficient callback k(x) = 1 + x/2 + y^2/4 (field-dependent-coefficient forms of
+    the reference's scalarFE suite): the adapter tabulates the callback at every (element, quadrature node), the engine's
+    quadrature-loop kernel multiplies it in; assembled system and Newton solution against the reference's own element loops."""
+    ref = _ref()
+    P = ref.RefProblem(os.path.join(ref.DATA_DIR, "square2.msh"), "var_diffusion", 2, 8, mu=0.7, b200=True)
+    sol0, _ = P.solution()
+    sol0[:P.n_inc] = np.random.default_rng(5).uniform(-1, 1, P.n_inc)
+    P.set_solution(sol0)
+    v_ref, r_ref, _ = P.assemble()
+    for devpat in (False, True):
+        v, r = P.assemble_b200(device_pattern=devpat)
+        assert np.abs(v - v_ref).max() <= 1e-12 * np.abs(v_ref).max()
+        assert np.abs(r - r_ref).max() <= 1e-12 * np.abs(r_ref).max()
+    s_gpu, info = P.newton_b200(1e-10, 1e-10, 10, rel_tol=1e-12)
+    assert info["converged"], info
+    s_cpu, _ = P.newton(1e-10, 1e-10, 10)
+    assert np.abs(s_gpu - s_cpu).max() <= 1e-9 * np.abs(s_cpu).max()
+    P.close()
