@@ -87,7 +87,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_problem(workload, n, rank, world):
+def build_problem(workload, n, rank, world, strong=False):
     from feng_b200 import mesh as M, partition as PT, problems as PB
     part = None
     if workload == "t2d":
@@ -106,10 +106,10 @@ def build_problem(workload, n, rank, world):
                 f"quad deg 8 (16 pts)")
     else:
         # slab r of the [0,1]^2 x [0,world] box: n^3 owned cells of 6 Kuhn tetrahedra plus one ghost layer of cells
-        pb, part = PT.slab_problem(n, rank, world, "ns_div", 6, 3, MU, RHO, build_pattern=False, with_source=False)
-        owned = 6 * n * n * n
+        pb, part = PT.slab_problem(n, rank, world, "ns_div", 6, 3, MU, RHO, build_pattern=False, with_source=False, strong=strong)
+        owned = 6 * n * n * int(np.diff(PT.layer_bounds(n, world, strong))[rank])
         name = (f"T3D({n}) P2/P1 Navier-Stokes tetrahedra (convU+divU+divSigma), trigonometric field + noise, "
-                f"quad deg 6 (24 pts)")
+                f"quad deg 6 (24 pts)" + (f", ONE cube cut into {world} slabs" if strong and world > 1 else ""))
     sol = PB.perturb_unknowns(pb)
     return pb, sol, owned, name, part
 
@@ -294,6 +294,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-solve", action="store_true", help="skip the Newton-step timing (assembly + GMRES)")
     ap.add_argument("--assembly", default="auto", choices=["auto", "scatter", "gather"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one T3D(n) cube per GPU (default); strong = ONE T3D(n) cube cut into N slabs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity_check block")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -317,7 +320,8 @@ def main():
     from feng_b200 import capi
     from feng_b200.linear_system import LinearSystemB200
 
-    pb, sol, owned, wl_name, part = build_problem(args.workload, n, rank, world)
+    strong = args.scaling == "strong" and args.workload == "t3d"
+    pb, sol, owned, wl_name, part = build_problem(args.workload, n, rank, world, strong)
     ls = LinearSystemB200(pb, device=local_rank, device_pattern=True, partition=part)
     S = ls.sys
     if args.assembly != "auto":
@@ -417,6 +421,10 @@ def main():
     extra = {}
     if not args.no_solve and not chns:
         extra["newton_step"] = newton_step(ls, sol, pb, args.solve_maxit)
+    if not args.no_parity and args.workload == "t3d":
+        pc_ = parity_check(rank, world, local_rank)
+        if rank == 0:
+            extra["parity_check"] = pc_
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -435,7 +443,7 @@ def main():
             traffic = per_elem * nE if per_elem else None       # per assembly pass, like `achieved`
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong and world > 1 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_name, "elements_per_gpu": int(owned), "ghost_elements_per_gpu": int(nE - owned),
                        "n_dof_per_gpu": int(pb.n_dof), "n_unknowns_per_gpu": int(pb.n_inc), "nnz_per_gpu": int(S.nnz),
@@ -499,6 +507,66 @@ def main():
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+
+
+def _seeded_vector(pb):
+    """x_i = a smooth function of the DOF's position, field and component: the same vector on every partition"""
+    from feng_b200 import problems as PB
+    x = np.zeros(pb.n_dof)
+    for f, fld in enumerate(pb.num.fields):
+        xyz = np.nan_to_num(PB.dof_coordinates(pb.mesh, pb.num, fld, pb.n_dof))
+        comp = PB.dof_components(pb.num, fld, pb.n_dof)
+        sel = comp >= 0
+        x[sel] = np.sin(3.1 * xyz[sel, 0] + 5.3 * xyz[sel, 1] + 7.7 * xyz[sel, 2] + 1.3 * (4 * f + comp[sel]))
+    return x[:pb.n_inc]
+
+
+def parity_check(rank, world, local_rank, n=8):
+    """Correctness stamp on the bench line itself.  N = 1: GPU assembly of T3D(n) against the CPU element loops applied
+    matrix-free (oracle/port_cpp.cpp), every row.  N > 1: the distributed operator and rhs of `world` slabs (owned rows, summed over
+    the ranks) against the undecomposed box assembled by rank 0 on its GPU alone -- sum of (A x)_i^2 and of rhs_i^2 for a seeded,
+    partition-independent x."""
+    import torch
+    import torch.distributed as dist
+    from feng_b200 import mesh as M, partition as PT, problems as PB
+    from feng_b200.linear_system import LinearSystemB200
+
+    def sums(pb, part):
+        ls = LinearSystemB200(pb, device=local_rank, device_pattern=True)     # no communicator: local products on complete inputs
+        ls.sys.set_solution(pb.sol)
+        ls.sys.set_to_zero(3)
+        ls.sys.assemble(3)
+        x = _seeded_vector(pb)
+        y, r = ls.sys.spmv(x), ls.sys.get_rhs()
+        own = np.ones(pb.n_inc, bool) if part is None else part.owned.astype(bool)
+        ls.sys.close()
+        return float((y[own] ** 2).sum()), float((r[own] ** 2).sum()), x, y, r
+
+    if world == 1:
+        from oracle import port
+        pb = PB.taylor_hood(M.cube_mesh(n), "ns_div", 6, 3, MU, RHO, build_pattern=False, with_source=False)
+        _, _, x, y, r = sums(pb, None)
+        if not port.available():
+            return {"ok": None, "note": "oracle/_ref/libfeng_port.so missing"}
+        cy, cr, _ = port.PortProblem(pb, pattern_free=True).apply(pb.sol, [x])
+        dy = float(np.abs(cy[0] - y).max() / np.abs(cy[0]).max())
+        dr = float(np.abs(cr - r).max() / np.abs(cr).max())
+        return {"against": f"CPU element loops (oracle/port_cpp.cpp, matrix-free) on T3D({n}), every row", "ax_max_rel_diff": dy,
+                "rhs_max_rel_diff": dr, "ok": bool(dy <= 1e-12 and dr <= 1e-12)}
+    pb, part = PT.slab_problem(n, rank, world, "ns_div", 6, 3, MU, RHO, build_pattern=False, with_source=False)
+    sy, sr, *_ = sums(pb, part)
+    t = torch.tensor([sy, sr], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t)
+    out = None
+    if rank == 0:
+        mg = M.box_mesh(n, n, n * world, float(world))
+        mg.point_pressure = 0
+        pg = PB.taylor_hood(mg, "ns_div", 6, 3, MU, RHO, build_pattern=False, with_source=False)
+        gy, gr, *_ = sums(pg, None)
+        dy, dr = abs(float(t[0]) - gy) / gy, abs(float(t[1]) - gr) / gr
+        out = {"against": f"the undecomposed {world} x T3D({n}) box assembled on one GPU", "sum_ax2_rel_diff": dy, "sum_rhs2_rel_diff": dr,
+               "ok": bool(dy <= 1e-12 and dr <= 1e-12)}
+    return out
 
 
 def newton_step(ls, sol, pb, maxit):

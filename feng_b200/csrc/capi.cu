@@ -928,10 +928,7 @@ int b200_time_spmv(b200_system *s, int reps, float *ms_per_spmv)
     if(rc == B200_OK) rc = spmv(s, dx, dy);
   }
   cudaEventRecord(s->ev0, s->stream);
-  for(int i = 0; i < reps && rc == B200_OK; ++i) {
-    rc = comm_halo_exchange(s, dx);
-    if(rc == B200_OK) rc = spmv(s, dx, dy);
-  }
+  for(int i = 0; i < reps && rc == B200_OK; ++i) rc = comm_spmv_overlapped(s, dx, dy);
   cudaEventRecord(s->ev1, s->stream);
   cudaEventSynchronize(s->ev1);
   float ms = 0.f;

@@ -84,7 +84,28 @@ struct Comm {
   double              *d_send_buf = nullptr, *d_recv_buf = nullptr;
   double              *d_mask = nullptr; // [nInc] 1 for owned rows, 0 for ghost rows
   int64_t              n_owned = 0;
+  // interior / boundary split of the SpMV (rows whose columns are all owned do not wait for the halo)
+  uint8_t             *d_bflag = nullptr; // [nInc] 1 = the row reads a ghost column (or is a ghost row)
+  int32_t             *d_brows = nullptr; // list of those rows
+  int64_t              n_brows = 0;
+  cudaStream_t         cstream = nullptr; // halo traffic runs here, next to the interior product on the system's stream
+  cudaEvent_t          ev_x = nullptr, ev_halo = nullptr;
 };
+
+__global__ void boundary_flag_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja, const double *__restrict__ mask,
+                                     uint8_t *flag)
+{
+  const int     lane = threadIdx.x & 7;
+  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3, ng = (gridDim.x * (int64_t)blockDim.x) >> 3;
+  for(int64_t i = g0; i < n; i += ng) {
+    int f = mask[i] == 0. ? 1 : 0;
+    for(int64_t k = ia[i] + lane; k < ia[i + 1] && !f; k += 8) f |= mask[ja[k]] == 0. ? 1 : 0;
+    f |= __shfl_xor_sync(0xffffffffu, f, 1, 8);
+    f |= __shfl_xor_sync(0xffffffffu, f, 2, 8);
+    f |= __shfl_xor_sync(0xffffffffu, f, 4, 8);
+    if(lane == 0) flag[i] = (uint8_t)f;
+  }
+}
 
 __global__ void pack_kernel(int64_t n, const int32_t *__restrict__ idx, const double *__restrict__ x, double *__restrict__ buf)
 {
@@ -105,6 +126,11 @@ void comm_free(System *S)
   cudaFree(C->d_send_buf);
   cudaFree(C->d_recv_buf);
   cudaFree(C->d_mask);
+  cudaFree(C->d_bflag);
+  cudaFree(C->d_brows);
+  if(C->cstream) cudaStreamDestroy(C->cstream);
+  if(C->ev_x) cudaEventDestroy(C->ev_x);
+  if(C->ev_halo) cudaEventDestroy(C->ev_halo);
   if(C->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(C->comm);
   delete C;
   S->comm = nullptr;
@@ -122,29 +148,54 @@ bool comm_active(const System *S)
   return C && C->world > 1;
 }
 
-// x[ghost] <- owner's value, on the system's stream
-int comm_halo_exchange(System *S, double *d_x)
+static int halo_on_stream(Comm *C, double *d_x, cudaStream_t st)
 {
-  Comm *C = static_cast<Comm *>(S->comm);
-  if(!C || C->world == 1 || C->n_nbr == 0) return B200_OK;
   const int64_t ns = C->send_ptr[C->n_nbr], nr = C->recv_ptr[C->n_nbr];
   if(ns > 0) {
-    pack_kernel<<<(unsigned)std::min<int64_t>((ns + 255) / 256, 148 * 8), 256, 0, S->stream>>>(ns, C->d_send_idx, d_x, C->d_send_buf);
+    pack_kernel<<<(unsigned)std::min<int64_t>((ns + 255) / 256, 148 * 8), 256, 0, st>>>(ns, C->d_send_idx, d_x, C->d_send_buf);
     count_launch();
   }
   B200_NCCL(g_nccl.GroupStart());
   for(int k = 0; k < C->n_nbr; ++k) {
     const int64_t s0 = C->send_ptr[k], s1 = C->send_ptr[k + 1], r0 = C->recv_ptr[k], r1 = C->recv_ptr[k + 1];
-    if(s1 > s0) B200_NCCL(g_nccl.Send(C->d_send_buf + s0, (size_t)(s1 - s0), ncclDouble, C->nbr[k], C->comm, S->stream));
-    if(r1 > r0) B200_NCCL(g_nccl.Recv(C->d_recv_buf + r0, (size_t)(r1 - r0), ncclDouble, C->nbr[k], C->comm, S->stream));
+    if(s1 > s0) B200_NCCL(g_nccl.Send(C->d_send_buf + s0, (size_t)(s1 - s0), ncclDouble, C->nbr[k], C->comm, st));
+    if(r1 > r0) B200_NCCL(g_nccl.Recv(C->d_recv_buf + r0, (size_t)(r1 - r0), ncclDouble, C->nbr[k], C->comm, st));
   }
   B200_NCCL(g_nccl.GroupEnd());
   if(nr > 0) {
-    unpack_kernel<<<(unsigned)std::min<int64_t>((nr + 255) / 256, 148 * 8), 256, 0, S->stream>>>(nr, C->d_recv_idx, C->d_recv_buf, d_x);
+    unpack_kernel<<<(unsigned)std::min<int64_t>((nr + 255) / 256, 148 * 8), 256, 0, st>>>(nr, C->d_recv_idx, C->d_recv_buf, d_x);
     count_launch();
   }
   B200_CUDA(cudaGetLastError());
   return B200_OK;
+}
+
+// x[ghost] <- owner's value, on the system's stream
+int comm_halo_exchange(System *S, double *d_x)
+{
+  Comm *C = static_cast<Comm *>(S->comm);
+  if(!C || C->world == 1 || C->n_nbr == 0) return B200_OK;
+  return halo_on_stream(C, d_x, S->stream);
+}
+
+// y = A x with the halo update of x overlapped: the exchange runs on its own stream while the system's stream multiplies the
+// rows that read owned columns only; the rows touching ghost columns follow once the halo has landed
+int comm_spmv_overlapped(System *S, double *d_x, double *d_y)
+{
+  Comm *C = static_cast<Comm *>(S->comm);
+  if(!C || C->world == 1 || C->n_nbr == 0 || !C->d_bflag) {
+    const int rc = comm_halo_exchange(S, d_x);
+    return rc != B200_OK ? rc : spmv(S, d_x, d_y);
+  }
+  B200_CUDA(cudaEventRecord(C->ev_x, S->stream));
+  B200_CUDA(cudaStreamWaitEvent(C->cstream, C->ev_x, 0));
+  int rc = halo_on_stream(C, d_x, C->cstream);
+  if(rc != B200_OK) return rc;
+  B200_CUDA(cudaEventRecord(C->ev_halo, C->cstream));
+  rc = spmv_rows(S, d_x, d_y, C->d_bflag, nullptr, 0); // interior rows
+  if(rc != B200_OK) return rc;
+  B200_CUDA(cudaStreamWaitEvent(S->stream, C->ev_halo, 0));
+  return spmv_rows(S, d_x, d_y, nullptr, C->d_brows, C->n_brows); // rows that needed the halo
 }
 
 int comm_allreduce(System *S, double *d_buf, int count, bool max_op)
@@ -231,6 +282,33 @@ int b200_set_halo(b200_system *s, const uint8_t *owned, int n_nbr, const int32_t
   }
   B200_CUDA(cudaMalloc(&C->d_mask, (size_t)s->nInc * sizeof(double)));
   B200_CUDA(cudaMemcpy(C->d_mask, mask.data(), (size_t)s->nInc * sizeof(double), cudaMemcpyHostToDevice));
+  // interior / boundary rows for the overlapped product
+  cudaFree(C->d_bflag);
+  cudaFree(C->d_brows);
+  C->d_bflag = nullptr;
+  C->d_brows = nullptr;
+  C->n_brows = 0;
+  if(C->world > 1 && n_nbr > 0 && s->d_ia && !getenv("B200_NO_OVERLAP")) {
+    B200_CUDA(cudaMalloc(&C->d_bflag, (size_t)s->nInc));
+    boundary_flag_kernel<<<148 * 8, 256, 0, s->stream>>>(s->nInc, s->d_ia, s->d_ja, C->d_mask, C->d_bflag);
+    count_launch();
+    std::vector<uint8_t> flag(s->nInc);
+    B200_CUDA(cudaMemcpyAsync(flag.data(), C->d_bflag, (size_t)s->nInc, cudaMemcpyDeviceToHost, s->stream));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    std::vector<int32_t> rows;
+    for(int64_t i = 0; i < s->nInc; ++i)
+      if(flag[i]) rows.push_back((int32_t)i);
+    C->n_brows = (int64_t)rows.size();
+    if(C->n_brows > 0) {
+      B200_CUDA(cudaMalloc(&C->d_brows, rows.size() * sizeof(int32_t)));
+      B200_CUDA(cudaMemcpy(C->d_brows, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    if(!C->cstream) {
+      B200_CUDA(cudaStreamCreateWithFlags(&C->cstream, cudaStreamNonBlocking));
+      B200_CUDA(cudaEventCreateWithFlags(&C->ev_x, cudaEventDisableTiming));
+      B200_CUDA(cudaEventCreateWithFlags(&C->ev_halo, cudaEventDisableTiming));
+    }
+  }
   return B200_OK;
 }
 

@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t n, const int64_t *__r
 // the r01a profile asked for (latency-bound at 39 % of DRAM peak with one chain per lane).
 template <int LPR, int RPG, bool CS>
 __global__ void __launch_bounds__(256) spmv_rpg_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
-                                                       const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y)
+                                                       const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
+                                                       const uint8_t *__restrict__ skip = nullptr)
 {
   const int     lane = threadIdx.x % LPR;
   const int64_t g0   = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR;
@@ -53,8 +54,9 @@ __global__ void __launch_bounds__(256) spmv_rpg_kernel(int64_t n, const int64_t 
 #pragma unroll
     for(int r = 0; r < RPG; ++r) {
       const int64_t row = row0 + r;
-      beg[r] = row < n ? ia[row] : 0;
-      end[r] = row < n ? ia[row + 1] : 0;
+      const bool    on  = row < n && !(skip && skip[row]);
+      beg[r] = on ? ia[row] : 0;
+      end[r] = on ? ia[row + 1] : 0;
     }
     double s[RPG];
 #pragma unroll
@@ -83,8 +85,28 @@ __global__ void __launch_bounds__(256) spmv_rpg_kernel(int64_t n, const int64_t 
     if(lane == 0) {
 #pragma unroll
       for(int r = 0; r < RPG; ++r)
-        if(row0 + r < n) y[row0 + r] = s[r];
+        if(row0 + r < n && !(skip && skip[row0 + r])) y[row0 + r] = s[r];
     }
+  }
+}
+
+// the same product restricted to a row subset: rows == nullptr: every row with skip[row] == 0; else the listed rows
+template <int LPR>
+__global__ void __launch_bounds__(256) spmv_subset_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
+                                                          const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
+                                                          const uint8_t *__restrict__ skip, const int32_t *__restrict__ rows, int64_t n_rows)
+{
+  const int     lane = threadIdx.x % LPR;
+  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR, ng = (gridDim.x * (int64_t)blockDim.x) / LPR;
+  const int64_t cnt = rows ? n_rows : n;
+  for(int64_t t = g0; t < cnt; t += ng) {
+    const int64_t row = rows ? (int64_t)rows[t] : t;
+    if(skip && skip[row]) continue;
+    double s = 0.;
+    for(int64_t k = ia[row] + lane; k < ia[row + 1]; k += LPR) s += val[k] * x[ja[k]];
+#pragma unroll
+    for(int o = LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LPR);
+    if(lane == 0) y[row] = s;
   }
 }
 
@@ -330,7 +352,7 @@ void krylov_free(System *S)
   S->krylov = nullptr;
 }
 
-int spmv(System *S, const double *d_x, double *d_y)
+static int spmv_skip(System *S, const double *d_x, double *d_y, const uint8_t *skip)
 {
   const int64_t n   = S->nInc;
   const double  avg = n > 0 ? (double)S->nnz / (double)n : 0.;
@@ -341,7 +363,7 @@ int spmv(System *S, const double *d_x, double *d_y)
   {                                                                                                           \
     const int64_t blocks = (n * L / R + 255) / 256;                                                           \
     spmv_rpg_kernel<L, R, false><<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, S->stream>>>(   \
-      n, S->d_ia, S->d_ja, S->d_val, d_x, d_y);                                                               \
+      n, S->d_ia, S->d_ja, S->d_val, d_x, d_y, skip);                                                         \
   }
   if(avg > 48.)
     B200_SPMV_V(8, 2)
@@ -350,6 +372,28 @@ int spmv(System *S, const double *d_x, double *d_y)
   else
     B200_SPMV_V(2, 2)
 #undef B200_SPMV_V
+  count_launch();
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int spmv(System *S, const double *d_x, double *d_y) { return spmv_skip(S, d_x, d_y, nullptr); }
+
+int spmv_rows(System *S, const double *d_x, double *d_y, const uint8_t *skip, const int32_t *rows, int64_t n_rows)
+{
+  if(!rows) return spmv_skip(S, d_x, d_y, skip); // all rows but the flagged ones: the tuned two-rows-per-group kernel
+  const int64_t cnt = rows ? n_rows : S->nInc;
+  if(cnt <= 0) return B200_OK;
+  const double  avg = S->nInc > 0 ? (double)S->nnz / (double)S->nInc : 0.;
+  if(avg > 48.) {
+    const int64_t blocks = (cnt * 8 + 255) / 256;
+    spmv_subset_kernel<8><<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, S->stream>>>(S->nInc, S->d_ia, S->d_ja, S->d_val, d_x, d_y,
+                                                                                                  skip, rows, n_rows);
+  } else {
+    const int64_t blocks = (cnt * 4 + 255) / 256;
+    spmv_subset_kernel<4><<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, S->stream>>>(S->nInc, S->d_ia, S->d_ja, S->d_val, d_x, d_y,
+                                                                                                  skip, rows, n_rows);
+  }
   count_launch();
   B200_CUDA(cudaGetLastError());
   return B200_OK;
@@ -523,10 +567,8 @@ int gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info
     for(; k < m && its < opt->max_iter; ++k) {
       ++its;
       double *vk = K->V + (int64_t)k * n, *vk1 = K->V + (int64_t)(k + 1) * n;
-      // w = M^-1 A v_k
-      rc = comm_halo_exchange(S, vk);
-      if(rc != B200_OK) return rc;
-      rc = spmv(S, vk, K->z);
+      // w = M^-1 A v_k (several GPUs: the halo update of v_k is hidden behind the interior rows of the product)
+      rc = comm_spmv_overlapped(S, vk, K->z);
       if(rc != B200_OK) return rc;
       rc = apply_pc(S, K, pc, K->z, K->w);
       if(rc != B200_OK) return rc;

@@ -178,9 +178,12 @@ void          comm_free(System *S);
 bool          comm_active(const System *S);
 const double *comm_mask(const System *S); // 1/0 per row (owned / ghost) or nullptr on a single GPU
 int           comm_halo_exchange(System *S, double *d_x);
+int           comm_spmv_overlapped(System *S, double *d_x, double *d_y); // halo update of x hidden behind the interior rows
 int           comm_allreduce(System *S, double *d_buf, int count, bool max_op);
 // krylov.cu
 int  spmv(System *S, const double *d_x, double *d_y);
+// rows with skip[row] == 0 (rows == nullptr) or the listed rows (skip == nullptr)
+int  spmv_rows(System *S, const double *d_x, double *d_y, const uint8_t *skip, const int32_t *rows, int64_t n_rows);
 int  gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info);
 void krylov_free(System *S);
 int  max_abs(System *S, const double *d_x, int64_t n, double *out);

@@ -52,20 +52,32 @@ def strip_mesh(n: int, rank: int, world: int) -> tuple[M.Mesh, int]:
     return m, 2 * n * n
 
 
-def slab_mesh(n: int, rank: int, world: int) -> tuple[M.Mesh, int]:
-    """Slab `rank` of the [0,1]^2 x [0,world] box: n^3 owned cells (6 n^3 tetrahedra) plus one ghost layer of cells towards
-    each neighbour; the artificial cuts carry no physical boundary."""
+def layer_bounds(n: int, world: int, strong: bool) -> np.ndarray:
+    """cell-layer boundaries of the parts along the cut axis: weak scaling = n layers per part of a box of height `world`;
+    strong scaling = the n layers of the unit cube dealt out as evenly as possible"""
+    if not strong:
+        return np.arange(world + 1, dtype=np.int64) * n
+    return (np.arange(world + 1, dtype=np.int64) * n) // world
+
+
+def slab_mesh(n: int, rank: int, world: int, strong: bool = False) -> tuple[M.Mesh, int]:
+    """Slab `rank` of the [0,1]^2 x [0,world] box (weak scaling: n^3 owned cells = 6 n^3 tetrahedra per rank) or of the unit
+    cube T3D(n) cut into `world` slabs (strong scaling), plus one ghost layer of cells towards each neighbour; the artificial
+    cuts carry no physical boundary."""
+    b = layer_bounds(n, world, strong)
+    k0, k1 = int(b[rank]), int(b[rank + 1])
+    assert world == 1 or np.diff(b).min() >= 2, "every slab needs at least two cell layers"
     gb, gt = (1 if rank > 0 else 0), (1 if rank < world - 1 else 0)
-    nz = n + gb + gt
-    m = M.box_mesh(n, n, nz, nz / n, rank - gb / n, cut_bottom=rank > 0, cut_top=rank < world - 1)
+    nz = (k1 - k0) + gb + gt
+    m = M.box_mesh(n, n, nz, nz / n, (k0 - gb) / n, cut_bottom=rank > 0, cut_top=rank < world - 1)
     if rank == 0:
         m.point_pressure = 0
-    return m, 6 * n * n * n
+    return m, 6 * n * n * (k1 - k0)
 
 
-def dof_keys_and_owner(pb: PB.HostProblem, n: int, world: int):
+def dof_keys_and_owner(pb: PB.HostProblem, n: int, world: int, bounds: np.ndarray | None = None):
     """Global key and owning rank of every unknown of a strip (2-D, cut along y) or slab (3-D, cut along z) problem:
-    unit cells of size 1/n, parts of height 1."""
+    unit cells of size 1/n; parts of height 1 (n layers each) unless `bounds` gives the cell-layer boundaries."""
     num, mesh, n_dof = pb.num, pb.mesh, pb.n_dof
     axis = pb.dim - 1
     keys = np.full(n_dof, -1, np.int64)
@@ -84,7 +96,10 @@ def dof_keys_and_owner(pb: PB.HostProblem, n: int, world: int):
             keys[sel] = ((f * 4 + comp[sel]) << 58) | (iz << 38) | (iy << 19) | ix
             ic = iz
         # part r owns the coordinate range (r, r + 1] along the cut axis; the bottom side belongs to rank 0
-        r = np.ceil(ic / (2.0 * n)).astype(np.int64) - 1
+        if bounds is None:
+            r = np.ceil(ic / (2.0 * n)).astype(np.int64) - 1
+        else:
+            r = np.searchsorted(2 * np.asarray(bounds, np.int64), ic, side="left") - 1     # (2 b_r, 2 b_{r+1}]
         own[sel] = np.clip(r, 0, world - 1)
     return keys[:pb.n_inc], own[:pb.n_inc]
 
@@ -141,13 +156,14 @@ def strip_problem(n: int, rank: int, world: int, kind: str = "ns_div", quad_degr
 
 def slab_problem(n: int, rank: int, world: int, kind: str = "ns_div", quad_degree: int = 6, field_id: int = 3,
                  mu: float = 1.0 / 40.0, rho: float = 1.0, allgather=None, build_pattern: bool = False,
-                 with_source: bool = False):
-    """(HostProblem, Partition) of slab `rank` of the tetrahedral box (the 3-D counterpart of strip_problem)."""
-    m, owned_cells = slab_mesh(n, rank, world)
+                 with_source: bool = False, strong: bool = False):
+    """(HostProblem, Partition) of slab `rank` of the tetrahedral box (the 3-D counterpart of strip_problem); strong = the
+    unit cube T3D(n) cut into `world` slabs instead of one T3D(n) cube per rank."""
+    m, owned_cells = slab_mesh(n, rank, world, strong)
     pb = PB.taylor_hood(m, kind, quad_degree, field_id, mu, rho, build_pattern=build_pattern, with_source=with_source)
     if world == 1:
         return pb, None
-    keys, owner = dof_keys_and_owner(pb, n, world)
+    keys, owner = dof_keys_and_owner(pb, n, world, layer_bounds(n, world, strong) if strong else None)
     if allgather is None:
         import torch.distributed as dist
 

@@ -13,7 +13,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, n, out, dim=2):
+def _worker(rank, world, port, n, out, dim=2, strong=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import scipy.sparse as sp
@@ -31,6 +31,12 @@ def _worker(rank, world, port, n, out, dim=2):
             mg = M.rect_mesh(n, n * world, 1.0, float(world))
             mg.point_pressure = 0
             pg = PB.taylor_hood(mg, "ns_div", 8, 1, 0.05, 1.0, with_source=True)
+        elif strong:
+            # strong scaling: ONE T3D(n) cube cut into `world` slabs of (nearly) equal thickness
+            pb, part = PT.slab_problem(n, rank, world, "ns_div", 6, 3, 0.05, 1.0, build_pattern=True, with_source=False, strong=True)
+            mg = M.box_mesh(n, n, n, 1.0)
+            mg.point_pressure = 0
+            pg = PB.taylor_hood(mg, "ns_div", 6, 3, 0.05, 1.0, with_source=False)
         else:
             pb, part = PT.slab_problem(n, rank, world, "ns_div", 6, 3, 0.05, 1.0, build_pattern=True, with_source=False)
             mg = M.box_mesh(n, n, n * world, float(world))
@@ -112,6 +118,19 @@ def test_slab_partition_over_gloo():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, 2, out, 3), nprocs=world, join=True)
+    for r in range(world):
+        assert out.get(r) == "ok", out.get(r)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_strong_scaling_slabs_over_gloo(world):
+    """strong scaling (bench.py --scaling strong): one T3D(5) cube dealt out in slabs of 2+3 cell layers, one T3D(6) cube in
+    2+2+2 (a part needs two layers: its ghost layer must not reach the physical boundary of the neighbour's side)"""
+    import torch.multiprocessing as mp
+    port = 33500 + (os.getpid() + world) % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, 5 if world == 2 else 6, out, 3, True), nprocs=world, join=True)
     for r in range(world):
         assert out.get(r) == "ok", out.get(r)
 
