@@ -575,23 +575,33 @@ def newton_step(ls, sol, pb, maxit):
     from feng_b200 import capi
     S = ls.sys
     s = sol.copy()
-    S.sync()
-    t0 = time.perf_counter()
-    S.set_solution(s)
-    S.set_to_zero(3)
-    S.assemble(1)
-    S.rhs_max_norm()
-    S.assemble(2)
-    S.constrain()
-    info = S.solve(1e-8, 1e-14, 1e6, maxit, 30, ls.pc, raise_on_fail=False)
-    S.correct_solution(s)
-    S.sync()
-    dt = time.perf_counter() - t0
+    out = {}
+    # two consecutive Newton iterations from the same state: the first pays the one-time, pattern-only set-up of the
+    # preconditioner (parents, aggregates, coarse patterns); `ms` is the second, i.e. every later iteration of the Newton loop
+    for which in ("first", "steady"):
+        S.sync()
+        t0 = time.perf_counter()
+        S.set_solution(s)
+        S.set_to_zero(3)
+        S.assemble(1)
+        S.rhs_max_norm()
+        S.assemble(2)
+        S.constrain()
+        info = S.solve(1e-8, 1e-14, 1e6, maxit, 30, ls.pc, raise_on_fail=False)
+        S.correct_solution(None)
+        S.sync()
+        dt = time.perf_counter() - t0
+        out[which] = (dt * 1e3, S.last_solve_ms(), info)
+    dt_ms, solve_ms, info = out["steady"]
     its = max(int(info.iterations), 1)
-    return {"ms": dt * 1e3, "gmres_iterations": info.iterations, "gmres_max_iterations": maxit,
-            "converged": bool(info.converged), "solve_ms": S.last_solve_ms(), "solve_ms_per_iteration": S.last_solve_ms() / its,
-            "rel_residual": info.rel_residual, "pc": ls.pc,
-            "assembly_and_update_ms": dt * 1e3 - S.last_solve_ms()}
+    return {"ms": dt_ms, "gmres_iterations": info.iterations, "gmres_max_iterations": maxit, "gmres_restart": 30,
+            "converged": bool(info.converged), "solve_ms": solve_ms, "solve_ms_per_iteration": solve_ms / its,
+            "rel_residual": info.rel_residual, "rel_tol": 1e-8, "pc": ls.pc,
+            "pc_name": {1: "jacobi", 4: "amg", 5: "schur_amg", 6: "auto (Schur complement + aggregation multigrid for Taylor-Hood)"}.get(ls.pc, str(ls.pc)),
+            "assembly_and_update_ms": dt_ms - solve_ms,
+            "first_step_ms": out["first"][0], "first_step_solve_ms": out["first"][1],
+            "note": "ms = assemble residual + matrix, constrain, GMRES(30) solve to rtol 1e-8, update; first_step_* includes the one-time "
+                    "symbolic set-up of the multigrid hierarchy"}
 
 
 if __name__ == "__main__":

@@ -51,6 +51,18 @@ for formulation, fo in (("abels", 1), ("abels", 2), ("mass_averaged", 1), ("khan
         Ae.append(a)
         Be.append(b)
     v, r, _ = P.assemble()
+    # the reference's OWN finite-difference noise: the same Jacobian from a state that differs by one unit in the last
+    # place in every unknown (computeMatrixFiniteDifference divides residual differences by delta = sqrt(eps) max(|u|, 1),
+    # src/feBilinearForm.cpp:404-422, so 1e-16-level differences of the residual come back multiplied by 6.7e7)
+    sol_ulp = sol.copy()
+    sol_ulp[:P.n_inc] = np.nextafter(sol[:P.n_inc], np.inf)
+    P.set_solution(sol_ulp, sd, c0, 0.0)
+    v_ulp, _, _ = P.assemble()
+    P.set_solution(sol, sd, c0, 0.0)
+    rowmax = np.maximum.reduceat(np.abs(v), ia[:-1])
+    fd_noise = float((np.maximum.reduceat(np.abs(v_ulp - v), ia[:-1]) / rowmax).max())
+    out["fd_noise"] = fd_noise
+    print("   reference FD noise (1-ulp state change), relative to the row maximum: %.3e" % fd_noise)
     out.update(sol_init=sol0, sol=sol, sol_dot=sd, c0=c0, elements=elements, Ae=np.array(Ae), Be=np.array(Be), values=v,
                rhs=r)
     path = os.path.join(HERE, f"ref_square1_chns_{formulation}_p{fo}.npz")

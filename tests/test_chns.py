@@ -7,8 +7,11 @@ pattern of four fields) bit-exactly against the same.  GPU: the CUDA kernel thro
 Tolerances: residual 1e-12 relative to max|rhs| (north_star).  The Jacobian is a FORWARD DIFFERENCE with
 delta = sqrt(eps) max(|u|, 1) (src/feBilinearForm.cpp:170, :404-422): rounding differences of 1e-16 |R| between two
 correct evaluations of the residual are amplified by 1/delta = 6.7e7, so two implementations of the same formula agree
-to ~1e-8 of the row scale, not 1e-12 (the oracle itself matches the compiled reference to 4e-8).  The matrix tolerance
-is 1e-6 relative to the largest entry of the row.
+to ~1e-8 of the row scale, not 1e-12.  The bound is MEASURED on the reference itself: tests/golden/make_golden_chns.py
+recomputes the reference's Jacobian from a state moved by one unit in the last place in every unknown and stores the
+largest change relative to the row maximum in the fixture (`fd_noise`: 2.9e-8 CHNS_Abels P1, 3.2e-8 P2, 7.1e-8
+CHNS_MassAveraged, 5.2e-8 CHNS_Khanwale).  Matrix tolerance: 4 x that noise against the fixtures, 3e-7 (4 x the largest
+measured value) for the synthetic cases.
 """
 import os
 
@@ -17,7 +20,11 @@ import pytest
 
 from conftest import GOLDEN_DIR, assert_close_rows, assert_close_vec
 
-FD_TOL = 1e-6
+FD_TOL = 3e-7          # 4 x the largest finite-difference noise measured on the reference (see the module docstring)
+
+
+def fixture_fd_tol(g):
+    return 4.0 * float(g["fd_noise"]) if "fd_noise" in g else FD_TOL
 KHANWALE = (40., 25., 0.07, 3.0, 1.7, 1.3, 0.7)      # Re, Pe, Cn, We, Fr, rhoA, rhoB
 DT = 0.02
 
@@ -119,10 +126,10 @@ def test_oracle_vs_golden_fixture(name):
     Ae, Be, adr = CO.element_systems(pb, g["sol"], g["sol_dot"], float(g["c0"]), sol_n=sol_n, dt=dt)
     for i, e in enumerate(g["elements"]):
         assert np.abs(Be[e] - g["Be"][i]).max() <= 1e-13 * np.abs(g["Be"][i]).max()
-        assert np.abs(Ae[e] - g["Ae"][i]).max() <= FD_TOL * np.abs(g["Ae"][i]).max()
+        assert np.abs(Ae[e] - g["Ae"][i]).max() <= fixture_fd_tol(g) * np.abs(g["Ae"][i]).max()
     ov, orr = CO.assemble(pb, g["ia"], g["ja"], g["sol"], g["sol_dot"], float(g["c0"]), sol_n=sol_n, dt=dt)
     assert_close_vec(orr, g["rhs"], 1e-13, "rhs")
-    assert_close_rows(ov, g["values"], g["ia"], FD_TOL, "FD matrix")
+    assert_close_rows(ov, g["values"], g["ia"], fixture_fd_tol(g), "FD matrix")
 
 
 def test_fd_jacobian_is_the_derivative_of_the_residual():
@@ -209,7 +216,7 @@ def test_cuda_chns_vs_golden_fixture(name):
     S.set_to_zero(3)
     S.assemble(3, False)
     assert_close_vec(S.get_rhs(), g["rhs"], 1e-12, "rhs")
-    assert_close_rows(S.get_matrix_values(), g["values"], g["ia"], FD_TOL, "FD matrix")
+    assert_close_rows(S.get_matrix_values(), g["values"], g["ia"], fixture_fd_tol(g), "FD matrix")
 
 
 @pytest.mark.gpu
