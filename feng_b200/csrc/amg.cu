@@ -630,6 +630,149 @@ __global__ void amg_dense_apply_kernel(int n, const double *__restrict__ inv, co
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------
+// global coarsest level (several GPUs)
+// ----------------------------------------------------------------------------------------------------------
+struct AmgChain {
+  const int32_t *par[AMG_MAX_LEVELS];
+  int            n;
+};
+
+// gid[v] = off + (coarsest aggregate of the level-1 unknown of vertex DOF v) for the owned vertex unknowns, -1 elsewhere
+__global__ void amg_gc_gid_kernel(int64_t n, const uint8_t *__restrict__ pkind0, const int32_t *__restrict__ par00, AmgChain ch, int off,
+                                  double *gid)
+{
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double g = -1.;
+    if(pkind0[i] == 1) {
+      int32_t cur = par00[i];
+      for(int l = 0; l < ch.n && cur >= 0; ++l) cur = ch.par[l][cur];
+      if(cur >= 0) g = (double)(off + cur);
+    }
+    gid[i] = g;
+  }
+}
+
+// (global coarse id, weight) of every unknown of the field, owned or ghost, from the element tables
+__global__ void amg_gc_parent_kernel(int64_t nElm, const int32_t *__restrict__ adr, int nloc, int nv, int nc, int dim, int64_t nInc,
+                                     const uint8_t *__restrict__ fld_all, int fld_lo, int fld_hi, const double *__restrict__ gid, int32_t *p0,
+                                     int32_t *p1, uint8_t *kind)
+{
+  const int     nS = nloc / nc;
+  const int64_t tot = nElm * nloc;
+  for(int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = idx / nloc;
+    const int     k = (int)(idx - e * nloc);
+    const int     a = k / nc, c = k - a * nc;
+    const int64_t dof = adr[idx];
+    if(dof >= nInc || fld_all[dof] < fld_lo || fld_all[dof] >= fld_hi) continue;
+    if(a < nv) {
+      p0[dof]   = (int32_t)gid[dof];
+      p1[dof]   = -1;
+      kind[dof] = 1;
+    } else if(a < nS) {
+      const int     ed = a - nv;
+      const int     va = dim == 2 ? c_edge_tri[ed][0] : c_edge_tet[ed][0], vb = dim == 2 ? c_edge_tri[ed][1] : c_edge_tet[ed][1];
+      const int64_t da = adr[e * nloc + va * nc + c], db = adr[e * nloc + vb * nc + c];
+      int32_t       pa = da < nInc ? (int32_t)gid[da] : -1, pb = db < nInc ? (int32_t)gid[db] : -1;
+      if(pa < pb) {
+        const int32_t t = pa;
+        pa = pb;
+        pb = t;
+      }
+      p0[dof]   = pa;
+      p1[dof]   = pb;
+      kind[dof] = 2;
+    }
+  }
+}
+
+// dense global coarse operator: Ac[I][J] += w_iI w_jJ a_ij over the OWNED rows of the field (owned = local pkind != 0), columns
+// of the same component, owned or ghost
+template <int LPR>
+__global__ void __launch_bounds__(256) amg_gc_galerkin_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
+                                                              const double *__restrict__ val, const uint8_t *__restrict__ fld_all,
+                                                              const uint8_t *__restrict__ pkind0, const int32_t *__restrict__ p0,
+                                                              const int32_t *__restrict__ p1, const uint8_t *__restrict__ kind, int nc,
+                                                              double *Ac)
+{
+  const int     lane = threadIdx.x % LPR;
+  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR, ng = (gridDim.x * (int64_t)blockDim.x) / LPR;
+  for(int64_t i = g0; i < n; i += ng) {
+    if(pkind0[i] == 0) continue;
+    const int32_t I0 = p0[i], I1 = p1[i];
+    const double  wi = kind[i] == 2 ? 0.5 : 1.;
+    const int     fi = fld_all[i];
+    for(int64_t k = ia[i] + lane; k < ia[i + 1]; k += LPR) {
+      const int32_t j = ja[k];
+      if(kind[j] == 0 || fld_all[j] != fi) continue;
+      const double  v = val[k] * wi * (kind[j] == 2 ? 0.5 : 1.);
+      const int32_t J0 = p0[j], J1 = p1[j];
+      if(I0 >= 0) {
+        if(J0 >= 0) atomicAdd(Ac + (size_t)I0 * nc + J0, v);
+        if(J1 >= 0) atomicAdd(Ac + (size_t)I0 * nc + J1, v);
+      }
+      if(I1 >= 0) {
+        if(J0 >= 0) atomicAdd(Ac + (size_t)I1 * nc + J0, v);
+        if(J1 >= 0) atomicAdd(Ac + (size_t)I1 * nc + J1, v);
+      }
+    }
+  }
+}
+
+// Gauss-Jordan without pivoting, one launch per pivot: M is n x 2n = [A | I]; after n steps the right half is A^-1.  Empty
+// rows / columns (an aggregate none of whose unknowns is active) get a unit pivot.
+__global__ void amg_gj_step_kernel(int n, int p, double *M)
+{
+  const int    ld = 2 * n;
+  const double piv = M[(size_t)p * ld + p];
+  const double ip = piv != 0. ? 1. / piv : 1.;
+  for(int r = blockIdx.x; r < n; r += gridDim.x) {
+    if(r == p) continue;
+    const double f = M[(size_t)r * ld + p] * ip;
+    if(f == 0.) continue;
+    for(int j = threadIdx.x; j < ld; j += blockDim.x)
+      if(j != p) M[(size_t)r * ld + j] -= f * M[(size_t)p * ld + j];
+  }
+}
+
+__global__ void amg_gj_finish_kernel(int n, int p, double *M)
+{
+  const int    ld = 2 * n;
+  const double piv = M[(size_t)p * ld + p];
+  const double ip = piv != 0. ? 1. / piv : 1.;
+  // column p of the other rows becomes zero, the pivot row is scaled (runs after amg_gj_step_kernel of the same p)
+  for(int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ld + n; idx += gridDim.x * blockDim.x) {
+    if(idx < ld) {
+      if(idx != p) M[(size_t)p * ld + idx] *= ip;
+    } else {
+      const int r = idx - ld;
+      if(r != p) M[(size_t)r * ld + p] = 0.;
+    }
+  }
+}
+
+__global__ void amg_gj_pivot_one_kernel(int n, int p, double *M) { M[(size_t)p * 2 * n + p] = 1.; }
+
+__global__ void amg_gc_fill_identity_kernel(int n, const double *__restrict__ A, double *M)
+{
+  const int ld = 2 * n;
+  for(int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < (int64_t)n * ld; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / ld), j = (int)(idx - (int64_t)i * ld);
+    M[idx] = j < n ? A[(size_t)i * n + j] : (j - n == i ? 1. : 0.);
+  }
+}
+
+__global__ void amg_gc_extract_kernel(int n, const double *__restrict__ M, double *inv)
+{
+  const int ld = 2 * n;
+  for(int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < (int64_t)n * n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / n), j = (int)(idx - (int64_t)i * n);
+    inv[idx] = M[(size_t)i * ld + n + j];
+  }
+}
+
 // ----------------------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------------------
@@ -662,6 +805,17 @@ void amg_free(Amg *A)
   cudaFree(A->cinv);
   cudaFree(A->d_nrm);
   cudaFree(A->d_active0);
+  cudaFree(A->gc_p0);
+  cudaFree(A->gc_p1);
+  cudaFree(A->gc_kind);
+  cudaFree(A->gc_A);
+  cudaFree(A->gc_inv);
+  cudaFree(A->gc_b);
+  cudaFree(A->gc_x);
+  A->gc_p0 = A->gc_p1 = nullptr;
+  A->gc_kind = nullptr;
+  A->gc_A = A->gc_inv = A->gc_b = A->gc_x = nullptr;
+  A->gc_active = false;
   A->dense = A->cinv = A->d_nrm = nullptr;
   A->d_active0 = nullptr;
   A->symbolic = false;
@@ -837,7 +991,7 @@ static int aggregate_level(System *S, Amg *A, int l, int64_t *ncoarse)
 
 // Symbolic set-up.  fld_lo..fld_hi-1 = the field ids (AmgFieldMap) of the rows the hierarchy acts on; space = the
 // interpolation space of that field (P2 -> P1 level when it has mid-edge functions).
-int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int fld_hi, int space)
+int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int fld_hi, int space, const uint8_t *d_fld_all)
 {
   amg_free(A);
   const int64_t n = S->nInc;
@@ -969,7 +1123,60 @@ int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int 
     B200_CUDA(cudaMalloc(&A->dense, (size_t)A->dense_n * 2 * A->dense_n * sizeof(double)));
     B200_CUDA(cudaMalloc(&A->cinv, (size_t)A->dense_n * A->dense_n * sizeof(double)));
   }
+  // several GPUs: global coarsest level (P2 hierarchies only; every rank must have reached a dense coarsest level)
+  if(comm_active(S) && d_fld_all && p2 && !getenv("B200_AMG_LOCAL_COARSE")) {
+    const int world = comm_world(S), rank = comm_rank(S);
+    std::vector<double> cnt(world + 1, 0.);
+    cnt[rank]  = (double)A->dense_n;
+    cnt[world] = (A->dense_n > 0 && A->L.size() >= 2) ? 0. : 1.; // somebody without a dense level: no global level
+    double *d_cnt = nullptr;
+    B200_CUDA(cudaMalloc(&d_cnt, (world + 1) * sizeof(double)));
+    B200_CUDA(cudaMemcpyAsync(d_cnt, cnt.data(), (world + 1) * sizeof(double), cudaMemcpyHostToDevice, S->stream));
+    int rc = comm_allreduce(S, d_cnt, world + 1, false);
+    if(rc != B200_OK) return rc;
+    B200_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (world + 1) * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    cudaFree(d_cnt);
+    int tot = 0, off = 0;
+    for(int r = 0; r < world; ++r) {
+      if(r == rank) off = tot;
+      tot += (int)cnt[r];
+    }
+    if(cnt[world] == 0. && tot > 0 && tot <= 4096) {
+      A->gc_n    = tot;
+      A->gc_off  = off;
+      A->gc_nloc = A->dense_n;
+      // global id of every owned vertex unknown, then of the ghost ones through the halo plan of the fine vectors
+      double *gid = nullptr;
+      B200_CUDA(cudaMalloc(&gid, (size_t)n * sizeof(double)));
+      AmgChain ch;
+      ch.n = 0;
+      for(size_t l = 1; l + 1 < A->L.size(); ++l) ch.par[ch.n++] = A->L[l].par0;
+      amg_gc_gid_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, A->L[0].pkind, A->L[0].par0, ch, off, gid);
+      count_launch();
+      rc = comm_halo_exchange(S, gid);
+      if(rc != B200_OK) return rc;
+      B200_CUDA(cudaMalloc(&A->gc_p0, (size_t)n * sizeof(int32_t)));
+      B200_CUDA(cudaMalloc(&A->gc_p1, (size_t)n * sizeof(int32_t)));
+      B200_CUDA(cudaMalloc(&A->gc_kind, (size_t)n));
+      B200_CUDA(cudaMemsetAsync(A->gc_p0, 0xff, (size_t)n * sizeof(int32_t), S->stream));
+      B200_CUDA(cudaMemsetAsync(A->gc_p1, 0xff, (size_t)n * sizeof(int32_t), S->stream));
+      B200_CUDA(cudaMemsetAsync(A->gc_kind, 0, (size_t)n, S->stream));
+      amg_gc_parent_kernel<<<GRID, 256, 0, S->stream>>>(S->nElm, sp.d_adr, nloc, nv, sp.nc, S->dim, n, d_fld_all, fld_lo, fld_hi, gid, A->gc_p0,
+                                                        A->gc_p1, A->gc_kind);
+      count_launch();
+      B200_CUDA(cudaStreamSynchronize(S->stream));
+      cudaFree(gid);
+      B200_CUDA(cudaMalloc(&A->gc_A, (size_t)tot * 2 * tot * sizeof(double)));
+      B200_CUDA(cudaMalloc(&A->gc_inv, (size_t)tot * tot * sizeof(double)));
+      B200_CUDA(cudaMalloc(&A->gc_b, (size_t)tot * sizeof(double)));
+      B200_CUDA(cudaMalloc(&A->gc_x, (size_t)tot * sizeof(double)));
+      A->gc_active = true;
+      A->d_fld_all = d_fld_all;
+    }
+  }
   if(A->verbose) {
+    if(A->gc_active) fprintf(stderr, "[feng_b200] amg: global coarsest level, %d unknowns (%d local at offset %d)\n", A->gc_n, A->gc_nloc, A->gc_off);
     fprintf(stderr, "[feng_b200] amg hierarchy:");
     for(auto &L : A->L) fprintf(stderr, " (%lld rows, %lld nnz)", (long long)L.n, (long long)L.nnz);
     fprintf(stderr, " dense %d\n", A->dense_n);
@@ -1052,7 +1259,28 @@ int amg_setup_numeric(System *S, Amg *A)
     int        rc = power_iteration(S, A, l, warm ? 3 : (l == 0 ? 8 : 12));
     if(rc != B200_OK) return rc;
   }
-  if(A->dense_n > 0) {
+  if(A->gc_active) {
+    const int      nc = A->gc_n;
+    const AmgLevel &L0 = A->L[0];
+    double        *Ac = A->gc_inv; // assembled here, all-reduced, then copied into [A | I]
+    B200_CUDA(cudaMemsetAsync(Ac, 0, (size_t)nc * nc * sizeof(double), S->stream));
+    const int64_t blocks = (L0.n * 8 + 255) / 256;
+    amg_gc_galerkin_kernel<8><<<(unsigned)std::min<int64_t>(blocks, 148 * 32), 256, 0, S->stream>>>(L0.n, L0.ia, L0.ja, L0.val, A->d_fld_all, L0.pkind,
+                                                                                                 A->gc_p0, A->gc_p1, A->gc_kind, nc, Ac);
+    count_launch();
+    // NCCL counts are size_t: nc^2 <= 16.8 M doubles
+    for(size_t o = 0; o < (size_t)nc * nc; o += (size_t)1 << 24) {
+      const int rc = comm_allreduce(S, Ac + o, (int)std::min<size_t>((size_t)1 << 24, (size_t)nc * nc - o), false);
+      if(rc != B200_OK) return rc;
+    }
+    amg_gc_fill_identity_kernel<<<GRID, 256, 0, S->stream>>>(nc, Ac, A->gc_A);
+    for(int p = 0; p < nc; ++p) {
+      amg_gj_step_kernel<<<std::min(nc, 148 * 4), 256, 0, S->stream>>>(nc, p, A->gc_A);
+      amg_gj_finish_kernel<<<(2 * nc + nc + 255) / 256, 256, 0, S->stream>>>(nc, p, A->gc_A);
+    }
+    amg_gc_extract_kernel<<<GRID, 256, 0, S->stream>>>(nc, A->gc_A, A->gc_inv);
+    count_launch(2 + 2 * nc);
+  } else if(A->dense_n > 0) {
     const AmgLevel &C = A->L.back();
     amg_dense_fill_kernel<<<std::min(A->dense_n, 148 * 4), 128, 0, S->stream>>>(A->dense_n, C.ia, C.ja, C.val, A->dense);
     amg_gauss_jordan_kernel<<<1, 1024, 0, S->stream>>>(A->dense_n, A->dense, A->cinv);
@@ -1106,6 +1334,17 @@ static int cycle(System *S, Amg *A, int l, const double *b, double *x, bool zero
   const int nl = (int)A->L.size();
   if(L.n <= 0) return B200_OK;
   if(l == nl - 1) {
+    if(A->gc_active) {
+      // global coarsest level: every rank contributes its slice of the right-hand side, solves redundantly, keeps its slice
+      B200_CUDA(cudaMemsetAsync(A->gc_b, 0, (size_t)A->gc_n * sizeof(double), S->stream));
+      B200_CUDA(cudaMemcpyAsync(A->gc_b + A->gc_off, b, (size_t)A->gc_nloc * sizeof(double), cudaMemcpyDeviceToDevice, S->stream));
+      int rc = comm_allreduce(S, A->gc_b, A->gc_n, false);
+      if(rc != B200_OK) return rc;
+      amg_dense_apply_kernel<<<std::max(1, std::min((A->gc_n + 7) / 8, 148 * 4)), 256, 0, S->stream>>>(A->gc_n, A->gc_inv, A->gc_b, A->gc_x);
+      count_launch();
+      B200_CUDA(cudaMemcpyAsync(x, A->gc_x + A->gc_off, (size_t)A->gc_nloc * sizeof(double), cudaMemcpyDeviceToDevice, S->stream));
+      return B200_OK;
+    }
     if(A->dense_n > 0) {
       amg_dense_apply_kernel<<<std::max(1, std::min((A->dense_n + 7) / 8, 148 * 4)), 256, 0, S->stream>>>(A->dense_n, A->cinv, b, x);
       count_launch();

@@ -51,12 +51,23 @@ struct Amg {
   int                   pre_degree = 0;                            // B200_AMG_PRE: degree of the pre-smoother (0 = cheb_degree)
   double                cheb_ratio = AMG_CHEB_RATIO;               // B200_AMG_RATIO
   bool                  use_f32 = true;                            // B200_AMG_F32=0: level 0 works on the FP64 system matrix
+  // several GPUs: the coarsest level is GLOBAL.  Levels 0 .. L-1 are rank-local (block-Jacobi across ranks, couplings to ghost
+  // columns dropped); the coarsest Galerkin operator is assembled from the fine matrix INCLUDING the couplings across the
+  // partition cuts, summed over the ranks, inverted redundantly and applied to the all-reduced coarse right-hand side, so
+  // that smooth error spanning several sub-domains is removed in one cycle (the iteration count of a one-dimensional chain
+  // of sub-domains otherwise grows with its length)
+  bool     gc_active = false;
+  int      gc_n = 0, gc_off = 0, gc_nloc = 0;
+  int32_t *gc_p0 = nullptr, *gc_p1 = nullptr; // [n fine] global coarse ids of the (up to two) vertex parents, -1 = none
+  uint8_t *gc_kind = nullptr;                 // [n fine] 0 none, 1 vertex unknown, 2 mid-edge unknown (weights 1 / one half)
+  const uint8_t *d_fld_all = nullptr;         // field map with the ghost rows still labelled (owned by the preconditioner)
+  double  *gc_A = nullptr, *gc_inv = nullptr, *gc_b = nullptr, *gc_x = nullptr;
 };
 
 void amg_free(Amg *A);
 int  amg_build_field_map(System *S, uint8_t **d_fld);
 int  amg_mask_ghosts(System *S, uint8_t *d_fld);
-int  amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int fld_hi, int space);
+int  amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int fld_hi, int space, const uint8_t *d_fld_all = nullptr);
 int  amg_setup_numeric(System *S, Amg *A);
 int  amg_vcycle(System *S, Amg *A, const double *b, double *x);
 

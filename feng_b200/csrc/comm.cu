@@ -142,6 +142,18 @@ const double *comm_mask(const System *S)
   return C ? C->d_mask : nullptr;
 }
 
+int comm_rank(const System *S)
+{
+  const Comm *C = static_cast<const Comm *>(S->comm);
+  return C ? C->rank : 0;
+}
+
+int comm_world(const System *S)
+{
+  const Comm *C = static_cast<const Comm *>(S->comm);
+  return C ? C->world : 1;
+}
+
 bool comm_active(const System *S)
 {
   const Comm *C = static_cast<const Comm *>(S->comm);

@@ -35,7 +35,7 @@ static const int GRID = 148 * 8;
 
 struct Precond {
   int      kind = 0;
-  uint8_t *d_fld = nullptr;
+  uint8_t *d_fld = nullptr, *d_fld_all = nullptr; // field id per row: ghost rows masked out / still labelled
   Amg      amg;
   // Schur part
   double  *d_alpha = nullptr;  // [n] S^-1 scaling of the pressure rows (0 elsewhere)
@@ -163,6 +163,7 @@ void precond_free(System *S)
   if(!P) return;
   amg_free(&P->amg);
   cudaFree(P->d_fld);
+  cudaFree(P->d_fld_all);
   cudaFree(P->d_alpha);
   cudaFree(P->d_pmass);
   cudaFree(P->d_pstart);
@@ -289,11 +290,15 @@ int precond_setup(System *S, int pc)
       P->pmin = thrust::transform_reduce(pol, c0, c0 + n, FldIs{P->d_fld, AMG_FLD_P, AMG_FLD_P + 1, n, true}, n, MinOp());
       P->umax = thrust::transform_reduce(pol, c0, c0 + n, FldIs{P->d_fld, 0, AMG_FLD_P, -1, false}, (int64_t)-1, MaxOp());
     }
+    if(comm_active(S)) {
+      B200_CUDA(cudaMalloc(&P->d_fld_all, (size_t)S->nInc));
+      B200_CUDA(cudaMemcpyAsync(P->d_fld_all, P->d_fld, (size_t)S->nInc, cudaMemcpyDeviceToDevice, S->stream));
+    }
     rc = amg_mask_ghosts(S, P->d_fld);
     if(rc != B200_OK) return rc;
     // B200_PC_AMG on a Taylor-Hood system would treat the pressure rows as part of the elliptic field: refuse
     const int fld_hi = pc == B200_PC_SCHUR_AMG ? S->dim : S->spaces[S->su].nc;
-    rc = amg_setup_symbolic(S, &P->amg, P->d_fld, 0, fld_hi, S->su);
+    rc = amg_setup_symbolic(S, &P->amg, P->d_fld, 0, fld_hi, S->su, P->d_fld_all);
     if(rc != B200_OK) return rc;
     if(pc == B200_PC_SCHUR_AMG) {
       rc = schur_symbolic(S, P);

@@ -176,6 +176,8 @@ int  flush_zero(System *S, int what);
 // comm.cu
 void          comm_free(System *S);
 bool          comm_active(const System *S);
+int           comm_rank(const System *S);
+int           comm_world(const System *S);
 const double *comm_mask(const System *S); // 1/0 per row (owned / ghost) or nullptr on a single GPU
 int           comm_halo_exchange(System *S, double *d_x);
 int           comm_spmv_overlapped(System *S, double *d_x, double *d_y); // halo update of x hidden behind the interior rows
