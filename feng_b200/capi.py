@@ -28,7 +28,7 @@ SYMBOLS = [
 
 SCATTER_ATOMIC, SCATTER_COLORED = 0, 1
 ASSEMBLY_AUTO, ASSEMBLY_SCATTER, ASSEMBLY_GATHER = 0, 1, 2
-PC_NONE, PC_JACOBI, PC_BLOCK_JACOBI, PC_ILU0, PC_AMG, PC_SCHUR_AMG, PC_AUTO = 0, 1, 2, 3, 4, 5, 6
+PC_NONE, PC_JACOBI, PC_BLOCK_JACOBI, PC_AMG, PC_SCHUR_AMG, PC_AUTO = 0, 1, 2, 4, 5, 6
 
 
 class SolverOptions(C.Structure):

@@ -566,6 +566,31 @@ int b200_set_blocks(b200_system *s, int64_t n_blocks, const int64_t *block_ptr, 
     set_error("b200_set_blocks: bad arguments");
     return B200_ERR_ARG;
   }
+  if(s->nInc == 0) {
+    set_error("b200_set_blocks: set the pattern first");
+    return B200_ERR_ARG;
+  }
+  if(block_ptr[0] != 0) {
+    set_error("b200_set_blocks: block_ptr[0] must be 0");
+    return B200_ERR_ARG;
+  }
+  {
+    std::vector<char> seen(s->nInc, 0);
+    for(int64_t b = 0; b < n_blocks; ++b) {
+      if(block_ptr[b + 1] <= block_ptr[b] || block_ptr[b + 1] - block_ptr[b] > 32) {
+        set_error("b200_set_blocks: every block needs 1..32 rows");
+        return B200_ERR_ARG;
+      }
+      for(int64_t k = block_ptr[b]; k < block_ptr[b + 1]; ++k) {
+        const int64_t r = block_rows[k];
+        if(r < 0 || r >= s->nInc || seen[r]) {
+          set_error("b200_set_blocks: row out of range or listed twice");
+          return B200_ERR_ARG;
+        }
+        seen[r] = 1;
+      }
+    }
+  }
   s->n_blocks = n_blocks;
   s->block_ptr.assign(block_ptr, block_ptr + n_blocks + 1);
   s->block_rows.assign(block_rows, block_rows + block_ptr[n_blocks]);

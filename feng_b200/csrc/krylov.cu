@@ -511,9 +511,9 @@ int gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info
     rc = precond_setup(S, pc);
     if(rc != B200_OK) return rc;
   }
-  if(pc == B200_PC_ILU0) {
-    set_error("B200_PC_ILU0 is not implemented yet");
-    return B200_ERR_UNSUPP;
+  if(pc < B200_PC_NONE || pc > B200_PC_SCHUR_AMG || pc == 3) {
+    set_error("b200_solve: unknown preconditioner");
+    return B200_ERR_ARG;
   }
   if(pc == B200_PC_JACOBI || pc == B200_PC_BLOCK_JACOBI) {
     jacobi_setup_kernel<<<GRID, 256, 0, S->stream>>>(n, S->d_ia, S->d_ja, S->d_val, K->dinv);
@@ -522,6 +522,14 @@ int gmres_solve(System *S, const b200_solver_options *opt, b200_solve_info *info
   if(pc == B200_PC_BLOCK_JACOBI) {
     rc = setup_blocks(S, K);
     if(rc != B200_OK) return rc;
+    int flag = 0;
+    B200_CUDA(cudaMemcpyAsync(&flag, K->d_flag, sizeof(int), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    if(flag) {
+      set_error("B200_PC_BLOCK_JACOBI: a diagonal block is singular (e.g. a block of pressure rows only: the P-P block of a Taylor-Hood "
+                "system is zero, src/feCompressedRowStorage.cpp:33) -- put every pressure row in a block with velocity rows");
+      return B200_ERR_SOLVER;
+    }
   }
 
   double *hbuf = K->h, *hacc = K->h + (m + 1), *nrm = K->h + (2 * m + 2);

@@ -96,8 +96,10 @@ enum {
 enum {
   B200_PC_NONE         = 0,
   B200_PC_JACOBI       = 1, /* point Jacobi; zero diagonals (pressure rows of Taylor-Hood) are replaced by 1 */
-  B200_PC_BLOCK_JACOBI = 2, /* dense LU of the diagonal blocks given by b200_set_blocks                      */
-  B200_PC_ILU0         = 3, /* ILU(0) on the CSR pattern (PETSc's sequential default, src/feLinearSystem.h:198) */
+  B200_PC_BLOCK_JACOBI = 2, /* dense inverses of the diagonal blocks given by b200_set_blocks (<= 32 rows each); rows outside
+                               every block fall back to point Jacobi; a singular block is reported (B200_ERR_SOLVER)    */
+  /* 3 is not used: PETSc's sequential default, ILU(0) (src/feLinearSystem.h:198), is a chain of sparse triangular solves and is
+     replaced on this hardware by the multigrid-based preconditioners below                                              */
   B200_PC_AMG          = 4, /* one multigrid V-cycle on the whole matrix (scalar diffusion-type systems): P2 -> P1 on the same
                                mesh, then MIS(2) aggregation levels, Chebyshev-Jacobi smoothing (csrc/amg.cu)              */
   B200_PC_SCHUR_AMG    = 5, /* Taylor-Hood saddle-point systems: block upper-triangular preconditioner, velocity block by

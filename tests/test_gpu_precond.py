@@ -79,3 +79,29 @@ def test_restart_is_validated():
     ls = _assemble(pb, pb.sol.copy())
     with pytest.raises(RuntimeError):
         ls.sys.solve(restart=100000, pc=capi.PC_JACOBI)
+
+
+def test_block_jacobi_node_blocks_and_validation():
+    """B200_PC_BLOCK_JACOBI: velocity node blocks (the dim components of one node) on a Stokes system with the pressure essential on
+    the boundary; argument validation of b200_set_blocks; a block of pressure rows alone (zero P-P block) is reported singular."""
+    from feng_b200 import capi, mesh as M, problems as PB
+    pb = PB.taylor_hood(M.square_mesh(6), "stokes_div", 8, 0, 1.0, 1.0, p_essential=True)
+    ls = _assemble(pb, pb.sol.copy())
+    A, r, du_ref = _direct(pb, ls)
+    nodes = pb.adrU.reshape(-1, pb.dim)
+    nodes = np.unique(nodes[(nodes < pb.n_inc).all(1)], axis=0)              # both components unknown
+    ptr = np.arange(nodes.shape[0] + 1, dtype=np.int64) * pb.dim
+    ls.sys.set_blocks(ptr, nodes.reshape(-1).astype(np.int64))
+    info = ls.sys.solve(rel_tol=1e-10, max_iter=20000, restart=100, pc=capi.PC_BLOCK_JACOBI)
+    assert info.converged == 1
+    assert np.abs(ls.sys.get_du() - du_ref).max() <= 1e-6 * np.abs(du_ref).max()
+    info_j = ls.sys.solve(rel_tol=1e-10, max_iter=20000, restart=100, pc=capi.PC_JACOBI)
+    assert info.iterations <= info_j.iterations
+    with pytest.raises(RuntimeError):                                        # row out of range
+        ls.sys.set_blocks(np.array([0, 2], np.int64), np.array([0, pb.n_inc], np.int64))
+    with pytest.raises(RuntimeError):                                        # the same row twice
+        ls.sys.set_blocks(np.array([0, 2], np.int64), np.array([3, 3], np.int64))
+    prow = np.unique(pb.adrP[pb.adrP < pb.n_inc])[:2].astype(np.int64)
+    ls.sys.set_blocks(np.array([0, 2], np.int64), prow)                      # pressure rows only: singular block
+    with pytest.raises(RuntimeError):
+        ls.sys.solve(rel_tol=1e-10, max_iter=10, restart=10, pc=capi.PC_BLOCK_JACOBI)
