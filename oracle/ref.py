@@ -231,6 +231,19 @@ class RefProblem:
         return sol, dict(errU=out[0], errP=out[1], n_solves=int(out[2]), krylov_iterations=int(out[3]),
                          norm_axb=out[4], converged=bool(out[5]))
 
+    def transient(self, b200=False, scheme=2, t0=0.0, t1=0.1, n_steps=3, tol_res=1e-10, tol_cor=1e-10, max_iter=20, rel_tol=1e-10,
+                  pc=6, restart=30, lin_max_iter=10000):
+        """n_steps of the reference's unmodified BDF1 / BDF2 integrator + Newton loop from the recipe's initial state, on the CPU
+        stub backend or (b200=True) on the CUDA backend through the adapter -> (solution, dict)"""
+        sol = np.zeros(self.n_dof)
+        out = np.zeros(4)
+        opts = np.array([pc, restart, lin_max_iter], np.int32)
+        rc = self.L.ref_transient(self.h, int(b200), int(scheme), C.c_double(t0), C.c_double(t1), int(n_steps), C.c_double(tol_res),
+                                  C.c_double(tol_cor), int(max_iter), C.c_double(rel_tol), _p(opts, C.c_int32), _p(sol), _p(out))
+        if rc != 0:
+            raise RuntimeError(f"transient run failed rc={rc}")
+        return sol, dict(n_solves=int(out[0]), krylov_iterations=int(out[1]), converged=bool(out[2]))
+
     def assemble_b200(self, matrix=True, residual=True, device_pattern=False):
         """One assembly of the current state by the CUDA backend, driven through adapter/feLinearSystemB200.h from the
         reference's own host objects (b200=True instances only)."""

@@ -1094,6 +1094,56 @@ int ref_newton(void *h, double tolRes, double tolCor, int maxIter, double *sol_o
   return 0;
 }
 
+// Transient run through the reference's unmodified time integrators (BDF1 / BDF2, src/feTimeIntegration.cpp) and Newton loop,
+// from the recipe's initial state: scheme 1 = BDF1, 2 = BDF2; backend 0 = CPU stub (Eigen SparseLU), 1 = the product's
+// feLinearSystemB200 (needs WITH_B200_ADAPTER).  opts = {pc, restart, linear max_iter}.  out: number of linear solves, total
+// Krylov iterations, converged flag of the last solve.
+int ref_transient(void *h, int backend, int scheme, double t0, double t1, int nSteps, double tolRes, double tolCor, int maxIter,
+                  double relTol, const int *opts, double *sol_out, double *out)
+{
+  RefProblem *P = (RefProblem *)h;
+  P->sol->initialize(P->mesh);
+  feLinearSystem *sys = nullptr;
+  bool            own = false;
+  if(backend == 1) {
+#ifdef WITH_B200_ADAPTER
+    feB200Options o;
+    o.preconditioner = opts[0];
+    o.restart        = opts[1];
+    if(createLinearSystemB200(sys, P->forms, P->numbering, o) != FE_STATUS_OK) return -1;
+    sys->setRelativeTol(relTol);
+    sys->setMaxIter(opts[2]);
+    own = true;
+#else
+    return -9;
+#endif
+  } else
+    sys = P->sys;
+  feNLSolverOptions     NL{tolRes, tolCor, 1e4, (double)maxIter, 4, 1e-1};
+  std::vector<feNorm *> norms = {};
+  TimeIntegrator       *solver;
+  const timeIntegratorScheme sch = scheme == 1 ? timeIntegratorScheme::BDF1 : timeIntegratorScheme::BDF2;
+  if(createTimeIntegrator(solver, sch, NL, sys, P->sol, P->mesh, norms, {nullptr, 1, ""}, t0, t1, nSteps) != FE_STATUS_OK) {
+    if(own) delete sys;
+    return -2;
+  }
+  const feStatus st = solver->makeSteps(nSteps);
+  delete solver;
+  out[0] = out[1] = out[2] = 0.;
+#ifdef WITH_B200_ADAPTER
+  if(backend == 1) {
+    feLinearSystemB200 *b = static_cast<feLinearSystemB200 *>(sys);
+    out[0] = b->getNumSolves();
+    out[1] = (double)b->getTotalKrylovIterations();
+    out[2] = b->getLastSolveInfo().converged;
+  }
+#endif
+  if(own) delete sys;
+  if(st != FE_STATUS_OK) return -3;
+  std::memcpy(sol_out, P->sol->getSolution().data(), P->sol->getNumDOFs() * sizeof(double));
+  return 0;
+}
+
 #ifdef WITH_B200_ADAPTER
 // The same stationary solve as ref_newton, but the UNMODIFIED createTimeIntegrator -> solveNewtonRaphson drives the
 // product's feLinearSystemB200 backend (adapter/feLinearSystemB200.h -> libfeng_b200.so) instead of the CPU stub:

@@ -139,3 +139,18 @@ def test_space_dependent_diffusivity_is_tabulated():
     s_cpu, _ = P.newton(1e-10, 1e-10, 10)
     assert np.abs(s_gpu - s_cpu).max() <= 1e-9 * np.abs(s_cpu).max()
     P.close()
+
+
+@pytest.mark.parametrize("scheme", [1, 2])
+def test_transient_navier_stokes_bdf_through_the_adapter(scheme):
+    """Three steps of the reference's unmodified BDF1 / BDF2 integrator (src/feTimeIntegration.cpp) + Newton loop with the transient
+    vector mass form: the CUDA backend (solDot and c0 from feSolution, Jacobian-reuse heuristic of src/feNonLinearSolver.cpp:12-32
+    toggling setRecomputeStatus) against the CPU stub backend under the same loop."""
+    ref = _ref()
+    P = ref.RefProblem(os.path.join(ref.DATA_DIR, "square2.msh"), "ns_div", 2, 8, field=0, mu=1.0, rho=1.0, transient=True,
+                       p_essential=True, b200=True)
+    s_cpu, _ = P.transient(False, scheme, 0.0, 0.06, 3)
+    s_gpu, info = P.transient(True, scheme, 0.0, 0.06, 3, rel_tol=1e-12)
+    assert info["converged"] and info["n_solves"] >= 3, info
+    assert np.abs(s_gpu - s_cpu).max() <= 1e-8 * np.abs(s_cpu).max(), info
+    P.close()
