@@ -825,14 +825,28 @@ static int csr_product(System *S, const AmgLevel &L, const double *x, double *y)
 {
   if(L.n <= 0) return B200_OK;
   if(L.val_s) {
-    const double  avg = (double)L.nnz_s / (double)L.n;
-    if(avg > 40.) {
-      const int64_t blocks = (L.n * 8 / 2 + 255) / 256;
-      amg_spmv_f32_kernel<8, 2><<<(unsigned)std::min<int64_t>(blocks, 148 * 32), 256, 0, S->stream>>>(L.n, L.ia_s, L.ja_s, L.val_s, x, y);
-    } else {
-      const int64_t blocks = (L.n * 4 / 2 + 255) / 256;
-      amg_spmv_f32_kernel<4, 2><<<(unsigned)std::min<int64_t>(blocks, 148 * 32), 256, 0, S->stream>>>(L.n, L.ia_s, L.ja_s, L.val_s, x, y);
+    // lanes per row / rows in flight per lane group: B200_AMG_SPMV=LR (e.g. 42, 82, 44) overrides the default
+    static const int cfg = [] {
+      const char *e = getenv("B200_AMG_SPMV");
+      return e ? atoi(e) : 0;
+    }();
+    const double avg = (double)L.nnz_s / (double)L.n;
+    const int    sel = cfg ? cfg : (avg > 40. ? 82 : 42);
+#define B200_F32_SPMV(LL, RR)                                                                                                     \
+  {                                                                                                                               \
+    const int64_t blocks = (L.n * LL / RR + 255) / 256;                                                                           \
+    amg_spmv_f32_kernel<LL, RR><<<(unsigned)std::min<int64_t>(blocks, 148 * 32), 256, 0, S->stream>>>(L.n, L.ia_s, L.ja_s, L.val_s, x, y); \
+  }
+    switch(sel) {
+      case 82: B200_F32_SPMV(8, 2) break;
+      case 84: B200_F32_SPMV(8, 4) break;
+      case 44: B200_F32_SPMV(4, 4) break;
+      case 24: B200_F32_SPMV(2, 4) break;
+      case 22: B200_F32_SPMV(2, 2) break;
+      case 162: B200_F32_SPMV(16, 2) break;
+      default: B200_F32_SPMV(4, 2) break;
     }
+#undef B200_F32_SPMV
     count_launch();
     return B200_OK;
   }

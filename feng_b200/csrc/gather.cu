@@ -25,9 +25,11 @@
 #include <thrust/scan.h>
 #include <thrust/sort.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "device_common.cuh"
 #include "system.h"
@@ -44,6 +46,7 @@ struct NodeSet {
   uint32_t *smoff = nullptr;    // [nNodes] offset (doubles) of the node's row buffer inside its CTA's shared memory
   uint32_t *cta_size = nullptr; // [nCta] doubles of row buffer per CTA
   int64_t  *cta_g0 = nullptr;   // [nCta] first CSR slot of the CTA's rows if they are consecutive in memory, else -1
+  int32_t  *cta_perm = nullptr; // [nCta] launch order inside every segment: CTAs sorted along a Morton curve through the mesh
   std::vector<int32_t>  seg_begin; // launch segments: CTAs with similar row-buffer sizes share one launch
   std::vector<uint32_t> seg_smem;  // doubles of row buffer for the segment
   std::vector<double>   seg_pairs; // average number of adjacent elements per node in the segment
@@ -57,6 +60,7 @@ struct NodeSet {
     cudaFree(smoff);
     cudaFree(cta_size);
     cudaFree(cta_g0);
+    cudaFree(cta_perm);
     cudaFree(off);
     *this = NodeSet();
   }
@@ -88,6 +92,7 @@ struct GatherArgs {
   const uint32_t *smoff, *cta_size;
   const int64_t  *cta_g0;
   int32_t         cta0; // first CTA of this launch segment
+  const int32_t  *cta_perm; // launch order (block index -> CTA), or nullptr
   const uint16_t *off;
   int32_t         nNodes;
   int64_t         nInc;
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(NPB, (D == 2 && !PIPE) ? 8 : 1) gather_u_kerne
 
   const int tid = threadIdx.x;
   for(int i = tid; i < a.ntab; i += NPB) s_tab[i] = a.tab[i];
-  const int32_t  cta  = a.cta0 + blockIdx.x;
+  const int32_t  cta  = a.cta_perm ? a.cta_perm[a.cta0 + blockIdx.x] : a.cta0 + (int32_t)blockIdx.x;
   const int32_t  n    = cta * NPB + tid;
   const bool     live = n < a.nNodes;
   const uint32_t tot  = MAT ? a.cta_size[cta] : 0;
@@ -573,7 +578,7 @@ __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
   __shared__ int32_t  s_len[NPB];
   const int tid = threadIdx.x;
   for(int i = tid; i < a.ntab; i += NPB) s_tab[i] = a.tab[i];
-  const int32_t  cta  = a.cta0 + blockIdx.x;
+  const int32_t  cta  = a.cta_perm ? a.cta_perm[a.cta0 + blockIdx.x] : a.cta0 + (int32_t)blockIdx.x;
   const int32_t  n    = cta * NPB + tid;
   const bool     live = n < a.nNodes;
   const uint32_t tot  = MAT ? a.cta_size[cta] : 0;
@@ -855,6 +860,76 @@ __global__ void node_offsets_kernel(int32_t nNodes, int nRow, int nLoc, int offw
   }
 }
 
+// 30-bit Morton code of the centroid of the first element adjacent to the first node of every CTA
+__device__ __forceinline__ uint32_t morton_spread(uint32_t v)
+{
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+__global__ void cta_key_kernel(int32_t nCta, int npb, int32_t nNodes, const int2 *__restrict__ range, const int32_t *__restrict__ pair, int nLoc,
+                               const int32_t *__restrict__ conn, const double *__restrict__ xyz, int dim, double x0, double y0, double z0,
+                               double sx, double sy, double sz, uint32_t *key)
+{
+  for(int32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nCta; c += gridDim.x * blockDim.x) {
+    const int32_t n = min(c * npb + npb / 2, nNodes - 1); // a node in the middle of the CTA
+    const int2    rg = range[n];
+    uint32_t      k = 0;
+    if(rg.y > 0) {
+      const int e = pair[rg.x] / nLoc, nv = dim + 1;
+      double    ctr[3] = {0., 0., 0.};
+      for(int v = 0; v < nv; ++v)
+        for(int m = 0; m < dim; ++m) ctr[m] += xyz[(int64_t)conn[e * nv + v] * dim + m] / nv;
+      const uint32_t qx = (uint32_t)fmin(1023., fmax(0., (ctr[0] - x0) * sx));
+      const uint32_t qy = (uint32_t)fmin(1023., fmax(0., (ctr[1] - y0) * sy));
+      const uint32_t qz = dim == 3 ? (uint32_t)fmin(1023., fmax(0., (ctr[2] - z0) * sz)) : 0u;
+      k = morton_spread(qx) | (morton_spread(qy) << 1) | (morton_spread(qz) << 2);
+    }
+    key[c] = k;
+  }
+}
+
+// Launch order of the CTAs inside every segment: nodes are numbered like the unknowns (the reference numbers vertices in file order
+// and mid-edge nodes in order of first appearance, src/feNumber.cpp:370-483), so consecutive CTAs sweep the mesh line by line and the
+// per-element records shared by neighbouring lines / planes have left the L2 cache when they are needed again.  Sorting the CTAs of
+// a segment along a Morton curve keeps the elements of one neighbourhood in flight together (B200_GATHER_ORDER=linear disables it).
+static int build_cta_order(System *S, NodeSet &N, int npb, int nLoc)
+{
+  const char *e = getenv("B200_GATHER_ORDER");
+  if((e && std::string(e) == "linear") || N.nCta == 0) return B200_OK;
+  const int dim = S->dim;
+  std::vector<double> xyz((size_t)S->nVert * dim);
+  B200_CUDA(cudaMemcpy(xyz.data(), S->d_xyz, xyz.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for(int64_t i = 0; i < S->nVert; ++i)
+    for(int m = 0; m < dim; ++m) {
+      lo[m] = std::min(lo[m], xyz[i * dim + m]);
+      hi[m] = std::max(hi[m], xyz[i * dim + m]);
+    }
+  double sc[3] = {0., 0., 0.};
+  for(int m = 0; m < dim; ++m) sc[m] = hi[m] > lo[m] ? 1023.999 / (hi[m] - lo[m]) : 0.;
+  uint32_t *d_key = nullptr;
+  B200_CUDA(cudaMalloc(&d_key, (size_t)N.nCta * sizeof(uint32_t)));
+  cta_key_kernel<<<148 * 4, 256, 0, S->stream>>>(N.nCta, npb, N.nNodes, N.range, N.pair, nLoc, S->d_conn, S->d_xyz, dim, lo[0], lo[1], dim == 3 ? lo[2] : 0.,
+                                                 sc[0], sc[1], sc[2], d_key);
+  count_launch();
+  std::vector<uint32_t> key(N.nCta);
+  B200_CUDA(cudaMemcpyAsync(key.data(), d_key, (size_t)N.nCta * sizeof(uint32_t), cudaMemcpyDeviceToHost, S->stream));
+  B200_CUDA(cudaStreamSynchronize(S->stream));
+  cudaFree(d_key);
+  std::vector<int32_t> perm(N.nCta);
+  for(int32_t i = 0; i < N.nCta; ++i) perm[i] = i;
+  for(size_t sg = 0; sg + 1 < N.seg_begin.size(); ++sg)
+    std::stable_sort(perm.begin() + N.seg_begin[sg], perm.begin() + N.seg_begin[sg + 1], [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+  B200_CUDA(cudaMalloc(&N.cta_perm, (size_t)N.nCta * sizeof(int32_t)));
+  B200_CUDA(cudaMemcpy(N.cta_perm, perm.data(), (size_t)N.nCta * sizeof(int32_t), cudaMemcpyHostToDevice));
+  return B200_OK;
+}
+
 static int build_node_set(System *S, NodeSet &N, const int32_t *d_adr, int nLoc, int nF, int nRow, int npb, int offw, int ncol, int NU, int NP,
                           int colmaskU, int colmaskP, double band = 1.25, int min_div = 50)
 {
@@ -955,7 +1030,7 @@ static int build_node_set(System *S, NodeSet &N, const int32_t *d_adr, int nLoc,
       N.seg_pairs.push_back(np / std::max(1., nn));
     }
   }
-  return B200_OK;
+  return build_cta_order(S, N, npb, nLoc);
 }
 
 // reference tensors from the host tables
@@ -1183,6 +1258,7 @@ template <int D, int NS, int NP, int NPB> static int launch_gather_t(System *S, 
     a.range    = N.range;
     a.row      = N.row;
     a.smoff    = N.smoff;
+    a.cta_perm = N.cta_perm;
     a.cta_size = N.cta_size;
     a.off      = N.off;
     a.nNodes   = N.nNodes;
@@ -1297,6 +1373,7 @@ template <int D, int NS, int NP, int NW, int L, int REGS> static int launch_gath
     a.range    = N.range;
     a.row      = N.row;
     a.smoff    = N.smoff;
+    a.cta_perm = N.cta_perm;
     a.cta_size = N.cta_size;
     a.off      = N.off;
     a.nNodes   = N.nNodes;

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) gather_lane_kernel(const Gather
   const int g = lane / L, l = lane - g * L;
   if(MAT)
     for(int i = tid; i < a.ntab; i += NT) s_tab[i] = a.tab[i];
-  const int32_t  cta  = a.cta0 + blockIdx.x;
+  const int32_t  cta  = a.cta_perm ? a.cta_perm[a.cta0 + blockIdx.x] : a.cta0 + (int32_t)blockIdx.x;
   const int      ln   = wid * GPW + g;
   const int32_t  n    = cta * NPB + ln;
   const bool     live = (g < GPW) && n < a.nNodes;
