@@ -896,11 +896,13 @@ __global__ void cta_key_kernel(int32_t nCta, int npb, int32_t nNodes, const int2
 // Launch order of the CTAs inside every segment: nodes are numbered like the unknowns (the reference numbers vertices in file order
 // and mid-edge nodes in order of first appearance, src/feNumber.cpp:370-483), so consecutive CTAs sweep the mesh line by line and the
 // per-element records shared by neighbouring lines / planes have left the L2 cache when they are needed again.  Sorting the CTAs of
-// a segment along a Morton curve keeps the elements of one neighbourhood in flight together (B200_GATHER_ORDER=linear disables it).
+// a segment along a Morton curve keeps the elements of one neighbourhood in flight together (opt-in: B200_GATHER_ORDER=morton).
 static int build_cta_order(System *S, NodeSet &N, int npb, int nLoc)
 {
+  // measured on T3D(92) / T2D(1024) (profiles/README.md, r02f): 173.0 vs 173.7 and 1 042 vs 1 065 Melem/s -- the row kernels are bound
+  // by the L1 / shared-memory pipe, not by where the element records come from, so the linear order stays the default
   const char *e = getenv("B200_GATHER_ORDER");
-  if((e && std::string(e) == "linear") || N.nCta == 0) return B200_OK;
+  if(!(e && std::string(e) == "morton") || N.nCta == 0) return B200_OK;
   const int dim = S->dim;
   std::vector<double> xyz((size_t)S->nVert * dim);
   B200_CUDA(cudaMemcpy(xyz.data(), S->d_xyz, xyz.size() * sizeof(double), cudaMemcpyDeviceToHost));
