@@ -218,7 +218,7 @@ def cpu_port_baseline(n_cpu, reps, threads=None):
     sol = PB.perturb_unknowns(pb)
     P.assemble(sol)                                  # warm-up
     times = [P.assemble(sol)[2] for _ in range(reps)]
-    return {"times": times, "n_elm": m.n_cells, "cores": port.max_threads(), "kind": "port-c++",
+    return {"times": times, "n_elm": m.n_cells, "cores": port.max_threads(), "kind": "port", "port": "oracle/port_cpp.cpp (C++/OpenMP)",
             "sample": f"T3D({n_cpu}) = {m.n_cells} tetrahedra, same forms (convU+divU+divSigma), Jacobian+residual, colour loop + "
                       f"sorted scatter, C++/OpenMP restatement of the reference's assembly path (the reference has no 3-D vector "
                       f"spaces), {reps} passes"}
@@ -255,7 +255,7 @@ def run_reference(args, rank, world):
         return
     if args.workload == "t3d":
         base = cpu_port_baseline(args.cpu_n3, max(args.steps, 1) + args.warmup)
-        kind, timing = "port-c++", "oracle/port_cpp.cpp (C++/OpenMP, all host threads), host steady_clock around the assembly"
+        kind, timing = "port", "oracle/port_cpp.cpp (C++/OpenMP, all host threads), host steady_clock around the assembly"
     else:
         base = cpu_reference_baseline(args.cpu_n_chns if args.workload == "chns" else args.cpu_n, max(args.steps, 1) + args.warmup,
                                       chns=args.workload == "chns")
