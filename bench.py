@@ -139,19 +139,26 @@ def chns_state(pb):
     return sol, dot, 150.0
 
 
-# FP64 work the shipped kernels EXECUTE per element, from the ncu instruction counts of the profiled launches (DFMA = 2
-# flop; profiles/README.md): 2-D row-owner kernels r01b, 3-D pre-pass + lane kernels r01i, CHNS kernel r01o (22 active
-# lanes x (2 x 1963 DFMA + 933 DMUL + 299 DADD) warp-instructions).
+# FP64 work the shipped kernels EXECUTE per element, from ncu instruction counts (DFMA = 2 flop).  t3d: counted over every launch
+# of one assembly pass at the bench size by scripts/gpu_r02e.sh and read from profiles/traffic.json ("t3d_flop_per_element",
+# stamped with its source); the others are the round-1 captures (profiles/README.md: 2-D row-owner kernels r01b, CHNS kernel r01o)
+# until they are re-captured.
 EXECUTED_FLOP_PER_ELEMENT = {"t2d": 5.0e3, "t3d": 27.0e3, "chns": 113.0e3}
 
 
 def fp64_roofline(workload, peak_tflops, n_elm, kernel_ms):
     """The second roofline SURVEY.md section 8(d) asks for: the assembly is not HBM-bound, so the executed FP64 rate is
     reported against the DFMA peak measured on this GPU in the same run."""
-    flop = EXECUTED_FLOP_PER_ELEMENT[workload]
+    flop, src = EXECUTED_FLOP_PER_ELEMENT[workload], "round-1 ncu capture (profiles/README.md)"
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        if tj.get(f"{workload}_flop_per_element"):
+            flop, src = float(tj[f"{workload}_flop_per_element"]), tj.get(f"{workload}_source", "profiles/traffic.json")
     achieved = flop * n_elm / (kernel_ms * 1e-3) / 1e12
     return {"measured_dfma_peak_tflops": peak_tflops, "executed_flop_per_element": flop, "achieved_tflops": achieved,
-            "frac": achieved / peak_tflops if peak_tflops else None,
+            "frac": achieved / peak_tflops if peak_tflops else None, "flop_source": src,
             "note": "flop per element = executed FP64 instructions of the profiled launches (ncu), FMA counted as 2"}
 
 
@@ -435,6 +442,7 @@ def main():
         achieved = bpe * nE / (k_ms * 1e-3) / 1e9
         spmv_bytes = S.nnz * 12 + (S.n_inc + 1) * 8 + 2 * 8 * S.n_inc
         fp64 = capi.measure_fp64_peak(local_rank)
+        dmma = capi.measure_dmma_peak(local_rank)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -468,7 +476,9 @@ def main():
                                     if gather else "th_kernel fused Jacobian+residual+scatter"),
                          "kernel_ms": k_ms, "algorithmic_bytes_per_element": bpe, "peak_source": peak_src,
                          "kernel_share_of_step": k_ms / ms_step,
-                         "fp64": fp64_roofline(args.workload, fp64, nE, k_ms)},
+                         "fp64": dict(fp64_roofline(args.workload, fp64, nE, k_ms), measured_dmma_peak_tflops=dmma,
+                                      tensor_core_gate="mma.sync.m8n8k4.f64 peak measured in the same run: no throughput over the "
+                                                       "FP64 CUDA-core path, so the contractions stay on DFMA")},
             "spmv": {"ms": spmv_ms, "achieved_gbs": spmv_bytes / (spmv_ms * 1e-3) / 1e9,
                      "frac": spmv_bytes / (spmv_ms * 1e-3) / 1e9 / peak, "bytes": spmv_bytes},
             "e2e": {"value": tot_owned / (e2e_ms / args.steps * 1e-3) / 1e6, "unit": UNIT,

@@ -21,6 +21,7 @@
 #include <thrust/execution_policy.h>
 #include <thrust/extrema.h>
 #include <thrust/iterator/counting_iterator.h>
+#include <thrust/scan.h>
 #include <thrust/transform_reduce.h>
 
 #include <cmath>
@@ -50,6 +51,11 @@ struct Precond {
   uint64_t numeric_epoch = ~0ull;
   double   schur_scale = 0.;
   int64_t  pmin = 0, umax = 0; // first pressure unknown / last velocity unknown of the local numbering (ghost rows included)
+  // compact single-precision copy of the block G = A[velocity rows, pressure columns] (the product G z_p of every application)
+  int64_t *d_iag = nullptr;
+  int32_t *d_jag = nullptr;
+  float   *d_valg = nullptr;
+  int64_t  nnz_g = 0;
 };
 
 __global__ void pc_pmass_kernel(int64_t nElm, int dim, const double *__restrict__ xyz, const int32_t *__restrict__ conn,
@@ -142,6 +148,67 @@ __global__ void __launch_bounds__(256) pc_rhs_tail_kernel(int64_t n, const int64
   }
 }
 
+// compact single-precision copy of the velocity-row x pressure-column block G (any numbering): count / fill like the level-0 copy of
+// amg.cu, one warp per row
+__global__ void __launch_bounds__(256) pc_g_count_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
+                                                         const uint8_t *__restrict__ fld, const uint8_t *__restrict__ fld_col, int64_t *cnt)
+{
+  const int     lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * (int64_t)blockDim.x) >> 5;
+  for(int64_t i = w0; i < n; i += nw) {
+    int c = 0;
+    if(fld[i] < AMG_FLD_P)
+      for(int64_t k = ia[i] + lane; k < ia[i + 1]; k += 32) c += fld_col[ja[k]] == AMG_FLD_P ? 1 : 0;
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if(lane == 0) cnt[i] = c;
+  }
+}
+
+template <bool WITH_JA>
+__global__ void __launch_bounds__(256) pc_g_fill_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
+                                                        const double *__restrict__ val, const uint8_t *__restrict__ fld,
+                                                        const uint8_t *__restrict__ fld_col, const int64_t *__restrict__ iag, int32_t *jag,
+                                                        float *valg)
+{
+  const int     lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * (int64_t)blockDim.x) >> 5;
+  for(int64_t i = w0; i < n; i += nw) {
+    if(fld[i] >= AMG_FLD_P) continue;
+    int64_t       out = iag[i];
+    const int64_t beg = ia[i], end = ia[i + 1];
+    for(int64_t k0 = beg; k0 < end; k0 += 32) {
+      const int64_t  k = k0 + lane;
+      const int32_t  j = k < end ? ja[k] : 0;
+      const bool     keep = k < end && fld_col[j] == AMG_FLD_P;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if(keep) {
+        const int64_t o = out + __popc(m & ((1u << lane) - 1u));
+        if(WITH_JA) jag[o] = j;
+        valg[o] = (float)val[k];
+      }
+      out += __popc(m);
+    }
+  }
+}
+
+// b = r - G zp on velocity rows (compact G), 0 elsewhere
+template <int LPR>
+__global__ void __launch_bounds__(256) pc_rhs_g_kernel(int64_t n, const int64_t *__restrict__ iag, const int32_t *__restrict__ jag,
+                                                       const float *__restrict__ valg, const uint8_t *__restrict__ fld,
+                                                       const double *__restrict__ r, const double *__restrict__ zp, double *__restrict__ b)
+{
+  const int     lane = threadIdx.x % LPR;
+  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR, ng = (gridDim.x * (int64_t)blockDim.x) / LPR;
+  for(int64_t i = g0; i < n; i += ng) {
+    double s = 0.;
+    for(int64_t k = iag[i] + lane; k < iag[i + 1]; k += LPR) s += (double)valg[k] * zp[jag[k]];
+#pragma unroll
+    for(int o = LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, LPR);
+    if(lane == 0) b[i] = fld[i] < AMG_FLD_P ? r[i] - s : 0.;
+  }
+}
+
 // b = r - t on velocity rows, 0 elsewhere (general numbering: t = A [0; zp] from a full product)
 __global__ void pc_rhs_full_kernel(int64_t n, const uint8_t *__restrict__ fld, const double *__restrict__ r, const double *__restrict__ t,
                                    double *__restrict__ b)
@@ -167,6 +234,9 @@ void precond_free(System *S)
   cudaFree(P->d_alpha);
   cudaFree(P->d_pmass);
   cudaFree(P->d_pstart);
+  cudaFree(P->d_iag);
+  cudaFree(P->d_jag);
+  cudaFree(P->d_valg);
   cudaFree(P->d_sum);
   cudaFree(P->d_zp);
   cudaFree(P->d_b);
@@ -256,6 +326,24 @@ static int schur_symbolic(System *S, Precond *P)
     count_launch();
     P->tail = true;
   }
+  if(!getenv("B200_PC_NO_G")) {
+    // pattern of the compact G block; columns are labelled by the UNMASKED field map (ghost pressure columns count)
+    const uint8_t *fcol = P->d_fld_all ? P->d_fld_all : P->d_fld;
+    int64_t       *cnt = nullptr;
+    B200_CUDA(cudaMalloc(&cnt, (size_t)(n + 1) * sizeof(int64_t)));
+    B200_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(n + 1) * sizeof(int64_t), S->stream));
+    pc_g_count_kernel<<<GRID * 4, 256, 0, S->stream>>>(n, S->d_ia, S->d_ja, P->d_fld, fcol, cnt);
+    count_launch();
+    thrust::device_ptr<int64_t> cp(cnt);
+    thrust::exclusive_scan(thrust::cuda::par.on(S->stream), cp, cp + n + 1, cp);
+    B200_CUDA(cudaMemcpyAsync(&P->nnz_g, cnt + n, sizeof(int64_t), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    P->d_iag = cnt;
+    B200_CUDA(cudaMalloc(&P->d_jag, (size_t)std::max<int64_t>(P->nnz_g, 1) * sizeof(int32_t)));
+    B200_CUDA(cudaMalloc(&P->d_valg, (size_t)std::max<int64_t>(P->nnz_g, 1) * sizeof(float)));
+    pc_g_fill_kernel<true><<<GRID * 4, 256, 0, S->stream>>>(n, S->d_ia, S->d_ja, S->d_val, P->d_fld, fcol, P->d_iag, P->d_jag, P->d_valg);
+    count_launch();
+  }
   B200_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -319,6 +407,11 @@ int precond_setup(System *S, int pc)
       P->schur_scale = -f / (d * g); // S^-1 ~ -(f / (d g)) M_p^-1
       pc_alpha_kernel<<<GRID, 256, 0, S->stream>>>(S->nInc, P->d_fld, P->d_pmass, P->schur_scale, P->d_alpha);
       count_launch();
+      if(P->d_valg) {
+        pc_g_fill_kernel<false><<<GRID * 4, 256, 0, S->stream>>>(S->nInc, S->d_ia, S->d_ja, S->d_val, P->d_fld,
+                                                                 P->d_fld_all ? P->d_fld_all : P->d_fld, P->d_iag, nullptr, P->d_valg);
+        count_launch();
+      }
     }
     P->numeric_epoch = S->val_epoch;
   }
@@ -349,7 +442,12 @@ int precond_apply(System *S, int pc, const double *r, double *z)
   int rc = comm_halo_exchange(S, P->d_zp);
   if(rc != B200_OK) return rc;
   // velocity right-hand side b = r_u - G z_p
-  if(P->tail) {
+  if(P->d_valg) {
+    const int64_t blocks = (n * 4 + 255) / 256;
+    pc_rhs_g_kernel<4><<<(unsigned)std::min<int64_t>(blocks, 148 * 32), 256, 0, S->stream>>>(n, P->d_iag, P->d_jag, P->d_valg, P->d_fld, r, P->d_zp,
+                                                                                            P->d_b);
+    count_launch();
+  } else if(P->tail) {
     const int64_t blocks = (n * 4 + 255) / 256;
     pc_rhs_tail_kernel<4><<<(unsigned)std::min<int64_t>(blocks, 148 * 32), 256, 0, S->stream>>>(n, S->d_ia, P->d_pstart, S->d_ja, S->d_val, P->d_fld,
                                                                                                r, P->d_zp, P->d_b);
