@@ -23,6 +23,7 @@
 #include <thrust/binary_search.h>
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
+#include <thrust/reduce.h>
 #include <thrust/scan.h>
 #include <thrust/sort.h>
 #include <thrust/unique.h>
@@ -688,89 +689,61 @@ __global__ void amg_gc_parent_kernel(int64_t nElm, const int32_t *__restrict__ a
   }
 }
 
-// dense global coarse operator: Ac[I][J] += w_iI w_jJ a_ij over the OWNED rows of the field (owned = local pkind != 0), columns
-// of the same component, owned or ghost
-template <int LPR>
-__global__ void __launch_bounds__(256) amg_gc_galerkin_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
-                                                              const double *__restrict__ val, const uint8_t *__restrict__ fld_all,
-                                                              const uint8_t *__restrict__ pkind0, const int32_t *__restrict__ p0,
-                                                              const int32_t *__restrict__ p1, const uint8_t *__restrict__ kind, int nc,
-                                                              double *Ac)
+// triplets (global row, global column, value) of the rank-local level-gl operator
+__global__ void amg_gl_local_triplets_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
+                                             const double *__restrict__ val, int64_t off, int64_t ng, uint64_t *key, double *tv)
 {
-  const int     lane = threadIdx.x % LPR;
-  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPR, ng = (gridDim.x * (int64_t)blockDim.x) / LPR;
-  for(int64_t i = g0; i < n; i += ng) {
-    if(pkind0[i] == 0) continue;
-    const int32_t I0 = p0[i], I1 = p1[i];
+  const int     lane = threadIdx.x & 7;
+  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3, nn = (gridDim.x * (int64_t)blockDim.x) >> 3;
+  for(int64_t i = g0; i < n; i += nn)
+    for(int64_t k = ia[i] + lane; k < ia[i + 1]; k += 8) {
+      key[k] = (uint64_t)(off + i) * (uint64_t)ng + (uint64_t)(off + ja[k]);
+      tv[k]  = val[k];
+    }
+}
+
+// Galerkin contributions w_iI w_jJ a_ij of the rows that read ghost columns, for the index pairs (I, J) with at least one
+// REMOTE member (the pairs with two local members are in the rank-local operator already).  count != nullptr: count only.
+__global__ void amg_gl_cut_triplets_kernel(int64_t n_rows, const int32_t *__restrict__ rows, const int64_t *__restrict__ ia,
+                                           const int32_t *__restrict__ ja, const double *__restrict__ val, const uint8_t *__restrict__ fld_all,
+                                           const uint8_t *__restrict__ pkind0, const int32_t *__restrict__ p0, const int32_t *__restrict__ p1,
+                                           const uint8_t *__restrict__ kind, int64_t off, int64_t nloc, int64_t ng, unsigned long long *cursor,
+                                           uint64_t *key, double *tv, int64_t cap, int count_only)
+{
+  const int     lane = threadIdx.x & 7;
+  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3, nn = (gridDim.x * (int64_t)blockDim.x) >> 3;
+  for(int64_t t = g0; t < n_rows; t += nn) {
+    const int64_t i = rows[t];
+    if(pkind0[i] == 0) continue; // ghost row or other field
+    const int32_t Ii[2] = {p0[i], p1[i]};
     const double  wi = kind[i] == 2 ? 0.5 : 1.;
     const int     fi = fld_all[i];
-    for(int64_t k = ia[i] + lane; k < ia[i + 1]; k += LPR) {
+    for(int64_t k = ia[i] + lane; k < ia[i + 1]; k += 8) {
       const int32_t j = ja[k];
       if(kind[j] == 0 || fld_all[j] != fi) continue;
       const double  v = val[k] * wi * (kind[j] == 2 ? 0.5 : 1.);
-      const int32_t J0 = p0[j], J1 = p1[j];
-      if(I0 >= 0) {
-        if(J0 >= 0) atomicAdd(Ac + (size_t)I0 * nc + J0, v);
-        if(J1 >= 0) atomicAdd(Ac + (size_t)I0 * nc + J1, v);
-      }
-      if(I1 >= 0) {
-        if(J0 >= 0) atomicAdd(Ac + (size_t)I1 * nc + J0, v);
-        if(J1 >= 0) atomicAdd(Ac + (size_t)I1 * nc + J1, v);
-      }
+      const int32_t Jj[2] = {p0[j], p1[j]};
+#pragma unroll
+      for(int a = 0; a < 2; ++a)
+#pragma unroll
+        for(int b = 0; b < 2; ++b) {
+          const int64_t I = Ii[a], J = Jj[b];
+          if(I < 0 || J < 0) continue;
+          const bool Iloc = I >= off && I < off + nloc, Jloc = J >= off && J < off + nloc;
+          if(Iloc && Jloc) continue;
+          const unsigned long long pos = atomicAdd(cursor, 1ull);
+          if(!count_only && (int64_t)pos < cap) {
+            key[pos] = (uint64_t)I * (uint64_t)ng + (uint64_t)J;
+            tv[pos]  = v;
+          }
+        }
     }
   }
 }
 
-// Gauss-Jordan without pivoting, one launch per pivot: M is n x 2n = [A | I]; after n steps the right half is A^-1.  Empty
-// rows / columns (an aggregate none of whose unknowns is active) get a unit pivot.
-__global__ void amg_gj_step_kernel(int n, int p, double *M)
+__global__ void amg_fill_u64_kernel(int64_t n, uint64_t v, uint64_t *x)
 {
-  const int    ld = 2 * n;
-  const double piv = M[(size_t)p * ld + p];
-  const double ip = piv != 0. ? 1. / piv : 1.;
-  for(int r = blockIdx.x; r < n; r += gridDim.x) {
-    if(r == p) continue;
-    const double f = M[(size_t)r * ld + p] * ip;
-    if(f == 0.) continue;
-    for(int j = threadIdx.x; j < ld; j += blockDim.x)
-      if(j != p) M[(size_t)r * ld + j] -= f * M[(size_t)p * ld + j];
-  }
-}
-
-__global__ void amg_gj_finish_kernel(int n, int p, double *M)
-{
-  const int    ld = 2 * n;
-  const double piv = M[(size_t)p * ld + p];
-  const double ip = piv != 0. ? 1. / piv : 1.;
-  // column p of the other rows becomes zero, the pivot row is scaled (runs after amg_gj_step_kernel of the same p)
-  for(int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ld + n; idx += gridDim.x * blockDim.x) {
-    if(idx < ld) {
-      if(idx != p) M[(size_t)p * ld + idx] *= ip;
-    } else {
-      const int r = idx - ld;
-      if(r != p) M[(size_t)r * ld + p] = 0.;
-    }
-  }
-}
-
-__global__ void amg_gj_pivot_one_kernel(int n, int p, double *M) { M[(size_t)p * 2 * n + p] = 1.; }
-
-__global__ void amg_gc_fill_identity_kernel(int n, const double *__restrict__ A, double *M)
-{
-  const int ld = 2 * n;
-  for(int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < (int64_t)n * ld; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(idx / ld), j = (int)(idx - (int64_t)i * ld);
-    M[idx] = j < n ? A[(size_t)i * n + j] : (j - n == i ? 1. : 0.);
-  }
-}
-
-__global__ void amg_gc_extract_kernel(int n, const double *__restrict__ M, double *inv)
-{
-  const int ld = 2 * n;
-  for(int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < (int64_t)n * n; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(idx / n), j = (int)(idx - (int64_t)i * n);
-    inv[idx] = M[(size_t)i * ld + n + j];
-  }
+  for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = v;
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -808,13 +781,29 @@ void amg_free(Amg *A)
   cudaFree(A->gc_p0);
   cudaFree(A->gc_p1);
   cudaFree(A->gc_kind);
-  cudaFree(A->gc_A);
-  cudaFree(A->gc_inv);
   cudaFree(A->gc_b);
   cudaFree(A->gc_x);
+  cudaFree(A->g_ia);
+  cudaFree(A->g_ja);
+  cudaFree(A->g_val);
+  cudaFree(A->t_key);
+  cudaFree(A->t_keyall);
+  cudaFree(A->t_val);
+  cudaFree(A->t_valall);
+  if(A->G) {
+    amg_free(A->G);
+    delete A->G;
+    A->G = nullptr;
+  }
   A->gc_p0 = A->gc_p1 = nullptr;
   A->gc_kind = nullptr;
-  A->gc_A = A->gc_inv = A->gc_b = A->gc_x = nullptr;
+  A->gc_b = A->gc_x = nullptr;
+  A->g_ia = nullptr;
+  A->g_ja = nullptr;
+  A->g_val = nullptr;
+  A->t_key = A->t_keyall = nullptr;
+  A->t_val = A->t_valall = nullptr;
+  A->t_cap = 0;
   A->gc_active = false;
   A->dense = A->cinv = A->d_nrm = nullptr;
   A->d_active0 = nullptr;
@@ -1003,6 +992,36 @@ static int aggregate_level(System *S, Amg *A, int l, int64_t *ncoarse)
   return B200_OK;
 }
 
+// aggregation levels below the last level built so far
+static int build_coarse_levels(System *S, Amg *A)
+{
+  for(int l = (int)A->L.size() - 1; l < AMG_MAX_LEVELS - 1; ++l) {
+    if(l > 0 && A->L[l].n <= AMG_MAX_DENSE) break;
+    int64_t nc2 = 0;
+    int     rc = aggregate_level(S, A, l, &nc2);
+    if(rc != B200_OK) return rc;
+    if(nc2 <= 0 || nc2 * 10 > A->L[l].n * 9) { // coarsening stalled: stop here
+      cudaFree(A->L[l].par0);
+      cudaFree(A->L[l].pkind);
+      A->L[l].par0  = nullptr;
+      A->L[l].pkind = nullptr;
+      break;
+    }
+    A->L.emplace_back();
+    AmgLevel &F = A->L[l];
+    uint64_t *keys = nullptr;
+    B200_CUDA(cudaMalloc(&keys, (size_t)std::max<int64_t>(F.nnz, 1) * sizeof(uint64_t)));
+    amg_agg_keys_kernel<<<grid_for(F.n * 8), 256, 0, S->stream>>>(F.n, F.ia, F.ja, F.par0, nc2, keys);
+    count_launch();
+    rc = keys_to_csr(S, keys, F.nnz, nc2, A->L[l + 1]);
+    cudaFree(keys);
+    if(rc != B200_OK) return rc;
+    rc = alloc_vectors(A->L[l + 1], true);
+    if(rc != B200_OK) return rc;
+  }
+  return B200_OK;
+}
+
 // Symbolic set-up.  fld_lo..fld_hi-1 = the field ids (AmgFieldMap) of the rows the hierarchy acts on; space = the
 // interpolation space of that field (P2 -> P1 level when it has mid-edge functions).
 int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int fld_hi, int space, const uint8_t *d_fld_all)
@@ -1087,29 +1106,8 @@ int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int 
     count_launch();
     A->L[0].decoupled = true;
   }
-  // aggregation levels
-  for(int l = (int)A->L.size() - 1; l < AMG_MAX_LEVELS - 1; ++l) {
-    if(l > 0 && A->L[l].n <= AMG_MAX_DENSE) break;
-    int64_t nc2 = 0;
-    int     rc = aggregate_level(S, A, l, &nc2);
-    if(rc != B200_OK) return rc;
-    if(nc2 <= 0 || nc2 * 10 > A->L[l].n * 9) { // coarsening stalled: stop here
-      cudaFree(A->L[l].par0);
-      cudaFree(A->L[l].pkind);
-      A->L[l].par0  = nullptr;
-      A->L[l].pkind = nullptr;
-      break;
-    }
-    A->L.emplace_back();
-    AmgLevel &F = A->L[l];
-    uint64_t *keys = nullptr;
-    B200_CUDA(cudaMalloc(&keys, (size_t)std::max<int64_t>(F.nnz, 1) * sizeof(uint64_t)));
-    amg_agg_keys_kernel<<<grid_for(F.n * 8), 256, 0, S->stream>>>(F.n, F.ia, F.ja, F.par0, nc2, keys);
-    count_launch();
-    rc = keys_to_csr(S, keys, F.nnz, nc2, A->L[l + 1]);
-    cudaFree(keys);
-    if(rc != B200_OK) return rc;
-    rc = alloc_vectors(A->L[l + 1], true);
+  {
+    const int rc = build_coarse_levels(S, A);
     if(rc != B200_OK) return rc;
   }
   // single-precision working copy of level 0 (pattern now, values in the numeric phase)
@@ -1137,36 +1135,39 @@ int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int 
     B200_CUDA(cudaMalloc(&A->dense, (size_t)A->dense_n * 2 * A->dense_n * sizeof(double)));
     B200_CUDA(cudaMalloc(&A->cinv, (size_t)A->dense_n * A->dense_n * sizeof(double)));
   }
-  // several GPUs: global coarsest level (P2 hierarchies only; every rank must have reached a dense coarsest level)
+  // several GPUs: global hierarchy from level gl on (P2 hierarchies only; every rank must have that level)
   if(comm_active(S) && d_fld_all && p2 && !getenv("B200_AMG_LOCAL_COARSE")) {
     const int world = comm_world(S), rank = comm_rank(S);
-    std::vector<double> cnt(world + 1, 0.);
-    cnt[rank]  = (double)A->dense_n;
-    cnt[world] = (A->dense_n > 0 && A->L.size() >= 2) ? 0. : 1.; // somebody without a dense level: no global level
+    const int gl = std::min(2, (int)A->L.size() - 1);
+    std::vector<double> cnt(world + 2, 0.);
+    cnt[rank]      = gl >= 1 ? (double)A->L[gl].n : 0.;
+    cnt[world]     = gl >= 1 ? 0. : 1.; // somebody without a coarse level: no global level
+    cnt[world + 1] = (double)gl;        // (summed: must be world * gl)
     double *d_cnt = nullptr;
-    B200_CUDA(cudaMalloc(&d_cnt, (world + 1) * sizeof(double)));
-    B200_CUDA(cudaMemcpyAsync(d_cnt, cnt.data(), (world + 1) * sizeof(double), cudaMemcpyHostToDevice, S->stream));
-    int rc = comm_allreduce(S, d_cnt, world + 1, false);
+    B200_CUDA(cudaMalloc(&d_cnt, (world + 2) * sizeof(double)));
+    B200_CUDA(cudaMemcpyAsync(d_cnt, cnt.data(), (world + 2) * sizeof(double), cudaMemcpyHostToDevice, S->stream));
+    int rc = comm_allreduce(S, d_cnt, world + 2, false);
     if(rc != B200_OK) return rc;
-    B200_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (world + 1) * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (world + 2) * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
     B200_CUDA(cudaStreamSynchronize(S->stream));
     cudaFree(d_cnt);
-    int tot = 0, off = 0;
+    int64_t tot = 0, off = 0;
     for(int r = 0; r < world; ++r) {
       if(r == rank) off = tot;
-      tot += (int)cnt[r];
+      tot += (int64_t)cnt[r];
     }
-    if(cnt[world] == 0. && tot > 0 && tot <= 4096) {
+    if(cnt[world] == 0. && cnt[world + 1] == (double)world * gl && tot > 0 && tot < (int64_t)2000000000) {
+      A->gl      = gl;
       A->gc_n    = tot;
       A->gc_off  = off;
-      A->gc_nloc = A->dense_n;
-      // global id of every owned vertex unknown, then of the ghost ones through the halo plan of the fine vectors
+      A->gc_nloc = A->L[gl].n;
+      // global level-gl id of every owned vertex unknown, then of the ghost ones through the halo plan of the fine vectors
       double *gid = nullptr;
       B200_CUDA(cudaMalloc(&gid, (size_t)n * sizeof(double)));
       AmgChain ch;
       ch.n = 0;
-      for(size_t l = 1; l + 1 < A->L.size(); ++l) ch.par[ch.n++] = A->L[l].par0;
-      amg_gc_gid_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, A->L[0].pkind, A->L[0].par0, ch, off, gid);
+      for(int l = 1; l < gl; ++l) ch.par[ch.n++] = A->L[l].par0;
+      amg_gc_gid_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, A->L[0].pkind, A->L[0].par0, ch, (int)off, gid);
       count_launch();
       rc = comm_halo_exchange(S, gid);
       if(rc != B200_OK) return rc;
@@ -1181,8 +1182,6 @@ int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int 
       count_launch();
       B200_CUDA(cudaStreamSynchronize(S->stream));
       cudaFree(gid);
-      B200_CUDA(cudaMalloc(&A->gc_A, (size_t)tot * 2 * tot * sizeof(double)));
-      B200_CUDA(cudaMalloc(&A->gc_inv, (size_t)tot * tot * sizeof(double)));
       B200_CUDA(cudaMalloc(&A->gc_b, (size_t)tot * sizeof(double)));
       B200_CUDA(cudaMalloc(&A->gc_x, (size_t)tot * sizeof(double)));
       A->gc_active = true;
@@ -1190,7 +1189,9 @@ int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int 
     }
   }
   if(A->verbose) {
-    if(A->gc_active) fprintf(stderr, "[feng_b200] amg: global coarsest level, %d unknowns (%d local at offset %d)\n", A->gc_n, A->gc_nloc, A->gc_off);
+    if(A->gc_active)
+      fprintf(stderr, "[feng_b200] amg: global hierarchy from level %d on, %lld unknowns (%lld local at offset %lld)\n", A->gl, (long long)A->gc_n,
+              (long long)A->gc_nloc, (long long)A->gc_off);
     fprintf(stderr, "[feng_b200] amg hierarchy:");
     for(auto &L : A->L) fprintf(stderr, " (%lld rows, %lld nnz)", (long long)L.n, (long long)L.nnz);
     fprintf(stderr, " dense %d\n", A->dense_n);
@@ -1227,6 +1228,141 @@ static int power_iteration(System *S, Amg *A, int l, int iters)
   L.have_eig = true;
   L.lam = (lam > 0. && std::isfinite(lam)) ? 1.1 * lam : 1.;
   return B200_OK;
+}
+
+int amg_setup_numeric(System *S, Amg *A);
+
+// hierarchy on a CSR matrix given as is (every row active): level 0 aliases the arrays
+static int amg_setup_symbolic_csr(System *S, Amg *G, int64_t n, int64_t nnz, const int64_t *ia, const int32_t *ja, const double *val)
+{
+  amg_free(G);
+  G->verbose = getenv("B200_VERBOSE") != nullptr;
+  G->use_f32 = false;
+  G->L.emplace_back();
+  AmgLevel &L0 = G->L[0];
+  L0.n = n;
+  L0.nnz = nnz;
+  L0.ia = ia;
+  L0.ja = ja;
+  L0.val = val;
+  int rc = alloc_vectors(L0, false);
+  if(rc != B200_OK) return rc;
+  B200_CUDA(cudaMalloc(&G->d_nrm, 4 * sizeof(double)));
+  rc = build_coarse_levels(S, G);
+  if(rc != B200_OK) return rc;
+  const AmgLevel &C = G->L.back();
+  G->dense_n = (C.n <= AMG_MAX_DENSE && G->L.size() > 1) ? (int)C.n : 0;
+  if(G->dense_n > 0) {
+    B200_CUDA(cudaMalloc(&G->dense, (size_t)G->dense_n * 2 * G->dense_n * sizeof(double)));
+    B200_CUDA(cudaMalloc(&G->cinv, (size_t)G->dense_n * G->dense_n * sizeof(double)));
+  }
+  if(G->verbose) {
+    fprintf(stderr, "[feng_b200] amg global hierarchy:");
+    for(auto &L : G->L) fprintf(stderr, " (%lld rows, %lld nnz)", (long long)L.n, (long long)L.nnz);
+    fprintf(stderr, " dense %d\n", G->dense_n);
+  }
+  G->symbolic = true;
+  return B200_OK;
+}
+
+// Merged level-gl operator of all ranks (values), its hierarchy (symbolic once, numeric every time)
+static int global_level_numeric(System *S, Amg *A)
+{
+  auto            pol = thrust::cuda::par.on(S->stream);
+  const int       world = comm_world(S);
+  const AmgLevel &L0 = A->L[0], &Lg = A->L[A->gl];
+  const int32_t  *brows = nullptr;
+  int64_t         nb = 0;
+  comm_boundary_rows(S, &brows, &nb);
+  unsigned long long *cursor = reinterpret_cast<unsigned long long *>(A->d_nrm + 2);
+  const unsigned      gb = (unsigned)std::max<int64_t>(1, std::min<int64_t>((nb * 8 + 255) / 256, 148 * 16));
+  if(A->t_cap == 0) {
+    // capacity: own level-gl entries + cut contributions (counted), the maximum over the ranks
+    B200_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), S->stream));
+    if(nb > 0) {
+      amg_gl_cut_triplets_kernel<<<gb, 256, 0, S->stream>>>(nb, brows, L0.ia, L0.ja, L0.val, A->d_fld_all, L0.pkind, A->gc_p0, A->gc_p1, A->gc_kind,
+                                                            A->gc_off, A->gc_nloc, A->gc_n, cursor, nullptr, nullptr, 0, 1);
+      count_launch();
+    }
+    unsigned long long ncut = 0;
+    B200_CUDA(cudaMemcpyAsync(&ncut, cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    double h = (double)(Lg.nnz + (int64_t)ncut);
+    B200_CUDA(cudaMemcpyAsync(S->d_scratch, &h, sizeof(double), cudaMemcpyHostToDevice, S->stream));
+    int rc = comm_allreduce(S, S->d_scratch, 1, true);
+    if(rc != B200_OK) return rc;
+    B200_CUDA(cudaMemcpyAsync(&h, S->d_scratch, sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    A->t_cap = (int64_t)h;
+    B200_CUDA(cudaMalloc(&A->t_key, (size_t)A->t_cap * sizeof(uint64_t)));
+    B200_CUDA(cudaMalloc(&A->t_val, (size_t)A->t_cap * sizeof(double)));
+    B200_CUDA(cudaMalloc(&A->t_keyall, (size_t)A->t_cap * world * sizeof(uint64_t)));
+    B200_CUDA(cudaMalloc(&A->t_valall, (size_t)A->t_cap * world * sizeof(double)));
+  }
+  // own triplets: [local level-gl entries | cut contributions | padding with the sentinel key]
+  amg_fill_u64_kernel<<<grid_for(A->t_cap), 256, 0, S->stream>>>(A->t_cap, ~0ull, A->t_key);
+  B200_CUDA(cudaMemsetAsync(A->t_val, 0, (size_t)A->t_cap * sizeof(double), S->stream));
+  if(Lg.n > 0) amg_gl_local_triplets_kernel<<<grid_for(Lg.n * 8), 256, 0, S->stream>>>(Lg.n, Lg.ia, Lg.ja, Lg.val, A->gc_off, A->gc_n, A->t_key, A->t_val);
+  B200_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), S->stream));
+  if(nb > 0)
+    amg_gl_cut_triplets_kernel<<<gb, 256, 0, S->stream>>>(nb, brows, L0.ia, L0.ja, L0.val, A->d_fld_all, L0.pkind, A->gc_p0, A->gc_p1, A->gc_kind,
+                                                          A->gc_off, A->gc_nloc, A->gc_n, cursor, A->t_key + Lg.nnz, A->t_val + Lg.nnz,
+                                                          A->t_cap - Lg.nnz, 0);
+  count_launch(3);
+  int rc = comm_allgather64(S, A->t_key, A->t_keyall, (size_t)A->t_cap);
+  if(rc != B200_OK) return rc;
+  rc = comm_allgather64(S, A->t_val, A->t_valall, (size_t)A->t_cap);
+  if(rc != B200_OK) return rc;
+  // merge: sort by key, sum duplicates
+  const int64_t nt = A->t_cap * world;
+  thrust::device_ptr<uint64_t> kp(A->t_keyall);
+  thrust::device_ptr<double>   vp(A->t_valall);
+  thrust::stable_sort_by_key(pol, kp, kp + nt, vp);
+  uint64_t *uk = nullptr;
+  double   *uv = nullptr;
+  B200_CUDA(cudaMalloc(&uk, (size_t)nt * sizeof(uint64_t)));
+  B200_CUDA(cudaMalloc(&uv, (size_t)nt * sizeof(double)));
+  auto    ends = thrust::reduce_by_key(pol, kp, kp + nt, vp, thrust::device_pointer_cast(uk), thrust::device_pointer_cast(uv));
+  int64_t nu = ends.first - thrust::device_pointer_cast(uk);
+  if(nu > 0) {
+    uint64_t last = 0;
+    B200_CUDA(cudaMemcpyAsync(&last, uk + nu - 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    if(last == ~0ull) --nu;
+  }
+  const bool first = A->G == nullptr;
+  if(first) {
+    A->g_nnz = nu;
+    B200_CUDA(cudaMalloc(&A->g_ia, (size_t)(A->gc_n + 1) * sizeof(int64_t)));
+    B200_CUDA(cudaMalloc(&A->g_ja, (size_t)std::max<int64_t>(nu, 1) * sizeof(int32_t)));
+    B200_CUDA(cudaMalloc(&A->g_val, (size_t)std::max<int64_t>(nu, 1) * sizeof(double)));
+    uint64_t *q = nullptr;
+    B200_CUDA(cudaMalloc(&q, (size_t)(A->gc_n + 1) * sizeof(uint64_t)));
+    amg_row_start_keys_kernel<<<grid_for(A->gc_n + 1), 256, 0, S->stream>>>(A->gc_n, q);
+    thrust::device_ptr<uint64_t> qp(q), ukp(uk);
+    thrust::lower_bound(pol, ukp, ukp + nu, qp, qp + A->gc_n + 1, thrust::device_pointer_cast(A->g_ia));
+    amg_split_keys_kernel<<<grid_for(nu), 256, 0, S->stream>>>(nu, A->gc_n, uk, A->g_ja);
+    count_launch(2);
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    cudaFree(q);
+  } else if(nu != A->g_nnz) {
+    cudaFree(uk);
+    cudaFree(uv);
+    set_error("amg: the merged global level changed its pattern between two numeric set-ups");
+    return B200_ERR_ARG;
+  }
+  B200_CUDA(cudaMemcpyAsync(A->g_val, uv, (size_t)nu * sizeof(double), cudaMemcpyDeviceToDevice, S->stream));
+  B200_CUDA(cudaStreamSynchronize(S->stream));
+  cudaFree(uk);
+  cudaFree(uv);
+  if(first) {
+    A->G = new Amg;
+    rc = amg_setup_symbolic_csr(S, A->G, A->gc_n, A->g_nnz, A->g_ia, A->g_ja, A->g_val);
+    if(rc != B200_OK) return rc;
+    A->G->cheb_degree = A->cheb_degree;
+    A->G->cheb_ratio  = A->cheb_ratio;
+  }
+  return amg_setup_numeric(S, A->G);
 }
 
 // Numeric set-up: Galerkin values level by level, inverse diagonals, spectral radii, coarsest inverse.
@@ -1274,27 +1410,10 @@ int amg_setup_numeric(System *S, Amg *A)
     if(rc != B200_OK) return rc;
   }
   if(A->gc_active) {
-    const int      nc = A->gc_n;
-    const AmgLevel &L0 = A->L[0];
-    double        *Ac = A->gc_inv; // assembled here, all-reduced, then copied into [A | I]
-    B200_CUDA(cudaMemsetAsync(Ac, 0, (size_t)nc * nc * sizeof(double), S->stream));
-    const int64_t blocks = (L0.n * 8 + 255) / 256;
-    amg_gc_galerkin_kernel<8><<<(unsigned)std::min<int64_t>(blocks, 148 * 32), 256, 0, S->stream>>>(L0.n, L0.ia, L0.ja, L0.val, A->d_fld_all, L0.pkind,
-                                                                                                 A->gc_p0, A->gc_p1, A->gc_kind, nc, Ac);
-    count_launch();
-    // NCCL counts are size_t: nc^2 <= 16.8 M doubles
-    for(size_t o = 0; o < (size_t)nc * nc; o += (size_t)1 << 24) {
-      const int rc = comm_allreduce(S, Ac + o, (int)std::min<size_t>((size_t)1 << 24, (size_t)nc * nc - o), false);
-      if(rc != B200_OK) return rc;
-    }
-    amg_gc_fill_identity_kernel<<<GRID, 256, 0, S->stream>>>(nc, Ac, A->gc_A);
-    for(int p = 0; p < nc; ++p) {
-      amg_gj_step_kernel<<<std::min(nc, 148 * 4), 256, 0, S->stream>>>(nc, p, A->gc_A);
-      amg_gj_finish_kernel<<<(2 * nc + nc + 255) / 256, 256, 0, S->stream>>>(nc, p, A->gc_A);
-    }
-    amg_gc_extract_kernel<<<GRID, 256, 0, S->stream>>>(nc, A->gc_A, A->gc_inv);
-    count_launch(2 + 2 * nc);
-  } else if(A->dense_n > 0) {
+    const int rc = global_level_numeric(S, A);
+    if(rc != B200_OK) return rc;
+  }
+  if(A->dense_n > 0) {
     const AmgLevel &C = A->L.back();
     amg_dense_fill_kernel<<<std::min(A->dense_n, 148 * 4), 128, 0, S->stream>>>(A->dense_n, C.ia, C.ja, C.val, A->dense);
     amg_gauss_jordan_kernel<<<1, 1024, 0, S->stream>>>(A->dense_n, A->dense, A->cinv);
@@ -1342,23 +1461,27 @@ static int smooth(System *S, Amg *A, int l, const double *b, double *x, bool zer
   return B200_OK;
 }
 
+int amg_vcycle(System *S, Amg *A, const double *b, double *x);
+
 static int cycle(System *S, Amg *A, int l, const double *b, double *x, bool zero_guess = true)
 {
   AmgLevel &L = A->L[l];
   const int nl = (int)A->L.size();
+  if(A->gc_active && l == A->gl) {
+    // global level: every rank contributes its slice of the right-hand side, runs the replicated hierarchy, keeps its slice
+    B200_CUDA(cudaMemsetAsync(A->gc_b, 0, (size_t)A->gc_n * sizeof(double), S->stream));
+    if(A->gc_nloc > 0)
+      B200_CUDA(cudaMemcpyAsync(A->gc_b + A->gc_off, b, (size_t)A->gc_nloc * sizeof(double), cudaMemcpyDeviceToDevice, S->stream));
+    int rc = comm_allreduce(S, A->gc_b, (int)A->gc_n, false);
+    if(rc != B200_OK) return rc;
+    rc = amg_vcycle(S, A->G, A->gc_b, A->gc_x);
+    if(rc != B200_OK) return rc;
+    if(A->gc_nloc > 0)
+      B200_CUDA(cudaMemcpyAsync(x, A->gc_x + A->gc_off, (size_t)A->gc_nloc * sizeof(double), cudaMemcpyDeviceToDevice, S->stream));
+    return B200_OK;
+  }
   if(L.n <= 0) return B200_OK;
   if(l == nl - 1) {
-    if(A->gc_active) {
-      // global coarsest level: every rank contributes its slice of the right-hand side, solves redundantly, keeps its slice
-      B200_CUDA(cudaMemsetAsync(A->gc_b, 0, (size_t)A->gc_n * sizeof(double), S->stream));
-      B200_CUDA(cudaMemcpyAsync(A->gc_b + A->gc_off, b, (size_t)A->gc_nloc * sizeof(double), cudaMemcpyDeviceToDevice, S->stream));
-      int rc = comm_allreduce(S, A->gc_b, A->gc_n, false);
-      if(rc != B200_OK) return rc;
-      amg_dense_apply_kernel<<<std::max(1, std::min((A->gc_n + 7) / 8, 148 * 4)), 256, 0, S->stream>>>(A->gc_n, A->gc_inv, A->gc_b, A->gc_x);
-      count_launch();
-      B200_CUDA(cudaMemcpyAsync(x, A->gc_x + A->gc_off, (size_t)A->gc_nloc * sizeof(double), cudaMemcpyDeviceToDevice, S->stream));
-      return B200_OK;
-    }
     if(A->dense_n > 0) {
       amg_dense_apply_kernel<<<std::max(1, std::min((A->dense_n + 7) / 8, 148 * 4)), 256, 0, S->stream>>>(A->dense_n, A->cinv, b, x);
       count_launch();

@@ -51,17 +51,28 @@ struct Amg {
   int                   pre_degree = 0;                            // B200_AMG_PRE: degree of the pre-smoother (0 = cheb_degree)
   double                cheb_ratio = AMG_CHEB_RATIO;               // B200_AMG_RATIO
   bool                  use_f32 = true;                            // B200_AMG_F32=0: level 0 works on the FP64 system matrix
-  // several GPUs: the coarsest level is GLOBAL.  Levels 0 .. L-1 are rank-local (block-Jacobi across ranks, couplings to ghost
-  // columns dropped); the coarsest Galerkin operator is assembled from the fine matrix INCLUDING the couplings across the
-  // partition cuts, summed over the ranks, inverted redundantly and applied to the all-reduced coarse right-hand side, so
-  // that smooth error spanning several sub-domains is removed in one cycle (the iteration count of a one-dimensional chain
-  // of sub-domains otherwise grows with its length)
+  // several GPUs: the hierarchy is rank-local down to level `gl` - 1 (block-Jacobi across ranks: couplings to ghost columns are
+  // dropped there); from level `gl` (= 2: the first aggregation level of a P2 hierarchy) on it is GLOBAL.  The level-gl operator
+  // of all ranks, INCLUDING the couplings across the partition cuts (Galerkin contributions of the rows that read ghost
+  // columns), is gathered as (row, column, value) triplets, merged into one CSR matrix that every rank holds, and coarsened /
+  // smoothed / solved redundantly by a second hierarchy `G`; a cycle all-reduces the level-gl right-hand side, runs G and keeps
+  // its own slice.  Smooth error spanning several sub-domains is removed at the resolution of level gl (6-8 fine cells), which is
+  // what keeps the iteration count of a chain of sub-domains from growing with its length.
   bool     gc_active = false;
-  int      gc_n = 0, gc_off = 0, gc_nloc = 0;
-  int32_t *gc_p0 = nullptr, *gc_p1 = nullptr; // [n fine] global coarse ids of the (up to two) vertex parents, -1 = none
+  int      gl = 0;                            // the global level
+  int64_t  gc_n = 0, gc_off = 0, gc_nloc = 0; // global / first own / own number of level-gl unknowns
+  int32_t *gc_p0 = nullptr, *gc_p1 = nullptr; // [n fine] global level-gl ids of the (up to two) vertex parents, -1 = none
   uint8_t *gc_kind = nullptr;                 // [n fine] 0 none, 1 vertex unknown, 2 mid-edge unknown (weights 1 / one half)
   const uint8_t *d_fld_all = nullptr;         // field map with the ghost rows still labelled (owned by the preconditioner)
-  double  *gc_A = nullptr, *gc_inv = nullptr, *gc_b = nullptr, *gc_x = nullptr;
+  Amg     *G = nullptr;                       // replicated hierarchy on the merged level-gl matrix
+  int64_t *g_ia = nullptr;
+  int32_t *g_ja = nullptr;
+  double  *g_val = nullptr;
+  int64_t  g_nnz = 0;
+  double  *gc_b = nullptr, *gc_x = nullptr;   // [gc_n]
+  uint64_t *t_key = nullptr, *t_keyall = nullptr; // triplets: own (capacity t_cap) / gathered (world * t_cap)
+  double   *t_val = nullptr, *t_valall = nullptr;
+  int64_t   t_cap = 0;
 };
 
 void amg_free(Amg *A);

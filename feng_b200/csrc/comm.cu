@@ -25,6 +25,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -54,6 +55,7 @@ static bool load_nccl()
   B200_SYM(CommInitRank, "ncclCommInitRank")
   B200_SYM(CommDestroy, "ncclCommDestroy")
   B200_SYM(AllReduce, "ncclAllReduce")
+  B200_SYM(AllGather, "ncclAllGather")
   B200_SYM(Send, "ncclSend")
   B200_SYM(Recv, "ncclRecv")
   B200_SYM(GroupStart, "ncclGroupStart")
@@ -216,6 +218,26 @@ int comm_allreduce(System *S, double *d_buf, int count, bool max_op)
   if(!C || C->world == 1) return B200_OK;
   B200_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)count, ncclDouble, max_op ? ncclMax : ncclSum, C->comm, S->stream));
   return B200_OK;
+}
+
+// every rank contributes `count` 8-byte words; recv holds world * count words in rank order
+int comm_allgather64(System *S, const void *send, void *recv, size_t count)
+{
+  Comm *C = static_cast<Comm *>(S->comm);
+  if(!C || C->world == 1) {
+    B200_CUDA(cudaMemcpyAsync(recv, send, count * 8, cudaMemcpyDeviceToDevice, S->stream));
+    return B200_OK;
+  }
+  B200_NCCL(g_nccl.AllGather(send, recv, count, ncclUint64, C->comm, S->stream));
+  return B200_OK;
+}
+
+// rows that read a ghost column (the interior / boundary split of the overlapped SpMV)
+void comm_boundary_rows(const System *S, const int32_t **rows, int64_t *n)
+{
+  const Comm *C = static_cast<const Comm *>(S->comm);
+  *rows = C ? C->d_brows : nullptr;
+  *n    = C ? C->n_brows : 0;
 }
 
 } // namespace b200

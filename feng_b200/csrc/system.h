@@ -182,6 +182,8 @@ const double *comm_mask(const System *S); // 1/0 per row (owned / ghost) or null
 int           comm_halo_exchange(System *S, double *d_x);
 int           comm_spmv_overlapped(System *S, double *d_x, double *d_y); // halo update of x hidden behind the interior rows
 int           comm_allreduce(System *S, double *d_buf, int count, bool max_op);
+int           comm_allgather64(System *S, const void *send, void *recv, size_t count);
+void          comm_boundary_rows(const System *S, const int32_t **rows, int64_t *n);
 // krylov.cu
 int  spmv(System *S, const double *d_x, double *d_y);
 // rows with skip[row] == 0 (rows == nullptr) or the listed rows (skip == nullptr)
