@@ -165,13 +165,14 @@ __global__ void amg_split_keys_kernel(int64_t nnz, int64_t n, const uint64_t *ke
 // ----------------------------------------------------------------------------------------------------------
 // level-0 single-precision working copy (same-field entries of the active rows)
 // ----------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool amg_keep(const uint8_t *__restrict__ fld, const uint8_t *__restrict__ pkind, int fi, int32_t j)
+__device__ __forceinline__ bool amg_keep(const uint8_t *__restrict__ fld_col, const uint8_t *__restrict__ kind_col, int fi, int32_t j)
 {
-  return pkind[j] != 0 && fld[j] == fi;
+  return kind_col[j] != 0 && fld_col[j] == fi;
 }
 
 __global__ void __launch_bounds__(256) amg_dec_count_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
-                                                            const uint8_t *__restrict__ fld, const uint8_t *__restrict__ pkind, int64_t *cnt)
+                                                            const uint8_t *__restrict__ fld, const uint8_t *__restrict__ pkind,
+                                                            const uint8_t *__restrict__ fld_col, const uint8_t *__restrict__ kind_col, int64_t *cnt)
 {
   const int     lane = threadIdx.x & 31;
   const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * (int64_t)blockDim.x) >> 5;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(256) amg_dec_count_kernel(int64_t n, const int
     int c = 0;
     if(pkind[i]) {
       const int fi = fld[i];
-      for(int64_t k = ia[i] + lane; k < ia[i + 1]; k += 32) c += amg_keep(fld, pkind, fi, ja[k]) ? 1 : 0;
+      for(int64_t k = ia[i] + lane; k < ia[i + 1]; k += 32) c += amg_keep(fld_col, kind_col, fi, ja[k]) ? 1 : 0;
     }
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
@@ -190,7 +191,8 @@ __global__ void __launch_bounds__(256) amg_dec_count_kernel(int64_t n, const int
 template <bool WITH_JA>
 __global__ void __launch_bounds__(256) amg_dec_fill_kernel(int64_t n, const int64_t *__restrict__ ia, const int32_t *__restrict__ ja,
                                                            const double *__restrict__ val, const uint8_t *__restrict__ fld,
-                                                           const uint8_t *__restrict__ pkind, const int64_t *__restrict__ ias, int32_t *jas,
+                                                           const uint8_t *__restrict__ pkind, const uint8_t *__restrict__ fld_col,
+                                                           const uint8_t *__restrict__ kind_col, const int64_t *__restrict__ ias, int32_t *jas,
                                                            float *vals)
 {
   const int     lane = threadIdx.x & 31;
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(256) amg_dec_fill_kernel(int64_t n, const int6
     for(int64_t k0 = beg; k0 < end; k0 += 32) {
       const int64_t  k = k0 + lane;
       const int32_t  j = k < end ? ja[k] : 0;
-      const bool     keep = k < end && amg_keep(fld, pkind, fi, j);
+      const bool     keep = k < end && amg_keep(fld_col, kind_col, fi, j);
       const unsigned m = __ballot_sync(0xffffffffu, keep);
       if(keep) {
         const int64_t o = out + __popc(m & ((1u << lane) - 1u));
@@ -813,6 +815,10 @@ void amg_free(Amg *A)
 static int csr_product(System *S, const AmgLevel &L, const double *x, double *y)
 {
   if(L.n <= 0) return B200_OK;
+  if(L.halo) {
+    const int rc = comm_halo_exchange(S, const_cast<double *>(x));
+    if(rc != B200_OK) return rc;
+  }
   if(L.val_s) {
     // lanes per row / rows in flight per lane group: B200_AMG_SPMV=LR (e.g. 42, 82, 44) overrides the default
     static const int cfg = [] {
@@ -1110,24 +1116,6 @@ int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int 
     const int rc = build_coarse_levels(S, A);
     if(rc != B200_OK) return rc;
   }
-  // single-precision working copy of level 0 (pattern now, values in the numeric phase)
-  if(A->use_f32 && A->L[0].pkind) {
-    AmgLevel &L0 = A->L[0];
-    int64_t  *cnt = nullptr;
-    B200_CUDA(cudaMalloc(&cnt, (size_t)(n + 1) * sizeof(int64_t)));
-    B200_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(n + 1) * sizeof(int64_t), S->stream));
-    amg_dec_count_kernel<<<GRID * 4, 256, 0, S->stream>>>(n, L0.ia, L0.ja, d_fld, L0.pkind, cnt);
-    count_launch();
-    thrust::device_ptr<int64_t> cp(cnt);
-    thrust::exclusive_scan(pol, cp, cp + n + 1, cp);
-    B200_CUDA(cudaMemcpyAsync(&L0.nnz_s, cnt + n, sizeof(int64_t), cudaMemcpyDeviceToHost, S->stream));
-    B200_CUDA(cudaStreamSynchronize(S->stream));
-    L0.ia_s = cnt;
-    B200_CUDA(cudaMalloc(&L0.ja_s, (size_t)std::max<int64_t>(L0.nnz_s, 1) * sizeof(int32_t)));
-    B200_CUDA(cudaMalloc(&L0.val_s, (size_t)std::max<int64_t>(L0.nnz_s, 1) * sizeof(float)));
-    amg_dec_fill_kernel<true><<<GRID * 4, 256, 0, S->stream>>>(n, L0.ia, L0.ja, L0.val, d_fld, L0.pkind, L0.ia_s, L0.ja_s, L0.val_s);
-    count_launch();
-  }
   // coarsest level
   const AmgLevel &C = A->L.back();
   A->dense_n = (C.n <= AMG_MAX_DENSE && !C.is_system) ? (int)C.n : 0;
@@ -1187,6 +1175,34 @@ int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int 
       A->gc_active = true;
       A->d_fld_all = d_fld_all;
     }
+  }
+  // single-precision working copy of level 0 (pattern now, values in the numeric phase)
+  if(A->use_f32 && A->L[0].pkind) {
+    AmgLevel &L0 = A->L[0];
+    // several GPUs with the global hierarchy: the rows of level 0 keep their couplings to ghost columns and every level-0 product
+    // is preceded by the halo update of its input -- the fine-level smoother and residual are those of the undecomposed operator
+    const uint8_t *fcol = A->gc_active ? A->d_fld_all : d_fld, *kcol = A->gc_active ? A->gc_kind : L0.pkind;
+    L0.halo = A->gc_active && !getenv("B200_AMG_LOCAL_SMOOTHER");
+    if(!L0.halo) {
+      fcol = d_fld;
+      kcol = L0.pkind;
+    }
+    A->d_fcol0 = fcol;
+    A->d_kcol0 = kcol;
+    int64_t  *cnt = nullptr;
+    B200_CUDA(cudaMalloc(&cnt, (size_t)(n + 1) * sizeof(int64_t)));
+    B200_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(n + 1) * sizeof(int64_t), S->stream));
+    amg_dec_count_kernel<<<GRID * 4, 256, 0, S->stream>>>(n, L0.ia, L0.ja, d_fld, L0.pkind, fcol, kcol, cnt);
+    count_launch();
+    thrust::device_ptr<int64_t> cp(cnt);
+    thrust::exclusive_scan(pol, cp, cp + n + 1, cp);
+    B200_CUDA(cudaMemcpyAsync(&L0.nnz_s, cnt + n, sizeof(int64_t), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    L0.ia_s = cnt;
+    B200_CUDA(cudaMalloc(&L0.ja_s, (size_t)std::max<int64_t>(L0.nnz_s, 1) * sizeof(int32_t)));
+    B200_CUDA(cudaMalloc(&L0.val_s, (size_t)std::max<int64_t>(L0.nnz_s, 1) * sizeof(float)));
+    amg_dec_fill_kernel<true><<<GRID * 4, 256, 0, S->stream>>>(n, L0.ia, L0.ja, L0.val, d_fld, L0.pkind, fcol, kcol, L0.ia_s, L0.ja_s, L0.val_s);
+    count_launch();
   }
   if(A->verbose) {
     if(A->gc_active)
@@ -1375,7 +1391,8 @@ int amg_setup_numeric(System *S, Amg *A)
   const int nl = (int)A->L.size();
   if(A->L[0].val_s) {
     AmgLevel &L0 = A->L[0];
-    amg_dec_fill_kernel<false><<<GRID * 4, 256, 0, S->stream>>>(L0.n, L0.ia, L0.ja, L0.val, A->d_fld, L0.pkind, L0.ia_s, nullptr, L0.val_s);
+    amg_dec_fill_kernel<false><<<GRID * 4, 256, 0, S->stream>>>(L0.n, L0.ia, L0.ja, L0.val, A->d_fld, L0.pkind, A->d_fcol0, A->d_kcol0, L0.ia_s, nullptr,
+                                                               L0.val_s);
     count_launch();
   }
   for(int l = 0; l < nl; ++l) {

@@ -23,6 +23,7 @@ struct AmgLevel {
   int32_t       *ja_own = nullptr;
   double        *val_own = nullptr;
   bool           is_system = false, decoupled = false;
+  bool           halo = false; // several GPUs: products on this level update the ghost entries of their input first
   // level 0 only: single-precision copy of the entries the hierarchy works on (active rows, columns of the same field):
   // the smoother, the residual and the Galerkin product of level 0 stream 8 bytes per entry of a third of the matrix
   // instead of 12 bytes of all of it
@@ -65,6 +66,7 @@ struct Amg {
   uint8_t *gc_kind = nullptr;                 // [n fine] 0 none, 1 vertex unknown, 2 mid-edge unknown (weights 1 / one half)
   const uint8_t *d_fld_all = nullptr;         // field map with the ghost rows still labelled (owned by the preconditioner)
   Amg     *G = nullptr;                       // replicated hierarchy on the merged level-gl matrix
+  const uint8_t *d_fcol0 = nullptr, *d_kcol0 = nullptr; // column labels used by the level-0 single-precision copy
   int64_t *g_ia = nullptr;
   int32_t *g_ja = nullptr;
   double  *g_val = nullptr;
