@@ -25,7 +25,7 @@ def _stale(target, deps):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "system.h"), os.path.join(CSRC, "device_common.cuh"), os.path.join(CSRC, "gather_lane.cuh"), os.path.join(CSRC, "amg.h"),
+    headers = [os.path.join(CSRC, "system.h"), os.path.join(CSRC, "device_common.cuh"), os.path.join(CSRC, "gather_lane.cuh"), os.path.join(CSRC, "gather_urow.cuh"), os.path.join(CSRC, "amg.h"),
                os.path.join(HERE, "..", "include", "feng_b200.h")]
     objs, jobs = [], []
     for src in SOURCES:

@@ -77,6 +77,15 @@ struct GatherPlan {
   bool     patch = true;    // patch kernel (patch.cu) instead of the row-owner kernels of this file
   bool     lane = true;     // lane-per-column kernels (gather_lane.cuh) or thread-per-node kernels (B200_GATHER_KERNEL=node)
   double  *d_es = nullptr;  // [nElm][ES::W] per-element convective state, rewritten by every assembly pass
+  // row-lane velocity kernels (gather_urow.cuh): P2/P1 tetrahedra
+  bool      urow = false;
+  double   *d_geo4 = nullptr;  // [nElm][4][4] gradients of the barycentric coordinates + detJ
+  int32_t  *d_order = nullptr; // velocity nodes sorted by (row length, signature)
+  uint64_t *d_lacnt = nullptr; // [node] pairs per local index, 6 bits each
+  void     *d_rec = nullptr;   // [nPairs] URowPair
+  std::vector<double>   utab;  // [10][URowTab::LEN] reference tensors per local row node
+  std::vector<int32_t>  useg_begin; // launch segments (in warps of 10 nodes)
+  std::vector<uint32_t> useg_lmax;  // longest row of the segment
 };
 
 struct GatherArgs {
@@ -669,6 +678,7 @@ __global__ void __launch_bounds__(NPB) gather_p_kernel(const GatherArgs a)
 
 } // namespace b200
 #include "gather_lane.cuh"
+#include "gather_urow.cuh"
 namespace b200 {
 
 // lanes per node -> (warps per CTA, register budget); the plan's nodes-per-CTA follows from it
@@ -933,7 +943,7 @@ static int build_cta_order(System *S, NodeSet &N, int npb, int nLoc)
 }
 
 static int build_node_set(System *S, NodeSet &N, const int32_t *d_adr, int nLoc, int nF, int nRow, int npb, int offw, int ncol, int NU, int NP,
-                          int colmaskU, int colmaskP, double band = 1.25, int min_div = 50)
+                          int colmaskU, int colmaskP, double band = 1.25, int min_div = 50, bool want_off = true)
 {
   auto          pol = thrust::cuda::par.on(S->stream);
   const int64_t np  = S->nElm * (int64_t)nLoc;
@@ -968,17 +978,20 @@ static int build_node_set(System *S, NodeSet &N, const int32_t *d_adr, int nLoc,
   B200_CUDA(cudaMalloc(&N.smoff, (size_t)N.nNodes * sizeof(uint32_t)));
   B200_CUDA(cudaMalloc(&N.cta_size, (size_t)N.nCta * sizeof(uint32_t)));
   B200_CUDA(cudaMalloc(&N.cta_g0, (size_t)N.nCta * sizeof(int64_t)));
-  B200_CUDA(cudaMalloc(&N.off, (size_t)np * offw * sizeof(uint16_t)));
-  B200_CUDA(cudaMemsetAsync(N.off, 0xFF, (size_t)np * offw * sizeof(uint16_t), S->stream));
+  if(want_off) {
+    B200_CUDA(cudaMalloc(&N.off, (size_t)np * offw * sizeof(uint16_t)));
+    B200_CUDA(cudaMemsetAsync(N.off, 0xFF, (size_t)np * offw * sizeof(uint16_t), S->stream));
+  }
   thrust::device_vector<int32_t> cta_pairs(N.nCta);
   int *d_err;
   B200_CUDA(cudaMalloc(&d_err, sizeof(int)));
   B200_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), S->stream));
   node_smem_kernel<<<(N.nCta + 127) / 128, 128, 0, S->stream>>>(N.nNodes, npb, nRow, S->nInc, S->d_ia, N.row, N.range, N.smoff, N.cta_size, N.cta_g0,
                                                             thrust::raw_pointer_cast(cta_pairs.data()), d_err);
-  node_offsets_kernel<<<148 * 16, 64, 0, S->stream>>>(N.nNodes, nRow, nLoc, offw, ncol, NU, NP, N.range, N.row, N.pair, S->spaces[S->su].d_adr,
-                                                     S->sp >= 0 ? S->spaces[S->sp].d_adr : nullptr, S->d_ia, S->d_ja, S->nInc, colmaskU, colmaskP,
-                                                     N.off, d_err);
+  if(want_off)
+    node_offsets_kernel<<<148 * 16, 64, 0, S->stream>>>(N.nNodes, nRow, nLoc, offw, ncol, NU, NP, N.range, N.row, N.pair, S->spaces[S->su].d_adr,
+                                                       S->sp >= 0 ? S->spaces[S->sp].d_adr : nullptr, S->d_ia, S->d_ja, S->nInc, colmaskU, colmaskP,
+                                                       N.off, d_err);
   count_launch(3);
   int h_err = 0;
   B200_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, S->stream));
@@ -1138,8 +1151,113 @@ void gather_free(System *S)
   cudaFree(G->d_tab);
   cudaFree(G->d_geo);
   cudaFree(G->d_es);
+  cudaFree(G->d_geo4);
+  cudaFree(G->d_order);
+  cudaFree(G->d_lacnt);
+  cudaFree(G->d_rec);
   delete G;
   S->gather = nullptr;
+}
+
+
+// ----------------------------------------------------------------------------------------------------------
+// row-lane plan (gather_urow.cuh)
+// ----------------------------------------------------------------------------------------------------------
+static const void *g_urow_owner = nullptr; // plan whose tensors are in b200_urow_tab
+
+static void urow_tables(const std::vector<double> &tab, std::vector<double> &ut)
+{
+  using T = GT<3, 10, 4>;
+  using CT = URowTab;
+  const double *K = tab.data() + T::O_K, *T3 = tab.data() + T::O_T3, *Mr = tab.data() + T::O_M, *B = tab.data() + T::O_B;
+  ut.assign((size_t)10 * CT::LEN, 0.);
+  for(int la = 0; la < 10; ++la) {
+    double *o = ut.data() + (size_t)la * CT::LEN;
+    for(int b = 0; b < 10; ++b) {
+      const double *Kb = K + (la * 10 + b) * 9;
+      for(int k = 0; k < 9; ++k) o[CT::O_K + b * 9 + k] = Kb[k];
+      const double ks[6] = {Kb[0], Kb[4], Kb[8], Kb[1] + Kb[3], Kb[2] + Kb[6], Kb[5] + Kb[7]};
+      for(int k = 0; k < 6; ++k) o[CT::O_KS + b * 6 + k] = ks[k];
+      for(int v = 0; v < 4; ++v) o[CT::O_T3 + b * 4 + v] = T3[(la * 10 + b) * 4 + v];
+      o[CT::O_M + b] = Mr[la * 10 + b];
+    }
+    for(int q = 0; q < 4; ++q)
+      for(int al = 0; al < 3; ++al) o[CT::O_B + q * 3 + al] = B[(q * 10 + la) * 3 + al];
+  }
+}
+
+// B200_OK, or B200_ERR_UNSUPP when the system does not have the structure the row-lane kernels assume (the lane-group kernels take over)
+static int build_urow_plan(System *S, GatherPlan *G, const std::vector<double> &tab)
+{
+  urow_tables(tab, G->utab);
+  NodeSet &N = G->U;
+  if(N.nNodes == 0) return B200_ERR_UNSUPP;
+  auto pol = thrust::cuda::par.on(S->stream);
+  B200_CUDA(cudaMalloc(&G->d_geo4, (size_t)S->nElm * 16 * sizeof(double)));
+  urow_geo4_kernel<<<148 * 8, 256, 0, S->stream>>>(S->nElm, G->d_geo, GT<3, 10, 4>::GW, G->d_geo4);
+  int *d_err;
+  B200_CUDA(cudaMalloc(&d_err, sizeof(int)));
+  B200_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), S->stream));
+  {
+    // pairs of every node: ascending local index, then ascending element (residual-only passes read the same order)
+    thrust::device_vector<uint64_t> pkey(N.nPairs);
+    urow_pair_key_init_kernel<<<148 * 8, 256, 0, S->stream>>>(N.nPairs, thrust::raw_pointer_cast(pkey.data()));
+    urow_pair_key_kernel<<<148 * 16, 64, 0, S->stream>>>(N.nNodes, N.range, N.pair, thrust::raw_pointer_cast(pkey.data()));
+    thrust::stable_sort_by_key(pol, pkey.begin(), pkey.end(), thrust::device_pointer_cast(N.pair));
+  }
+  thrust::device_vector<uint64_t> key(N.nNodes);
+  B200_CUDA(cudaMalloc(&G->d_order, (size_t)N.nNodes * sizeof(int32_t)));
+  B200_CUDA(cudaMalloc(&G->d_lacnt, (size_t)N.nNodes * sizeof(uint64_t)));
+  urow_node_key_kernel<<<148 * 8, 256, 0, S->stream>>>(N.nNodes, N.range, N.pair, N.row, S->d_ia, S->nInc, thrust::raw_pointer_cast(key.data()), G->d_order,
+                                                      G->d_lacnt, d_err);
+  thrust::stable_sort_by_key(pol, key.begin(), key.end(), thrust::device_pointer_cast(G->d_order));
+  count_launch(5);
+  std::vector<uint64_t> h_key(N.nNodes);
+  B200_CUDA(cudaMemcpyAsync(h_key.data(), thrust::raw_pointer_cast(key.data()), (size_t)N.nNodes * sizeof(uint64_t), cudaMemcpyDeviceToHost, S->stream));
+  B200_CUDA(cudaMalloc(&G->d_rec, (size_t)N.nPairs * sizeof(URowPair)));
+  urow_pairs_kernel<<<148 * 16, 64, 0, S->stream>>>(N.nNodes, N.range, N.row, N.pair, S->spaces[S->su].d_adr, S->spaces[S->sp].d_adr, S->d_ia, S->d_ja,
+                                                   S->nInc, S->has_matrix_block[0][0] ? 1 : 0, S->has_matrix_block[0][1] ? 1 : 0,
+                                                   static_cast<URowPair *>(G->d_rec), d_err);
+  count_launch();
+  int h_err = 0;
+  B200_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, S->stream));
+  B200_CUDA(cudaStreamSynchronize(S->stream));
+  cudaFree(d_err);
+  if(h_err) {
+    set_error("row-lane plan: columns of a velocity node are not three adjacent unknowns, or > 63 elements share a local index (code " +
+              std::to_string(h_err) + ")");
+    return B200_ERR_UNSUPP;
+  }
+  // launch segments: warps of 10 nodes; consecutive warps whose longest rows differ by < 25 % share one launch
+  G->useg_begin.clear();
+  G->useg_lmax.clear();
+  const int32_t cnt = N.nNodes, nw = (cnt + 9) / 10;
+  auto lmax_of = [&](int32_t w) { // keys are sorted by length: the last node of the warp has the longest row
+    const int32_t last = std::min(cnt, (w + 1) * 10) - 1;
+    return (uint32_t)(h_key[last] >> 40);
+  };
+  int32_t  b = 0;
+  uint32_t mn = lmax_of(0);
+  for(int32_t w = 1; w <= nw; ++w) {
+    const bool last = w == nw;
+    if(!last) {
+      const uint32_t v = lmax_of(w);
+      const bool cut = (double)v > 1.25 * (double)std::max<uint32_t>(mn, 1u) && w - b >= 64 && nw - w >= 64 && G->useg_begin.size() < 6;
+      if(!cut) continue;
+    }
+    G->useg_begin.push_back(b);
+    G->useg_lmax.push_back(lmax_of(w - 1));
+    if(!last) {
+      b  = w;
+      mn = lmax_of(w);
+    }
+  }
+  G->useg_begin.push_back(nw);
+  if((size_t)(G->useg_lmax.back() + 3) * 32 * 8 + 2048 > 200 * 1024) {
+    set_error("row-lane plan: row images exceed shared memory");
+    return B200_ERR_UNSUPP;
+  }
+  return B200_OK;
 }
 
 // Builds the gather plan if the registered problem qualifies (Taylor-Hood P2/P1, no P-P block); B200_ERR_UNSUPP otherwise.
@@ -1175,8 +1293,11 @@ int build_gather_plan(System *S)
     // from the L2-resident state vector win (the per-element state is 512 B/element of extra HBM traffic); in 3-D the
     // lane-group kernels win 2.3x (the row images of one node are 2-5 KB, one thread per node leaves the SM empty)
     const char *k = getenv("B200_GATHER_KERNEL");
-    G->lane       = k ? std::string(k) == "lane" : D == 3;
+    G->lane       = k ? (std::string(k) == "lane" || std::string(k) == "urow") : D == 3;
     G->patch      = false; // the round-1 patch / row-slice kernels were measured slower and moved to experiments/
+    // row-lane velocity rows (gather_urow.cuh): P2/P1 tetrahedra, lane-group pressure rows
+    G->urow       = D == 3 && NS == 10 && NP == 4 && (!k || std::string(k) == "urow");
+    if(G->urow && lane_default(D) != 10) G->urow = false;
   }
   if(G->lane) {
     const LaneCfg lc = lane_cfg(D, lane_default(D));
@@ -1196,18 +1317,38 @@ int build_gather_plan(System *S)
       geometry_kernel<3><<<148 * 8, 256, 0, S->stream>>>(S->nElm, S->d_xyz, S->d_conn, G->d_geo);
     count_launch();
     B200_CUDA(cudaStreamSynchronize(S->stream));
-    if(G->lane) {
-      const size_t esw = (size_t)(NP * D * D + NS * NS + NS * D + NP + 1) / 2 * 2; // ES<D,NS,NP>::W
-      B200_CUDA(cudaMalloc(&G->d_es, (size_t)S->nElm * esw * sizeof(double)));
-    }
     log_stage("gather plan: geometry");
     const int offwU = (M + 7) / 8 * 8, offwP = (NU + 7) / 8 * 8;
     // lane-group kernels are not limited by the shared memory of the longest rows: few, large launch segments
     const double band    = (G->lane && G->lanes > 1) ? 1.6 : 1.25;
     const int    min_div = (G->lane && G->lanes > 1) ? 12 : 50;
     int       rc = build_node_set(S, G->U, S->spaces[S->su].d_adr, NS, NU, D, G->npbU, offwU, M, NU, NP, S->has_matrix_block[0][0] ? 1 : 0,
-                                  S->has_matrix_block[0][1] ? 1 : 0, band, min_div);
+                                  S->has_matrix_block[0][1] ? 1 : 0, band, min_div, !G->urow);
     log_stage("gather plan: U node set");
+    if(rc == B200_OK && G->urow) {
+      const int crc = build_urow_plan(S, G, tab);
+      log_stage("gather plan: row-lane pair records");
+      if(crc == B200_ERR_UNSUPP) {
+        // not the structure the row-lane kernels assume: the lane-group kernels need the per-column offsets after all
+        G->urow = false;
+        cudaFree(G->d_geo4);
+        cudaFree(G->d_order);
+        cudaFree(G->d_lacnt);
+        cudaFree(G->d_rec);
+        G->d_geo4  = nullptr;
+        G->d_order = nullptr;
+        G->d_lacnt = nullptr;
+        G->d_rec   = nullptr;
+        if(getenv("B200_VERBOSE")) fprintf(stderr, "[b200] row-lane plan not applicable: %s\n", b200_last_error());
+        rc = build_node_set(S, G->U, S->spaces[S->su].d_adr, NS, NU, D, G->npbU, offwU, M, NU, NP, S->has_matrix_block[0][0] ? 1 : 0,
+                            S->has_matrix_block[0][1] ? 1 : 0, band, min_div, true);
+      } else if(crc != B200_OK)
+        rc = crc;
+    }
+    if(rc == B200_OK && G->lane) {
+      const size_t esw = G->urow ? (size_t)ESC::W : (size_t)(NP * D * D + NS * NS + NS * D + NP + 1) / 2 * 2; // ES<D,NS,NP>::W
+      B200_CUDA(cudaMalloc(&G->d_es, (size_t)S->nElm * esw * sizeof(double)));
+    }
     if(rc == B200_OK)
       rc = build_node_set(S, G->P, S->spaces[S->sp].d_adr, NP, NP, 1, G->npbP, offwP, NU, NU, NP, S->has_matrix_block[1][0] ? 1 : 0, 0, band,
                           min_div);
@@ -1421,10 +1562,156 @@ template <int D, int NS, int NP, int NW, int L, int REGS> static int launch_gath
   return B200_OK;
 }
 
+
+// row-lane kernels: pre-pass, velocity rows per launch segment, lane-group pressure rows
+static int launch_gather_urow(System *S, int what, const THCoeffs &c)
+{
+  constexpr int D = 3, NS = 10, NP = 4, NW = 4, L = 10, NT = NW * 32, MINB = 4;
+  GatherPlan *G = static_cast<GatherPlan *>(S->gather);
+  using T = GT<D, NS, NP>;
+  const double *d_source = (c.c_src != 0.) ? S->d_source : nullptr;
+  const int     ntab     = d_source ? G->tab_len_src : G->tab_len;
+  {
+    ElementStateArgs ea;
+    ea.nElm   = S->nElm;
+    ea.adrU   = S->spaces[S->su].d_adr;
+    ea.adrP   = S->spaces[S->sp].d_adr;
+    ea.sol    = S->d_sol;
+    ea.soldot = S->have_soldot ? S->d_soldot : nullptr;
+    ea.source = d_source;
+    ea.geo    = G->d_geo;
+    ea.tab    = G->d_tab;
+    ea.es     = G->d_es;
+    ea.nq     = S->nq;
+    ea.ntab   = ntab;
+    ea.c      = c;
+    for(int i = 0; i < 120; ++i) ea.E[i] = G->E[i];
+    const size_t smem = (size_t)(ntab - T::O_T3) * sizeof(double);
+    B200_CUDA(cudaFuncSetAttribute(element_state_urow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    element_state_urow_kernel<<<(unsigned)((S->nElm + 127) / 128), 128, smem, S->stream>>>(ea);
+    count_launch();
+  }
+  const bool mat = what & 2, res = what & 1;
+  GatherArgs a;
+  a.xyz    = S->d_xyz;
+  a.conn   = S->d_conn;
+  a.adrU   = S->spaces[S->su].d_adr;
+  a.adrP   = S->spaces[S->sp].d_adr;
+  a.sol    = S->d_sol;
+  a.soldot = S->have_soldot ? S->d_soldot : nullptr;
+  a.source = d_source;
+  a.tab    = G->d_tab;
+  a.geo    = G->d_geo;
+  a.es     = G->d_es;
+  a.ia     = S->d_ia;
+  a.val    = S->d_val;
+  a.rhs    = S->d_rhs;
+  a.nInc   = S->nInc;
+  a.nq     = S->nq;
+  a.ntab   = G->tab_len;
+  a.c      = c;
+  a.c0     = S->c0;
+  for(int i = 0; i < 120; ++i) a.E[i] = G->E[i];
+  if(mat) {
+    if(g_urow_owner != G) {
+      // the tensors of another system (another quadrature rule) are in the constant bank: drain the device before replacing them
+      if(g_urow_owner != nullptr) B200_CUDA(cudaDeviceSynchronize());
+      B200_CUDA(cudaMemcpyToSymbolAsync(b200_urow_tab, G->utab.data(), G->utab.size() * sizeof(double), 0, cudaMemcpyHostToDevice, S->stream));
+      g_urow_owner = G;
+    }
+    URowArgs ua;
+    ua.geo4  = G->d_geo4;
+    ua.es    = G->d_es;
+    ua.rec   = static_cast<const URowPair *>(G->d_rec);
+    ua.order = G->d_order;
+    ua.lacnt = G->d_lacnt;
+    ua.range = G->U.range;
+    ua.row   = G->U.row;
+    ua.ia    = S->d_ia;
+    ua.val   = S->d_val;
+    ua.rhs   = S->d_rhs;
+    ua.count = G->U.nNodes;
+    ua.nInc  = S->nInc;
+    ua.nsm   = -c.sig_mu;
+    ua.cdk   = c.diff_k - c.sig_mu;
+    ua.mass0 = c.c_mass * S->c0;
+    ua.cpr   = c.c_sig - c.c_gradp;
+    const int nseg = (int)G->useg_lmax.size();
+    for(int sg = 0; sg < nseg; ++sg) {
+      ua.warp0          = G->useg_begin[sg];
+      const int    nc   = G->useg_begin[sg + 1] - G->useg_begin[sg];
+      const size_t smem = ((size_t)(G->useg_lmax[sg] + 3) * 32 + 32 * 8) * sizeof(double);
+#define B200_LAUNCH_C(KERN)                                                                                         \
+  do {                                                                                                              \
+    B200_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+    KERN<<<nc, 32, smem, S->stream>>>(ua);                                                                          \
+    count_launch();                                                                                                 \
+  } while(0)
+      // long rows (vertex nodes): 4 warps per SM fit anyway, no register cap; short rows: 10 warps per SM
+      if(smem > 26 * 1024) {
+        if(res)
+          B200_LAUNCH_C((gather_urow_kernel<true, 4>));
+        else
+          B200_LAUNCH_C((gather_urow_kernel<false, 4>));
+      } else {
+        if(res)
+          B200_LAUNCH_C((gather_urow_kernel<true, 10>));
+        else
+          B200_LAUNCH_C((gather_urow_kernel<false, 10>));
+      }
+#undef B200_LAUNCH_C
+    }
+  }
+  for(int pass = mat ? 1 : 0; pass < 2; ++pass) {
+    const NodeSet &N = pass == 0 ? G->U : G->P;
+    if(N.nNodes == 0) continue;
+    a.pair     = N.pair;
+    a.range    = N.range;
+    a.row      = N.row;
+    a.smoff    = N.smoff;
+    a.cta_perm = N.cta_perm;
+    a.cta_size = N.cta_size;
+    a.off      = N.off;
+    a.nNodes   = N.nNodes;
+    a.cta_g0   = N.cta_g0;
+    if(!mat) {
+      a.cta0 = 0;
+      const int nc = (N.nNodes + 255) / 256;
+      if(pass == 0)
+        gather_lane_kernel<D, NS, NP, 8, 1, 1, false, true, false, true><<<nc, 256, 0, S->stream>>>(a);
+      else
+        gather_lane_kernel<D, NS, NP, 8, 1, 1, false, true, true, true><<<nc, 256, 0, S->stream>>>(a);
+      count_launch();
+      continue;
+    }
+    const size_t smem_max = ((size_t)a.ntab + N.max_cta + NT) * sizeof(double);
+    const int    nseg     = (int)N.seg_smem.size();
+#define B200_LAUNCH_L(KERN)                                                                                                              \
+  do {                                                                                                                                   \
+    B200_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));                                   \
+    for(int sg = 0; sg < nseg; ++sg) {                                                                                                   \
+      a.cta0            = N.seg_begin[sg];                                                                                               \
+      const int    nc   = N.seg_begin[sg + 1] - N.seg_begin[sg];                                                                         \
+      const size_t smem = ((size_t)a.ntab + N.seg_smem[sg] + NT) * sizeof(double);                                                       \
+      KERN<<<nc, NT, smem, S->stream>>>(a);                                                                                              \
+      count_launch();                                                                                                                    \
+    }                                                                                                                                    \
+  } while(0)
+    if(res)
+      B200_LAUNCH_L((gather_lane_kernel<D, NS, NP, NW, L, MINB, true, true, true, true>));
+    else
+      B200_LAUNCH_L((gather_lane_kernel<D, NS, NP, NW, L, MINB, true, false, true, true>));
+#undef B200_LAUNCH_L
+  }
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
 // what: bit 0 residual, bit 1 matrix; OVERWRITES val / rhs (every row is written exactly once)
 int launch_gather(System *S, int what, const THCoeffs &c)
 {
   const GatherPlan *G = static_cast<const GatherPlan *>(S->gather);
+  if(G->urow) return launch_gather_urow(S, what, c);
   if(G->lane) {
     if(S->dim == 2) {
       switch(G->lanes) {

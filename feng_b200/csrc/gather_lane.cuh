@@ -31,6 +31,25 @@ template <int D, int NS, int NP> struct ES {
   static constexpr int O_RU = O_C1 + NS * NS;       // [NS][D]
   static constexpr int O_RP = O_RU + NS * D;        // [NP]
   static constexpr int W    = (O_RP + NP + 1) / 2 * 2; // doubles per element (16-byte aligned records)
+  __host__ __device__ static constexpr int ru(int la, int i) { return O_RU + la * D + i; }
+  __host__ __device__ static constexpr int rp(int q) { return O_RP + q; }
+};
+
+// per-element state of the canonical kernels (gather_canon.cuh; P2/P1 tetrahedra; records are 128-byte aligned: 208 * 8 = 13 * 128)
+struct ESC {
+  static constexpr int O_DVT = 0;   // [3][4][4]   DvT[i][v][j] = c_conv J d_j u_i (vertex v), j = 3: padding
+  static constexpr int O_ROW = 48;  // [10][16]    per local row node la: C1c[0..9] (canonical column order of la), RU[0..2] at 10..12,
+                                    //             slot 13 of rows 0..3: the pressure-row residual RP[q]
+  static constexpr int W = 208;
+  static constexpr int O_DV = 0, O_C1 = 0; // not used through this layout (names needed by the shared row kernel)
+  __host__ __device__ static constexpr int ru(int la, int i) { return O_ROW + la * 16 + 10 + i; }
+  __host__ __device__ static constexpr int rp(int q) { return O_ROW + q * 16 + 13; }
+};
+template <int D, int NS, int NP, bool CAN> struct ESelect {
+  using type = ES<D, NS, NP>;
+};
+template <int D, int NS, int NP> struct ESelect<D, NS, NP, true> {
+  using type = ESC;
 };
 
 struct ElementStateArgs {
@@ -242,11 +261,13 @@ template <int D, int NS, int NP> __global__ void __launch_bounds__(128) element_
 
 // PROW = false: velocity nodes (D rows per node); PROW = true: pressure nodes (1 row per node).
 // L lanes per node (a divisor of NS), GPW = 32 / L node groups per warp, NW warps per CTA, NPB = NW * GPW nodes per CTA.
-template <int D, int NS, int NP, int NW, int L, int MINB, bool MAT, bool RES, bool PROW>
+// CAN: the per-element records have the layout of the canonical kernels (pressure rows and residual-only passes)
+template <int D, int NS, int NP, int NW, int L, int MINB, bool MAT, bool RES, bool PROW, bool CAN = false>
 __global__ void __launch_bounds__(NW * 32, MINB) gather_lane_kernel(const GatherArgs a)
 {
   using T = GT<D, NS, NP>;
-  using X = ES<D, NS, NP>;
+  using X = typename ESelect<D, NS, NP, CAN>::type;
+  static_assert(!CAN || PROW || !MAT, "canonical records: velocity rows are assembled by gather_canon_kernel");
   static_assert(NS % L == 0, "lanes per node must divide the number of velocity nodes");
   constexpr int NU = NS * D, GPW = 32 / L, NPB = NW * GPW, NT = NW * 32, GW = T::GW, NBL = NS / L;
   constexpr int NR   = PROW ? 1 : D;
@@ -330,10 +351,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) gather_lane_kernel(const Gather
       const double *es = a.es + (int64_t)e * X::W;
       if(RES && l == 0) {
         if(PROW) {
-          res[0] += es[X::O_RP + la];
+          res[0] += es[X::rp(la)];
         } else {
 #pragma unroll
-          for(int i = 0; i < D; ++i) res[i] += es[X::O_RU + la * D + i];
+          for(int i = 0; i < D; ++i) res[i] += es[X::ru(la, i)];
         }
       }
       if(MAT) {

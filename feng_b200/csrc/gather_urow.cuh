@@ -1,0 +1,597 @@
+// Row-lane velocity-row kernels for P2/P1 tetrahedra (included by gather.cu after gather_lane.cuh).
+//
+// What the r02h capture of gather_lane_kernel says (profiles/README.md): the velocity rows run at the speed of the L1 /
+// shared-memory data stage -- per (row node, element) pair 55 shared wavefronts (14 of them loads of the reference
+// tensors K[la][b], T3[la][b], M[la][b] indexed by the LANE, 46 % bank-conflict replays of the scattered row-image
+// updates) and 38 global sectors (three lane groups per warp read three element records) for 17 cycles of FP64 work.
+// This file removes those three costs with the same sums as gather_lane_kernel (feSysElm_*::computeAe,
+// src/feVectorSysElm.cpp:1171-1204, :1454-1494, :449-503, :528-578, re-associated as in gather.cu):
+//
+//  1. One lane per MATRIX ROW: lane (g, i) owns row i of node g of its warp (10 nodes x 3 components = 30 lanes) and
+//     computes row i of every 3 x 3 block of that node's pairs.  The pairs of every node are sorted by the LOCAL index
+//     `la` the node has in the element, the nodes are sorted by the signature (number of pairs per la), and the warp
+//     walks la = 0 .. 9 together: at any time all lanes of a warp work on the same (la, column b).  The reference
+//     tensors are therefore indexed by warp-uniform values: they live in __constant__ memory and reach the DFMAs through
+//     uniform registers (LDCU) -- no shared-memory or L1 traffic at all.
+//  2. The row image of lane l is INTERLEAVED in shared memory: entry k of lane l lives at word k * 32 + l, so a warp-wide
+//     read-modify-write touches 32 different bank pairs whatever the column offsets are -- zero bank conflicts by
+//     construction, and no __syncwarp between elements (images are lane-private).
+//  3. 256-bit global loads (ld.global.nc.v4.f64, sm_100) of 32-byte-aligned records: a pair needs 12 load instructions
+//     instead of 39 sectors spread over 25.
+//  The finished images are transposed through a swizzled 2 KB staging tile and written once with 64-byte runs.
+//  A lane whose node has no pair for the (la, step) its warp is at recomputes one of its pairs into its trash entries
+//  (the loop stays convergent, which keeps the constant loads on the uniform datapath); with nodes sorted by signature
+//  that only happens where the sort changes signature.
+#pragma once
+
+namespace b200 {
+
+struct __align__(32) D4 {
+  double x, y, z, w;
+};
+__device__ __forceinline__ D4 ldg256(const void *p)
+{
+  D4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+struct U8 {
+  uint32_t w[8];
+};
+__device__ __forceinline__ U8 ldg256u(const void *p)
+{
+  U8 r;
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+               : "l"(p));
+  return r;
+}
+// 16-bit field t of a pair record held in registers (word 0 = ea, fields start at word 1); t is a compile-time constant after unrolling
+__device__ __forceinline__ uint32_t rec_off(const U8 &r, int t) { return (t & 1) ? (r.w[1 + (t >> 1)] >> 16) : (r.w[1 + (t >> 1)] & 0xffffu); }
+__device__ __forceinline__ void stg256(void *p, const D4 &v)
+{
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+
+// Reference tensors per local row node la, unscaled (the coefficients of the registered forms are folded into per-pair geometry
+// factors).  They are indexed with warp-uniform values: la, plus an offset that depends on the loop counter and is always 0,
+// which the compiler cannot prove.  FP64 instructions of sm_100 take constants through UNIFORM REGISTERS (DFMA R, R, UR, R fed
+// by LDCU); without that dependence ptxas hoists all 212 constants of a row out of the pair loop, runs out of uniform registers,
+// copies them to vector registers and spills (measured: 255 registers + 260 bytes of spill traffic per pair).
+struct URowTab {
+  static constexpr int O_K = 0;    // [10][3][3] Kref[la][b][al][be]
+  static constexpr int O_KS = 90;  // [10][6]    {K00, K11, K22, K01 + K10, K02 + K20, K12 + K21}
+  static constexpr int O_T3 = 150; // [10][4]    T3[la][b][v]
+  static constexpr int O_M = 190;  // [10]       Mref[la][b]
+  static constexpr int O_B = 200;  // [4][3]     Bref[q][la][al]
+  static constexpr int LEN = 212;
+};
+__constant__ double b200_urow_tab[10][URowTab::LEN];
+
+// ----------------------------------------------------------------------------------------------------------------------
+// pre-pass: everything that depends on the element only (as element_state_kernel), in the record layout ESC
+// ----------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) element_state_urow_kernel(const ElementStateArgs a)
+{
+  constexpr int D = 3, NS = 10, NP = 4;
+  using T = GT<D, NS, NP>;
+  using X = ESC;
+  constexpr int NU = NS * D, GW = T::GW, TOFF = T::O_T3;
+  extern __shared__ double s_tab[];
+  for(int i = threadIdx.x; i < a.ntab - TOFF; i += blockDim.x) s_tab[i] = a.tab[TOFF + i];
+  __syncthreads();
+  const double *s_t3 = s_tab + (T::O_T3 - TOFF), *s_m = s_tab + (T::O_M - TOFF), *s_b = s_tab + (T::O_B - TOFF), *s_w = s_tab + (T::O_W - TOFF);
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if(e >= a.nElm) return;
+  double G[D * D], J;
+  {
+    const double2 *ge = reinterpret_cast<const double2 *>(a.geo + e * GW);
+    double         g[GW];
+#pragma unroll
+    for(int i = 0; i < GW / 2; ++i) {
+      const double2 v = ge[i];
+      g[2 * i]     = v.x;
+      g[2 * i + 1] = v.y;
+    }
+#pragma unroll
+    for(int i = 0; i < D * D; ++i) G[i] = g[i];
+    J = g[D * D];
+  }
+  int32_t ad[NU];
+  double  U[NS][D];
+  {
+    const int2 *a2 = reinterpret_cast<const int2 *>(a.adrU + e * NU);
+#pragma unroll
+    for(int k = 0; k < NU / 2; ++k) {
+      const int2 v  = a2[k];
+      ad[2 * k + 0] = v.x;
+      ad[2 * k + 1] = v.y;
+    }
+#pragma unroll
+    for(int c = 0; c < NS; ++c)
+#pragma unroll
+      for(int m = 0; m < D; ++m) U[c][m] = a.sol[ad[c * D + m]];
+  }
+  double P[NP];
+#pragma unroll
+  for(int q = 0; q < NP; ++q) P[q] = a.sol[a.adrP[e * NP + q]];
+  const THCoeffs c   = a.c;
+  double        *out = a.es + e * X::W;
+  // velocity gradient at the vertices: gu[v][j][i] = d_j u_i (v)   (src/feSpace.cpp:1352-1405)
+  double gu[NP * D * D];
+#pragma unroll
+  for(int i = 0; i < D; ++i) {
+    double Xi[D][NP];
+#pragma unroll
+    for(int al = 0; al < D; ++al)
+#pragma unroll
+      for(int v = 0; v < NP; ++v) Xi[al][v] = 0.;
+#pragma unroll
+    for(int cc = 0; cc < NS; ++cc)
+#pragma unroll
+      for(int al = 0; al < D; ++al)
+#pragma unroll
+        for(int v = 0; v < NP; ++v) Xi[al][v] += U[cc][i] * a.E[(cc * D + al) * NP + v];
+#pragma unroll
+    for(int v = 0; v < NP; ++v)
+#pragma unroll
+      for(int j = 0; j < D; ++j) {
+        double s = 0.;
+#pragma unroll
+        for(int al = 0; al < D; ++al) s += G[al * D + j] * Xi[al][v];
+        gu[(v * D + j) * D + i] = s;
+      }
+  }
+  {
+    const double sJ = c.c_conv * J;
+#pragma unroll
+    for(int i = 0; i < D; ++i)
+#pragma unroll
+      for(int v = 0; v < NP; ++v) {
+        D4 o;
+        o.x = sJ * gu[(v * D + 0) * D + i];
+        o.y = sJ * gu[(v * D + 1) * D + i];
+        o.z = sJ * gu[(v * D + 2) * D + i];
+        o.w = 0.;
+        stg256(out + X::O_DVT + (i * NP + v) * 4, o);
+      }
+  }
+  // contravariant velocity DOFs (scaled by c_conv J)
+  double Ut[NS][D];
+#pragma unroll
+  for(int cc = 0; cc < NS; ++cc)
+#pragma unroll
+    for(int al = 0; al < D; ++al) {
+      double s = 0.;
+#pragma unroll
+      for(int m = 0; m < D; ++m) s += U[cc][m] * G[al * D + m];
+      Ut[cc][al] = c.c_conv * J * s;
+    }
+  // divergence part of the residual, P rows
+  double rp[NP];
+#pragma unroll
+  for(int q = 0; q < NP; ++q) rp[q] = 0.;
+#pragma unroll
+  for(int q = 0; q < NP; ++q)
+#pragma unroll
+    for(int b = 0; b < NS; ++b) {
+      const double *Br = s_b + (q * NS + b) * D;
+#pragma unroll
+      for(int j = 0; j < D; ++j) {
+        double s = 0.;
+#pragma unroll
+        for(int al = 0; al < D; ++al) s += G[al * D + j] * Br[al];
+        rp[q] -= c.c_div * J * s * U[b][j];
+      }
+    }
+  const bool   domass = (c.c_mass != 0.) && (a.soldot != nullptr);
+  const double cvis1 = c.sig_mu - c.diff_k, cvis2 = c.sig_mu, cpre = c.c_gradp - c.c_sig;
+#pragma unroll 1
+  for(int aa = 0; aa < NS; ++aa) {
+    double Z[D * NP];
+#pragma unroll
+    for(int i = 0; i < D * NP; ++i) Z[i] = 0.;
+    const double *t3 = s_t3 + aa * NS * NP;
+#pragma unroll
+    for(int cc = 0; cc < NS; ++cc)
+#pragma unroll
+      for(int v = 0; v < NP; ++v) {
+        const double t = t3[cc * NP + v];
+#pragma unroll
+        for(int al = 0; al < D; ++al) Z[al * NP + v] += Ut[cc][al] * t;
+      }
+    double r[D];
+#pragma unroll
+    for(int i = 0; i < D; ++i) r[i] = 0.;
+    double *orow = out + X::O_ROW + aa * 16;
+#pragma unroll
+    for(int b = 0; b < NS; ++b) {
+      double s = 0.;
+#pragma unroll
+      for(int i = 0; i < D * NP; ++i) s += a.E[b * D * NP + i] * Z[i];
+      orow[b] = s;
+#pragma unroll
+      for(int i = 0; i < D; ++i) r[i] -= s * U[b][i];
+    }
+#pragma unroll
+    for(int v = 0; v < NP; ++v) {
+      const double *Br = s_b + (v * NS + aa) * D;
+#pragma unroll
+      for(int m = 0; m < D; ++m) {
+        double s = 0.;
+#pragma unroll
+        for(int al = 0; al < D; ++al) s += G[al * D + m] * Br[al];
+        const double bp = J * s;
+        r[m] += cpre * bp * P[v];
+#pragma unroll
+        for(int i = 0; i < D; ++i) r[i] += bp * (cvis1 * gu[(v * D + m) * D + i] + cvis2 * gu[(v * D + i) * D + m]);
+      }
+    }
+    if(domass) {
+#pragma unroll
+      for(int b = 0; b < NS; ++b) {
+        const double mab = c.c_mass * J * s_m[aa * NS + b];
+#pragma unroll
+        for(int i = 0; i < D; ++i) r[i] -= mab * a.soldot[ad[b * D + i]];
+      }
+    }
+    if(a.source != nullptr) {
+      const double *src = a.source + e * a.nq * D;
+      for(int k = 0; k < a.nq; ++k) {
+        const double wj = J * s_w[k * NS + aa];
+#pragma unroll
+        for(int i = 0; i < D; ++i) r[i] -= wj * src[k * D + i];
+      }
+    }
+#pragma unroll
+    for(int i = 0; i < D; ++i) orow[10 + i] = r[i];
+    // slot 13: pressure-row residual of local pressure node aa (rows 0..3), zero padding elsewhere
+    double p13 = 0.;
+#pragma unroll
+    for(int q = 0; q < NP; ++q) p13 = (aa == q) ? rp[q] : p13;
+    orow[13] = p13;
+    orow[14] = 0.;
+    orow[15] = 0.;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// plan kernels
+// ----------------------------------------------------------------------------------------------------------------------
+// geo4[e][v][0..2] = physical gradient of the barycentric coordinate lambda_v (rows 1..3 = the inverse affine map), [v][3] = detJ
+__global__ void urow_geo4_kernel(int64_t nElm, const double *__restrict__ geo, int gw, double *__restrict__ geo4)
+{
+  for(int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nElm; e += (int64_t)gridDim.x * blockDim.x) {
+    const double *g = geo + e * gw;
+    const double  J = g[9];
+    double       *o = geo4 + e * 16;
+    double        s[3] = {0., 0., 0.};
+    for(int al = 0; al < 3; ++al) {
+      for(int m = 0; m < 3; ++m) {
+        o[(al + 1) * 4 + m] = g[al * 3 + m];
+        s[m] -= g[al * 3 + m];
+      }
+      o[(al + 1) * 4 + 3] = J;
+    }
+    for(int m = 0; m < 3; ++m) o[m] = s[m];
+    o[3] = J;
+  }
+}
+
+// sort key of a pair: (first pair of its node, local index of the node in the element); the stable sort keeps the elements of one
+// (node, la) ascending.  Pairs of nodes without unknown rows are not covered by any range: their key is their own position, which
+// keeps them where they are (urow_pair_key_init_kernel runs first).
+__global__ void urow_pair_key_init_kernel(int64_t nPairs, uint64_t *key)
+{
+  for(int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nPairs; p += (int64_t)gridDim.x * blockDim.x) key[p] = (uint64_t)p << 4;
+}
+__global__ void urow_pair_key_kernel(int32_t nNodes, const int2 *__restrict__ range, const int32_t *__restrict__ pair, uint64_t *key)
+{
+  for(int32_t n = blockIdx.x; n < nNodes; n += gridDim.x) {
+    const int2 rg = range[n];
+    for(int k = threadIdx.x; k < rg.y; k += blockDim.x) key[rg.x + k] = ((uint64_t)rg.x << 4) | (uint64_t)(pair[rg.x + k] % 10);
+  }
+}
+
+// per node: pairs per local index (6 bits each) and the sort key (row length, signature = pairs per local index clamped to 15)
+__global__ void urow_node_key_kernel(int32_t nNodes, const int2 *__restrict__ range, const int32_t *__restrict__ pair, const int32_t *__restrict__ row,
+                                     const int64_t *__restrict__ ia, int64_t nInc, uint64_t *key, int32_t *idx, uint64_t *lacnt, int *err)
+{
+  for(int32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < nNodes; n += gridDim.x * blockDim.x) {
+    const int2 rg = range[n];
+    int        c[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for(int k = 0; k < rg.y; ++k) {
+      const int la = pair[rg.x + k] % 10;
+#pragma unroll
+      for(int l = 0; l < 10; ++l) c[l] += la == l;
+    }
+    int64_t len = 0;
+    for(int cc = 2; cc >= 0; --cc) {
+      const int32_t r = row[(int64_t)n * 3 + cc];
+      if(r < nInc) len = ia[r + 1] - ia[r];
+    }
+    uint64_t pk = 0, sig = 0;
+#pragma unroll
+    for(int l = 0; l < 10; ++l) {
+      if(c[l] > 63) atomicExch(err, 6);
+      pk |= (uint64_t)(c[l] & 63) << (6 * l);
+      sig |= (uint64_t)min(c[l], 15) << (4 * l);
+    }
+    lacnt[n] = pk;
+    key[n]   = ((uint64_t)len << 40) | sig;
+    idx[n]   = n;
+  }
+}
+
+struct __align__(32) URowPair {
+  int32_t  ea;      // (element << 4) | local row node
+  uint16_t off[14]; // row-local offset of component 0 of the column nodes 0..9, then of the pressure columns 0..3; 0xFFFF: not assembled
+};
+
+// one block per node: records of its pairs.  err: 1 column missing from the pattern, 5 the three components of a column node are
+// not adjacent columns / only partly unknown (the general lane kernels handle those systems)
+__global__ void urow_pairs_kernel(int32_t nNodes, const int2 *__restrict__ range, const int32_t *__restrict__ row, const int32_t *__restrict__ pair,
+                                  const int32_t *__restrict__ adrU, const int32_t *__restrict__ adrP, const int64_t *__restrict__ ia,
+                                  const int32_t *__restrict__ ja, int64_t nInc, int colmaskU, int colmaskP, URowPair *rec, int *err)
+{
+  for(int32_t n = blockIdx.x; n < nNodes; n += gridDim.x) {
+    const int2 rg = range[n];
+    int32_t    r0 = -1;
+    for(int c = 2; c >= 0; --c)
+      if(row[(int64_t)n * 3 + c] < nInc) r0 = row[(int64_t)n * 3 + c];
+    const int64_t beg = ia[r0], end = ia[r0 + 1];
+    for(int idx = threadIdx.x; idx < rg.y * 16; idx += blockDim.x) {
+      const int     pp = idx >> 4, t = idx & 15;
+      const int64_t p  = rg.x + pp;
+      const int     ea = pair[p];
+      const int64_t e  = ea / 10;
+      const int     la = ea - (int)e * 10;
+      if(t == 15) {
+        rec[p].ea = (int32_t)((e << 4) | la);
+        continue;
+      }
+      if(t == 14) continue;
+      uint16_t   o = 0xFFFF;
+      int32_t    col = -1;
+      const bool isU = t < 10;
+      if(isU) {
+        if(colmaskU) {
+          const int32_t c0 = adrU[e * 30 + t * 3], c1 = adrU[e * 30 + t * 3 + 1], c2 = adrU[e * 30 + t * 3 + 2];
+          if(c0 < nInc || c1 < nInc || c2 < nInc) {
+            if(c0 < nInc && c1 == c0 + 1 && c2 == c0 + 2 && c2 < nInc)
+              col = c0;
+            else
+              atomicExch(err, 5);
+          }
+        }
+      } else if(colmaskP) {
+        const int32_t cq = adrP[e * 4 + (t - 10)];
+        if(cq < nInc) col = cq;
+      }
+      if(col >= 0) {
+        int64_t lo = beg, hi = end - 1;
+        while(lo < hi) {
+          const int64_t mid = (lo + hi) >> 1;
+          if(ja[mid] < col)
+            lo = mid + 1;
+          else
+            hi = mid;
+        }
+        if(lo < end && ja[lo] == col) {
+          o = (uint16_t)(lo - beg);
+          if(isU && (lo + 2 >= end || ja[lo + 1] != col + 1 || ja[lo + 2] != col + 2)) atomicExch(err, 5);
+        } else
+          atomicExch(err, 1);
+      }
+      rec[p].off[t] = o;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// velocity rows
+// ----------------------------------------------------------------------------------------------------------------------
+struct URowArgs {
+  const double   *geo4, *es;
+  const URowPair *rec;
+  const int32_t  *order; // nodes sorted by (row length, signature)
+  const uint64_t *lacnt; // [node] pairs per local index, 6 bits each
+  const int2     *range;
+  const int32_t  *row;
+  const int64_t  *ia;
+  double         *val, *rhs;
+  int32_t         count, warp0; // nodes, first warp of this launch
+  int64_t         nInc;
+  double          nsm, cdk, mass0, cpr; // -sig_mu, diff_k - sig_mu, c_mass c0, c_sig - c_gradp
+};
+
+template <bool RES, int MINB> __global__ void __launch_bounds__(32, MINB) gather_urow_kernel(const URowArgs a)
+{
+  using X = ESC;
+  using CT = URowTab;
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x;
+  const int g = lane / 3, i = lane - 3 * g;
+  const int w = a.warp0 + (int)blockIdx.x;
+  int32_t   row = 0x7fffffff;
+  int       len = 0, cnt = 0, p0 = 0;
+  uint64_t  cnts = 0;
+  {
+    const int k = w * 10 + g;
+    if(g < 10 && k < a.count) {
+      const int32_t n  = a.order[k];
+      row              = a.row[(int64_t)n * 3 + i];
+      const int2    rg = a.range[n];
+      p0               = rg.x;
+      cnt              = rg.y;
+      cnts             = a.lacnt[n];
+      // the unknown rows of a node share their length
+#pragma unroll
+      for(int c = 2; c >= 0; --c) {
+        const int32_t r = a.row[(int64_t)n * 3 + c];
+        if(r < a.nInc) len = (int)(a.ia[r + 1] - a.ia[r]);
+      }
+    }
+  }
+  const int Lmax = __reduce_max_sync(0xffffffffu, len);
+  double   *S    = sm;                           // [Lmax + 3][32] interleaved row images, rows Lmax .. Lmax + 2 = trash
+  double   *T    = sm + (size_t)(Lmax + 3) * 32; // [32][8] staging tile of the write-out
+  {
+    double2 *z = reinterpret_cast<double2 *>(S);
+    for(int k = lane; k < (Lmax + 3) * 16; k += 32) z[k] = make_double2(0., 0.);
+  }
+  __syncwarp();
+  double  res = 0.;
+  double *Sl  = S + lane;
+
+  // warp-uniform walk over (la, step): two counted loops with uniform bounds (ptxas keeps the constant loads on the uniform datapath
+  // only in control flow it can prove convergent).  The lane consumes its pairs in order (they are sorted by la): `pn` is its next
+  // pair, whose record is already in registers; the lane is active at step t of phase la iff it still has a pair with this la.
+  const int plast = cnt > 0 ? p0 + cnt - 1 : 0;
+  int       pn    = cnt > 0 ? p0 : 0;
+  U8        rec_next = ldg256u(a.rec + (cnt > 0 ? p0 : 0));
+#pragma unroll 1
+  for(int la_c = 0; la_c < 10; ++la_c) {
+    const int mc   = (int)((cnts >> (6 * la_c)) & 63u);
+    const int maxc = __reduce_max_sync(0xffffffffu, mc);
+#pragma unroll 1
+    for(int it = 0; it < maxc; ++it) {
+      const bool act = it < mc;
+      const U8   rec = rec_next;
+      pn += act ? 1 : 0;
+      rec_next = ldg256u(a.rec + min(pn, plast)); // branch-free (an idle lane reloads the record it already holds)
+    {
+      const int64_t e  = (int64_t)(rec.w[0] >> 4);
+      const double *ge = a.geo4 + e * 16;
+      const double *es = a.es + e * X::W;
+      const D4      g1 = ldg256(ge + 4), g2 = ldg256(ge + 8), g3 = ldg256(ge + 12);
+      D4            dv[4];
+#pragma unroll
+      for(int v = 0; v < 4; ++v) dv[v] = ldg256(es + X::O_DVT + (i * 4 + v) * 4);
+      // the row index comes from the record, NOT from la_c (equal for active lanes): a use of la_c in per-lane address arithmetic
+      // makes ptxas keep it in a vector register and turn the 212 uniform constant loads below into vector LDCs
+      const double *er = es + X::O_ROW + (int)(rec.w[0] & 15u) * 16;
+      const D4      r0 = ldg256(er), r1 = ldg256(er + 4), r2 = ldg256(er + 8), r3 = ldg256(er + 12);
+      const double  J = g1.w;
+      const double  Gp[3][3] = {{g1.x, g1.y, g1.z}, {g2.x, g2.y, g2.z}, {g3.x, g3.y, g3.z}};
+      const double  c1[10] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y};
+      if(RES) res += act ? (i == 0 ? r2.z : i == 1 ? r2.w : r3.x) : 0.;
+      // it >> 24 == 0, which the compiler cannot prove: keeps the constant loads (LDCU, uniform datapath) inside the step loop
+      const double *ct = &b200_urow_tab[la_c][it >> 24];
+      // column i of the inverse map; -sig_mu J G; (diff_k - sig_mu) J G G^T (symmetric: 00, 11, 22, 01, 02, 12)
+      double gi[3], GJ[3][3], GG[6];
+#pragma unroll
+      for(int be = 0; be < 3; ++be) gi[be] = i == 0 ? Gp[be][0] : i == 1 ? Gp[be][1] : Gp[be][2];
+      {
+        const double nJ = a.nsm * J;
+#pragma unroll
+        for(int al = 0; al < 3; ++al)
+#pragma unroll
+          for(int m = 0; m < 3; ++m) GJ[al][m] = nJ * Gp[al][m];
+        constexpr int pa[6] = {0, 1, 2, 0, 0, 1}, pb[6] = {0, 1, 2, 1, 2, 2};
+        const double  cJ = a.cdk * J;
+#pragma unroll
+        for(int k = 0; k < 6; ++k) GG[k] = cJ * (Gp[pa[k]][0] * Gp[pb[k]][0] + Gp[pa[k]][1] * Gp[pb[k]][1] + Gp[pa[k]][2] * Gp[pb[k]][2]);
+      }
+      const double dvv[4][3] = {{dv[0].x, dv[0].y, dv[0].z}, {dv[1].x, dv[1].y, dv[1].z}, {dv[2].x, dv[2].y, dv[2].z}, {dv[3].x, dv[3].y, dv[3].z}};
+      const double mJ = a.mass0 * J;
+
+      // two column nodes per batch: six independent read-modify-writes in flight
+#pragma unroll
+      for(int bb = 0; bb < 10; bb += 2) {
+        double  A[2][3];
+        double *q[2];
+#pragma unroll
+        for(int h = 0; h < 2; ++h) {
+          const int     b  = bb + h;
+          const double *Kr = ct + CT::O_K + b * 9;
+          const double *Ks = ct + CT::O_KS + b * 6;
+          const double *t3 = ct + CT::O_T3 + b * 4;
+          double        H[3];
+#pragma unroll
+          for(int al = 0; al < 3; ++al) H[al] = Kr[al * 3 + 0] * gi[0] + Kr[al * 3 + 1] * gi[1] + Kr[al * 3 + 2] * gi[2];
+          double s = c1[b] + mJ * ct[CT::O_M + b];
+#pragma unroll
+          for(int k = 0; k < 6; ++k) s += Ks[k] * GG[k];
+          double tv[4];
+#pragma unroll
+          for(int v = 0; v < 4; ++v) tv[v] = t3[v];
+#pragma unroll
+          for(int j = 0; j < 3; ++j) {
+            // one DFMA chain per entry: (i == j ? s : 0) - sig_mu K[j][i] + c_conv int phi_a phi_b d_j u_i
+            double x = i == j ? s : 0.;
+#pragma unroll
+            for(int al = 0; al < 3; ++al) x = fma(GJ[al][j], H[al], x);
+#pragma unroll
+            for(int v = 0; v < 4; ++v) x = fma(dvv[v][j], tv[v], x);
+            A[h][j] = x;
+          }
+          const uint32_t o = rec_off(rec, b);
+          q[h]             = Sl + (size_t)((act && o != 0xFFFFu) ? (int)o : Lmax) * 32;
+        }
+        double old[2][3];
+#pragma unroll
+        for(int h = 0; h < 2; ++h)
+#pragma unroll
+          for(int j = 0; j < 3; ++j) old[h][j] = q[h][j * 32];
+#pragma unroll
+        for(int h = 0; h < 2; ++h)
+#pragma unroll
+          for(int j = 0; j < 3; ++j) q[h][j * 32] = old[h][j] + A[h][j];
+      }
+      // pressure columns: A[(a, i)][q] = (c_sig - c_gradp) int psi_q d_i phi_a   (src/feVectorSysElm.cpp:449-503, :528-578)
+      {
+        double  v[4], old[4];
+        double *q[4];
+        const double pJ    = a.cpr * J;
+        const double gj[3] = {pJ * gi[0], pJ * gi[1], pJ * gi[2]};
+#pragma unroll
+        for(int qq = 0; qq < 4; ++qq) {
+          const double *Br = ct + CT::O_B + qq * 3;
+          v[qq]            = gj[0] * Br[0] + gj[1] * Br[1] + gj[2] * Br[2];
+          const uint32_t o = rec_off(rec, 10 + qq);
+          q[qq]            = Sl + (size_t)((act && o != 0xFFFFu) ? (int)o : Lmax) * 32;
+        }
+#pragma unroll
+        for(int qq = 0; qq < 4; ++qq) old[qq] = *q[qq];
+#pragma unroll
+        for(int qq = 0; qq < 4; ++qq) *q[qq] = old[qq] + v[qq];
+      }
+      }
+    }
+  }
+  const bool valid = row < a.nInc;
+  if(RES && valid) a.rhs[row] = res;
+  __syncwarp();
+  // write-out: 8 entries of every image per round through a swizzled [32][8] tile, then 64-byte runs per row
+  {
+    const int64_t myia  = valid ? a.ia[row] : -1;
+    const int     mylen = valid ? len : 0;
+    int64_t       ia_t[8];
+    int           len_t[8];
+    const int     kk = lane & 7;
+#pragma unroll
+    for(int tt = 0; tt < 8; ++tt) {
+      const int rr = tt * 4 + (lane >> 3);
+      ia_t[tt]     = __shfl_sync(0xffffffffu, myia, rr);
+      len_t[tt]    = __shfl_sync(0xffffffffu, mylen, rr);
+    }
+    const int swz = (lane >> 1) & 7;
+    for(int k0 = 0; k0 < Lmax; k0 += 8) {
+      double v[8];
+#pragma unroll
+      for(int k = 0; k < 8; ++k) v[k] = Sl[(size_t)min(k0 + k, Lmax) * 32];
+#pragma unroll
+      for(int k = 0; k < 8; ++k) T[lane * 8 + (k ^ swz)] = v[k];
+      __syncwarp();
+#pragma unroll
+      for(int tt = 0; tt < 8; ++tt) {
+        const int rr = tt * 4 + (lane >> 3);
+        if(k0 + kk < len_t[tt]) a.val[ia_t[tt] + k0 + kk] = T[rr * 8 + (kk ^ ((rr >> 1) & 7))];
+      }
+      __syncwarp();
+    }
+  }
+}
+
+} // namespace b200
