@@ -83,6 +83,9 @@ struct GatherPlan {
   int32_t  *d_order = nullptr; // velocity nodes sorted by (row length, signature)
   uint64_t *d_lacnt = nullptr; // [node] pairs per local index, 6 bits each
   void     *d_rec = nullptr;   // [nPairs] URowPair
+  int32_t  *d_wstep = nullptr; // [warp + 1] first schedule step of every warp (10 nodes)
+  int32_t  *d_sched = nullptr; // [step][10] pair of group g at this step, or -1
+  uint64_t *d_sla = nullptr;   // [warp] steps the warp spends on every local index, 6 bits each
   std::vector<double>   utab;  // [10][URowTab::LEN] reference tensors per local row node
   std::vector<int32_t>  useg_begin; // launch segments (in warps of 10 nodes)
   std::vector<uint32_t> useg_lmax;  // longest row of the segment
@@ -1155,6 +1158,9 @@ void gather_free(System *S)
   cudaFree(G->d_order);
   cudaFree(G->d_lacnt);
   cudaFree(G->d_rec);
+  cudaFree(G->d_wstep);
+  cudaFree(G->d_sched);
+  cudaFree(G->d_sla);
   delete G;
   S->gather = nullptr;
 }
@@ -1205,20 +1211,59 @@ static int build_urow_plan(System *S, GatherPlan *G, const std::vector<double> &
     urow_pair_key_kernel<<<148 * 16, 64, 0, S->stream>>>(N.nNodes, N.range, N.pair, thrust::raw_pointer_cast(pkey.data()));
     thrust::stable_sort_by_key(pol, pkey.begin(), pkey.end(), thrust::device_pointer_cast(N.pair));
   }
+  // bounding box of the mesh (Morton cells of ~16 K nodes order the launch)
+  double lo[3] = {1e300, 1e300, 1e300}, sc[3] = {0., 0., 0.};
+  {
+    std::vector<double> xyz((size_t)S->nVert * 3);
+    B200_CUDA(cudaMemcpyAsync(xyz.data(), S->d_xyz, xyz.size() * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    double hi[3] = {-1e300, -1e300, -1e300};
+    for(int64_t v = 0; v < S->nVert; ++v)
+      for(int m = 0; m < 3; ++m) {
+        lo[m] = std::min(lo[m], xyz[v * 3 + m]);
+        hi[m] = std::max(hi[m], xyz[v * 3 + m]);
+      }
+    for(int m = 0; m < 3; ++m) sc[m] = hi[m] > lo[m] ? 1023.999 / (hi[m] - lo[m]) : 0.;
+  }
+  int cellbits = 0;
+  {
+    const char *ev = getenv("B200_UROW_CELL");
+    const double per = ev ? atof(ev) : 16384.;
+    while(cellbits < 20 && (double)N.nNodes / (double)(1u << cellbits) > per) ++cellbits;
+  }
   thrust::device_vector<uint64_t> key(N.nNodes);
   B200_CUDA(cudaMalloc(&G->d_order, (size_t)N.nNodes * sizeof(int32_t)));
   B200_CUDA(cudaMalloc(&G->d_lacnt, (size_t)N.nNodes * sizeof(uint64_t)));
-  urow_node_key_kernel<<<148 * 8, 256, 0, S->stream>>>(N.nNodes, N.range, N.pair, N.row, S->d_ia, S->nInc, thrust::raw_pointer_cast(key.data()), G->d_order,
-                                                      G->d_lacnt, d_err);
+  urow_node_key_kernel<<<148 * 8, 256, 0, S->stream>>>(N.nNodes, N.range, N.pair, N.row, S->d_ia, S->nInc, S->d_conn, S->d_xyz, lo[0], lo[1], lo[2], sc[0],
+                                                      sc[1], sc[2], 30 - cellbits, thrust::raw_pointer_cast(key.data()), G->d_order, G->d_lacnt, d_err);
   thrust::stable_sort_by_key(pol, key.begin(), key.end(), thrust::device_pointer_cast(G->d_order));
   count_launch(5);
   std::vector<uint64_t> h_key(N.nNodes);
   B200_CUDA(cudaMemcpyAsync(h_key.data(), thrust::raw_pointer_cast(key.data()), (size_t)N.nNodes * sizeof(uint64_t), cudaMemcpyDeviceToHost, S->stream));
   B200_CUDA(cudaMalloc(&G->d_rec, (size_t)N.nPairs * sizeof(URowPair)));
+  B200_CUDA(cudaMemsetAsync(G->d_rec, 0, (size_t)N.nPairs * sizeof(URowPair), S->stream)); // record 0 serves the idle lanes: must be readable
   urow_pairs_kernel<<<148 * 16, 64, 0, S->stream>>>(N.nNodes, N.range, N.row, N.pair, S->spaces[S->su].d_adr, S->spaces[S->sp].d_adr, S->d_ia, S->d_ja,
                                                    S->nInc, S->has_matrix_block[0][0] ? 1 : 0, S->has_matrix_block[0][1] ? 1 : 0,
                                                    static_cast<URowPair *>(G->d_rec), d_err);
   count_launch();
+  // schedule of every warp of 10 consecutive nodes
+  const int32_t cnt = N.nNodes, nw = (cnt + 9) / 10;
+  {
+    thrust::device_vector<int32_t> nsteps(nw + 1, 0);
+    urow_sched_count_kernel<<<(nw + 255) / 256, 256, 0, S->stream>>>(nw, cnt, G->d_order, G->d_lacnt, thrust::raw_pointer_cast(nsteps.data()));
+    B200_CUDA(cudaMalloc(&G->d_wstep, (size_t)(nw + 1) * sizeof(int32_t)));
+    thrust::exclusive_scan(pol, nsteps.begin(), nsteps.end(), thrust::device_pointer_cast(G->d_wstep));
+    int32_t tot = 0;
+    B200_CUDA(cudaMemcpyAsync(&tot, G->d_wstep + nw, sizeof(int32_t), cudaMemcpyDeviceToHost, S->stream));
+    B200_CUDA(cudaStreamSynchronize(S->stream));
+    B200_CUDA(cudaMalloc(&G->d_sched, (size_t)std::max(tot, 1) * 10 * sizeof(int32_t)));
+    B200_CUDA(cudaMalloc(&G->d_sla, (size_t)nw * sizeof(uint64_t)));
+    urow_sched_fill_kernel<<<(nw + 255) / 256, 256, 0, S->stream>>>(nw, cnt, G->d_order, G->d_lacnt, N.range, G->d_wstep, G->d_sched, G->d_sla);
+    count_launch(3);
+    if(getenv("B200_VERBOSE"))
+      fprintf(stderr, "[b200] row-lane plan: %d nodes in %d warps, %d steps for %lld pairs (lane efficiency %.3f), %d Morton cells\n", cnt, nw, tot,
+              (long long)N.nPairs, (double)N.nPairs / (10. * std::max(tot, 1)), 1 << cellbits);
+  }
   int h_err = 0;
   B200_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, S->stream));
   B200_CUDA(cudaStreamSynchronize(S->stream));
@@ -1228,32 +1273,27 @@ static int build_urow_plan(System *S, GatherPlan *G, const std::vector<double> &
               std::to_string(h_err) + ")");
     return B200_ERR_UNSUPP;
   }
-  // launch segments: warps of 10 nodes; consecutive warps whose longest rows differ by < 25 % share one launch
+  // launch segments: runs of warps of one shared-memory class (the class of a warp is that of its last, longest-class node)
   G->useg_begin.clear();
   G->useg_lmax.clear();
-  const int32_t cnt = N.nNodes, nw = (cnt + 9) / 10;
-  auto lmax_of = [&](int32_t w) { // keys are sorted by length: the last node of the warp has the longest row
-    const int32_t last = std::min(cnt, (w + 1) * 10) - 1;
-    return (uint32_t)(h_key[last] >> 40);
-  };
-  int32_t  b = 0;
-  uint32_t mn = lmax_of(0);
-  for(int32_t w = 1; w <= nw; ++w) {
-    const bool last = w == nw;
-    if(!last) {
-      const uint32_t v = lmax_of(w);
-      const bool cut = (double)v > 1.25 * (double)std::max<uint32_t>(mn, 1u) && w - b >= 64 && nw - w >= 64 && G->useg_begin.size() < 6;
-      if(!cut) continue;
+  {
+    int      cur = -1;
+    uint32_t mx = 0;
+    for(int32_t w = 0; w < nw; ++w) {
+      const int32_t k0 = w * 10, k1 = std::min(cnt, k0 + 10);
+      const int     cls = (int)(h_key[k1 - 1] >> 62);
+      if(cls != cur) {
+        if(cur >= 0) G->useg_lmax.push_back(mx);
+        G->useg_begin.push_back(w);
+        cur = cls;
+        mx  = 0;
+      }
+      for(int32_t k = k0; k < k1; ++k) mx = std::max(mx, (uint32_t)((h_key[k] >> 26) & 0xffffu));
     }
-    G->useg_begin.push_back(b);
-    G->useg_lmax.push_back(lmax_of(w - 1));
-    if(!last) {
-      b  = w;
-      mn = lmax_of(w);
-    }
+    G->useg_lmax.push_back(mx);
+    G->useg_begin.push_back(nw);
   }
-  G->useg_begin.push_back(nw);
-  if((size_t)(G->useg_lmax.back() + 3) * 32 * 8 + 2048 > 200 * 1024) {
+  if((size_t)(*std::max_element(G->useg_lmax.begin(), G->useg_lmax.end()) + 3) * 32 * 8 + 2048 > 200 * 1024) {
     set_error("row-lane plan: row images exceed shared memory");
     return B200_ERR_UNSUPP;
   }
@@ -1335,6 +1375,12 @@ int build_gather_plan(System *S)
         cudaFree(G->d_order);
         cudaFree(G->d_lacnt);
         cudaFree(G->d_rec);
+        cudaFree(G->d_wstep);
+        cudaFree(G->d_sched);
+        cudaFree(G->d_sla);
+        G->d_wstep = nullptr;
+        G->d_sched = nullptr;
+        G->d_sla   = nullptr;
         G->d_geo4  = nullptr;
         G->d_order = nullptr;
         G->d_lacnt = nullptr;
@@ -1624,7 +1670,9 @@ static int launch_gather_urow(System *S, int what, const THCoeffs &c)
     ua.es    = G->d_es;
     ua.rec   = static_cast<const URowPair *>(G->d_rec);
     ua.order = G->d_order;
-    ua.lacnt = G->d_lacnt;
+    ua.wstep = G->d_wstep;
+    ua.sched = G->d_sched;
+    ua.wmax  = G->d_sla;
     ua.range = G->U.range;
     ua.row   = G->U.row;
     ua.ia    = S->d_ia;
@@ -1647,17 +1695,17 @@ static int launch_gather_urow(System *S, int what, const THCoeffs &c)
     KERN<<<nc, 32, smem, S->stream>>>(ua);                                                                          \
     count_launch();                                                                                                 \
   } while(0)
-      // long rows (vertex nodes): 4 warps per SM fit anyway, no register cap; short rows: 10 warps per SM
-      if(smem > 26 * 1024) {
+      // long rows (vertex nodes): 4 warps per SM fit anyway; short rows: up to 8 warps per SM, 255 registers for the software pipeline
+      if(smem > 28 * 1024) {
         if(res)
           B200_LAUNCH_C((gather_urow_kernel<true, 4>));
         else
           B200_LAUNCH_C((gather_urow_kernel<false, 4>));
       } else {
         if(res)
-          B200_LAUNCH_C((gather_urow_kernel<true, 10>));
+          B200_LAUNCH_C((gather_urow_kernel<true, 8>));
         else
-          B200_LAUNCH_C((gather_urow_kernel<false, 10>));
+          B200_LAUNCH_C((gather_urow_kernel<false, 8>));
       }
 #undef B200_LAUNCH_C
     }

@@ -67,6 +67,9 @@ struct URowTab {
   static constexpr int LEN = 212;
 };
 __constant__ double b200_urow_tab[10][URowTab::LEN];
+// local edge -> end vertices of the reference's P2 tetrahedron (src/feTetrahedron.h:31; amg.cu checks the same table against the basis
+// tabulation); used only to place mid-edge nodes in space for the launch order
+__constant__ int c_edge_tet_u[6][2] = {{0, 2}, {2, 1}, {1, 0}, {1, 3}, {3, 0}, {3, 2}};
 
 // ----------------------------------------------------------------------------------------------------------------------
 // pre-pass: everything that depends on the element only (as element_state_kernel), in the record layout ESC
@@ -145,15 +148,15 @@ __global__ void __launch_bounds__(128) element_state_urow_kernel(const ElementSt
   {
     const double sJ = c.c_conv * J;
 #pragma unroll
-    for(int i = 0; i < D; ++i)
+    for(int v = 0; v < NP; ++v)
 #pragma unroll
-      for(int v = 0; v < NP; ++v) {
+      for(int i = 0; i < D; ++i) {
         D4 o;
         o.x = sJ * gu[(v * D + 0) * D + i];
         o.y = sJ * gu[(v * D + 1) * D + i];
         o.z = sJ * gu[(v * D + 2) * D + i];
         o.w = 0.;
-        stg256(out + X::O_DVT + (i * NP + v) * 4, o);
+        stg256(out + X::O_DVT + (v * 4 + i) * 4, o);
       }
   }
   // contravariant velocity DOFs (scaled by c_conv J)
@@ -293,9 +296,26 @@ __global__ void urow_pair_key_kernel(int32_t nNodes, const int2 *__restrict__ ra
   }
 }
 
-// per node: pairs per local index (6 bits each) and the sort key (row length, signature = pairs per local index clamped to 15)
+// per node: pairs per local index (6 bits each) and the sort key
+//   [shared-memory class : 2][Morton cell of the node : 20][row length : 16][hash of the signature : 26]
+// class: rows of similar length share a launch (its shared-memory request); cell: nodes of one neighbourhood are processed together,
+// so the ten (node, element) pairs that read the record of an element find it in L2; signature (pairs per local index): the nodes of
+// a warp walk the local indices together, equal signatures leave no lane idle.
+__device__ __forceinline__ uint32_t urow_spread3(uint32_t v)
+{
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__host__ __device__ inline int urow_class(int64_t len) { return len <= 96 ? 0 : len <= 256 ? 1 : 2; }
+
 __global__ void urow_node_key_kernel(int32_t nNodes, const int2 *__restrict__ range, const int32_t *__restrict__ pair, const int32_t *__restrict__ row,
-                                     const int64_t *__restrict__ ia, int64_t nInc, uint64_t *key, int32_t *idx, uint64_t *lacnt, int *err)
+                                     const int64_t *__restrict__ ia, int64_t nInc, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
+                                     double x0, double y0, double z0, double sx, double sy, double sz, int cellshift, uint64_t *key, int32_t *idx,
+                                     uint64_t *lacnt, int *err)
 {
   for(int32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < nNodes; n += gridDim.x * blockDim.x) {
     const int2 rg = range[n];
@@ -317,9 +337,67 @@ __global__ void urow_node_key_kernel(int32_t nNodes, const int2 *__restrict__ ra
       pk |= (uint64_t)(c[l] & 63) << (6 * l);
       sig |= (uint64_t)min(c[l], 15) << (4 * l);
     }
+    // position of the node: its corner / mid-edge point in the first adjacent element
+    uint32_t cell = 0;
+    {
+      const int     ea = pair[rg.x];
+      const int64_t e  = ea / 10;
+      const int     la = ea - (int)e * 10;
+      const int     va = la < 4 ? la : c_edge_tet_u[la - 4][0], vb = la < 4 ? la : c_edge_tet_u[la - 4][1];
+      const double *pa = xyz + 3 * (int64_t)conn[e * 4 + va], *pb = xyz + 3 * (int64_t)conn[e * 4 + vb];
+      const uint32_t qx = (uint32_t)fmin(1023., fmax(0., (0.5 * (pa[0] + pb[0]) - x0) * sx));
+      const uint32_t qy = (uint32_t)fmin(1023., fmax(0., (0.5 * (pa[1] + pb[1]) - y0) * sy));
+      const uint32_t qz = (uint32_t)fmin(1023., fmax(0., (0.5 * (pa[2] + pb[2]) - z0) * sz));
+      cell = (urow_spread3(qx) | (urow_spread3(qy) << 1) | (urow_spread3(qz) << 2)) >> cellshift;
+    }
+    const uint64_t h = (sig * 0x9E3779B97F4A7C15ull) >> 38; // 26 bits
     lacnt[n] = pk;
-    key[n]   = ((uint64_t)len << 40) | sig;
+    key[n]   = ((uint64_t)urow_class(len) << 62) | ((uint64_t)(cell & 0xfffffu) << 42) | ((uint64_t)(len & 0xffff) << 26) | h;
     idx[n]   = n;
+  }
+}
+
+// schedule of a warp (10 consecutive nodes of the sorted order): the warp walks la = 0 .. 9, max_g cnt_g(la) steps each
+__global__ void urow_sched_count_kernel(int32_t nWarps, int32_t nNodes, const int32_t *__restrict__ order, const uint64_t *__restrict__ lacnt, int32_t *nsteps)
+{
+  for(int32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nWarps; w += gridDim.x * blockDim.x) {
+    int tot = 0;
+    for(int la = 0; la < 10; ++la) {
+      int mx = 0;
+      for(int g = 0; g < 10; ++g) {
+        const int32_t k = w * 10 + g;
+        if(k < nNodes) mx = max(mx, (int)((lacnt[order[k]] >> (6 * la)) & 63u));
+      }
+      tot += mx;
+    }
+    nsteps[w] = tot;
+  }
+}
+
+// sched[step][g] = pair of group g at this step or -1 (the node has no pair left with this local index); wmax[warp] = steps the
+// warp spends on every local index la, 6 bits each
+__global__ void urow_sched_fill_kernel(int32_t nWarps, int32_t nNodes, const int32_t *__restrict__ order, const uint64_t *__restrict__ lacnt,
+                                       const int2 *__restrict__ range, const int32_t *__restrict__ wstep, int32_t *sched, uint64_t *wmax)
+{
+  for(int32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nWarps; w += gridDim.x * blockDim.x) {
+    uint64_t cn[10];
+    int      base[10];
+    for(int g = 0; g < 10; ++g) {
+      const int32_t k = w * 10 + g;
+      cn[g]   = k < nNodes ? lacnt[order[k]] : 0ull;
+      base[g] = k < nNodes ? range[order[k]].x : 0;
+    }
+    int64_t  s = wstep[w];
+    uint64_t pk = 0;
+    for(int la = 0; la < 10; ++la) {
+      int mx = 0;
+      for(int g = 0; g < 10; ++g) mx = max(mx, (int)((cn[g] >> (6 * la)) & 63u));
+      pk |= (uint64_t)mx << (6 * la);
+      for(int t = 0; t < mx; ++t, ++s)
+        for(int g = 0; g < 10; ++g) sched[s * 10 + g] = t < (int)((cn[g] >> (6 * la)) & 63u) ? base[g] + t : -1;
+      for(int g = 0; g < 10; ++g) base[g] += (int)((cn[g] >> (6 * la)) & 63u);
+    }
+    wmax[w] = pk;
   }
 }
 
@@ -394,8 +472,10 @@ __global__ void urow_pairs_kernel(int32_t nNodes, const int2 *__restrict__ range
 struct URowArgs {
   const double   *geo4, *es;
   const URowPair *rec;
-  const int32_t  *order; // nodes sorted by (row length, signature)
-  const uint64_t *lacnt; // [node] pairs per local index, 6 bits each
+  const int32_t  *order; // nodes sorted by (class, cell, row length, signature)
+  const int32_t  *wstep; // [warp + 1] first step of the warp
+  const int32_t  *sched; // [step][10] pair of group g or -1
+  const uint64_t *wmax;  // [warp] steps per local index la, 6 bits each
   const int2     *range;
   const int32_t  *row;
   const int64_t  *ia;
@@ -415,7 +495,6 @@ template <bool RES, int MINB> __global__ void __launch_bounds__(32, MINB) gather
   const int w = a.warp0 + (int)blockIdx.x;
   int32_t   row = 0x7fffffff;
   int       len = 0, cnt = 0, p0 = 0;
-  uint64_t  cnts = 0;
   {
     const int k = w * 10 + g;
     if(g < 10 && k < a.count) {
@@ -424,7 +503,6 @@ template <bool RES, int MINB> __global__ void __launch_bounds__(32, MINB) gather
       const int2    rg = a.range[n];
       p0               = rg.x;
       cnt              = rg.y;
-      cnts             = a.lacnt[n];
       // the unknown rows of a node share their length
 #pragma unroll
       for(int c = 2; c >= 0; --c) {
@@ -443,45 +521,73 @@ template <bool RES, int MINB> __global__ void __launch_bounds__(32, MINB) gather
   __syncwarp();
   double  res = 0.;
   double *Sl  = S + lane;
+  // component selectors as 0 / 1 factors: a per-lane `i == j ? x : y` inside the step loop may be compiled into a divergent branch,
+  // and a divergent branch in the loop body makes ptxas give up the uniform datapath for the constant loads (products with 0 / 1 and
+  // sums with +-0 are exact)
+  const double mi[3] = {i == 0 ? 1. : 0., i == 1 ? 1. : 0., i == 2 ? 1. : 0.};
 
-  // warp-uniform walk over (la, step): two counted loops with uniform bounds (ptxas keeps the constant loads on the uniform datapath
-  // only in control flow it can prove convergent).  The lane consumes its pairs in order (they are sorted by la): `pn` is its next
-  // pair, whose record is already in registers; the lane is active at step t of phase la iff it still has a pair with this la.
-  const int plast = cnt > 0 ? p0 + cnt - 1 : 0;
-  int       pn    = cnt > 0 ? p0 : 0;
-  U8        rec_next = ldg256u(a.rec + (cnt > 0 ? p0 : 0));
+  // The warp follows its precomputed schedule: it walks the local indices la = 0 .. 9, wmax[w][la] steps each; at flat step s group g
+  // works on pair sched[s][g] (idle: record 0 into the trash entries).  Two counted loops with uniform bounds and NO branch in the body:
+  // ptxas keeps the constant loads on the uniform datapath only when the table index is a plain loop counter (a REDUX result or a
+  // loaded value ends up in vector LDCs, measured) and the control flow is provably convergent.  The global loads are software-
+  // pipelined over the flat step index: schedule entries three steps ahead, pair records two, element data one.
+  const int s0 = a.wstep[w];
+  const int ns = a.wstep[w + 1] - s0;
+  const int gc = min(g, 9);
+  auto sched_at = [&](int s) -> int {
+    const int v = a.sched[(size_t)(s0 + max(min(s, ns - 1), 0)) * 10 + gc];
+    return (s < ns && g < 10) ? v : -1;
+  };
+  const uint64_t wm = a.wmax[w];
+  struct PData {
+    D4 g1, g2, g3, dv[4], r0, r1, r2, r3;
+  };
+  auto load_data = [&](const U8 &rec, PData &d) {
+    const int64_t e  = (int64_t)(rec.w[0] >> 4);
+    const double *ge = a.geo4 + e * 16;
+    const double *es = a.es + e * X::W;
+    d.g1 = ldg256(ge + 4);
+    d.g2 = ldg256(ge + 8);
+    d.g3 = ldg256(ge + 12);
+#pragma unroll
+    for(int v = 0; v < 4; ++v) d.dv[v] = ldg256(es + X::O_DVT + (v * 4 + i) * 4); // the three lanes of a node read one 128-byte line
+    // the row index comes from the record, NOT from the step's la (equal for active lanes): a use of the warp-uniform la in per-lane
+    // address arithmetic makes ptxas keep it in a vector register and turn the 212 uniform constant loads into vector LDCs
+    const double *er = es + X::O_ROW + (int)(rec.w[0] & 15u) * 16;
+    d.r0 = ldg256(er);
+    d.r1 = ldg256(er + 4);
+    d.r2 = ldg256(er + 8);
+    d.r3 = ldg256(er + 12);
+  };
+  int   iA = sched_at(0), iB = sched_at(1), iC = sched_at(2);
+  U8    rA = ldg256u(a.rec + max(iA, 0)), rB = ldg256u(a.rec + max(iB, 0));
+  PData dA;
+  load_data(rA, dA);
+  int fs = 0; // flat step
 #pragma unroll 1
   for(int la_c = 0; la_c < 10; ++la_c) {
-    const int mc   = (int)((cnts >> (6 * la_c)) & 63u);
-    const int maxc = __reduce_max_sync(0xffffffffu, mc);
+   const int maxc = __reduce_max_sync(0xffffffffu, (int)((wm >> (6 * la_c)) & 63u));
 #pragma unroll 1
-    for(int it = 0; it < maxc; ++it) {
-      const bool act = it < mc;
-      const U8   rec = rec_next;
-      pn += act ? 1 : 0;
-      rec_next = ldg256u(a.rec + min(pn, plast)); // branch-free (an idle lane reloads the record it already holds)
+   for(int it = 0; it < maxc; ++it) {
+    PData dB;
+    load_data(rB, dB);                            // step fs + 1
+    const U8  rC = ldg256u(a.rec + max(iC, 0));   // step fs + 2
+    const int iD = sched_at(fs + 3);
     {
-      const int64_t e  = (int64_t)(rec.w[0] >> 4);
-      const double *ge = a.geo4 + e * 16;
-      const double *es = a.es + e * X::W;
-      const D4      g1 = ldg256(ge + 4), g2 = ldg256(ge + 8), g3 = ldg256(ge + 12);
-      D4            dv[4];
-#pragma unroll
-      for(int v = 0; v < 4; ++v) dv[v] = ldg256(es + X::O_DVT + (i * 4 + v) * 4);
-      // the row index comes from the record, NOT from la_c (equal for active lanes): a use of la_c in per-lane address arithmetic
-      // makes ptxas keep it in a vector register and turn the 212 uniform constant loads below into vector LDCs
-      const double *er = es + X::O_ROW + (int)(rec.w[0] & 15u) * 16;
-      const D4      r0 = ldg256(er), r1 = ldg256(er + 4), r2 = ldg256(er + 8), r3 = ldg256(er + 12);
-      const double  J = g1.w;
-      const double  Gp[3][3] = {{g1.x, g1.y, g1.z}, {g2.x, g2.y, g2.z}, {g3.x, g3.y, g3.z}};
-      const double  c1[10] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y};
-      if(RES) res += act ? (i == 0 ? r2.z : i == 1 ? r2.w : r3.x) : 0.;
-      // it >> 24 == 0, which the compiler cannot prove: keeps the constant loads (LDCU, uniform datapath) inside the step loop
+      const bool   act = iA >= 0;
+      const U8    &rec = rA;
+      const PData &d   = dA;
+      // it >> 24 == 0, which the compiler cannot prove: keeps the constant loads inside the step loop (otherwise ptxas hoists the 212
+      // constants of the row into registers and spills); la_c and it are used for nothing else
       const double *ct = &b200_urow_tab[la_c][it >> 24];
+      const double  J = d.g1.w;
+      const double  Gp[3][3] = {{d.g1.x, d.g1.y, d.g1.z}, {d.g2.x, d.g2.y, d.g2.z}, {d.g3.x, d.g3.y, d.g3.z}};
+      const double  c1[10] = {d.r0.x, d.r0.y, d.r0.z, d.r0.w, d.r1.x, d.r1.y, d.r1.z, d.r1.w, d.r2.x, d.r2.y};
+      if(RES) res += (act ? 1. : 0.) * (mi[0] * d.r2.z + mi[1] * d.r2.w + mi[2] * d.r3.x);
       // column i of the inverse map; -sig_mu J G; (diff_k - sig_mu) J G G^T (symmetric: 00, 11, 22, 01, 02, 12)
       double gi[3], GJ[3][3], GG[6];
 #pragma unroll
-      for(int be = 0; be < 3; ++be) gi[be] = i == 0 ? Gp[be][0] : i == 1 ? Gp[be][1] : Gp[be][2];
+      for(int be = 0; be < 3; ++be) gi[be] = mi[0] * Gp[be][0] + mi[1] * Gp[be][1] + mi[2] * Gp[be][2];
       {
         const double nJ = a.nsm * J;
 #pragma unroll
@@ -493,7 +599,8 @@ template <bool RES, int MINB> __global__ void __launch_bounds__(32, MINB) gather
 #pragma unroll
         for(int k = 0; k < 6; ++k) GG[k] = cJ * (Gp[pa[k]][0] * Gp[pb[k]][0] + Gp[pa[k]][1] * Gp[pb[k]][1] + Gp[pa[k]][2] * Gp[pb[k]][2]);
       }
-      const double dvv[4][3] = {{dv[0].x, dv[0].y, dv[0].z}, {dv[1].x, dv[1].y, dv[1].z}, {dv[2].x, dv[2].y, dv[2].z}, {dv[3].x, dv[3].y, dv[3].z}};
+      const double dvv[4][3] = {{d.dv[0].x, d.dv[0].y, d.dv[0].z}, {d.dv[1].x, d.dv[1].y, d.dv[1].z}, {d.dv[2].x, d.dv[2].y, d.dv[2].z},
+                                {d.dv[3].x, d.dv[3].y, d.dv[3].z}};
       const double mJ = a.mass0 * J;
 
       // two column nodes per batch: six independent read-modify-writes in flight
@@ -519,7 +626,7 @@ template <bool RES, int MINB> __global__ void __launch_bounds__(32, MINB) gather
 #pragma unroll
           for(int j = 0; j < 3; ++j) {
             // one DFMA chain per entry: (i == j ? s : 0) - sig_mu K[j][i] + c_conv int phi_a phi_b d_j u_i
-            double x = i == j ? s : 0.;
+            double x = mi[j] * s;
 #pragma unroll
             for(int al = 0; al < 3; ++al) x = fma(GJ[al][j], H[al], x);
 #pragma unroll
@@ -557,8 +664,15 @@ template <bool RES, int MINB> __global__ void __launch_bounds__(32, MINB) gather
 #pragma unroll
         for(int qq = 0; qq < 4; ++qq) *q[qq] = old[qq] + v[qq];
       }
-      }
     }
+    iA = iB;
+    iB = iC;
+    iC = iD;
+    rA = rB;
+    rB = rC;
+    dA = dB;
+    fs = __shfl_sync(0xffffffffu, fs + 1, 0); // opaque to the induction-variable optimiser: `it` must stay a pure loop counter
+   }
   }
   const bool valid = row < a.nInc;
   if(RES && valid) a.rhs[row] = res;

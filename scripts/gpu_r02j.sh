@@ -17,7 +17,7 @@ opb = O.Problem(pb.dim, m.xyz, m.cells, pb.adrU, pb.adrP, pb.ncomp, pb.w, pb.LU,
 ov, orr = O.assemble(opb, pb.ia, pb.ja, sol)
 print("T3D(4) urow: matrix rel err %.3e rhs rel err %.3e" % (np.abs(v - ov).max() / np.abs(ov).max(), np.abs(r - orr).max() / np.abs(orr).max()))
 PY
-grep -v 'MiB' gpurun_out/${T}_plan.log | tail -5; grep -c row-lane gpurun_out/${T}_plan.log
+grep -v 'MiB' gpurun_out/${T}_plan.log | tail -5; grep "row-lane plan" gpurun_out/${T}_plan.log
 timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py tests/test_gpu_stepping.py -q -x -k "3d or t3d or stepping" > gpurun_out/${T}_pytest.log 2>&1
 tail -4 gpurun_out/${T}_pytest.log
 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-solve > gpurun_out/${T}_bench_t3d92.json 2> gpurun_out/${T}_bench.err
