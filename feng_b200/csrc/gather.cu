@@ -1293,7 +1293,7 @@ static int build_urow_plan(System *S, GatherPlan *G, const std::vector<double> &
     G->useg_lmax.push_back(mx);
     G->useg_begin.push_back(nw);
   }
-  if((size_t)(*std::max_element(G->useg_lmax.begin(), G->useg_lmax.end()) + 3) * 32 * 8 + 2048 > 200 * 1024) {
+  if((size_t)(*std::max_element(G->useg_lmax.begin(), G->useg_lmax.end()) + 3) * 32 * 8 + 4096 > 200 * 1024) {
     set_error("row-lane plan: row images exceed shared memory");
     return B200_ERR_UNSUPP;
   }
@@ -1686,9 +1686,12 @@ static int launch_gather_urow(System *S, int what, const THCoeffs &c)
     ua.cpr   = c.c_sig - c.c_gradp;
     const int nseg = (int)G->useg_lmax.size();
     for(int sg = 0; sg < nseg; ++sg) {
+      constexpr int NGRP = 4; // node groups per CTA
       ua.warp0          = G->useg_begin[sg];
-      const int    nc   = G->useg_begin[sg + 1] - G->useg_begin[sg];
-      const size_t smem = ((size_t)(G->useg_lmax[sg] + 3) * 32 + 32 * 8) * sizeof(double);
+      ua.warp_end       = G->useg_begin[sg + 1];
+      const int    nc   = (ua.warp_end - ua.warp0 + NGRP - 1) / NGRP;
+      const bool   big  = (size_t)(G->useg_lmax[sg] + 3) * 32 * sizeof(double) > 24 * 1024;
+      const size_t smem = ((size_t)(G->useg_lmax[sg] + 3) * 32 + 32 * (big ? 8 : 16)) * sizeof(double);
 #define B200_LAUNCH_C(KERN)                                                                                         \
   do {                                                                                                              \
     B200_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
@@ -1696,16 +1699,16 @@ static int launch_gather_urow(System *S, int what, const THCoeffs &c)
     count_launch();                                                                                                 \
   } while(0)
       // long rows (vertex nodes): 4 warps per SM fit anyway; short rows: up to 8 warps per SM, 255 registers for the software pipeline
-      if(smem > 28 * 1024) {
+      if(big) {
         if(res)
-          B200_LAUNCH_C((gather_urow_kernel<true, 4>));
+          B200_LAUNCH_C((gather_urow_kernel<true, 4, NGRP, 8>));
         else
-          B200_LAUNCH_C((gather_urow_kernel<false, 4>));
+          B200_LAUNCH_C((gather_urow_kernel<false, 4, NGRP, 8>));
       } else {
         if(res)
-          B200_LAUNCH_C((gather_urow_kernel<true, 8>));
+          B200_LAUNCH_C((gather_urow_kernel<true, 8, NGRP, 16>));
         else
-          B200_LAUNCH_C((gather_urow_kernel<false, 8>));
+          B200_LAUNCH_C((gather_urow_kernel<false, 8, NGRP, 16>));
       }
 #undef B200_LAUNCH_C
     }

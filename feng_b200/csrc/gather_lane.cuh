@@ -35,12 +35,12 @@ template <int D, int NS, int NP> struct ES {
   __host__ __device__ static constexpr int rp(int q) { return O_RP + q; }
 };
 
-// per-element state of the canonical kernels (gather_canon.cuh; P2/P1 tetrahedra; records are 128-byte aligned: 224 * 8 = 14 * 128)
+// per-element state of the canonical kernels (gather_canon.cuh; P2/P1 tetrahedra; records are 128-byte aligned: 208 * 8 = 13 * 128)
 struct ESC {
-  static constexpr int O_DVT = 0;   // [4][4][4]   DvT[v][i][j] = c_conv J d_j u_i (vertex v); i = 3, j = 3: padding (one 128-byte line per vertex)
-  static constexpr int O_ROW = 64;  // [10][16]    per local row node la: C1c[0..9] (canonical column order of la), RU[0..2] at 10..12,
+  static constexpr int O_DVT = 0;   // [3][4][3]   DvT[i][v][j] = c_conv J d_j u_i (vertex v): 96 contiguous bytes per component i; 36 .. 47 unused
+  static constexpr int O_ROW = 48;  // [10][16]    per local row node la: C1[la][0..9], RU[0..2] at 10..12,
                                     //             slot 13 of rows 0..3: the pressure-row residual RP[q]
-  static constexpr int W = 224;
+  static constexpr int W = 208;
   static constexpr int O_DV = 0, O_C1 = 0; // not used through this layout (names needed by the shared row kernel)
   __host__ __device__ static constexpr int ru(int la, int i) { return O_ROW + la * 16 + 10 + i; }
   __host__ __device__ static constexpr int rp(int q) { return O_ROW + q * 16 + 13; }

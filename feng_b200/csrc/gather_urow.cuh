@@ -35,6 +35,7 @@ __device__ __forceinline__ D4 ldg256(const void *p)
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
   return r;
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 struct U8 {
   uint32_t w[8];
 };
@@ -148,16 +149,22 @@ __global__ void __launch_bounds__(128) element_state_urow_kernel(const ElementSt
   {
     const double sJ = c.c_conv * J;
 #pragma unroll
-    for(int v = 0; v < NP; ++v)
+    for(int i = 0; i < D; ++i) {
+      double t[12]; // DvT[i][v][j]
 #pragma unroll
-      for(int i = 0; i < D; ++i) {
+      for(int v = 0; v < NP; ++v)
+#pragma unroll
+        for(int j = 0; j < D; ++j) t[v * 3 + j] = sJ * gu[(v * D + j) * D + i];
+#pragma unroll
+      for(int k = 0; k < 3; ++k) {
         D4 o;
-        o.x = sJ * gu[(v * D + 0) * D + i];
-        o.y = sJ * gu[(v * D + 1) * D + i];
-        o.z = sJ * gu[(v * D + 2) * D + i];
-        o.w = 0.;
-        stg256(out + X::O_DVT + (v * 4 + i) * 4, o);
+        o.x = t[4 * k];
+        o.y = t[4 * k + 1];
+        o.z = t[4 * k + 2];
+        o.w = t[4 * k + 3];
+        stg256(out + X::O_DVT + i * 12 + k * 4, o);
       }
+    }
   }
   // contravariant velocity DOFs (scaled by c_conv J)
   double Ut[NS][D];
@@ -480,67 +487,64 @@ struct URowArgs {
   const int32_t  *row;
   const int64_t  *ia;
   double         *val, *rhs;
-  int32_t         count, warp0; // nodes, first warp of this launch
+  int32_t         count, warp0, warp_end; // nodes, first and one-past-last node group (10 nodes) of this launch
   int64_t         nInc;
   double          nsm, cdk, mass0, cpr; // -sig_mu, diff_k - sig_mu, c_mass c0, c_sig - c_gradp
 };
 
-template <bool RES, int MINB> __global__ void __launch_bounds__(32, MINB) gather_urow_kernel(const URowArgs a)
+// One warp per CTA; the CTA works through NGRP consecutive node groups (10 nodes each) of its launch segment.  The schedule steps of
+// consecutive groups are consecutive in `sched`, so the software pipeline of the global loads runs across the group boundaries: the
+// first steps of the next group are in flight while the finished images of this group are written out (a warp that handles a single
+// group of mid-edge nodes lives for ~5 steps and spends a third of them waiting for its first loads, r02m).
+template <bool RES, int MINB, int NGRP, int TW> __global__ void __launch_bounds__(32, MINB) gather_urow_kernel(const URowArgs a)
 {
   using X = ESC;
   using CT = URowTab;
   extern __shared__ double sm[];
   const int lane = threadIdx.x;
   const int g = lane / 3, i = lane - 3 * g;
-  const int w = a.warp0 + (int)blockIdx.x;
-  int32_t   row = 0x7fffffff;
-  int       len = 0, cnt = 0, p0 = 0;
-  {
-    const int k = w * 10 + g;
-    if(g < 10 && k < a.count) {
-      const int32_t n  = a.order[k];
-      row              = a.row[(int64_t)n * 3 + i];
-      const int2    rg = a.range[n];
-      p0               = rg.x;
-      cnt              = rg.y;
-      // the unknown rows of a node share their length
-#pragma unroll
-      for(int c = 2; c >= 0; --c) {
-        const int32_t r = a.row[(int64_t)n * 3 + c];
-        if(r < a.nInc) len = (int)(a.ia[r + 1] - a.ia[r]);
-      }
-    }
-  }
-  const int Lmax = __reduce_max_sync(0xffffffffu, len);
-  double   *S    = sm;                           // [Lmax + 3][32] interleaved row images, rows Lmax .. Lmax + 2 = trash
-  double   *T    = sm + (size_t)(Lmax + 3) * 32; // [32][8] staging tile of the write-out
-  {
-    double2 *z = reinterpret_cast<double2 *>(S);
-    for(int k = lane; k < (Lmax + 3) * 16; k += 32) z[k] = make_double2(0., 0.);
-  }
-  __syncwarp();
-  double  res = 0.;
-  double *Sl  = S + lane;
+  const int gc = min(g, 9);
+  const int wbeg = a.warp0 + (int)blockIdx.x * NGRP, wend = min(wbeg + NGRP, a.warp_end);
   // component selectors as 0 / 1 factors: a per-lane `i == j ? x : y` inside the step loop may be compiled into a divergent branch,
   // and a divergent branch in the loop body makes ptxas give up the uniform datapath for the constant loads (products with 0 / 1 and
   // sums with +-0 are exact)
   const double mi[3] = {i == 0 ? 1. : 0., i == 1 ? 1. : 0., i == 2 ? 1. : 0.};
 
-  // The warp follows its precomputed schedule: it walks the local indices la = 0 .. 9, wmax[w][la] steps each; at flat step s group g
-  // works on pair sched[s][g] (idle: record 0 into the trash entries).  Two counted loops with uniform bounds and NO branch in the body:
-  // ptxas keeps the constant loads on the uniform datapath only when the table index is a plain loop counter (a REDUX result or a
-  // loaded value ends up in vector LDCs, measured) and the control flow is provably convergent.  The global loads are software-
-  // pipelined over the flat step index: schedule entries three steps ahead, pair records two, element data one.
-  const int s0 = a.wstep[w];
-  const int ns = a.wstep[w + 1] - s0;
-  const int gc = min(g, 9);
-  auto sched_at = [&](int s) -> int {
-    const int v = a.sched[(size_t)(s0 + max(min(s, ns - 1), 0)) * 10 + gc];
-    return (s < ns && g < 10) ? v : -1;
+  // per-group data of lane (g, i): its row, the length of the rows of its node, the first CSR slot of its row
+  struct Meta {
+    int32_t row;
+    int     len;
+    int64_t ia;
   };
-  const uint64_t wm = a.wmax[w];
+  auto load_meta = [&](int w) -> Meta {
+    Meta      m = {0x7fffffff, 0, -1};
+    const int k = w * 10 + g;
+    if(g < 10 && w < wend && k < a.count) {
+      const int32_t n = a.order[k];
+      m.row           = a.row[(int64_t)n * 3 + i];
+      // the unknown rows of a node share their length
+#pragma unroll
+      for(int c = 2; c >= 0; --c) {
+        const int32_t r = a.row[(int64_t)n * 3 + c];
+        if(r < a.nInc) m.len = (int)(a.ia[r + 1] - a.ia[r]);
+      }
+      if(m.row < a.nInc) m.ia = a.ia[m.row];
+    }
+    return m;
+  };
+
+  // The warp follows the precomputed schedule: per group it walks the local indices la = 0 .. 9, wmax[w] steps each; at flat step s
+  // group g works on pair sched[s][g] (idle: record 0 into the trash entries).  Counted loops with uniform bounds and NO branch in the
+  // body: ptxas keeps the constant loads on the uniform datapath only when the table index is a plain loop counter (a REDUX result or
+  // a loaded value ends up in vector LDCs, measured) and the control flow is provably convergent.  The global loads are software-
+  // pipelined over the flat step index: schedule entries three steps ahead, pair records two, element data one.
+  const int s_beg = a.wstep[wbeg], s_end = a.wstep[wend];
+  auto sched_at = [&](int s) -> int { // branch-free (clamped load + select)
+    const int v = a.sched[(size_t)max(min(s, s_end - 1), s_beg) * 10 + gc];
+    return (s < s_end && g < 10) ? v : -1;
+  };
   struct PData {
-    D4 g1, g2, g3, dv[4], r0, r1, r2, r3;
+    D4 g1, g2, g3, dv[3], r0, r1, r2, r3;
   };
   auto load_data = [&](const U8 &rec, PData &d) {
     const int64_t e  = (int64_t)(rec.w[0] >> 4);
@@ -550,7 +554,7 @@ template <bool RES, int MINB> __global__ void __launch_bounds__(32, MINB) gather
     d.g2 = ldg256(ge + 8);
     d.g3 = ldg256(ge + 12);
 #pragma unroll
-    for(int v = 0; v < 4; ++v) d.dv[v] = ldg256(es + X::O_DVT + (v * 4 + i) * 4); // the three lanes of a node read one 128-byte line
+    for(int v = 0; v < 3; ++v) d.dv[v] = ldg256(es + X::O_DVT + i * 12 + v * 4); // DvT[i][0..11]: 96 contiguous bytes per lane
     // the row index comes from the record, NOT from the step's la (equal for active lanes): a use of the warp-uniform la in per-lane
     // address arithmetic makes ptxas keep it in a vector register and turn the 212 uniform constant loads into vector LDCs
     const double *er = es + X::O_ROW + (int)(rec.w[0] & 15u) * 16;
@@ -559,151 +563,199 @@ template <bool RES, int MINB> __global__ void __launch_bounds__(32, MINB) gather
     d.r2 = ldg256(er + 8);
     d.r3 = ldg256(er + 12);
   };
-  int   iA = sched_at(0), iB = sched_at(1), iC = sched_at(2);
+  int   fs = s_beg; // flat step
+  int   iA = sched_at(fs), iB = sched_at(fs + 1), iC = sched_at(fs + 2);
   U8    rA = ldg256u(a.rec + max(iA, 0)), rB = ldg256u(a.rec + max(iB, 0));
   PData dA;
   load_data(rA, dA);
-  int fs = 0; // flat step
-#pragma unroll 1
-  for(int la_c = 0; la_c < 10; ++la_c) {
-   const int maxc = __reduce_max_sync(0xffffffffu, (int)((wm >> (6 * la_c)) & 63u));
-#pragma unroll 1
-   for(int it = 0; it < maxc; ++it) {
-    PData dB;
-    load_data(rB, dB);                            // step fs + 1
-    const U8  rC = ldg256u(a.rec + max(iC, 0));   // step fs + 2
-    const int iD = sched_at(fs + 3);
-    {
-      const bool   act = iA >= 0;
-      const U8    &rec = rA;
-      const PData &d   = dA;
-      // it >> 24 == 0, which the compiler cannot prove: keeps the constant loads inside the step loop (otherwise ptxas hoists the 212
-      // constants of the row into registers and spills); la_c and it are used for nothing else
-      const double *ct = &b200_urow_tab[la_c][it >> 24];
-      const double  J = d.g1.w;
-      const double  Gp[3][3] = {{d.g1.x, d.g1.y, d.g1.z}, {d.g2.x, d.g2.y, d.g2.z}, {d.g3.x, d.g3.y, d.g3.z}};
-      const double  c1[10] = {d.r0.x, d.r0.y, d.r0.z, d.r0.w, d.r1.x, d.r1.y, d.r1.z, d.r1.w, d.r2.x, d.r2.y};
-      if(RES) res += (act ? 1. : 0.) * (mi[0] * d.r2.z + mi[1] * d.r2.w + mi[2] * d.r3.x);
-      // column i of the inverse map; -sig_mu J G; (diff_k - sig_mu) J G G^T (symmetric: 00, 11, 22, 01, 02, 12)
-      double gi[3], GJ[3][3], GG[6];
-#pragma unroll
-      for(int be = 0; be < 3; ++be) gi[be] = mi[0] * Gp[be][0] + mi[1] * Gp[be][1] + mi[2] * Gp[be][2];
-      {
-        const double nJ = a.nsm * J;
-#pragma unroll
-        for(int al = 0; al < 3; ++al)
-#pragma unroll
-          for(int m = 0; m < 3; ++m) GJ[al][m] = nJ * Gp[al][m];
-        constexpr int pa[6] = {0, 1, 2, 0, 0, 1}, pb[6] = {0, 1, 2, 1, 2, 2};
-        const double  cJ = a.cdk * J;
-#pragma unroll
-        for(int k = 0; k < 6; ++k) GG[k] = cJ * (Gp[pa[k]][0] * Gp[pb[k]][0] + Gp[pa[k]][1] * Gp[pb[k]][1] + Gp[pa[k]][2] * Gp[pb[k]][2]);
-      }
-      const double dvv[4][3] = {{d.dv[0].x, d.dv[0].y, d.dv[0].z}, {d.dv[1].x, d.dv[1].y, d.dv[1].z}, {d.dv[2].x, d.dv[2].y, d.dv[2].z},
-                                {d.dv[3].x, d.dv[3].y, d.dv[3].z}};
-      const double mJ = a.mass0 * J;
+  Meta     mt = load_meta(wbeg);
+  uint64_t wm = a.wmax[wbeg];
 
-      // two column nodes per batch: six independent read-modify-writes in flight
+#pragma unroll 1
+  for(int w = wbeg; w < wend; ++w) {
+    const Meta     m   = mt;
+    const uint64_t wmc = wm;
+    mt = load_meta(w + 1); // next group: in flight during this group's steps
+    wm = a.wmax[min(w + 1, wend - 1)];
+    const int Lmax = __reduce_max_sync(0xffffffffu, m.len);
+    const int uz   = __reduce_max_sync(0xffffffffu, (int)(wmc >> 60)); // 0 (the ten 6-bit counts end at bit 59)
+    double   *S    = sm;                           // [Lmax + 3][32] interleaved row images, rows Lmax .. Lmax + 2 = trash
+    double   *T    = sm + (size_t)(Lmax + 3) * 32; // [32][TW] staging tile of the write-out
+    {
+      double2 *z = reinterpret_cast<double2 *>(S);
+      for(int k = lane; k < (Lmax + 3) * 16; k += 32) z[k] = make_double2(0., 0.);
+    }
+    __syncwarp();
+    double  res = 0.;
+    double *Sl  = S + lane;
+#pragma unroll 1
+    for(int la_c = 0; la_c < 10; ++la_c) {
+      const int maxc = __reduce_max_sync(0xffffffffu, (int)((wmc >> (6 * la_c)) & 63u));
+#pragma unroll 1
+      for(int it = 0; it < maxc; ++it) {
+        // ptxas sinks the register loads of step fs + 1 to the middle of this step whatever the source order says (r02o: a third of
+        // the stall samples sit on their first use), so the lines they will read are first pulled into L2 here, at the top of the
+        // step: lane i of a node asks for the i-th line of the vertex gradients, then for the geometry / the row / the next record.
+        // The prefetches sit in a basic block of their own (the scheduler does not move instructions across the always-taken uniform
+        // branch `uz == 0` below), otherwise they are sunk next to the loads.
+        {
+          const int64_t e  = (int64_t)(rB.w[0] >> 4);
+          const double *es = a.es + e * X::W;
+          prefetch_l2(es + i * 16);
+          const void *p2 = i == 0 ? (const void *)(a.geo4 + e * 16) : i == 1 ? (const void *)(es + X::O_ROW + (int)(rB.w[0] & 15u) * 16)
+                                                                              : (const void *)(a.rec + max(iC, 0));
+          prefetch_l2(p2);
+        }
+        if(uz != 0) continue; // never: uz is 0 in a uniform register, which the compiler cannot know
+        PData dB;
+        load_data(rB, dB);                          // step fs + 1
+        const U8  rC = ldg256u(a.rec + max(iC, 0)); // step fs + 2
+        const int iD = sched_at(fs + 3);
+        {
+          const bool   act = iA >= 0;
+          const U8    &rec = rA;
+          const PData &d   = dA;
+          // it >> 24 == 0, which the compiler cannot prove: keeps the constant loads inside the step loop (otherwise ptxas hoists the
+          // 212 constants of the row into registers and spills); la_c and it are used for nothing else
+          const double *ct = &b200_urow_tab[la_c][it >> 24];
+          const double  J = d.g1.w;
+          const double  Gp[3][3] = {{d.g1.x, d.g1.y, d.g1.z}, {d.g2.x, d.g2.y, d.g2.z}, {d.g3.x, d.g3.y, d.g3.z}};
+          const double  c1[10] = {d.r0.x, d.r0.y, d.r0.z, d.r0.w, d.r1.x, d.r1.y, d.r1.z, d.r1.w, d.r2.x, d.r2.y};
+          if(RES) res += (act ? 1. : 0.) * (mi[0] * d.r2.z + mi[1] * d.r2.w + mi[2] * d.r3.x);
+          // column i of the inverse map; -sig_mu J G; (diff_k - sig_mu) J G G^T (symmetric: 00, 11, 22, 01, 02, 12)
+          double gi[3], GJ[3][3], GG[6];
 #pragma unroll
-      for(int bb = 0; bb < 10; bb += 2) {
-        double  A[2][3];
-        double *q[2];
+          for(int be = 0; be < 3; ++be) gi[be] = mi[0] * Gp[be][0] + mi[1] * Gp[be][1] + mi[2] * Gp[be][2];
+          {
+            const double nJ = a.nsm * J;
 #pragma unroll
-        for(int h = 0; h < 2; ++h) {
-          const int     b  = bb + h;
-          const double *Kr = ct + CT::O_K + b * 9;
-          const double *Ks = ct + CT::O_KS + b * 6;
-          const double *t3 = ct + CT::O_T3 + b * 4;
-          double        H[3];
+            for(int al = 0; al < 3; ++al)
 #pragma unroll
-          for(int al = 0; al < 3; ++al) H[al] = Kr[al * 3 + 0] * gi[0] + Kr[al * 3 + 1] * gi[1] + Kr[al * 3 + 2] * gi[2];
-          double s = c1[b] + mJ * ct[CT::O_M + b];
+              for(int mm = 0; mm < 3; ++mm) GJ[al][mm] = nJ * Gp[al][mm];
+            constexpr int pa[6] = {0, 1, 2, 0, 0, 1}, pb[6] = {0, 1, 2, 1, 2, 2};
+            const double  cJ = a.cdk * J;
 #pragma unroll
-          for(int k = 0; k < 6; ++k) s += Ks[k] * GG[k];
-          double tv[4];
-#pragma unroll
-          for(int v = 0; v < 4; ++v) tv[v] = t3[v];
-#pragma unroll
-          for(int j = 0; j < 3; ++j) {
-            // one DFMA chain per entry: (i == j ? s : 0) - sig_mu K[j][i] + c_conv int phi_a phi_b d_j u_i
-            double x = mi[j] * s;
-#pragma unroll
-            for(int al = 0; al < 3; ++al) x = fma(GJ[al][j], H[al], x);
-#pragma unroll
-            for(int v = 0; v < 4; ++v) x = fma(dvv[v][j], tv[v], x);
-            A[h][j] = x;
+            for(int k = 0; k < 6; ++k) GG[k] = cJ * (Gp[pa[k]][0] * Gp[pb[k]][0] + Gp[pa[k]][1] * Gp[pb[k]][1] + Gp[pa[k]][2] * Gp[pb[k]][2]);
           }
-          const uint32_t o = rec_off(rec, b);
-          q[h]             = Sl + (size_t)((act && o != 0xFFFFu) ? (int)o : Lmax) * 32;
+          // DvT[i][v][j] = c_conv J d_j u_i (vertex v)
+          const double dvv[4][3] = {{d.dv[0].x, d.dv[0].y, d.dv[0].z}, {d.dv[0].w, d.dv[1].x, d.dv[1].y}, {d.dv[1].z, d.dv[1].w, d.dv[2].x},
+                                    {d.dv[2].y, d.dv[2].z, d.dv[2].w}};
+          const double mJ = a.mass0 * J;
+
+          // NB column nodes per batch: 3 NB independent read-modify-writes in flight
+          constexpr int NB = 5;
+#pragma unroll
+          for(int bb = 0; bb < 10; bb += NB) {
+            double  A[NB][3];
+            double *q[NB];
+#pragma unroll
+            for(int h = 0; h < NB; ++h) {
+              const int     b  = bb + h;
+              const double *Kr = ct + CT::O_K + b * 9;
+              const double *Ks = ct + CT::O_KS + b * 6;
+              const double *t3 = ct + CT::O_T3 + b * 4;
+              double        H[3];
+#pragma unroll
+              for(int al = 0; al < 3; ++al) H[al] = Kr[al * 3 + 0] * gi[0] + Kr[al * 3 + 1] * gi[1] + Kr[al * 3 + 2] * gi[2];
+              double s = c1[b] + mJ * ct[CT::O_M + b];
+#pragma unroll
+              for(int k = 0; k < 6; ++k) s += Ks[k] * GG[k];
+              double tv[4];
+#pragma unroll
+              for(int v = 0; v < 4; ++v) tv[v] = t3[v];
+#pragma unroll
+              for(int j = 0; j < 3; ++j) {
+                // one DFMA chain per entry: (i == j ? s : 0) - sig_mu K[j][i] + c_conv int phi_a phi_b d_j u_i
+                double x = mi[j] * s;
+#pragma unroll
+                for(int al = 0; al < 3; ++al) x = fma(GJ[al][j], H[al], x);
+#pragma unroll
+                for(int v = 0; v < 4; ++v) x = fma(dvv[v][j], tv[v], x);
+                A[h][j] = x;
+              }
+              const uint32_t o = rec_off(rec, b);
+              q[h]             = Sl + (size_t)((act && o != 0xFFFFu) ? (int)o : Lmax) * 32;
+            }
+            double old[NB][3];
+#pragma unroll
+            for(int h = 0; h < NB; ++h)
+#pragma unroll
+              for(int j = 0; j < 3; ++j) old[h][j] = q[h][j * 32];
+#pragma unroll
+            for(int h = 0; h < NB; ++h)
+#pragma unroll
+              for(int j = 0; j < 3; ++j) q[h][j * 32] = old[h][j] + A[h][j];
+          }
+          // pressure columns: A[(a, i)][q] = (c_sig - c_gradp) int psi_q d_i phi_a   (src/feVectorSysElm.cpp:449-503, :528-578)
+          {
+            double  v[4], old[4];
+            double *q[4];
+            const double pJ    = a.cpr * J;
+            const double gj[3] = {pJ * gi[0], pJ * gi[1], pJ * gi[2]};
+#pragma unroll
+            for(int qq = 0; qq < 4; ++qq) {
+              const double *Br = ct + CT::O_B + qq * 3;
+              v[qq]            = gj[0] * Br[0] + gj[1] * Br[1] + gj[2] * Br[2];
+              const uint32_t o = rec_off(rec, 10 + qq);
+              q[qq]            = Sl + (size_t)((act && o != 0xFFFFu) ? (int)o : Lmax) * 32;
+            }
+#pragma unroll
+            for(int qq = 0; qq < 4; ++qq) old[qq] = *q[qq];
+#pragma unroll
+            for(int qq = 0; qq < 4; ++qq) *q[qq] = old[qq] + v[qq];
+          }
         }
-        double old[2][3];
-#pragma unroll
-        for(int h = 0; h < 2; ++h)
-#pragma unroll
-          for(int j = 0; j < 3; ++j) old[h][j] = q[h][j * 32];
-#pragma unroll
-        for(int h = 0; h < 2; ++h)
-#pragma unroll
-          for(int j = 0; j < 3; ++j) q[h][j * 32] = old[h][j] + A[h][j];
-      }
-      // pressure columns: A[(a, i)][q] = (c_sig - c_gradp) int psi_q d_i phi_a   (src/feVectorSysElm.cpp:449-503, :528-578)
-      {
-        double  v[4], old[4];
-        double *q[4];
-        const double pJ    = a.cpr * J;
-        const double gj[3] = {pJ * gi[0], pJ * gi[1], pJ * gi[2]};
-#pragma unroll
-        for(int qq = 0; qq < 4; ++qq) {
-          const double *Br = ct + CT::O_B + qq * 3;
-          v[qq]            = gj[0] * Br[0] + gj[1] * Br[1] + gj[2] * Br[2];
-          const uint32_t o = rec_off(rec, 10 + qq);
-          q[qq]            = Sl + (size_t)((act && o != 0xFFFFu) ? (int)o : Lmax) * 32;
-        }
-#pragma unroll
-        for(int qq = 0; qq < 4; ++qq) old[qq] = *q[qq];
-#pragma unroll
-        for(int qq = 0; qq < 4; ++qq) *q[qq] = old[qq] + v[qq];
+        iA = iB;
+        iB = iC;
+        iC = iD;
+        rA = rB;
+        rB = rC;
+        dA = dB;
+        fs = __shfl_sync(0xffffffffu, fs + 1, 0); // opaque to the induction-variable optimiser: `it` must stay a pure loop counter
       }
     }
-    iA = iB;
-    iB = iC;
-    iC = iD;
-    rA = rB;
-    rB = rC;
-    dA = dB;
-    fs = __shfl_sync(0xffffffffu, fs + 1, 0); // opaque to the induction-variable optimiser: `it` must stay a pure loop counter
-   }
-  }
-  const bool valid = row < a.nInc;
-  if(RES && valid) a.rhs[row] = res;
-  __syncwarp();
-  // write-out: 8 entries of every image per round through a swizzled [32][8] tile, then 64-byte runs per row
-  {
-    const int64_t myia  = valid ? a.ia[row] : -1;
-    const int     mylen = valid ? len : 0;
-    int64_t       ia_t[8];
-    int           len_t[8];
-    const int     kk = lane & 7;
+    const bool valid = m.ia >= 0;
+    if(RES && valid) a.rhs[m.row] = res;
+    __syncwarp();
+    // write-out: TW entries of every image per round through a swizzled [32][TW] tile, then runs of TW * 8 bytes per row with 16-byte
+    // stores.  A row whose first CSR slot is odd shifts its rounds by one entry (p = 1) so that every 16-byte store is aligned; its
+    // entry 0 is stored on its own.  (TW = 8 where the 4 KB tile would cost a resident warp: the long rows of the vertex nodes.)
+    {
+      constexpr int PR = TW / 2, RPR = 32 / PR; // 16-byte pairs per row of the tile, rows per store round
+      const int mylen = valid ? m.len : 0;
+      const int p     = valid ? (int)(m.ia & 1) : 0;
+      if(valid && p) a.val[m.ia] = Sl[0];
+      int64_t   ia_t[PR];
+      int       len_t[PR];
+      const int c = lane % PR;
 #pragma unroll
-    for(int tt = 0; tt < 8; ++tt) {
-      const int rr = tt * 4 + (lane >> 3);
-      ia_t[tt]     = __shfl_sync(0xffffffffu, myia, rr);
-      len_t[tt]    = __shfl_sync(0xffffffffu, mylen, rr);
-    }
-    const int swz = (lane >> 1) & 7;
-    for(int k0 = 0; k0 < Lmax; k0 += 8) {
-      double v[8];
-#pragma unroll
-      for(int k = 0; k < 8; ++k) v[k] = Sl[(size_t)min(k0 + k, Lmax) * 32];
-#pragma unroll
-      for(int k = 0; k < 8; ++k) T[lane * 8 + (k ^ swz)] = v[k];
-      __syncwarp();
-#pragma unroll
-      for(int tt = 0; tt < 8; ++tt) {
-        const int rr = tt * 4 + (lane >> 3);
-        if(k0 + kk < len_t[tt]) a.val[ia_t[tt] + k0 + kk] = T[rr * 8 + (kk ^ ((rr >> 1) & 7))];
+      for(int tt = 0; tt < PR; ++tt) {
+        const int rr = tt * RPR + lane / PR;
+        ia_t[tt]     = __shfl_sync(0xffffffffu, m.ia, rr);
+        len_t[tt]    = __shfl_sync(0xffffffffu, mylen, rr);
       }
-      __syncwarp();
+      double2 *T2 = reinterpret_cast<double2 *>(T);
+      // 16-byte bank groups: a quarter warp (8 lanes) must hit 8 different ones, in the fill (lane = row) and in the drain (lane = pair)
+      auto swz = [](int r) { return TW == 16 ? (r & 7) : ((r >> 1) & 3); };
+      for(int k0 = 0; k0 < Lmax; k0 += TW) {
+        double v[TW];
+#pragma unroll
+        for(int k = 0; k < TW; ++k) v[k] = Sl[(size_t)min(k0 + p + k, Lmax + 2) * 32];
+#pragma unroll
+        for(int k = 0; k < PR; ++k) T2[lane * PR + (k ^ swz(lane))] = make_double2(v[2 * k], v[2 * k + 1]);
+        __syncwarp();
+#pragma unroll
+        for(int tt = 0; tt < PR; ++tt) {
+          const int     rr = tt * RPR + lane / PR;
+          const double2 x  = T2[rr * PR + (c ^ swz(rr))];
+          const int     kg = k0 + (int)(ia_t[tt] & 1) + 2 * c;
+          if(kg + 1 < len_t[tt])
+            *reinterpret_cast<double2 *>(a.val + ia_t[tt] + kg) = x;
+          else if(kg < len_t[tt])
+            a.val[ia_t[tt] + kg] = x.x;
+        }
+        __syncwarp();
+      }
     }
   }
 }

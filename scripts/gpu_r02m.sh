@@ -1,0 +1,9 @@
+#!/bin/bash
+# r02m: ncu --set full of the velocity-row launches of one assembly pass at T3D(92)
+T=${1:-r02m}
+timeout 1200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'gather_urow_kernel' \
+    --launch-skip 6 --launch-count 2 -o gpurun_out/${T}_full_urow_t3d92 -f \
+    python bench.py --steps 1 --warmup 3 --no-cpu --no-solve --no-parity > /dev/null 2>&1
+ncu -i gpurun_out/${T}_full_urow_t3d92.ncu-rep --page raw --csv > gpurun_out/${T}_full_urow_t3d92.csv 2>/dev/null
+ncu -i gpurun_out/${T}_full_urow_t3d92.ncu-rep --page source --csv --print-source sass > gpurun_out/${T}_urow_source_sass.csv 2>/dev/null
+ls -la gpurun_out/${T}_*
