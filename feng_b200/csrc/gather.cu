@@ -87,6 +87,7 @@ struct GatherPlan {
   int32_t  *d_sched = nullptr; // [step][10] pair of group g at this step, or -1
   uint64_t *d_sla = nullptr;   // [warp] steps the warp spends on every local index, 6 bits each
   std::vector<double>   utab;  // [10][URowTab::LEN] reference tensors per local row node
+  std::vector<double>   estab; // [ESTab::LEN] reference tensors of the pre-pass
   std::vector<int32_t>  useg_begin; // launch segments (in warps of 10 nodes)
   std::vector<uint32_t> useg_lmax;  // longest row of the segment
 };
@@ -1134,6 +1135,8 @@ static bool build_tables(const System *S, int D, int NS, int NP, std::vector<dou
   return true;
 }
 
+static const void *g_urow_owner = nullptr; // plan whose reference tensors are in the __constant__ bank (gather_urow.cuh)
+
 bool gather_tables(const System *S, GatherTables *out)
 {
   const GatherPlan *G = static_cast<const GatherPlan *>(S->gather);
@@ -1149,6 +1152,7 @@ void gather_free(System *S)
 {
   GatherPlan *G = static_cast<GatherPlan *>(S->gather);
   if(!G) return;
+  if(g_urow_owner == G) g_urow_owner = nullptr; // a later plan may be allocated at the same address
   G->U.release();
   G->P.release();
   cudaFree(G->d_tab);
@@ -1169,8 +1173,6 @@ void gather_free(System *S)
 // ----------------------------------------------------------------------------------------------------------
 // row-lane plan (gather_urow.cuh)
 // ----------------------------------------------------------------------------------------------------------
-static const void *g_urow_owner = nullptr; // plan whose tensors are in b200_urow_tab
-
 static void urow_tables(const std::vector<double> &tab, std::vector<double> &ut)
 {
   using T = GT<3, 10, 4>;
@@ -1196,6 +1198,13 @@ static void urow_tables(const std::vector<double> &tab, std::vector<double> &ut)
 static int build_urow_plan(System *S, GatherPlan *G, const std::vector<double> &tab)
 {
   urow_tables(tab, G->utab);
+  {
+    using T = GT<3, 10, 4>;
+    G->estab.assign(ESTab::LEN, 0.);
+    for(int k = 0; k < 400; ++k) G->estab[ESTab::O_T3 + k] = tab[T::O_T3 + k];
+    for(int k = 0; k < 120; ++k) G->estab[ESTab::O_B + k] = tab[T::O_B + k];
+    for(int k = 0; k < 100; ++k) G->estab[ESTab::O_M + k] = tab[T::O_M + k];
+  }
   NodeSet &N = G->U;
   if(N.nNodes == 0) return B200_ERR_UNSUPP;
   auto pol = thrust::cuda::par.on(S->stream);
@@ -1617,6 +1626,13 @@ static int launch_gather_urow(System *S, int what, const THCoeffs &c)
   using T = GT<D, NS, NP>;
   const double *d_source = (c.c_src != 0.) ? S->d_source : nullptr;
   const int     ntab     = d_source ? G->tab_len_src : G->tab_len;
+  if(g_urow_owner != G) {
+    // the tensors of another system (another quadrature rule) are in the constant bank: drain the device before replacing them
+    if(g_urow_owner != nullptr) B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaMemcpyToSymbolAsync(b200_urow_tab, G->utab.data(), G->utab.size() * sizeof(double), 0, cudaMemcpyHostToDevice, S->stream));
+    B200_CUDA(cudaMemcpyToSymbolAsync(b200_es_tab, G->estab.data(), G->estab.size() * sizeof(double), 0, cudaMemcpyHostToDevice, S->stream));
+    g_urow_owner = G;
+  }
   {
     ElementStateArgs ea;
     ea.nElm   = S->nElm;
@@ -1632,8 +1648,7 @@ static int launch_gather_urow(System *S, int what, const THCoeffs &c)
     ea.ntab   = ntab;
     ea.c      = c;
     for(int i = 0; i < 120; ++i) ea.E[i] = G->E[i];
-    const size_t smem = (size_t)(ntab - T::O_T3) * sizeof(double);
-    B200_CUDA(cudaFuncSetAttribute(element_state_urow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = d_source ? (size_t)S->nq * NS * sizeof(double) : 0;
     element_state_urow_kernel<<<(unsigned)((S->nElm + 127) / 128), 128, smem, S->stream>>>(ea);
     count_launch();
   }
@@ -1659,12 +1674,6 @@ static int launch_gather_urow(System *S, int what, const THCoeffs &c)
   a.c0     = S->c0;
   for(int i = 0; i < 120; ++i) a.E[i] = G->E[i];
   if(mat) {
-    if(g_urow_owner != G) {
-      // the tensors of another system (another quadrature rule) are in the constant bank: drain the device before replacing them
-      if(g_urow_owner != nullptr) B200_CUDA(cudaDeviceSynchronize());
-      B200_CUDA(cudaMemcpyToSymbolAsync(b200_urow_tab, G->utab.data(), G->utab.size() * sizeof(double), 0, cudaMemcpyHostToDevice, S->stream));
-      g_urow_owner = G;
-    }
     URowArgs ua;
     ua.geo4  = G->d_geo4;
     ua.es    = G->d_es;

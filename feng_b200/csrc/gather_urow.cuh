@@ -75,16 +75,28 @@ __constant__ int c_edge_tet_u[6][2] = {{0, 2}, {2, 1}, {1, 0}, {1, 3}, {3, 0}, {
 // ----------------------------------------------------------------------------------------------------------------------
 // pre-pass: everything that depends on the element only (as element_state_kernel), in the record layout ESC
 // ----------------------------------------------------------------------------------------------------------------------
+// Reference tensors of the pre-pass in __constant__ memory, indexed by the row counter aa of its (not unrolled) loop: they reach the
+// DFMAs through uniform registers; the shared-memory copy of element_state_kernel cost 22 of the 126 L1 cycles per element (r02p).
+struct ESTab {
+  static constexpr int O_T3 = 0;   // [10][10][4] T3[a][c][v]
+  static constexpr int O_B = 400;  // [4][10][3]  Bref[q][a][al]
+  static constexpr int O_M = 520;  // [10][10]    Mref[a][b]
+  static constexpr int LEN = 620;
+};
+__constant__ double b200_es_tab[ESTab::LEN];
+
 __global__ void __launch_bounds__(128) element_state_urow_kernel(const ElementStateArgs a)
 {
   constexpr int D = 3, NS = 10, NP = 4;
   using T = GT<D, NS, NP>;
   using X = ESC;
-  constexpr int NU = NS * D, GW = T::GW, TOFF = T::O_T3;
-  extern __shared__ double s_tab[];
-  for(int i = threadIdx.x; i < a.ntab - TOFF; i += blockDim.x) s_tab[i] = a.tab[TOFF + i];
-  __syncthreads();
-  const double *s_t3 = s_tab + (T::O_T3 - TOFF), *s_m = s_tab + (T::O_M - TOFF), *s_b = s_tab + (T::O_B - TOFF), *s_w = s_tab + (T::O_W - TOFF);
+  using ET = ESTab;
+  constexpr int NU = NS * D, GW = T::GW;
+  extern __shared__ double s_w[]; // W[k][a] = w_k phi_a(k): source forms only
+  if(a.source != nullptr) {
+    for(int i = threadIdx.x; i < a.nq * NS; i += blockDim.x) s_w[i] = a.tab[T::O_W + i];
+    __syncthreads();
+  }
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if(e >= a.nElm) return;
   double G[D * D], J;
@@ -101,20 +113,15 @@ __global__ void __launch_bounds__(128) element_state_urow_kernel(const ElementSt
     for(int i = 0; i < D * D; ++i) G[i] = g[i];
     J = g[D * D];
   }
-  int32_t ad[NU];
-  double  U[NS][D];
+  double U[NS][D];
   {
     const int2 *a2 = reinterpret_cast<const int2 *>(a.adrU + e * NU);
 #pragma unroll
     for(int k = 0; k < NU / 2; ++k) {
-      const int2 v  = a2[k];
-      ad[2 * k + 0] = v.x;
-      ad[2 * k + 1] = v.y;
+      const int2 v = a2[k];
+      U[(2 * k) / D][(2 * k) % D]         = a.sol[v.x];
+      U[(2 * k + 1) / D][(2 * k + 1) % D] = a.sol[v.y];
     }
-#pragma unroll
-    for(int c = 0; c < NS; ++c)
-#pragma unroll
-      for(int m = 0; m < D; ++m) U[c][m] = a.sol[ad[c * D + m]];
   }
   double P[NP];
 #pragma unroll
@@ -146,101 +153,107 @@ __global__ void __launch_bounds__(128) element_state_urow_kernel(const ElementSt
         gu[(v * D + j) * D + i] = s;
       }
   }
-  {
-    const double sJ = c.c_conv * J;
+  const double sJ = c.c_conv * J;
 #pragma unroll
-    for(int i = 0; i < D; ++i) {
-      double t[12]; // DvT[i][v][j]
+  for(int i = 0; i < D; ++i) {
+    double t[12]; // DvT[i][v][j]
 #pragma unroll
-      for(int v = 0; v < NP; ++v)
+    for(int v = 0; v < NP; ++v)
 #pragma unroll
-        for(int j = 0; j < D; ++j) t[v * 3 + j] = sJ * gu[(v * D + j) * D + i];
+      for(int j = 0; j < D; ++j) t[v * 3 + j] = sJ * gu[(v * D + j) * D + i];
 #pragma unroll
-      for(int k = 0; k < 3; ++k) {
-        D4 o;
-        o.x = t[4 * k];
-        o.y = t[4 * k + 1];
-        o.z = t[4 * k + 2];
-        o.w = t[4 * k + 3];
-        stg256(out + X::O_DVT + i * 12 + k * 4, o);
-      }
+    for(int k = 0; k < 3; ++k) {
+      D4 o;
+      o.x = t[4 * k];
+      o.y = t[4 * k + 1];
+      o.z = t[4 * k + 2];
+      o.w = t[4 * k + 3];
+      stg256(out + X::O_DVT + i * 12 + k * 4, o);
     }
   }
-  // contravariant velocity DOFs (scaled by c_conv J)
-  double Ut[NS][D];
+  // divergence part of the residual, P rows: rp[q] = -c_div J sum_{b, j, al} G[al][j] Bref[q][b][al] U[b][j]
+  double rp[NP];
+  {
+    double GU[NS][D]; // GU[b][al] = sum_j G[al][j] U[b][j]
 #pragma unroll
-  for(int cc = 0; cc < NS; ++cc)
+    for(int b = 0; b < NS; ++b)
 #pragma unroll
-    for(int al = 0; al < D; ++al) {
+      for(int al = 0; al < D; ++al) GU[b][al] = G[al * D + 0] * U[b][0] + G[al * D + 1] * U[b][1] + G[al * D + 2] * U[b][2];
+#pragma unroll
+    for(int q = 0; q < NP; ++q) {
       double s = 0.;
 #pragma unroll
-      for(int m = 0; m < D; ++m) s += U[cc][m] * G[al * D + m];
-      Ut[cc][al] = c.c_conv * J * s;
+      for(int b = 0; b < NS; ++b)
+#pragma unroll
+        for(int al = 0; al < D; ++al) s += b200_es_tab[ET::O_B + (q * NS + b) * D + al] * GU[b][al];
+      rp[q] = -c.c_div * J * s;
     }
-  // divergence part of the residual, P rows
-  double rp[NP];
-#pragma unroll
-  for(int q = 0; q < NP; ++q) rp[q] = 0.;
-#pragma unroll
-  for(int q = 0; q < NP; ++q)
-#pragma unroll
-    for(int b = 0; b < NS; ++b) {
-      const double *Br = s_b + (q * NS + b) * D;
-#pragma unroll
-      for(int j = 0; j < D; ++j) {
-        double s = 0.;
-#pragma unroll
-        for(int al = 0; al < D; ++al) s += G[al * D + j] * Br[al];
-        rp[q] -= c.c_div * J * s * U[b][j];
-      }
-    }
+  }
   const bool   domass = (c.c_mass != 0.) && (a.soldot != nullptr);
   const double cvis1 = c.sig_mu - c.diff_k, cvis2 = c.sig_mu, cpre = c.c_gradp - c.c_sig;
+  // the loop counter aa indexes the constant tables ONLY (uniform datapath); everything per-thread that depends on the row goes
+  // through `orow` / `av`, which the compiler cannot merge with aa
+  double *orow = out + X::O_ROW;
+  int     av   = 0;
 #pragma unroll 1
   for(int aa = 0; aa < NS; ++aa) {
-    double Z[D * NP];
+    const double *t3 = &b200_es_tab[ET::O_T3 + aa * NS * NP];
+    // C1[aa][b] = c_conv J sum_{al, v} E[b][al][v] Z[al][v],  Z[al][v] = sum_m G[al][m] Y[m][v],  Y[m][v] = sum_c U[c][m] T3[aa][c][v]
+    double Y[D * NP];
 #pragma unroll
-    for(int i = 0; i < D * NP; ++i) Z[i] = 0.;
-    const double *t3 = s_t3 + aa * NS * NP;
+    for(int i = 0; i < D * NP; ++i) Y[i] = 0.;
 #pragma unroll
     for(int cc = 0; cc < NS; ++cc)
 #pragma unroll
       for(int v = 0; v < NP; ++v) {
         const double t = t3[cc * NP + v];
 #pragma unroll
-        for(int al = 0; al < D; ++al) Z[al * NP + v] += Ut[cc][al] * t;
+        for(int m = 0; m < D; ++m) Y[m * NP + v] += U[cc][m] * t;
       }
+    double Z[D * NP];
+#pragma unroll
+    for(int al = 0; al < D; ++al)
+#pragma unroll
+      for(int v = 0; v < NP; ++v) Z[al * NP + v] = sJ * (G[al * D + 0] * Y[0 * NP + v] + G[al * D + 1] * Y[1 * NP + v] + G[al * D + 2] * Y[2 * NP + v]);
     double r[D];
 #pragma unroll
     for(int i = 0; i < D; ++i) r[i] = 0.;
-    double *orow = out + X::O_ROW + aa * 16;
+    {
+      double c1[NS];
 #pragma unroll
-    for(int b = 0; b < NS; ++b) {
-      double s = 0.;
-#pragma unroll
-      for(int i = 0; i < D * NP; ++i) s += a.E[b * D * NP + i] * Z[i];
-      orow[b] = s;
-#pragma unroll
-      for(int i = 0; i < D; ++i) r[i] -= s * U[b][i];
-    }
-#pragma unroll
-    for(int v = 0; v < NP; ++v) {
-      const double *Br = s_b + (v * NS + aa) * D;
-#pragma unroll
-      for(int m = 0; m < D; ++m) {
+      for(int b = 0; b < NS; ++b) {
         double s = 0.;
 #pragma unroll
-        for(int al = 0; al < D; ++al) s += G[al * D + m] * Br[al];
-        const double bp = J * s;
+        for(int i = 0; i < D * NP; ++i) s += a.E[b * D * NP + i] * Z[i];
+        c1[b] = s;
+#pragma unroll
+        for(int i = 0; i < D; ++i) r[i] -= s * U[b][i];
+      }
+      D4 o;
+      o.x = c1[0], o.y = c1[1], o.z = c1[2], o.w = c1[3];
+      stg256(orow, o);
+      o.x = c1[4], o.y = c1[5], o.z = c1[6], o.w = c1[7];
+      stg256(orow + 4, o);
+      orow[8] = c1[8];
+      orow[9] = c1[9];
+    }
+    // viscous and pressure parts through Bp[v][aa][m] = J sum_al G[al][m] Bref[v][aa][al]
+#pragma unroll
+    for(int v = 0; v < NP; ++v) {
+      const double *Br = &b200_es_tab[ET::O_B + v * NS * D + aa * D];
+#pragma unroll
+      for(int m = 0; m < D; ++m) {
+        const double bp = J * (G[0 * D + m] * Br[0] + G[1 * D + m] * Br[1] + G[2 * D + m] * Br[2]);
         r[m] += cpre * bp * P[v];
 #pragma unroll
         for(int i = 0; i < D; ++i) r[i] += bp * (cvis1 * gu[(v * D + m) * D + i] + cvis2 * gu[(v * D + i) * D + m]);
       }
     }
     if(domass) {
+      const int32_t *ad = a.adrU + e * NU;
 #pragma unroll
       for(int b = 0; b < NS; ++b) {
-        const double mab = c.c_mass * J * s_m[aa * NS + b];
+        const double mab = c.c_mass * J * b200_es_tab[ET::O_M + aa * NS + b];
 #pragma unroll
         for(int i = 0; i < D; ++i) r[i] -= mab * a.soldot[ad[b * D + i]];
       }
@@ -248,20 +261,24 @@ __global__ void __launch_bounds__(128) element_state_urow_kernel(const ElementSt
     if(a.source != nullptr) {
       const double *src = a.source + e * a.nq * D;
       for(int k = 0; k < a.nq; ++k) {
-        const double wj = J * s_w[k * NS + aa];
+        const double wj = J * s_w[k * NS + av];
 #pragma unroll
         for(int i = 0; i < D; ++i) r[i] -= wj * src[k * D + i];
       }
     }
-#pragma unroll
-    for(int i = 0; i < D; ++i) orow[10 + i] = r[i];
-    // slot 13: pressure-row residual of local pressure node aa (rows 0..3), zero padding elsewhere
+    // slots 10..12: the velocity-row residual; slot 13: pressure-row residual of local pressure node aa (rows 0..3)
     double p13 = 0.;
 #pragma unroll
-    for(int q = 0; q < NP; ++q) p13 = (aa == q) ? rp[q] : p13;
-    orow[13] = p13;
-    orow[14] = 0.;
-    orow[15] = 0.;
+    for(int q = 0; q < NP; ++q) p13 = (av == q) ? rp[q] : p13;
+    orow[10] = r[0];
+    orow[11] = r[1];
+    {
+      D4 o;
+      o.x = r[2], o.y = p13, o.z = 0., o.w = 0.;
+      stg256(orow + 12, o);
+    }
+    orow += 16;
+    av = __shfl_sync(0xffffffffu, av + 1, threadIdx.x & 31); // same value, opaque to the induction-variable optimiser
   }
 }
 
