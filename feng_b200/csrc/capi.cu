@@ -623,6 +623,8 @@ int b200_set_assembly_mode(b200_system *s, int mode)
 
 int b200_has_gather_plan(const b200_system *s) { return s && s->gather != nullptr ? (s->patch != nullptr ? 2 : 1) : 0; }
 
+int b200_gather_kernel(const b200_system *s) { return s ? gather_kernel_kind(s) : 0; }
+
 int64_t b200_system_size(const b200_system *s) { return s ? s->nInc : 0; }
 
 int b200_set_solution(b200_system *s, const double *sol, const double *sol_dot, double c0, double t)

@@ -1148,6 +1148,12 @@ bool gather_tables(const System *S, GatherTables *out)
   return true;
 }
 
+int gather_kernel_kind(const System *S)
+{
+  const GatherPlan *G = static_cast<const GatherPlan *>(S->gather);
+  return !G ? 0 : G->urow ? 3 : G->lane ? 2 : 1;
+}
+
 void gather_free(System *S)
 {
   GatherPlan *G = static_cast<GatherPlan *>(S->gather);

@@ -166,6 +166,7 @@ struct GatherTables {
   int           tab_len = 0, tab_len_src = 0;
 };
 bool gather_tables(const System *S, GatherTables *out);
+int  gather_kernel_kind(const System *S); // 0 no plan, 1 thread per node, 2 lane groups, 3 row lanes
 // chns.cu
 int  chns_analyze(System *S);
 int  chns_build_plan(System *S);

@@ -138,6 +138,31 @@ def cube_mesh(n: int) -> Mesh:
     return box_mesh(n, n, n)
 
 
+def unstructured_tet_mesh(n: int, seed: int = 0, jitter: float = 0.3) -> Mesh:
+    """Unstructured tetrahedral mesh of the unit cube: Delaunay triangulation (scipy) of an (n+1)^3 lattice whose INTERIOR points
+    are moved by up to `jitter` cells; slivers are dropped, every tetrahedron is positively oriented.  Vertex and edge valences
+    vary from node to node (3 ... 9 tetrahedra around an edge), unlike the Kuhn meshes: the parity tests use it to exercise the
+    signature sort and the idle lanes of the row-lane kernels."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    g = np.linspace(0.0, 1.0, n + 1)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    interior = np.all((pts > 1e-12) & (pts < 1 - 1e-12), axis=1)
+    pts[interior] += (rng.random((int(interior.sum()), 3)) - 0.5) * 2.0 * jitter / n
+    cells = Delaunay(pts).simplices.astype(np.int64)
+    P = pts[cells]
+    vol = np.einsum("ei,ei->e", np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0]), P[:, 3] - P[:, 0]) / 6.0
+    keep = np.abs(vol) > 1e-3 / (6.0 * n ** 3)
+    cells, vol = cells[keep], vol[keep]
+    neg = vol < 0
+    cells[neg] = cells[neg][:, [0, 2, 1, 3]]
+    cells = np.ascontiguousarray(cells).astype(np.int32)
+    # vertices that lost all their tetrahedra would be orphan unknowns: the lattice + jitter never produces any, but check
+    assert np.unique(cells).size == pts.shape[0]
+    return Mesh(3, np.ascontiguousarray(pts), cells, boundary_facets(cells), point_pressure=0)
+
+
 def write_msh(mesh: Mesh, path: str) -> None:
     """Gmsh 4.1 ASCII with physical groups Domaine / Bord / PointPression, one geometric entity each."""
     dim, nV, nE, nB = mesh.dim, mesh.n_vertices, mesh.n_cells, mesh.bfacets.shape[0]

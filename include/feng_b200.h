@@ -193,6 +193,10 @@ int b200_set_assembly_mode(b200_system *s, int mode);
 /* 0: no write-once plan (scatter kernels); 1: the last b200_finalize built the row-owner gather plan; 2: it built the
  * patch plan (block-slot owners over Morton patches of elements, the default where the numbering qualifies) */
 int b200_has_gather_plan(const b200_system *s);
+/* which kernels the gather plan of the last b200_finalize launches for the velocity rows: 0 no plan, 1 thread per node, 2 lane
+ * groups (10 lanes per node), 3 row lanes (lane per matrix row, P2/P1 tetrahedra whose velocity nodes are three adjacent unknowns;
+ * csrc/gather_urow.cuh).  Diagnostic: the choice is made by the engine (B200_GATHER_KERNEL overrides it). */
+int b200_gather_kernel(const b200_system *s);
 /* rows of essential vector components (src/feLinearSystemMklPardiso.cpp:998-1041) and periodic (master, slave)
  * pairs (feMetaNumber::PeriodicDOF, src/feNumber.h:234) */
 int b200_set_constraints(b200_system *s, int64_t n_rows, const int64_t *rows, int64_t n_periodic,

@@ -101,6 +101,82 @@ def test_taylor_hood_3d_vs_oracle(kind, assembly):
     assert_close_vec(r, orr, 1e-12, "rhs")
 
 
+def _permute_unknowns(pb, sol, seed):
+    """Renumbers the unknowns by a random permutation (tables, pattern and state follow): the three components of a velocity
+    node are no longer adjacent unknowns, which the row-lane plan rejects -- the lane-group kernels must take over."""
+    perm = np.random.default_rng(seed).permutation(pb.n_inc)
+    ren = lambda a: np.where(a < pb.n_inc, perm[np.minimum(a, pb.n_inc - 1)], a).astype(a.dtype)
+    pb.adrU, pb.adrP = ren(pb.adrU), ren(pb.adrP)
+    pb.build_pattern()
+    out = sol.copy()
+    out[perm] = sol[:pb.n_inc]
+    return out
+
+
+@pytest.mark.parametrize("variant", ["row-lane", "lane", "permuted"])
+def test_taylor_hood_3d_unstructured_vs_oracle(variant, monkeypatch):
+    """Unstructured Delaunay tetrahedra (3 ... 10 tetrahedra around an edge, node stars of every shape: the signature sort and the
+    idle lanes of the row-lane schedule are exercised, unlike on Kuhn meshes), transient Navier-Stokes with a source: the default
+    row-lane kernels, the lane-group kernels, and a permuted numbering on which the row-lane plan must step aside; fused,
+    matrix-only + residual-only and transient-only passes against the oracle."""
+    from feng_b200 import mesh as M, problems as PB
+    from oracle import fe_oracle as O
+    if variant == "lane":
+        monkeypatch.setenv("B200_GATHER_KERNEL", "lane")
+    else:
+        monkeypatch.delenv("B200_GATHER_KERNEL", raising=False)
+    m = M.unstructured_tet_mesh(5, seed=3)
+    pb = PB.taylor_hood(m, "ns_div", 6, 3, 0.05, 1.1, transient=True)
+    sol = PB.perturb_unknowns(pb)
+    if variant == "permuted":
+        sol = _permute_unknowns(pb, sol, 11)
+    sd = np.random.default_rng(3).standard_normal(pb.n_dof)
+    ov, orr = O.assemble(to_oracle_problem(pb), pb.ia, pb.ja, sol, sd, 3.5)
+    ls, v, r = _cuda_assemble(pb, sol, sd, 3.5, assembly="gather")
+    assert ls.sys.gather_kernel() == (3 if variant == "row-lane" else 2)
+    assert_close_rows(v, ov, pb.ia, 1e-12, "matrix")
+    assert_close_vec(r, orr, 1e-12, "rhs")
+    ls.sys.set_to_zero(3)
+    ls.sys.assemble(2, False)
+    ls.sys.assemble(1, False)
+    assert_close_rows(ls.sys.get_matrix_values(), ov, pb.ia, 1e-12, "matrix (split)")
+    assert_close_vec(ls.sys.get_rhs(), orr, 1e-12, "rhs (split)")
+    opb = to_oracle_problem(pb)
+    opb.forms = [f for f in opb.forms if f.kind == O.TRANSIENT_VECTOR_MASS]
+    om, _ = O.assemble(opb, pb.ia, pb.ja, sol, sd, 3.5)
+    ls.sys.set_to_zero(3)
+    ls.sys.assemble(2, True)
+    assert_close_rows(ls.sys.get_matrix_values(), om, pb.ia, 1e-12, "transient-only matrix")
+    # write-once kernels: a second pass repeats bitwise
+    ls.sys.set_to_zero(3)
+    ls.sys.assemble(3, False)
+    v1, r1 = ls.sys.get_matrix_values(), ls.sys.get_rhs()
+    ls.sys.set_to_zero(3)
+    ls.sys.assemble(3, False)
+    assert np.array_equal(v1, ls.sys.get_matrix_values()) and np.array_equal(r1, ls.sys.get_rhs())
+
+
+def test_row_lane_is_the_default_3d_kernel_and_two_systems_coexist():
+    """Kuhn tetrahedra use the row-lane kernels by default; two systems with DIFFERENT quadrature rules (their reference tensors
+    share one __constant__ bank) assembled alternately still match the oracle."""
+    from feng_b200 import mesh as M, problems as PB
+    from oracle import fe_oracle as O
+    m = M.cube_mesh(3)
+    pbs = [PB.taylor_hood(m, "ns_div", 6, 3, 0.05, 1.1), PB.taylor_hood(m, "ns_lap", 4, 3, 0.2, 0.9)]
+    sols = [PB.perturb_unknowns(pb) for pb in pbs]
+    from feng_b200.linear_system import LinearSystemB200
+    lss = [LinearSystemB200(pb) for pb in pbs]
+    assert all(ls.sys.gather_kernel() == 3 for ls in lss)
+    for rep in range(2):
+        for pb, sol, ls in zip(pbs, sols, lss):
+            ls.sys.set_solution(sol, None, 0.0, 0.0)
+            ls.sys.set_to_zero(3)
+            ls.sys.assemble(3, False)
+            ov, orr = O.assemble(to_oracle_problem(pb), pb.ia, pb.ja, sol)
+            assert_close_rows(ls.sys.get_matrix_values(), ov, pb.ia, 1e-12, "matrix")
+            assert_close_vec(ls.sys.get_rhs(), orr, 1e-12, "rhs")
+
+
 @pytest.mark.parametrize("name", ["ref_square1_ns_div", "ref_square1_ns_lap", "ref_square1_stokes_div",
                                   "ref_square1_ns_div_transient", "syn_t2d5_ns_div_ppoint"])
 @pytest.mark.parametrize("assembly", ["scatter", "gather"])
