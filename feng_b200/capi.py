@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libfeng_b200.so")
 SYMBOLS = [
     "b200_last_error", "b200_kernel_launches", "b200_reset_kernel_launches", "b200_create", "b200_destroy",
     "b200_set_mesh", "b200_set_quadrature", "b200_add_space", "b200_add_form", "b200_set_source", "b200_set_form_coefficient", "b200_set_pattern",
-    "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode", "b200_set_assembly_mode", "b200_has_gather_plan", "b200_gather_kernel", "b200_add_form_chns",
+    "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode", "b200_set_assembly_mode", "b200_has_gather_plan", "b200_gather_kernel", "b200_error_norm", "b200_add_form_chns",
     "b200_set_constraints", "b200_set_periodic", "b200_set_blocks", "b200_finalize", "b200_system_size", "b200_set_solution",
     "b200_set_solution_n", "b200_set_essential", "b200_state_push", "b200_state_bdf", "b200_set_to_zero", "b200_assemble", "b200_rhs_max_norm", "b200_du_max_norm", "b200_constrain",
     "b200_apply_periodicity", "b200_solve", "b200_correct_solution", "b200_get_rhs", "b200_axpy_rhs",
@@ -217,6 +217,14 @@ class System:
     def gather_kernel(self) -> int:
         """velocity-row kernels of the gather plan: 0 none, 1 thread per node, 2 lane groups, 3 row lanes (gather_urow.cuh)"""
         return int(self.L.b200_gather_kernel(self.h))
+
+    def error_norm(self, space: int, kind: int = 0, p: int = 2, exact=None) -> float:
+        """feNorm on the device: kind 0 = Lp norm of (exact - uh), kind 1 = H1 seminorm; exact[nElm, nq, ncomp(, dim)] or None"""
+        ex = None if exact is None else np.ascontiguousarray(exact, np.float64)
+        out = C.c_double(0.)
+        check(self.L.b200_error_norm(self.h, int(space), int(kind), int(p), None if ex is None else _d(ex), C.byref(out)),
+              "b200_error_norm")
+        return float(out.value)
 
     def gather_plan_kind(self) -> int:
         """0 scatter kernels, 1 row-owner gather plan, 2 patch plan"""

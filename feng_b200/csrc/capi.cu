@@ -625,6 +625,12 @@ int b200_has_gather_plan(const b200_system *s) { return s && s->gather != nullpt
 
 int b200_gather_kernel(const b200_system *s) { return s ? gather_kernel_kind(s) : 0; }
 
+int b200_error_norm(b200_system *s, int space, int kind, int p, const double *exact, double *out)
+{
+  CHECK_S(s);
+  return error_norm(s, space, kind, p, exact, out);
+}
+
 int64_t b200_system_size(const b200_system *s) { return s ? s->nInc : 0; }
 
 int b200_set_solution(b200_system *s, const double *sol, const double *sol_dot, double c0, double t)

@@ -185,6 +185,8 @@ int           comm_spmv_overlapped(System *S, double *d_x, double *d_y); // halo
 int           comm_allreduce(System *S, double *d_buf, int count, bool max_op);
 int           comm_allgather64(System *S, const void *send, void *recv, size_t count);
 void          comm_boundary_rows(const System *S, const int32_t **rows, int64_t *n);
+// norms.cu
+int  error_norm(System *S, int space, int kind, int p, const double *exact, double *out);
 // krylov.cu
 int  spmv(System *S, const double *d_x, double *d_y);
 // rows with skip[row] == 0 (rows == nullptr) or the listed rows (skip == nullptr)

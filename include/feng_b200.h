@@ -197,6 +197,15 @@ int b200_has_gather_plan(const b200_system *s);
  * groups (10 lanes per node), 3 row lanes (lane per matrix row, P2/P1 tetrahedra whose velocity nodes are three adjacent unknowns;
  * csrc/gather_urow.cuh).  Diagnostic: the choice is made by the engine (B200_GATHER_KERNEL overrides it). */
 int b200_gather_kernel(const b200_system *s);
+/* Error norms of the state on the device (b200_set_solution / b200_correct_solution) for one space, feNorm of the reference:
+ *   kind = B200_NORM_LP:       ( int sum_i |u_i - uh_i|^p )^(1/p)      computeLpNorm / computeVectorLpNorm, src/feNorm.cpp:323-398, :1399-1443
+ *   kind = B200_NORM_H1_SEMI:  sqrt( int |grad u - grad uh|^2 )        computeH1SemiNorm / computeVectorH1SemiNorm, :1643-1732, :1794-1846
+ * `exact` tabulates the exact field (the reference evaluates its feFunction at the physical quadrature node):
+ * [n_elements][n_quad][n_components] values for B200_NORM_LP, [n_elements][n_quad][n_components][dim] gradients for
+ * B200_NORM_H1_SEMI; NULL: the norm of uh itself.  Deterministic (fixed summation order).  Single-GPU systems only. */
+#define B200_NORM_LP 0
+#define B200_NORM_H1_SEMI 1
+int b200_error_norm(b200_system *s, int space, int kind, int p, const double *exact, double *out);
 /* rows of essential vector components (src/feLinearSystemMklPardiso.cpp:998-1041) and periodic (master, slave)
  * pairs (feMetaNumber::PeriodicDOF, src/feNumber.h:234) */
 int b200_set_constraints(b200_system *s, int64_t n_rows, const int64_t *rows, int64_t n_periodic,
