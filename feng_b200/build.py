@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfeng_b200.so")
-SOURCES = ["capi.cu", "assemble.cu", "krylov.cu", "pattern.cu", "gather.cu", "comm.cu", "chns.cu", "amg.cu", "precond.cu", "norms.cu"]
+SOURCES = ["capi.cu", "assemble.cu", "krylov.cu", "pattern.cu", "gather.cu", "comm.cu", "chns.cu", "amg.cu", "precond.cu", "norms.cu", "numbering.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-I/usr/include"]

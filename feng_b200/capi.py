@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libfeng_b200.so")
 SYMBOLS = [
     "b200_last_error", "b200_kernel_launches", "b200_reset_kernel_launches", "b200_create", "b200_destroy",
     "b200_set_mesh", "b200_set_quadrature", "b200_add_space", "b200_add_form", "b200_set_source", "b200_set_form_coefficient", "b200_set_pattern",
-    "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode", "b200_set_assembly_mode", "b200_has_gather_plan", "b200_gather_kernel", "b200_error_norm", "b200_add_form_chns",
+    "b200_build_pattern", "b200_get_pattern_size", "b200_get_pattern", "b200_set_colors", "b200_set_scatter_mode", "b200_set_assembly_mode", "b200_has_gather_plan", "b200_gather_kernel", "b200_error_norm", "b200_unique_edges", "b200_add_form_chns",
     "b200_set_constraints", "b200_set_periodic", "b200_set_blocks", "b200_finalize", "b200_system_size", "b200_set_solution",
     "b200_set_solution_n", "b200_set_essential", "b200_state_push", "b200_state_bdf", "b200_set_to_zero", "b200_assemble", "b200_rhs_max_norm", "b200_du_max_norm", "b200_constrain",
     "b200_apply_periodicity", "b200_solve", "b200_correct_solution", "b200_get_rhs", "b200_axpy_rhs",
@@ -92,6 +92,20 @@ def _i32(a):
 
 def _i64(a):
     return _ptr(a, C.c_int64)
+
+
+def unique_edges(n_vertices: int, pairs, device: int = 0):
+    """Device version of numbering.build_edges' numpy.unique: (edge_of_pair int32[n], edges int32[nEdges, 2])."""
+    pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+    n = pairs.shape[0]
+    eop = np.empty(n, np.int32)
+    edges = np.empty((n, 2), np.int32)
+    ne = C.c_int64(0)
+    L = lib()
+    L.b200_unique_edges.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+    check(L.b200_unique_edges(int(device), int(n_vertices), int(n), pairs.ctypes.data_as(C.c_void_p), eop.ctypes.data_as(C.c_void_p),
+                              edges.ctypes.data_as(C.c_void_p), C.byref(ne)), "b200_unique_edges")
+    return eop, np.ascontiguousarray(edges[:ne.value])
 
 
 def check(rc, what=""):

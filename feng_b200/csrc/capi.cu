@@ -623,6 +623,12 @@ int b200_set_assembly_mode(b200_system *s, int mode)
 
 int b200_has_gather_plan(const b200_system *s) { return s && s->gather != nullptr ? (s->patch != nullptr ? 2 : 1) : 0; }
 
+int b200_unique_edges(int device, int64_t n_vertices, int64_t n_pairs, const int32_t *pairs, int32_t *edge_of_pair, int32_t *edges,
+                      int64_t *n_edges)
+{
+  return unique_edges(device, n_vertices, n_pairs, pairs, edge_of_pair, edges, n_edges);
+}
+
 int b200_gather_kernel(const b200_system *s) { return s ? gather_kernel_kind(s) : 0; }
 
 int b200_error_norm(b200_system *s, int space, int kind, int p, const double *exact, double *out)

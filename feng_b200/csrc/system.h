@@ -185,6 +185,8 @@ int           comm_spmv_overlapped(System *S, double *d_x, double *d_y); // halo
 int           comm_allreduce(System *S, double *d_buf, int count, bool max_op);
 int           comm_allgather64(System *S, const void *send, void *recv, size_t count);
 void          comm_boundary_rows(const System *S, const int32_t **rows, int64_t *n);
+// numbering.cu
+int  unique_edges(int device, int64_t nV, int64_t n, const int32_t *pairs, int32_t *edge_of_pair, int32_t *edges, int64_t *n_edges);
 // norms.cu
 int  error_norm(System *S, int space, int kind, int p, const double *exact, double *out);
 // krylov.cu

@@ -66,7 +66,23 @@ class Numbering:
         return np.ascontiguousarray(np.concatenate(parts, 1))
 
 
-def build_edges(mesh: Mesh):
+def _edge_device(n_pairs: int):
+    """Device index for the edge tags, or None: the GPU path is taken for meshes where numpy.unique is the slowest step of the
+    set-up (>= 2 M vertex pairs) when a CUDA device is visible; B200_EDGES=host | device overrides."""
+    import os
+    mode = os.environ.get("B200_EDGES", "auto")
+    if mode == "host" or (mode == "auto" and n_pairs < 2_000_000):
+        return None
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        return int(os.environ.get("LOCAL_RANK", "0")) % max(torch.cuda.device_count(), 1)
+    except Exception:
+        return None
+
+
+def build_edges(mesh: Mesh, device="auto"):
     """Unique edges in order of first appearance and the (nE, n_local_edges) cell->edge table."""
     loc = TRI_EDGES if mesh.dim == 2 else TET_EDGES
     ev = mesh.cells[:, loc].astype(np.int64)                   # (nE, ne, 2)
@@ -79,6 +95,14 @@ def build_edges(mesh: Mesh):
         pre = mesh.bfacets[:, TRI_EDGES].astype(np.int64).reshape(-1, 2)
         n_pre = pre.shape[0]
         flat = np.concatenate([pre, flat], 0)
+    if device == "auto":
+        device = _edge_device(flat.shape[0])
+    if device is not None and flat.shape[0] < 2 ** 31 - 1:
+        # same tags from the device (csrc/numbering.cu: sort / segment / rank on the GPU); bit-identical, tests/test_gpu_numbering.py
+        from . import capi
+        eop, edges = capi.unique_edges(mesh.n_vertices, flat, device)
+        cell_edges = eop[n_pre:].reshape(mesh.n_cells, loc.shape[0]).astype(np.int64)
+        return edges.astype(np.int64), cell_edges
     lo = flat.min(1)
     hi = flat.max(1)
     key = lo * np.int64(mesh.n_vertices) + hi

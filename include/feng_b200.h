@@ -193,6 +193,14 @@ int b200_set_assembly_mode(b200_system *s, int mode);
 /* 0: no write-once plan (scatter kernels); 1: the last b200_finalize built the row-owner gather plan; 2: it built the
  * patch plan (block-slot owners over Morton patches of elements, the default where the numbering qualifies) */
 int b200_has_gather_plan(const b200_system *s);
+/* Edge tags of a simplicial mesh, computed on the device: `pairs` lists the vertex pairs (v0, v1) of every local edge in the order
+ * the reference's reader sweeps them (boundary triangles first, then the cells; local edges as src/feTriangle.cpp:3-26 /
+ * src/feTetrahedron.h:31).  edge_of_pair[i] = tag of pair i = rank of its edge by FIRST appearance (std::set insertion of
+ * src/feMeshRead.cpp:1412-1456, :1613-1614); edges[tag] = the pair as first met (NULL to skip; capacity n_pairs pairs);
+ * *n_edges = number of distinct edges.  feNumber numbers the mid-edge DOFs of a P2 space in tag order (src/feNumber.cpp:370-483).
+ * Needs no b200_system. */
+int b200_unique_edges(int device, int64_t n_vertices, int64_t n_pairs, const int32_t *pairs, int32_t *edge_of_pair, int32_t *edges,
+                      int64_t *n_edges);
 /* which kernels the gather plan of the last b200_finalize launches for the velocity rows: 0 no plan, 1 thread per node, 2 lane
  * groups (10 lanes per node), 3 row lanes (lane per matrix row, P2/P1 tetrahedra whose velocity nodes are three adjacent unknowns;
  * csrc/gather_urow.cuh).  Diagnostic: the choice is made by the engine (B200_GATHER_KERNEL overrides it). */
