@@ -1276,8 +1276,8 @@ static int build_urow_plan(System *S, GatherPlan *G, const std::vector<double> &
     urow_sched_fill_kernel<<<(nw + 255) / 256, 256, 0, S->stream>>>(nw, cnt, G->d_order, G->d_lacnt, N.range, G->d_wstep, G->d_sched, G->d_sla);
     count_launch(3);
     if(getenv("B200_VERBOSE"))
-      fprintf(stderr, "[b200] row-lane plan: %d nodes in %d warps, %d steps for %lld pairs (lane efficiency %.3f), %d Morton cells\n", cnt, nw, tot,
-              (long long)N.nPairs, (double)N.nPairs / (10. * std::max(tot, 1)), 1 << cellbits);
+      fprintf(stderr, "[b200] row-lane plan: %d nodes in %d groups of 10, %d schedule steps (%.2f per node), %d Morton cells\n", cnt, nw, tot,
+              (double)tot * 10. / std::max(cnt, 1), 1 << cellbits);
   }
   int h_err = 0;
   B200_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, S->stream));
