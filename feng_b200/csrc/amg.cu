@@ -492,7 +492,7 @@ __global__ void amg_restrict_kernel(int64_t n, const double *__restrict__ b, con
 }
 
 __global__ void amg_prolong_kernel(int64_t n, const double *__restrict__ xc, const int32_t *__restrict__ par0, const int32_t *__restrict__ par1,
-                                   const uint8_t *__restrict__ pkind, double *__restrict__ x)
+                                   const uint8_t *__restrict__ pkind, double w, double *__restrict__ x)
 {
   for(int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = pkind[i];
@@ -501,7 +501,7 @@ __global__ void amg_prolong_kernel(int64_t n, const double *__restrict__ xc, con
     double        s = 0.;
     if(p0 >= 0) s += xc[p0];
     if(p1 >= 0) s += xc[p1];
-    x[i] += (k == 2 ? 0.5 : 1.) * s;
+    x[i] += (k == 2 ? 0.5 : 1.) * w * s;
   }
 }
 
@@ -954,9 +954,9 @@ static int aggregate_level(System *S, Amg *A, int l, int64_t *ncoarse)
   count_launch();
   for(int round = 0; round < 200; ++round) {
     amg_mis_prop_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, L.ia, L.ja, active, key, m1);
-    amg_mis_prop_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, L.ia, L.ja, active, m1, m2);
+    if(A->mis_distance >= 2) amg_mis_prop_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, L.ia, L.ja, active, m1, m2);
     B200_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int), S->stream));
-    amg_mis_update_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, key, m2, d_cnt);
+    amg_mis_update_kernel<<<grid_for(n), 256, 0, S->stream>>>(n, key, A->mis_distance >= 2 ? m2 : m1, d_cnt);
     count_launch(3);
     int cnt = 0;
     B200_CUDA(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, S->stream));
@@ -1043,6 +1043,9 @@ int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int 
   if(const char *e = getenv("B200_AMG_CYCLES")) A->cycles = std::max(1, atoi(e));
   if(const char *e = getenv("B200_AMG_RATIO")) A->cheb_ratio = std::max(1.5, atof(e));
   if(const char *e = getenv("B200_AMG_F32")) A->use_f32 = atoi(e) != 0;
+  if(const char *e = getenv("B200_AMG_MIS")) A->mis_distance = atoi(e) == 1 ? 1 : 2;
+  if(const char *e = getenv("B200_AMG_GAMMA")) A->gamma = std::max(1, atoi(e));
+  if(const char *e = getenv("B200_AMG_OVERCORRECT")) A->overcorrect = std::max(0.1, atof(e));
   A->L.emplace_back();
   {
     AmgLevel &L0 = A->L[0];
@@ -1126,7 +1129,12 @@ int amg_setup_symbolic(System *S, Amg *A, const uint8_t *d_fld, int fld_lo, int 
   // several GPUs: global hierarchy from level gl on (P2 hierarchies only; every rank must have that level)
   if(comm_active(S) && d_fld_all && p2 && !getenv("B200_AMG_LOCAL_COARSE")) {
     const int world = comm_world(S), rank = comm_rank(S);
-    const int gl = std::min(2, (int)A->L.size() - 1);
+    // first global level: 1 by default -- the P1 level is replicated too, so the hierarchy is that of the undecomposed operator at N
+    // times the level-1 work per rank (measured, T3D(92) on 2 GPUs: 240 iterations / 4.24 s against 270 / 4.62 s with
+    // B200_AMG_GLOBAL_LEVEL=2; T3D(48) on 4 GPUs: 224 / 0.71 s against 280 / 0.79 s)
+    int gl_first = 1;
+    if(const char *e = getenv("B200_AMG_GLOBAL_LEVEL")) gl_first = std::max(1, atoi(e));
+    const int gl = std::min(gl_first, (int)A->L.size() - 1);
     std::vector<double> cnt(world + 2, 0.);
     cnt[rank]      = gl >= 1 ? (double)A->L[gl].n : 0.;
     cnt[world]     = gl >= 1 ? 0. : 1.; // somebody without a coarse level: no global level
@@ -1373,9 +1381,13 @@ static int global_level_numeric(System *S, Amg *A)
   cudaFree(uv);
   if(first) {
     A->G = new Amg;
+    A->G->mis_distance = A->mis_distance;
     rc = amg_setup_symbolic_csr(S, A->G, A->gc_n, A->g_nnz, A->g_ia, A->g_ja, A->g_val);
     if(rc != B200_OK) return rc;
     A->G->cheb_degree = A->cheb_degree;
+    A->G->gamma       = A->gamma;
+    A->G->gamma_from  = 0;
+    A->G->overcorrect = A->overcorrect;
     A->G->cheb_ratio  = A->cheb_ratio;
   }
   return amg_setup_numeric(S, A->G);
@@ -1519,8 +1531,12 @@ static int cycle(System *S, Amg *A, int l, const double *b, double *x, bool zero
     amg_restrict_kernel<<<grid_for(L.n), 256, 0, S->stream>>>(L.n, b, L.t, L.par0, L.par1, L.pkind, C.b);
     count_launch();
     rc = cycle(S, A, l + 1, C.b, C.x);
+    // cycle index gamma (2 = W-cycle) below the finest level; the global replicated levels and the dense level are visited once
+    for(int v = 1; v < A->gamma && rc == B200_OK && l >= A->gamma_from && l + 1 < nl - 1 && !(A->gc_active && l + 1 == A->gl); ++v) rc = cycle(S, A, l + 1, C.b, C.x, false);
     if(rc != B200_OK) return rc;
-    amg_prolong_kernel<<<grid_for(L.n), 256, 0, S->stream>>>(L.n, C.x, L.par0, L.par1, L.pkind, x);
+    // plain aggregation under-estimates the coarse correction: over-correction factor on the aggregation levels (not on the P2 -> P1 step)
+    const double w = (l >= 1 || !L.par1) ? A->overcorrect : 1.;
+    amg_prolong_kernel<<<grid_for(L.n), 256, 0, S->stream>>>(L.n, C.x, L.par0, L.par1, L.pkind, w, x);
     count_launch();
   }
   return smooth(S, A, l, b, x, false);

@@ -51,6 +51,10 @@ struct Amg {
   int                   cheb_degree = AMG_CHEB_DEGREE, cycles = 1; // B200_AMG_DEGREE / B200_AMG_CYCLES
   int                   pre_degree = 0;                            // B200_AMG_PRE: degree of the pre-smoother (0 = cheb_degree)
   double                cheb_ratio = AMG_CHEB_RATIO;               // B200_AMG_RATIO
+  int                   gamma_from = 1;                            // first level whose coarse level is visited gamma times
+  int                   mis_distance = 1;                          // B200_AMG_MIS: roots of the aggregates = maximal independent set of distance 2 (or 1)
+  int                   gamma = 2;                                 // B200_AMG_GAMMA: cycle index below the finest level (2 = W-cycle)
+  double                overcorrect = 1.5;                          // B200_AMG_OVERCORRECT: scaling of the aggregation-level corrections
   bool                  use_f32 = true;                            // B200_AMG_F32=0: level 0 works on the FP64 system matrix
   // several GPUs: the hierarchy is rank-local down to level `gl` - 1 (block-Jacobi across ranks: couplings to ghost columns are
   // dropped there); from level `gl` (= 2: the first aggregation level of a P2 hierarchy) on it is GLOBAL.  The level-gl operator
