@@ -21,11 +21,16 @@ def main():
     ap.add_argument("--restart", type=int, default=30)
     ap.add_argument("--maxit", type=int, default=600)
     ap.add_argument("--kind", default="ns_div")
+    ap.add_argument("--box", type=int, default=0, help="3-D: n x n x (box * n) cells on [0,1]^2 x [0, box] instead of the cube (the weak-scaling domain of "
+                    "`box` GPUs, undecomposed)")
     args = ap.parse_args()
     from feng_b200 import mesh as M, problems as PB
     from feng_b200.linear_system import LinearSystemB200
     for n in args.n:
         m = M.cube_mesh(n) if args.dim == 3 else M.square_mesh(n)
+        if args.dim == 3 and args.box > 1:
+            m = M.box_mesh(n, n, n * args.box, float(args.box))
+            m.point_pressure = 0
         pb = PB.taylor_hood(m, args.kind, 6 if args.dim == 3 else 8, 3 if args.dim == 3 else 1, 1. / 40., 1.0, with_source=False,
                             build_pattern=False)
         sol = PB.perturb_unknowns(pb)

@@ -98,7 +98,9 @@ def test_periodic_pairs_pattern_extras_and_apply_periodicity(device_pattern):
     assert info["converged"], info
     s_cpu, _ = P.newton(1e-10, 1e-10, 10)
     assert np.abs(s_gpu - s_cpu).max() <= 1e-9 * np.abs(s_cpu).max()
-    assert np.abs(s_gpu[master] - s_gpu[slave]).max() <= 1e-12
+    # the constraint rows du_slave - du_master = 0 are rows of the system the Krylov method solves to rel_tol = 1e-12 (preconditioned
+    # residual, solution of order one): they hold to a small multiple of that tolerance, not to rounding
+    assert np.abs(s_gpu[master] - s_gpu[slave]).max() <= 1e-11
     P.close()
 
 
