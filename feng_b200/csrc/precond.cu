@@ -8,7 +8,8 @@
 //                      with F^-1 ~ one V-cycle of the velocity hierarchy (amg.cu) and the Schur complement S = -D F^-1 G
 //                      replaced by the scaled diagonal of the pressure mass matrix: with F ~ f K (K the vector Laplacian,
 //                      f = VectorDiffusion coeff*k - DivergenceNewtonianStress coeff*mu), G = g B^T (g = stress coeff - MixedGradient
-//                      coeff), D = d B (d = MixedDivergence coeff) the inf-sup property gives S ~ -(d g / f) M_p.
+//                      coeff), D = d B (d = MixedDivergence coeff) the inf-sup property gives S ~ -(d g / f_S) M_p, where the
+//                      stress form enters f_S twice (its symbol is mu (|k|^2 I + k k^T): k^T F^-1 k = 1 / (2 mu)).
 //                      When a single pressure unknown is pinned (the reference's `PointPression` essential space,
 //                      tests/withLinearSolver/navier_stokes.cpp:63-81) the constant pressure mode survives in S with an O(h^dim)
 //                      eigenvalue; it is treated by a rank-one term: z_p += beta sum(r_p).
@@ -404,7 +405,12 @@ int precond_setup(System *S, int pc)
         set_error("B200_PC_SCHUR_AMG: the system has no viscous / pressure-gradient / divergence form");
         return B200_ERR_UNSUPP;
       }
-      P->schur_scale = -f / (d * g); // S^-1 ~ -(f / (d g)) M_p^-1
+      // S^-1 ~ -(f_S / (d g)) M_p^-1.  The stress-divergence form counts twice in f_S: for F = mu (|k|^2 I + k k^T) (Fourier symbol of
+      // -div(mu (grad u + grad u^T))) k^T F^-1 k = 1 / (2 mu), against 1 / mu for the Laplacian form.  Measured at T3D(92), divergence
+      // form: factor 1 -> 103 iterations, 1.5 -> 98, 2 -> 92, 2.5 -> 90, 4 -> 91, 0.7 -> 113 (B200_PC_SCHUR_SCALE multiplies on top).
+      const double f_schur = c.diff_k - 2. * c.sig_mu;
+      P->schur_scale = -f_schur / (d * g);
+      if(const char *e = getenv("B200_PC_SCHUR_SCALE")) P->schur_scale *= atof(e);
       pc_alpha_kernel<<<GRID, 256, 0, S->stream>>>(S->nInc, P->d_fld, P->d_pmass, P->schur_scale, P->d_alpha);
       count_launch();
       if(P->d_valg) {
