@@ -10,16 +10,20 @@
 //             every row of a scalar problem); nothing is copied
 //   level 1   for P2 spaces: the P1 sub-space on the same mesh (vertex unknowns keep their value, a mid-edge unknown
 //             is the mean of its two end vertices) -- Galerkin product P^T A P of the component-diagonal blocks
-//   level 2+  plain aggregation on a distance-2 maximal independent set of the matrix graph (Bell, Dalton, Olson,
-//             SIAM J. Sci. Comput. 34 (2012)): roots = MIS(2), every unknown joins the nearest root, Galerkin product =
-//             sum of the entries of an aggregate pair
+//   level 2+  plain aggregation around a maximal independent set of the matrix graph (Bell, Dalton, Olson, SIAM J. Sci.
+//             Comput. 34 (2012)): roots = MIS(1) by default (MIS(2): B200_AMG_MIS=2), every unknown joins the nearest root,
+//             Galerkin product = sum of the entries of an aggregate pair
 //   coarsest  dense inverse (Gauss-Jordan in one CTA)
 //
-// Cycle: V(2,2) with Chebyshev-accelerated Jacobi (spectral radius of D^-1 A from a few power iterations).  The symbolic
-// part (parents, aggregates, coarse patterns) depends on the mesh and the pattern only and is built once; the numeric
-// part (Galerkin values, inverse diagonals, spectral radii, coarse inverse) is redone whenever the matrix changed.
-// On several GPUs the hierarchy is rank-local (ghost rows are masked out): block-Jacobi across ranks, as PETSc's
-// parallel default.
+// Cycle: Chebyshev-accelerated Jacobi smoothing, 2 + 2 sweeps (spectral radius of D^-1 A from a few power iterations); V on the
+// P2 -> P1 step, W below it (B200_AMG_GAMMA), corrections of the aggregation levels scaled by 1.5 (B200_AMG_OVERCORRECT:
+// piecewise-constant prolongation under-estimates them; a fixed factor keeps the cycle a linear operator).  Measured at
+// T3D(92): 197 -> 103 Krylov iterations against MIS(2) / V / 1 (profiles/README.md r02y).  The symbolic part (parents,
+// aggregates, coarse patterns) depends on the mesh and the pattern only and is built once; the numeric part (Galerkin values,
+// inverse diagonals, spectral radii, coarse inverse) is redone whenever the matrix changed.
+// On several GPUs level 0 is rank-local but keeps its couplings to ghost columns (halo update before every product), and the
+// hierarchy from level 1 on is global and replicated: the level-1 triplets of all ranks (couplings across the cuts included)
+// are all-gathered, merged and coarsened identically everywhere; B200_AMG_GLOBAL_LEVEL=2 keeps the P1 level rank-local.
 #include <thrust/binary_search.h>
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
@@ -328,7 +332,7 @@ __global__ void amg_dinv_kernel(int64_t n, const int64_t *__restrict__ ia, const
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// MIS(2) aggregation
+// MIS aggregation (distance 2: two propagation steps per round; distance 1: one)
 // ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t amg_hash(uint32_t x)
 {
@@ -931,7 +935,7 @@ static bool check_p2_edges(const Space &sp, int dim, int nq)
   return true;
 }
 
-// aggregation of level `l` (symbolic): MIS(2) roots, two rings of growth, orphans as singletons
+// aggregation of level `l` (symbolic): MIS roots, two rings of growth (the second finds nothing after MIS(1)), orphans as singletons
 static int aggregate_level(System *S, Amg *A, int l, int64_t *ncoarse)
 {
   AmgLevel     &L = A->L[l];
@@ -1542,7 +1546,7 @@ static int cycle(System *S, Amg *A, int l, const double *b, double *x, bool zero
   return smooth(S, A, l, b, x, false);
 }
 
-// x = one V-cycle applied to b (both n-vectors of the system; inactive rows of x come out 0)
+// x = one multigrid cycle applied to b (both n-vectors of the system; inactive rows of x come out 0)
 int amg_vcycle(System *S, Amg *A, const double *b, double *x)
 {
   int rc = cycle(S, A, 0, b, x, true);

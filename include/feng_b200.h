@@ -100,10 +100,11 @@ enum {
                                every block fall back to point Jacobi; a singular block is reported (B200_ERR_SOLVER)    */
   /* 3 is not used: PETSc's sequential default, ILU(0) (src/feLinearSystem.h:198), is a chain of sparse triangular solves and is
      replaced on this hardware by the multigrid-based preconditioners below                                              */
-  B200_PC_AMG          = 4, /* one multigrid V-cycle on the whole matrix (scalar diffusion-type systems): P2 -> P1 on the same
-                               mesh, then MIS(2) aggregation levels, Chebyshev-Jacobi smoothing (csrc/amg.cu)              */
+  B200_PC_AMG          = 4, /* one multigrid cycle on the whole matrix (scalar diffusion-type systems): P2 -> P1 on the same
+                               mesh, then aggregation levels (W-cycle, over-corrected), Chebyshev-Jacobi smoothing
+                               (csrc/amg.cu)                                                                                */
   B200_PC_SCHUR_AMG    = 5, /* Taylor-Hood saddle-point systems: block upper-triangular preconditioner, velocity block by
-                               the multigrid V-cycle, Schur complement by the scaled pressure mass diagonal with a rank-one
+                               one multigrid cycle, Schur complement by the scaled pressure mass diagonal with a rank-one
                                term for a pinned pressure (csrc/precond.cu)                                                 */
   B200_PC_AUTO         = 6  /* SCHUR_AMG for Taylor-Hood systems, AMG for scalar systems, JACOBI otherwise (CHNS)           */
 };
