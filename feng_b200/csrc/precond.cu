@@ -250,6 +250,7 @@ bool precond_fallback(System *S)
   Precond *P = static_cast<Precond *>(S->precond);
   if(!P || P->amg.cheb_degree <= 1) return false;
   P->amg.cheb_degree = 1; // sticky: the following Newton iterations of this system start in the safe mode
+  if(P->amg.G) P->amg.G->cheb_degree = 1; // the replicated global levels (several GPUs) follow
   if(P->amg.verbose) fprintf(stderr, "[feng_b200] GMRES stagnates: multigrid smoother degraded to damped Jacobi\n");
   return true;
 }
